@@ -1,0 +1,125 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in this container.
+
+TEST INFRASTRUCTURE ONLY.  Run once from the repo root in the build container
+(where /root/reference exists); the resulting small fixtures are committed so
+that the GPU box, which has no /root/reference, can check against them.
+
+    python oracle/make_golden.py
+
+How the reference is made importable without editing it:
+  * oracle/shims/opt_einsum  -> numpy.einsum(optimize=True)
+  * oracle/shims/mpi4py      -> single-process COMM_WORLD
+  * numpy.lib.format._read_array_header alias (numpy >= 2 moved it)
+Inputs go through the reference's own stock loaders (`GaugeFieldBinary`,
+`EigenvectorNpy`), the generators are driven exactly like
+tests/test_elemental.py:41-44 and tests/test_displacement_elemental.py:40-43.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = os.environ.get("EDK_REFERENCE_ROOT", "/root/reference")
+
+
+def import_reference():
+    sys.path.insert(0, os.path.join(HERE, "shims"))
+    sys.path.insert(1, REF)
+    import numpy.lib.format as fmt
+
+    if not hasattr(fmt, "_read_array_header"):
+        import numpy.lib._format_impl as impl
+
+        fmt._read_array_header = impl._read_array_header
+    import lattice
+
+    lattice.set_backend("numpy")
+    return lattice
+
+
+def run_reference(lattice, latt_size, Ne, U_file, V_file, *, num_nabla=None, distance=None, momentum_list, dilution=None):
+    """U_file [Lt,Lz,Ly,Lx,4,3,3] c16, V_file [Lt,Ne,Lz,Ly,Lx,3] c16 -> [Lt,Nop,Nmom,Ne,Ne]."""
+    Lx, Ly, Lz, Lt = latt_size
+    with tempfile.TemporaryDirectory() as tmp:
+        prefix = tmp + "/"
+        U_file.astype("<c16").tofile(prefix + "cfg.dat")
+        np.save(prefix + "cfg.eigenvector.npy", V_file.astype("<c16"))
+        gauge = lattice.preset.GaugeFieldBinary(prefix, ".dat", [Lt, Lz, Ly, Lx, 4, 3, 3], "<c16")
+        evec = lattice.EigenvectorNpy(prefix, ".eigenvector.npy", [Lt, Ne, Lz, Ly, Lx, 3], Ne)
+        if distance is None:
+            if dilution is None:
+                gen = lattice.ElementalGenerator(latt_size, gauge, evec, num_nabla, momentum_list)
+            else:
+                gen = lattice.ElementalGenerator(latt_size, gauge, evec, num_nabla, momentum_list, dilution, True)
+        else:
+            gen = lattice.DisplacementElementalGenerator(latt_size, gauge, evec, distance, momentum_list)
+        gen.load("cfg")
+        out = []
+        for t in range(Lt):
+            out.append(np.array(gen.calc(t), copy=True))
+    return np.stack(out)
+
+
+def main():
+    sys.path.insert(0, REPO)
+    from oracle import elemental_oracle as orc
+
+    lattice = import_reference()
+    outdir = os.path.join(REPO, "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+
+    cases = {
+        # name: (latt_size [Lx,Ly,Lz,Lt], Ne, link kind, kwargs)
+        "deriv_weak_4x4x4x2": ([4, 4, 4, 2], 8, "weak", dict(num_nabla=2, momentum_list=[(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 2), (0, 1, 2), (1, 1, 2)])),
+        "deriv_random_4x6x8x1": ([4, 6, 8, 1], 6, "random", dict(num_nabla=2, momentum_list=[(0, 0, 0), (1, 0, 0), (0, -1, 2), (-1, 1, -1), (3, 2, 1)])),
+        "deriv_n1_random_6x4x2x1": ([6, 4, 2, 1], 5, "random", dict(num_nabla=1, momentum_list=[(0, 0, 0), (0, 1, 0), (-2, 0, 1)])),
+        "deriv_blend_4x4x4x1": ([4, 4, 4, 1], 6, "random", dict(num_nabla=1, momentum_list=[(0, 0, 0), (1, 0, -1)], dilution=([10, 7], [4, 2]))),
+        "disp_weak_4x4x4x2": ([4, 4, 4, 2], 8, "weak", dict(distance=8, momentum_list=[(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 1, 2), (1, 1, 2)])),
+        "disp_random_4x6x8x1": ([4, 6, 8, 1], 6, "random", dict(distance=3, momentum_list=[(0, 0, 0), (1, 0, 0), (0, -1, 2)])),
+    }
+    for name, (latt, Ne, kind, kw) in cases.items():
+        Lx, Ly, Lz, Lt = latt
+        U_file = np.stack([orc.synthetic_links(latt, t, kind) for t in range(Lt)])
+        V_file = np.stack([orc.synthetic_eigvecs(latt, Ne, t) for t in range(Lt)])
+        ref = run_reference(lattice, latt, Ne, U_file, V_file, **kw)
+        meta = dict(latt_size=np.array(latt), Ne=Ne, momentum_list=np.array(kw["momentum_list"]))
+        if "num_nabla" in kw:
+            meta["num_nabla"] = kw["num_nabla"]
+        if "distance" in kw:
+            meta["distance"] = kw["distance"]
+        if kw.get("dilution") is not None:
+            meta["dilution_tot"] = np.array(kw["dilution"][0])
+            meta["dilution_used"] = np.array(kw["dilution"][1])
+        # eigenvectors are stored as complex64: the reference rounds them through
+        # complex64 before use, so nothing the path sees is lost
+        np.savez_compressed(
+            os.path.join(outdir, name + ".npz"),
+            U=U_file.astype("<c16"),
+            V=V_file.astype("<c8"),
+            E=ref.astype("<c16"),
+            **meta,
+        )
+        print(f"{name}: U{U_file.shape} V{V_file.shape} -> E{ref.shape}  |E|={np.linalg.norm(ref):.6e}")
+
+    # index-map and phase goldens straight from the reference's insertion module
+    from lattice.insertion.derivative import derivative
+    from lattice.insertion.phase import MomentumPhase
+
+    tuples = [list(derivative(n)) + [-1] * (3 - len(derivative(n))) for n in range(40)]
+    mp = MomentumPhase([4, 6, 8, 2])
+    moms = [(0, 0, 0), (1, 0, 0), (0, -1, 2), (3, 2, 1), (-2, 5, -7)]
+    np.savez_compressed(
+        os.path.join(outdir, "insertion_maps.npz"),
+        derivative_tuples=np.array(tuples),
+        phase_latt=np.array([4, 6, 8, 2]),
+        phase_moms=np.array(moms),
+        phases=np.stack([mp.get(p) for p in moms]),
+    )
+    print("insertion_maps written")
+
+
+if __name__ == "__main__":
+    main()

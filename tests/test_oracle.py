@@ -1,0 +1,109 @@
+"""Pin the CPU oracle against outputs of the reference itself (tests/golden/*.npz,
+made by oracle/make_golden.py from the unmodified reference)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+from oracle import elemental_oracle as orc
+
+TOL = 1e-12  # oracle and reference share numpy/BLAS; only summation order differs
+
+DERIV_CASES = ["deriv_weak_4x4x4x2", "deriv_random_4x6x8x1", "deriv_n1_random_6x4x2x1"]
+DISP_CASES = ["disp_weak_4x4x4x2", "disp_random_4x6x8x1"]
+
+
+def test_derivative_tuple_matches_reference():
+    g = load_golden("insertion_maps")
+    for n, row in enumerate(g["derivative_tuples"]):
+        assert orc.derivative_tuple(n) == tuple(int(v) for v in row if v >= 0)
+    assert [orc.derivative_tuple(n) for n in range(5)] == [(), (0,), (1,), (2,), (0, 0)]
+    assert orc.derivative_tuple(5) == (0, 1) and orc.derivative_tuple(12) == (2, 2)
+    assert [orc.num_derivative(n) for n in range(4)] == [1, 4, 13, 40]
+
+
+def test_momentum_phase_matches_reference():
+    g = load_golden("insertion_maps")
+    latt = [int(v) for v in g["phase_latt"]]
+    for p, ref in zip(g["phase_moms"], g["phases"]):
+        got = orc.momentum_phase(latt, tuple(int(v) for v in p))
+        assert got.shape == ref.shape == (latt[2], latt[1], latt[0])
+        assert np.max(np.abs(got - ref)) < 1e-14
+
+
+@pytest.mark.parametrize("name", DERIV_CASES)
+def test_elemental_faithful_and_closed_form(name):
+    g = load_golden(name)
+    latt = [int(v) for v in g["latt_size"]]
+    moms = [tuple(int(v) for v in p) for p in g["momentum_list"]]
+    for t in range(latt[3]):
+        U_t = orc.links_file_to_spatial(g["U"][t])
+        ref = g["E"][t]
+        a = orc.elemental_timeslice(g["V"][t], U_t, latt, int(g["num_nabla"]), moms)
+        b = orc.elemental_timeslice_closed_form(g["V"][t], U_t, latt, int(g["num_nabla"]), moms)
+        for d in range(ref.shape[0]):
+            for p in range(ref.shape[1]):
+                assert rel_err(a[d, p], ref[d, p]) < TOL, (name, t, d, p)
+                assert rel_err(b[d, p], ref[d, p]) < TOL, (name, t, d, p)
+
+
+def test_blending_matches_reference():
+    g = load_golden("deriv_blend_4x4x4x1")
+    latt = [int(v) for v in g["latt_size"]]
+    moms = [tuple(int(v) for v in p) for p in g["momentum_list"]]
+    coeff = orc.blending_matrix(int(g["Ne"]), (list(g["dilution_tot"]), list(g["dilution_used"])))
+    U_t = orc.links_file_to_spatial(g["U"][0])
+    a = orc.elemental_timeslice(g["V"][0], U_t, latt, int(g["num_nabla"]), moms, coeff)
+    assert rel_err(a, g["E"][0]) < TOL
+    # scalar form of the second dilution entry
+    c2 = orc.blending_matrix(4, ([10, 6], 2))
+    assert c2[0, 0] == 5.0 and c2[0, 1] == 5.0 * 9 and c2[0, 2] == 15.0
+
+
+@pytest.mark.parametrize("name", DISP_CASES)
+def test_displacement_matches_reference(name):
+    g = load_golden(name)
+    latt = [int(v) for v in g["latt_size"]]
+    moms = [tuple(int(v) for v in p) for p in g["momentum_list"]]
+    for t in range(latt[3]):
+        U_t = orc.links_file_to_spatial(g["U"][t])
+        a = orc.displacement_timeslice(g["V"][t], U_t, latt, int(g["distance"]), moms)
+        ref = g["E"][t]
+        for k in range(ref.shape[0]):
+            for p in range(ref.shape[1]):
+                assert rel_err(a[k, p], ref[k, p]) < TOL, (name, t, k, p)
+
+
+def test_c8_rounding_is_part_of_the_contract():
+    """Skipping the complex64 staging changes the answer by ~1e-8 (hard part i)."""
+    latt = [4, 4, 4, 1]
+    U = orc.links_file_to_spatial(orc.synthetic_links(latt, 0))
+    V = orc.synthetic_eigvecs(latt, 4, 0)
+    with_round = orc.elemental_timeslice_closed_form(V, U, latt, 1, [(0, 0, 0)])
+    W0 = V.astype(np.complex128)
+    no_round = np.einsum("ezyxc,fzyxc->ef", W0.conj(), W0)
+    assert 1e-9 < rel_err(no_round, with_round[0, 0]) < 1e-6
+
+
+def test_hermiticity_property():
+    """G(L,R,p)^dagger = G(R,L,-p): E[0,p]^dagger = E[0,-p]; E[a,p]^dagger = -E[a,-p]."""
+    latt = [4, 6, 2, 1]
+    U = orc.links_file_to_spatial(orc.synthetic_links(latt, 3))
+    V = orc.synthetic_eigvecs(latt, 5, 3)
+    E = orc.elemental_timeslice_closed_form(V, U, latt, 1, [(1, -1, 0), (-1, 1, 0)])
+    assert rel_err(E[0, 0].conj().T, E[0, 1]) < 1e-13
+    for a in range(1, 4):
+        assert rel_err(-E[a, 0].conj().T, E[a, 1]) < 1e-13
+
+
+def test_synthetic_inputs_are_seeded_and_unitary():
+    latt = [4, 4, 4, 2]
+    u0 = orc.synthetic_links(latt, 1)
+    assert np.array_equal(u0, orc.synthetic_links(latt, 1))
+    eye = np.einsum("...ab,...cb->...ac", u0, u0.conj())
+    assert np.max(np.abs(eye - np.eye(3))) < 1e-13
+    assert np.max(np.abs(np.linalg.det(u0) - 1)) < 1e-13
+    v = orc.synthetic_eigvecs(latt, 3, 0)
+    assert np.allclose((np.abs(v) ** 2).sum(axis=(1, 2, 3, 4)), 1.0)
+    m33 = orc.momentum_set(33)
+    assert len(m33) == 33 and m33[0] == (0, 0, 0) and max(sum(c * c for c in p) for p in m33) == 4
+    assert set(m33) == {tuple(-c for c in p) for p in m33}
