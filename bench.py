@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Elemental-generation benchmark: timeslices/s on N B200s, roofline and CPU baseline beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config5] [--impl reference]
+
+A "step" is one timeslice of the workload: all Nop x Nmom matrices E[d,p](t) of size Ne x Ne.
+Native arm: `value` is measured with the step's inputs already resident in HBM, `e2e` through
+the host-buffer C-ABI call (edk_calc_host) with H2D/D2H inside the timed region.  For N > 1 each
+rank owns its own timeslices (weak scaling), and the timed region ends with the NCCL gather of
+all results onto rank 0 - the only exchange step this path has.
+Reference arm (`--impl reference`): the numpy restatement of the reference algorithm
+(oracle/elemental_oracle.py, kind "port": the reference itself is a Python package that does
+not exist on the GPU box) timed on the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (Lx, Ly, Lz, Lt, Ne, num_nabla, nmom)  -- BASELINE.json configs[1..4]; tiny is for smoke runs
+    "tiny": (8, 8, 8, 8, 16, 2, 7),
+    "config2": (16, 16, 16, 128, 100, 1, 9),
+    "config3": (24, 24, 24, 72, 100, 2, 33),
+    "config4": (32, 32, 32, 64, 200, 2, 33),
+    "config5": (48, 48, 48, 96, 200, 2, 33),
+}
+PAIRS_DISTINCT = {0: 1, 1: 7, 2: 34}     # distinct (left, right) pair-GEMMs per momentum
+PAIRS_REFERENCE = {0: 1, 1: 7, 2: 43}    # pair-einsums the reference executes: sum_k 3^k 2^k
+HOPS_REFERENCE = {0: 0, 1: 6, 2: 78}     # single-direction _nD applications per timeslice
+SRC_OUT = {0: (0, 0), 1: (1, 3), 2: (4, 12)}  # stencil source / output fields per timeslice
+
+
+def workload_desc(name):
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    return (f"{name}: {Lx}x{Ly}x{Lz}x{Lt} synthetic gauge field, Ne={Ne}, num_nabla={nabla}, {nmom} momenta, "
+            "ElementalGenerator, one timeslice per step")
+
+
+def algorithmic(name):
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    V = Lx * Ly * Lz
+    flops = 8.0 * Ne * Ne * 3 * V * nmom * PAIRS_DISTINCT[nabla]
+    nsrc, nout = SRC_OUT[nabla]
+    stencil_bytes = (nsrc + nout) * Ne * V * 48.0 + nsrc * 3 * V * 144.0
+    return flops, stencil_bytes
+
+
+def momentum_set(count):
+    r = range(-3, 4)
+    allp = sorted(((px * px + py * py + pz * pz, (px, py, pz)) for px in r for py in r for pz in r))
+    return [p for _, p in allp[:count]]
+
+
+# --------------------------------------------------------------------------------------------
+# clocks during the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self.dev)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_sample(name, W0=None, U=None, hop_frac=8):
+    """Time the reference's two primitives at the workload's size and compose one timeslice
+    (SURVEY 8d): T = hops * t_hop + pairs * Nmom * t_pair.  One hop is run on Ne/hop_frac of the
+    eigenvectors (its cost is linear in Ne) and scaled; the pair contraction is run in full.
+    Validated in the build container on config 3: composed 335 s vs 335.7 s for the complete
+    reference run."""
+    from oracle import elemental_oracle as orc
+
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    latt = [Lx, Ly, Lz, Lt]
+    rng = np.random.default_rng(orc.SEED0)
+    if W0 is None:
+        W0 = (rng.standard_normal((Ne, Lz, Ly, Lx, 3)) + 1j * rng.standard_normal((Ne, Lz, Ly, Lx, 3))).astype(np.complex64)
+    if U is None:
+        U = orc.links_file_to_spatial(orc.synthetic_links(latt, 0))
+    ne_hop = max(1, Ne // hop_frac)
+    # each primitive is run once untimed first: the reference calls them 78 / 43*Nmom times per
+    # timeslice, so the warm figure (BLAS threads up, einsum path cached) is the representative one
+    orc.covariant_hop(W0[:ne_hop], U, 0)
+    t0 = time.perf_counter()
+    W1 = orc.covariant_hop(W0[:ne_hop], U, 0)
+    t_hop = (time.perf_counter() - t0) * (Ne / ne_hop)
+    right = np.ascontiguousarray(np.broadcast_to(W1[:1], W0.shape)) if ne_hop < Ne else W1
+    phase = orc.momentum_phase(latt, (0, 0, 1))
+    orc.gram(W0, right, -1 * phase)
+    t0 = time.perf_counter()
+    orc.gram(W0, right, -1 * phase)
+    t_pair = time.perf_counter() - t0
+    T = HOPS_REFERENCE[nabla] * t_hop + PAIRS_REFERENCE[nabla] * nmom * t_pair
+    sample = (f"1 _nD hop on {ne_hop}/{Ne} eigenvectors (scaled x{Ne / ne_hop:.0f}) = {t_hop:.2f}s, "
+              f"1 (pair, momentum) einsum at full size = {t_pair:.2f}s; composed "
+              f"{HOPS_REFERENCE[nabla]} hops + {PAIRS_REFERENCE[nabla]}x{nmom} einsums = {T:.1f}s per timeslice")
+    return 1.0 / T, sample
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle.elemental_oracle  # noqa: F401  (loads numpy/BLAS before threads are counted)
+
+    name = args.workload
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, sample = cpu_sample(name)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(len(vals) / sum(1.0 / v for v in vals))
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+        "config": {"workload": workload_desc(name)},
+        "cpu_baseline": {"value": value, "unit": "timeslices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "timeslices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# native arm
+# --------------------------------------------------------------------------------------------
+def synth_device_inputs(torch, dev, name, seed):
+    """Random SU(3) links [V,4,3,3] c128 (file order of one timeslice) and unit-norm complex64
+    eigenvectors [Ne,V,3], generated on the device (bench only; tests use the oracle's numpy ones)."""
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    V = Lx * Ly * Lz
+    g = torch.Generator(device=dev)
+    g.manual_seed(20261017 + seed)
+    a = torch.randn((V, 4, 3, 3), dtype=torch.complex128, device=dev, generator=g)
+    q, r = torch.linalg.qr(a)
+    d = torch.diagonal(r, dim1=-2, dim2=-1)
+    q = q * (d / d.abs()).unsqueeze(-2)
+    det = torch.linalg.det(q)
+    U = (q / det.pow(1.0 / 3.0)[..., None, None]).contiguous()
+    v = torch.randn((Ne, V, 3), dtype=torch.complex64, device=dev, generator=g)
+    v = v / torch.linalg.vector_norm(v.reshape(Ne, -1), dim=1)[:, None, None]
+    return U, v.contiguous()
+
+
+def fp64_gemm_peak(torch, dev):
+    """cuBLAS FP64 GEMM on this device, best of 10 (same method as MEASURED_PEAKS.json):
+    the denominator of the contraction roofline."""
+    n = 8192
+    out = {}
+    for label, dt, flop in (("dgemm", torch.float64, 2.0 * n**3), ("zgemm", torch.complex128, 8.0 * n**3)):
+        m = n if dt == torch.float64 else n // 2
+        fl = flop if dt == torch.float64 else 8.0 * m**3
+        a = torch.randn((m, m), dtype=dt, device=dev)
+        b = torch.randn((m, m), dtype=dt, device=dev)
+        torch.matmul(a, b)
+        best = 0.0
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            e1.synchronize()
+            best = max(best, fl / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        out[label] = best
+        del a, b
+    return out
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from easydistillation_b200 import _capi
+    from easydistillation_b200.engine import ElementalEngine, microbench_fp64
+    from easydistillation_b200.sharding import gather_timeslices
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    name = args.workload
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    V = Lx * Ly * Lz
+    K, W = args.steps, args.warmup
+    moms = momentum_set(nmom)
+    eng = ElementalEngine((Lx, Ly, Lz), Ne, _capi.MODE_DERIVATIVE, nabla, moms, device=local)
+
+    # two resident input sets, alternated, each far larger than L2 at the graded workloads
+    inputs = [synth_device_inputs(torch, dev, name, 1000 * rank + i) for i in range(2)]
+    outs = torch.empty((K,) + eng.out_shape, dtype=torch.complex128, device=dev)
+
+    def step(i, out):
+        U, v = inputs[i % 2]
+        eng.set_links(U, _capi.LINKS_FILE_T)
+        eng.set_eigvecs(v)
+        eng.calc(out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    scratch = torch.empty(eng.out_shape, dtype=torch.complex128, device=dev)
+    for i in range(W):
+        step(i, scratch)
+    barrier()
+
+    # ---- device-resident throughput --------------------------------------------------------
+    launches0 = eng.launch_count
+    eng.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for i in range(K):
+            step(i, outs[i])
+        gathered = gather_timeslices(outs, K * world, dst=0) if world > 1 else outs
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    prof = eng.get_profile()
+    eng.set_profiling(False)
+    launches = eng.launch_count - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * K / (ms_max * 1e-3)
+    del gathered
+
+    # ---- end to end through the host-buffer C-ABI call ------------------------------------------
+    U0, v0 = inputs[0]
+    U_host = torch.empty(U0.shape, dtype=U0.dtype, pin_memory=True).copy_(U0)
+    V_host = torch.empty(v0.shape, dtype=v0.dtype, pin_memory=True).copy_(v0)
+    out_host = _capi.PinnedBuffer(eng.out_shape, np.complex128)
+    U_np, V_np = U_host.numpy(), V_host.numpy().reshape(eng.field_shape)
+    for _ in range(min(W, 1)):
+        eng.calc_host(U_np, _capi.LINKS_FILE_T, V_np, out_host.array)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        eng.calc_host(U_np, _capi.LINKS_FILE_T, V_np, out_host.array)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * K / (float(t.item()) * 1e-3)
+    h2d = U_np.nbytes + V_np.nbytes
+    d2h = out_host.nbytes
+    checksum = float(np.abs(out_host.array[0, 0]).sum())
+
+    line = None
+    if rank == 0:
+        flops, st_bytes = algorithmic(name)
+        gram_ms = prof["contraction"]["ms"] / max(1, prof["contraction"]["launches"])
+        st_launch = max(1, prof["stencil"]["launches"])
+        st_ms = prof["stencil"]["ms"] / st_launch
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        gemm = fp64_gemm_peak(torch, dev)
+        dmma_tf, dfma_tf = microbench_fp64(local)
+        fp64_peak = max(gemm.values())
+        achieved_tf = flops / (gram_ms * 1e-3) / 1e12
+        # stencil: bytes of ONE nabla3 launch (1 source, 3 outputs, links once)
+        st_bytes_launch = 4 * Ne * V * 48.0 + 3 * V * 144.0
+        st_gbs = st_bytes_launch / (st_ms * 1e-3) / 1e9 if prof["stencil"]["launches"] else None
+        cpu_val, cpu_smp = (None, "skipped (--no-cpu-baseline)")
+        if not args.no_cpu_baseline and world == 1:
+            W0 = eng.debug_field(0).cpu().numpy()
+            U_sp = np.ascontiguousarray(np.moveaxis(U0.cpu().numpy().reshape(Lz, Ly, Lx, 4, 3, 3), 3, 0)[:3])
+            cpu_val, cpu_smp = cpu_sample(name, W0.astype(np.complex64), U_sp)
+        line = {
+            "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
+            "config": {
+                "workload": workload_desc(name), "lattice": [Lx, Ly, Lz], "Ne": Ne, "num_nabla": nabla, "momenta": nmom,
+                "sharding": f"timeslices, {K} per rank, {world} rank(s)" + (", NCCL gather to rank 0 inside the timed region" if world > 1 else ""),
+                "l2": f"step inputs+fields ({(v0.numel() * 8 + Ne * V * 48 * SRC_OUT[nabla][1]) / 1e6:.0f} MB) exceed the 126 MB L2; two input sets alternated",
+                "dmma_tile": {"mfrag": "auto", "workspace_MB": eng.workspace_bytes / 1e6},
+            },
+            "e2e": {"value": e2e_value, "unit": "timeslices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "edk_calc_host (host pinned links+eigenvectors in, result out)", "checksum": checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {
+                "kernel": "gram_dmma_kernel (momentum-phased contraction, DMMA.8x8x4)", "bound": "tensor",
+                "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+                "traffic": None,
+                "peak_source": f"cuBLAS FP64 GEMM measured in this run (dgemm {gemm['dgemm']:.1f}, zgemm {gemm['zgemm']:.1f} TFLOP/s); "
+                               f"DMMA issue-rate microbench {dmma_tf:.1f}, DFMA {dfma_tf:.1f} TFLOP/s; nominal 37-40",
+                "algorithmic_flops_per_launch": flops, "ms_per_launch": gram_ms,
+                "share_of_step": prof["contraction"]["ms"] / ms,
+            },
+            "roofline_stencil": {
+                "kernel": "nabla3_kernel (covariant central differences, 3 directions per pass)", "bound": "hbm",
+                "achieved": st_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (st_gbs / hbm_peak) if st_gbs else None,
+                "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_launch": st_bytes_launch,
+                "ms_per_launch": st_ms, "launches_per_step": st_launch / K,
+                "share_of_step": prof["stencil"]["ms"] / ms,
+            },
+            "phase_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
+            "cpu_baseline": {"value": cpu_val, "unit": "timeslices/s", "cores": host_threads(), "kind": "port", "sample": cpu_smp},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("EDK_BENCH_WORKLOAD", "config5"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

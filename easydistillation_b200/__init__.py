@@ -1,0 +1,21 @@
+"""B200-native elemental generation: the ElementalGenerator / DisplacementElementalGenerator
+path of IHEP-LQCD/EasyDistillation behind the reference's own class API, running on
+hand-written sm_100a kernels (libedk_sm100a.so).  See DESIGN.md."""
+from .constant import Nc, Nd, Ns
+from .generator import DisplacementElementalGenerator, ElementalGenerator
+from .insertion.derivative import derivative
+from .insertion.phase import MomentumPhase
+from .preset import (
+    EigenvectorHostmem,
+    EigenvectorNpy,
+    ElementalNpy,
+    GaugeFieldBinary,
+    GaugeFieldHostmem,
+    GaugeFieldNpy,
+)
+
+__all__ = [
+    "ElementalGenerator", "DisplacementElementalGenerator", "MomentumPhase", "derivative",
+    "GaugeFieldBinary", "GaugeFieldNpy", "GaugeFieldHostmem", "EigenvectorNpy", "EigenvectorHostmem",
+    "ElementalNpy", "Nc", "Ns", "Nd",
+]

@@ -1,0 +1,119 @@
+"""ctypes binding of include/edk.h (libedk_sm100a.so).  No CPU fallback: if the library
+is missing, or there is no CUDA device when a kernel is asked for, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libedk_sm100a.so")
+
+EDK_OK = 0
+EDK_ERR_ARG = -1
+EDK_ERR_CUDA = -2
+EDK_ERR_STATE = -3
+EDK_ERR_NOMEM = -4
+MODE_DERIVATIVE = 0
+MODE_DISPLACEMENT = 1
+LINKS_DIR_MAJOR = 0
+LINKS_FILE_T = 1
+
+# every symbol include/edk.h declares: (restype, argtypes)
+_vp, _i, _sz, _dp = C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_double)
+SIGNATURES = {
+    "edk_version": (_i, []),
+    "edk_last_error": (C.c_char_p, []),
+    "edk_create": (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_vp)]),
+    "edk_destroy": (_i, [_vp]),
+    "edk_phase_table": (_i, [_i, _i, _i, _i, C.POINTER(_i), _vp, _i, _vp]),
+    "edk_num_operators": (_i, [_vp]),
+    "edk_output_bytes": (_sz, [_vp]),
+    "edk_workspace_bytes": (_sz, [_vp]),
+    "edk_set_links": (_i, [_vp, _vp, _i, _vp]),
+    "edk_set_eigvecs": (_i, [_vp, _vp, _i, _vp]),
+    "edk_set_blending": (_i, [_vp, _vp, _vp]),
+    "edk_calc": (_i, [_vp, _vp, _vp]),
+    "edk_calc_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "edk_host_alloc": (_i, [C.POINTER(_vp), _sz]),
+    "edk_host_free": (_i, [_vp]),
+    "edk_set_profiling": (_i, [_vp, _i]),
+    "edk_get_profile": (_i, [_vp, _dp, C.POINTER(_i)]),
+    "edk_launch_count": (C.c_longlong, [_vp]),
+    "edk_debug_field": (_i, [_vp, _i, _vp, _vp]),
+    "edk_debug_phase": (_i, [_vp, _i, _vp, _vp]),
+    "edk_debug_use_naive_gram": (_i, [_vp, _i]),
+    "edk_debug_gram_config": (_i, [_vp, _i, _i]),
+    "edk_microbench_fp64": (_i, [_i, _dp, _dp]),
+}
+
+_lib = None
+
+
+class EdkError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the shared library once.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the sm_100a kernels first "
+                "(python -m easydistillation_b200.build, or __graft_entry__.build()). "
+                "easydistillation_b200 has no CPU or PyTorch fallback."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "edk"):
+    if rc == EDK_OK:
+        return
+    msg = lib().edk_last_error().decode(errors="replace")
+    if rc == EDK_ERR_ARG:
+        raise ValueError(f"{what}: {msg}")
+    if rc == EDK_ERR_NOMEM:
+        raise MemoryError(f"{what}: {msg}")
+    raise EdkError(f"{what} failed ({rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise EdkError("no CUDA device: the elemental kernels are sm_100a-only and there is no CPU fallback")
+    return torch
+
+
+class PinnedBuffer:
+    """Page-locked host memory from edk_host_alloc, exposed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        import numpy as np
+
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(lib().edk_host_alloc(C.byref(p), max(self.nbytes, 16)), "edk_host_alloc")
+        self.ptr = p.value
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().edk_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

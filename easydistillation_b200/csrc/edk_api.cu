@@ -1,0 +1,676 @@
+// C ABI (include/edk.h) over the sm_100a kernels: handle, workspace, job lists, calc flows.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "edk_common.cuh"
+
+namespace edk {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+enum { PH_PREP = 0, PH_STENCIL = 1, PH_GRAM = 2, PH_COMBINE = 3, PH_COUNT = 4 };
+
+struct EventPair {
+    cudaEvent_t a, b;
+    int phase;
+};
+
+}  // namespace edk
+
+using namespace edk;
+
+struct edk_handle {
+    Geom g;
+    int Ne, mode, order, nmom, device;
+    int nop;
+    size_t field_cplx;  // Ne * V * 3
+    // device buffers
+    cplx* links = nullptr;    // [3][V][9]
+    cplx* fields = nullptr;   // nfield fields
+    int nfield = 0;
+    cplx* lines = nullptr;    // displacement: 12 line buffers (ping-pong)
+    cplx* phase = nullptr;    // [nmom][Vpad]
+    cplx* partial = nullptr;  // [ksplit][njobs][nmom][Ne][Ne]
+    double* coeff = nullptr;  // [Ne][Ne] or null
+    bool have_coeff = false;
+    GramJob* jobs_dev = nullptr;
+    CombineOp* ops_dev = nullptr;
+    int njobs = 0;
+    int ksplit = 1, mfrag = 13;
+    int force_mfrag = 0, force_ksplit = 0;
+    bool naive = false;
+    // staging for the host-buffer entry point
+    void* stage_U = nullptr;
+    size_t stage_U_bytes = 0;
+    void* stage_V = nullptr;
+    size_t stage_V_bytes = 0;
+    cplx* stage_out = nullptr;
+    // state
+    bool links_set = false, evecs_set = false;
+    size_t ws_bytes = 0;
+    long long launches = 0;
+    // profiling
+    bool profiling = false;
+    std::vector<EventPair> events;
+    std::vector<EventPair> pool;
+    int n_launch[PH_COUNT] = {0, 0, 0, 0};
+    // derivative-mode stencil schedule: (source field, first child field)
+    std::vector<std::pair<int, int>> hops;
+    std::vector<GramJob> jobs_host;
+    std::vector<CombineOp> ops_host;
+
+    cplx* field(int i) const { return fields + (size_t)i * field_cplx; }
+};
+
+namespace {
+
+struct PhaseTimer {
+    edk_handle* h;
+    cudaStream_t s;
+    int phase;
+    EventPair ev{};
+    bool on;
+    PhaseTimer(edk_handle* h_, cudaStream_t s_, int phase_, int launches) : h(h_), s(s_), phase(phase_), on(h_->profiling) {
+        h->launches += launches;
+        h->n_launch[phase] += launches;
+        if (!on) return;
+        if (!h->pool.empty()) {
+            ev = h->pool.back();
+            h->pool.pop_back();
+        } else {
+            cudaEventCreate(&ev.a);
+            cudaEventCreate(&ev.b);
+        }
+        ev.phase = phase;
+        cudaEventRecord(ev.a, s);
+    }
+    ~PhaseTimer() {
+        if (!on) return;
+        cudaEventRecord(ev.b, s);
+        h->events.push_back(ev);
+    }
+};
+
+// field index of a direction sequence in application order (see edk.h, edk_debug_field)
+int seq_index(const std::vector<int>& seq) {
+    int base = 1, off = 0;
+    for (size_t i = 0; i < seq.size(); ++i) {
+        off += base;
+        base *= 3;
+    }
+    int v = 0;
+    for (int d : seq) v = v * 3 + d;
+    return off + v;
+}
+
+// the reference's derivative(n): lattice/insertion/derivative.py:23-33
+std::vector<int> derivative_tuple(int n) {
+    int order = 0, p = 1;
+    while (n >= p) {
+        n -= p;
+        p *= 3;
+        ++order;
+    }
+    std::vector<int> digits(order);
+    for (int i = 0; i < order; ++i) {
+        digits[order - 1 - i] = n % 3;
+        n /= 3;
+    }
+    return digits;
+}
+
+int pow3sum(int n) {  // (3^(n+1)-1)/2
+    int s = 0, p = 1;
+    for (int i = 0; i <= n; ++i) {
+        s += p;
+        p *= 3;
+    }
+    return s;
+}
+
+// Build the job list of the derivative elementals (elemental.py:299-329).
+// Every output operator is a signed sum over left/right splits of G(L, R); (L, R) pairs that
+// occur in more than one operator (e.g. (nabla_a W0, nabla_b W0) for num_nabla = 2) become
+// shared single-segment jobs so no pair is contracted twice: 34 instead of 43 pair-GEMMs.
+void build_derivative_jobs(edk_handle* h) {
+    struct Term {
+        int L, R, sign;
+    };
+    std::vector<std::vector<Term>> per_op(h->nop);
+    std::map<std::pair<int, int>, int> uses;
+    for (int n = 0; n < h->nop; ++n) {
+        std::vector<int> dirs = derivative_tuple(n);
+        const int len = (int)dirs.size();
+        for (int pick = 0; pick < (1 << len); ++pick) {
+            std::vector<int> right, left;
+            for (int i = 0; i < len; ++i) ((pick >> i) & 1 ? right : left).push_back(dirs[i]);
+            std::reverse(left.begin(), left.end());
+            Term t{seq_index(left), seq_index(right), (right.size() & 1) ? -1 : 1};
+            per_op[n].push_back(t);
+            ++uses[{t.L, t.R}];
+        }
+    }
+    std::map<std::pair<int, int>, int> shared_job;
+    h->jobs_host.clear();
+    h->ops_host.assign(h->nop, CombineOp{});
+    // private multi-segment jobs first (longest first helps the tail of the grid)
+    struct Pending {
+        int op;
+        GramJob job;
+    };
+    std::vector<Pending> priv;
+    for (int n = 0; n < h->nop; ++n) {
+        GramJob j{};
+        for (const Term& t : per_op[n]) {
+            if (uses[{t.L, t.R}] > 1) continue;
+            j.sign[j.nseg] = t.sign;
+            j.L[j.nseg] = h->field(t.L);
+            j.R[j.nseg] = h->field(t.R);
+            ++j.nseg;
+        }
+        if (j.nseg) priv.push_back({n, j});
+    }
+    std::stable_sort(priv.begin(), priv.end(), [](const Pending& a, const Pending& b) { return a.job.nseg > b.job.nseg; });
+    for (const Pending& p : priv) {
+        CombineOp& o = h->ops_host[p.op];
+        o.job[o.nterm] = (int)h->jobs_host.size();
+        o.weight[o.nterm] = 1.0;
+        ++o.nterm;
+        h->jobs_host.push_back(p.job);
+    }
+    for (int n = 0; n < h->nop; ++n) {
+        for (const Term& t : per_op[n]) {
+            if (uses[{t.L, t.R}] <= 1) continue;
+            auto key = std::make_pair(t.L, t.R);
+            auto it = shared_job.find(key);
+            int jid;
+            if (it == shared_job.end()) {
+                GramJob j{};
+                j.nseg = 1;
+                j.sign[0] = 1;
+                j.L[0] = h->field(t.L);
+                j.R[0] = h->field(t.R);
+                jid = (int)h->jobs_host.size();
+                h->jobs_host.push_back(j);
+                shared_job[key] = jid;
+            } else {
+                jid = it->second;
+            }
+            CombineOp& o = h->ops_host[n];
+            bool merged = false;
+            for (int k = 0; k < o.nterm; ++k)
+                if (o.job[k] == jid) {
+                    o.weight[k] += t.sign;
+                    merged = true;
+                }
+            if (!merged) {
+                o.job[o.nterm] = jid;
+                o.weight[o.nterm] = t.sign;
+                ++o.nterm;
+            }
+        }
+    }
+    // stencil schedule: every field of length < order spawns its three children
+    h->hops.clear();
+    const int nparents = h->order >= 1 ? pow3sum(h->order - 1) : 0;
+    for (int f = 0; f < nparents; ++f) {
+        // children of sequence s are s+(a): index = off(len+1) + 3*v(s) + a
+        int len = 0, off = 0, p = 1;
+        while (f >= off + p) {
+            off += p;
+            p *= 3;
+            ++len;
+        }
+        const int v = f - off;
+        const int child0 = off + p + 3 * v;
+        h->hops.push_back({f, child0});
+    }
+}
+
+void build_displacement_jobs(edk_handle* h) {
+    h->jobs_host.clear();
+    h->ops_host.assign(h->nop, CombineOp{});
+    for (int k = 0; k < h->nop; ++k) {
+        GramJob j{};
+        j.nseg = 1;
+        j.sign[0] = 1;
+        j.L[0] = h->field(0);
+        j.R[0] = h->field(k);  // field k = D_k (field 0 = W0 = D_0)
+        h->ops_host[k].nterm = 1;
+        h->ops_host[k].job[0] = k;
+        h->ops_host[k].weight[0] = 1.0;
+        h->jobs_host.push_back(j);
+    }
+}
+
+void pick_gram_config(edk_handle* h) {
+    h->mfrag = h->force_mfrag ? h->force_mfrag : gram_pick_mfrag(h->Ne);
+    const int rows = gram_rows_per_tile(h->mfrag);
+    const int n_mt = (h->Ne + rows - 1) / rows;
+    const int nfrag_f = (h->Ne + 3) / 4;
+    const int n_nt = (nfrag_f * h->nmom + gram_nfrag_per_tile() - 1) / gram_nfrag_per_tile();
+    const long long tiles = (long long)h->njobs * n_mt * n_nt;
+    const int ksteps = h->g.Vpad / 8;
+    int ks = 1;
+    if (!h->force_ksplit) {
+        // fill the 148 SMs at least ~4 times over, but keep >= 16 stages per CTA
+        const long long want = 148LL * 4;
+        if (tiles < want) ks = (int)((want + tiles - 1) / tiles);
+        ks = std::min(ks, std::max(1, ksteps / 16));
+        ks = std::min(ks, 64);
+    } else {
+        ks = std::min(h->force_ksplit, ksteps);
+    }
+    h->ksplit = std::max(1, ks);
+}
+
+int ensure_partial(edk_handle* h) {
+    const size_t need = (size_t)h->ksplit * h->njobs * h->nmom * h->Ne * h->Ne * sizeof(cplx);
+    static_assert(sizeof(cplx) == 16, "complex128");
+    if (h->partial) EDK_CUDA_TRY(cudaFree(h->partial));
+    h->partial = nullptr;
+    EDK_CUDA_TRY(cudaMalloc(&h->partial, need));
+    return EDK_OK;
+}
+
+int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
+    GramParams P{};
+    P.jobs = h->jobs_dev;
+    P.njobs = h->njobs;
+    P.Ne = h->Ne;
+    P.nmom = h->nmom;
+    P.Kc = 3 * h->g.V;
+    P.ksteps = h->g.Vpad / 8;
+    P.Vpad = h->g.Vpad;
+    P.ksplit = h->naive ? 1 : h->ksplit;
+    const int rows = gram_rows_per_tile(h->mfrag);
+    P.n_mt = (h->Ne + rows - 1) / rows;
+    const int nfrag_f = (h->Ne + 3) / 4;
+    P.n_nt = (nfrag_f * h->nmom + gram_nfrag_per_tile() - 1) / gram_nfrag_per_tile();
+    P.phase = h->phase;
+    P.partial = h->partial;
+    {
+        PhaseTimer t(h, s, PH_GRAM, 1);
+        EDK_CUDA_TRY(h->naive ? launch_gram_naive(P, s) : launch_gram_dmma(P, h->mfrag, s));
+    }
+    {
+        PhaseTimer t(h, s, PH_COMBINE, 1);
+        EDK_CUDA_TRY(launch_combine(h->ops_dev, h->nop, h->partial, h->njobs, P.ksplit, h->nmom, h->Ne,
+                                    h->have_coeff ? h->coeff : nullptr, out, s));
+    }
+    return EDK_OK;
+}
+
+void recycle_events(edk_handle* h) {
+    for (auto& e : h->events) h->pool.push_back(e);
+    h->events.clear();
+    for (int i = 0; i < PH_COUNT; ++i) h->n_launch[i] = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int edk_version(void) { return 1; }
+const char* edk_last_error(void) { return g_err; }
+
+int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, const int* mom3, int device,
+               edk_handle** out) {
+    if (!out) {
+        set_error("edk_create: out is NULL");
+        return EDK_ERR_ARG;
+    }
+    *out = nullptr;
+    if (Lx < 1 || Ly < 1 || Lz < 1 || Ne < 1 || nmom < 1 || !mom3) {
+        set_error("edk_create: lattice extents, Ne and nmom must be positive (got %d %d %d, Ne=%d, nmom=%d)", Lx, Ly, Lz, Ne,
+                  nmom);
+        return EDK_ERR_ARG;
+    }
+    if (mode != EDK_MODE_DERIVATIVE && mode != EDK_MODE_DISPLACEMENT) {
+        set_error("edk_create: unknown mode %d", mode);
+        return EDK_ERR_ARG;
+    }
+    if (order < 0 || (mode == EDK_MODE_DERIVATIVE && order > 3)) {
+        set_error("edk_create: order %d out of range (num_nabla 0..3, distance >= 0)", order);
+        return EDK_ERR_ARG;
+    }
+    if ((long long)Lx * Ly * Lz * 3 >= (1LL << 31) / 2) {
+        set_error("edk_create: spatial volume too large for 32-bit k indices");
+        return EDK_ERR_ARG;
+    }
+    EDK_CUDA_TRY(cudaSetDevice(device));
+    edk_handle* h = new edk_handle();
+    h->g.Lx = Lx;
+    h->g.Ly = Ly;
+    h->g.Lz = Lz;
+    h->g.V = Lx * Ly * Lz;
+    h->g.Vpad = (h->g.V + 7) / 8 * 8;
+    h->Ne = Ne;
+    h->mode = mode;
+    h->order = order;
+    h->nmom = nmom;
+    h->device = device;
+    h->field_cplx = (size_t)Ne * h->g.V * 3;
+    if (mode == EDK_MODE_DERIVATIVE) {
+        h->nop = pow3sum(order);
+        h->nfield = h->nop;
+    } else {
+        h->nop = order + 1;
+        h->nfield = order + 1;
+    }
+    size_t ws = 0;
+    auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
+        ws += bytes;
+        return cudaMalloc(p, bytes);
+    };
+#define EDK_ALLOC(ptr, bytes)                                                                      \
+    do {                                                                                           \
+        cudaError_t _e = alloc((void**)&(ptr), (bytes));                                           \
+        if (_e != cudaSuccess) {                                                                   \
+            set_error("edk_create: cudaMalloc of %zu bytes failed: %s", (size_t)(bytes), cudaGetErrorString(_e)); \
+            edk_destroy(h);                                                                        \
+            return _e == cudaErrorMemoryAllocation ? EDK_ERR_NOMEM : EDK_ERR_CUDA;                 \
+        }                                                                                          \
+    } while (0)
+    EDK_ALLOC(h->links, (size_t)3 * h->g.V * 9 * sizeof(cplx));
+    EDK_ALLOC(h->fields, (size_t)h->nfield * h->field_cplx * sizeof(cplx));
+    if (mode == EDK_MODE_DISPLACEMENT && order >= 1) EDK_ALLOC(h->lines, (size_t)12 * h->field_cplx * sizeof(cplx));
+    EDK_ALLOC(h->phase, (size_t)nmom * h->g.Vpad * sizeof(cplx));
+    EDK_ALLOC(h->coeff, (size_t)Ne * Ne * sizeof(double));
+    int* mom_dev = nullptr;
+    EDK_ALLOC(mom_dev, (size_t)nmom * 3 * sizeof(int));
+    cudaError_t e = cudaMemcpy(mom_dev, mom3, (size_t)nmom * 3 * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_phase_table(h->phase, mom_dev, nmom, h->g, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(mom_dev);
+    ws -= (size_t)nmom * 3 * sizeof(int);
+    if (e != cudaSuccess) {
+        set_error("edk_create: phase table failed: %s", cudaGetErrorString(e));
+        edk_destroy(h);
+        return EDK_ERR_CUDA;
+    }
+    h->launches += 1;
+    if (mode == EDK_MODE_DERIVATIVE)
+        build_derivative_jobs(h);
+    else
+        build_displacement_jobs(h);
+    h->njobs = (int)h->jobs_host.size();
+    EDK_ALLOC(h->jobs_dev, h->jobs_host.size() * sizeof(GramJob));
+    EDK_ALLOC(h->ops_dev, h->ops_host.size() * sizeof(CombineOp));
+    e = cudaMemcpy(h->jobs_dev, h->jobs_host.data(), h->jobs_host.size() * sizeof(GramJob), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(h->ops_dev, h->ops_host.data(), h->ops_host.size() * sizeof(CombineOp), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("edk_create: job upload failed: %s", cudaGetErrorString(e));
+        edk_destroy(h);
+        return EDK_ERR_CUDA;
+    }
+    pick_gram_config(h);
+    const size_t partial_bytes = (size_t)h->ksplit * h->njobs * nmom * Ne * Ne * sizeof(cplx);
+    EDK_ALLOC(h->partial, partial_bytes);
+#undef EDK_ALLOC
+    h->ws_bytes = ws;
+    *out = h;
+    return EDK_OK;
+}
+
+int edk_destroy(edk_handle* h) {
+    if (!h) return EDK_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->links);
+    cudaFree(h->fields);
+    cudaFree(h->lines);
+    cudaFree(h->phase);
+    cudaFree(h->partial);
+    cudaFree(h->coeff);
+    cudaFree(h->jobs_dev);
+    cudaFree(h->ops_dev);
+    cudaFree(h->stage_U);
+    cudaFree(h->stage_V);
+    cudaFree(h->stage_out);
+    for (auto& e : h->events) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    for (auto& e : h->pool) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    delete h;
+    return EDK_OK;
+}
+
+int edk_phase_table(int Lx, int Ly, int Lz, int nmom, const int* mom3, void* out_dev, int device, void* stream) {
+    if (Lx < 1 || Ly < 1 || Lz < 1 || nmom < 1 || !mom3 || !out_dev) {
+        set_error("edk_phase_table: bad argument");
+        return EDK_ERR_ARG;
+    }
+    EDK_CUDA_TRY(cudaSetDevice(device));
+    Geom g{Lx, Ly, Lz, Lx * Ly * Lz, Lx * Ly * Lz};  // unpadded rows: the caller's buffer is [nmom][V]
+    int* mom_dev = nullptr;
+    EDK_CUDA_TRY(cudaMalloc(&mom_dev, (size_t)nmom * 3 * sizeof(int)));
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(mom_dev, mom3, (size_t)nmom * 3 * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = launch_phase_table((cplx*)out_dev, mom_dev, nmom, g, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(mom_dev);
+    if (e != cudaSuccess) {
+        set_error("edk_phase_table: %s", cudaGetErrorString(e));
+        return EDK_ERR_CUDA;
+    }
+    return EDK_OK;
+}
+
+int edk_num_operators(const edk_handle* h) { return h ? h->nop : EDK_ERR_ARG; }
+size_t edk_output_bytes(const edk_handle* h) {
+    return h ? (size_t)h->nop * h->nmom * h->Ne * h->Ne * sizeof(cplx) : 0;
+}
+size_t edk_workspace_bytes(const edk_handle* h) { return h ? h->ws_bytes : 0; }
+
+int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream) {
+    if (!h || !U_dev || (layout != EDK_LINKS_DIR_MAJOR && layout != EDK_LINKS_FILE_T)) {
+        set_error("edk_set_links: bad argument");
+        return EDK_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    PhaseTimer t(h, s, PH_PREP, 1);
+    EDK_CUDA_TRY(launch_reorder_links((const cplx*)U_dev, layout, h->links, h->g, s));
+    h->links_set = true;
+    return EDK_OK;
+}
+
+int edk_set_eigvecs(edk_handle* h, const void* V_dev, int is_c8, void* stream) {
+    if (!h || !V_dev) {
+        set_error("edk_set_eigvecs: bad argument");
+        return EDK_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    PhaseTimer t(h, s, PH_PREP, 1);
+    EDK_CUDA_TRY(launch_round_eigvecs(V_dev, is_c8 ? 1 : 0, h->field(0), h->field_cplx, s));
+    h->evecs_set = true;
+    return EDK_OK;
+}
+
+int edk_set_blending(edk_handle* h, const double* coeff_dev, void* stream) {
+    if (!h) {
+        set_error("edk_set_blending: NULL handle");
+        return EDK_ERR_ARG;
+    }
+    if (!coeff_dev) {
+        h->have_coeff = false;
+        return EDK_OK;
+    }
+    EDK_CUDA_TRY(cudaMemcpyAsync(h->coeff, coeff_dev, (size_t)h->Ne * h->Ne * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream));
+    h->have_coeff = true;
+    return EDK_OK;
+}
+
+int edk_calc(edk_handle* h, void* out_dev, void* stream) {
+    if (!h || !out_dev) {
+        set_error("edk_calc: bad argument");
+        return EDK_ERR_ARG;
+    }
+    if (!h->links_set || !h->evecs_set) {
+        set_error("edk_calc: links and eigenvectors of the timeslice must be set first");
+        return EDK_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    EDK_CUDA_TRY(cudaSetDevice(h->device));
+    if (h->mode == EDK_MODE_DERIVATIVE) {
+        for (const auto& hop : h->hops) {
+            PhaseTimer t(h, s, PH_STENCIL, 1);
+            EDK_CUDA_TRY(launch_nabla3(h->field(hop.first), h->field(hop.second), h->field(hop.second + 1),
+                                       h->field(hop.second + 2), h->links, h->g, h->Ne, s));
+        }
+    } else {
+        for (int k = 1; k <= h->order; ++k) {
+            Ptr6 p;
+            for (int l = 0; l < 6; ++l) {
+                p.src[l] = (k == 1) ? h->field(0) : h->lines + (size_t)(((k - 1) & 1) * 6 + l) * h->field_cplx;
+                p.dst[l] = h->lines + (size_t)((k & 1) * 6 + l) * h->field_cplx;
+            }
+            PhaseTimer t(h, s, PH_STENCIL, 1);
+            EDK_CUDA_TRY(launch_displace_step6(p, h->field(k), h->links, h->g, h->Ne, s));
+        }
+    }
+    return run_gram_and_combine(h, (cplx*)out_dev, s);
+}
+
+int edk_calc_host(edk_handle* h, const void* U_host, int layout, const void* V_host, int is_c8, void* out_host,
+                  void* stream) {
+    if (!h || !U_host || !V_host || !out_host) {
+        set_error("edk_calc_host: bad argument");
+        return EDK_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    EDK_CUDA_TRY(cudaSetDevice(h->device));
+    const size_t ub = (size_t)(layout == EDK_LINKS_FILE_T ? 4 : 3) * h->g.V * 9 * sizeof(cplx);
+    const size_t vb = h->field_cplx * (is_c8 ? 8 : 16);
+    if (h->stage_U_bytes < ub) {
+        cudaFree(h->stage_U);
+        h->stage_U = nullptr;
+        h->stage_U_bytes = 0;
+        EDK_CUDA_TRY(cudaMalloc(&h->stage_U, ub));
+        h->stage_U_bytes = ub;
+    }
+    if (h->stage_V_bytes < vb) {
+        cudaFree(h->stage_V);
+        h->stage_V = nullptr;
+        h->stage_V_bytes = 0;
+        EDK_CUDA_TRY(cudaMalloc(&h->stage_V, vb));
+        h->stage_V_bytes = vb;
+    }
+    if (!h->stage_out) EDK_CUDA_TRY(cudaMalloc(&h->stage_out, edk_output_bytes(h)));
+    EDK_CUDA_TRY(cudaMemcpyAsync(h->stage_U, U_host, ub, cudaMemcpyHostToDevice, s));
+    EDK_CUDA_TRY(cudaMemcpyAsync(h->stage_V, V_host, vb, cudaMemcpyHostToDevice, s));
+    int rc = edk_set_links(h, h->stage_U, layout, stream);
+    if (rc) return rc;
+    rc = edk_set_eigvecs(h, h->stage_V, is_c8, stream);
+    if (rc) return rc;
+    rc = edk_calc(h, h->stage_out, stream);
+    if (rc) return rc;
+    EDK_CUDA_TRY(cudaMemcpyAsync(out_host, h->stage_out, edk_output_bytes(h), cudaMemcpyDeviceToHost, s));
+    EDK_CUDA_TRY(cudaStreamSynchronize(s));
+    return EDK_OK;
+}
+
+int edk_host_alloc(void** p, size_t bytes) {
+    if (!p) return EDK_ERR_ARG;
+    EDK_CUDA_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return EDK_OK;
+}
+int edk_host_free(void* p) {
+    EDK_CUDA_TRY(cudaFreeHost(p));
+    return EDK_OK;
+}
+
+int edk_set_profiling(edk_handle* h, int on) {
+    if (!h) return EDK_ERR_ARG;
+    h->profiling = on != 0;
+    recycle_events(h);
+    return EDK_OK;
+}
+
+int edk_get_profile(edk_handle* h, double ms[4], int n_launch[4]) {
+    if (!h || !ms || !n_launch) return EDK_ERR_ARG;
+    for (int i = 0; i < PH_COUNT; ++i) {
+        ms[i] = 0.0;
+        n_launch[i] = h->n_launch[i];
+    }
+    for (auto& e : h->events) {
+        EDK_CUDA_TRY(cudaEventSynchronize(e.b));
+        float t = 0.f;
+        EDK_CUDA_TRY(cudaEventElapsedTime(&t, e.a, e.b));
+        ms[e.phase] += t;
+    }
+    recycle_events(h);
+    return EDK_OK;
+}
+
+long long edk_launch_count(const edk_handle* h) { return h ? h->launches : 0; }
+
+int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream) {
+    if (!h || !dst_dev || idx < 0 || idx >= h->nfield) {
+        set_error("edk_debug_field: bad argument");
+        return EDK_ERR_ARG;
+    }
+    EDK_CUDA_TRY(cudaMemcpyAsync(dst_dev, h->field(idx), h->field_cplx * sizeof(cplx), cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream));
+    return EDK_OK;
+}
+
+int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream) {
+    if (!h || !dst_dev || ip < 0 || ip >= h->nmom) {
+        set_error("edk_debug_phase: bad argument");
+        return EDK_ERR_ARG;
+    }
+    EDK_CUDA_TRY(cudaMemcpyAsync(dst_dev, h->phase + (size_t)ip * h->g.Vpad, (size_t)h->g.V * sizeof(cplx),
+                                 cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return EDK_OK;
+}
+
+int edk_debug_use_naive_gram(edk_handle* h, int on) {
+    if (!h) return EDK_ERR_ARG;
+    h->naive = on != 0;
+    return EDK_OK;
+}
+
+int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit) {
+    if (!h || mfrag < 0 || ksplit < 0) return EDK_ERR_ARG;
+    if (mfrag) {
+        const int rows = gram_rows_per_tile(mfrag);
+        (void)rows;
+        bool ok = false;
+        for (int v : {2, 4, 5, 7, 9, 10, 11, 13}) ok |= (v == mfrag);
+        if (!ok) {
+            set_error("edk_debug_gram_config: mfrag %d not instantiated", mfrag);
+            return EDK_ERR_ARG;
+        }
+    }
+    h->force_mfrag = mfrag;
+    h->force_ksplit = ksplit;
+    pick_gram_config(h);
+    return ensure_partial(h);
+}
+
+int edk_microbench_fp64(int device, double* dmma_tflops, double* dfma_tflops) {
+    if (!dmma_tflops || !dfma_tflops) return EDK_ERR_ARG;
+    EDK_CUDA_TRY(cudaSetDevice(device));
+    EDK_CUDA_TRY(microbench_fp64(dmma_tflops, dfma_tflops));
+    return EDK_OK;
+}
+
+}  // extern "C"

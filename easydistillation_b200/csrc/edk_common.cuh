@@ -1,0 +1,95 @@
+// Shared declarations of the elemental-distillation kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "edk.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "edk kernels are written for sm_100a (B200) only"
+#endif
+
+namespace edk {
+
+typedef double2 cplx;  // (re, im)
+
+// ---- error plumbing (thread-local message, C-ABI status codes) ----------------------
+void set_error(const char* fmt, ...);
+#define EDK_CUDA_TRY(expr)                                                                       \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            edk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return EDK_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+// ---- lattice geometry of one timeslice ------------------------------------------------
+struct Geom {
+    int Lx, Ly, Lz;
+    int V;     // Lx*Ly*Lz
+    int Vpad;  // V rounded up to a multiple of 8 sites (k-stage granularity of the contraction)
+};
+
+// ---- contraction job description --------------------------------------------------------
+// One job = sum over segments s of  sign_s * L_s^dagger diag(phase_p) R_s  for every momentum p,
+// written to partial[split][job][p][e][f].
+#define EDK_MAX_SEG 8
+struct GramJob {
+    int nseg;
+    int sign[EDK_MAX_SEG];
+    const cplx* L[EDK_MAX_SEG];  // [Ne][3V]
+    const cplx* R[EDK_MAX_SEG];  // [Ne][3V]
+};
+
+struct GramParams {
+    const GramJob* jobs;
+    int njobs;
+    int Ne;
+    int nmom;
+    int Kc;       // 3*V complex entries per row
+    int ksteps;   // Vpad/8 : stages of 8 sites (24 complex) per segment
+    int Vpad;     // row stride of the phase table
+    int ksplit;   // split-K factor
+    int n_mt;     // tiles along e (rows)
+    int n_nt;     // tiles along the flattened (f-fragment, momentum) axis
+    const cplx* phase;  // [nmom][Vpad]
+    cplx* partial;      // [ksplit][njobs][nmom][Ne][Ne]
+};
+
+// Output operator n = coeff * sum_terms weight * sum_split partial[split][job]
+#define EDK_MAX_TERMS 8
+struct CombineOp {
+    int nterm;
+    int job[EDK_MAX_TERMS];
+    double weight[EDK_MAX_TERMS];
+};
+
+// ---- launchers (defined in the .cu files) -------------------------------------------------
+// prepare
+cudaError_t launch_round_eigvecs(const void* V_in, int is_c8, cplx* W0, size_t n_cplx, cudaStream_t s);
+cudaError_t launch_reorder_links(const cplx* U_in, int layout, cplx* U_out, Geom g, cudaStream_t s);
+cudaError_t launch_phase_table(cplx* phase, const int* mom3_dev, int nmom, Geom g, cudaStream_t s);
+// stencil
+cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
+                          cudaStream_t s);
+cudaError_t launch_displace_step(const cplx* const* src6, cplx* const* dst6, const cplx* links, Geom g, int Ne,
+                                 cudaStream_t s);
+struct Ptr6 {
+    const cplx* src[6];
+    cplx* dst[6];
+};
+cudaError_t launch_displace_step6(Ptr6 p, cplx* mean_out, const cplx* links, Geom g, int Ne, cudaStream_t s);
+// contraction
+cudaError_t launch_gram_dmma(const GramParams& P, int mfrag, cudaStream_t s);
+cudaError_t launch_gram_naive(const GramParams& P, cudaStream_t s);
+int gram_pick_mfrag(int Ne);
+int gram_rows_per_tile(int mfrag);
+int gram_nfrag_per_tile();
+cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom, int Ne,
+                           const double* coeff, cplx* out, cudaStream_t s);
+// microbench
+cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops);
+
+}  // namespace edk

@@ -1,0 +1,277 @@
+// Prepare + stencil kernels of the elemental path (sm_100a).
+//
+//   round_eigvecs   : the complex64 staging of the reference (elemental.py:55,297-298)
+//   reorder_links   : file-order timeslice -> direction-major spatial links (elemental.py:103)
+//   phase_table     : exp(+2 pi i p.x/L)                        (insertion/phase.py:11-13,41-46)
+//   nabla3          : all three covariant central differences of one field in one pass
+//                     (nabla_d W)(x) = U_d(x) W(x+d) - U_d(x-d)^dagger W(x-d)   (elemental.py:279-288)
+//   displace_step6  : extend the six straight Wilson lines by one link and average them
+//                     (displacement_elemental.py:53-71)
+//
+// Data layout in HBM: fields [Ne][Lz][Ly][Lx][3] complex128 (48 B per site, x fastest after
+// colour), links [3][Lz][Ly][Lx][3][3] complex128 (144 B per site and direction).
+//
+// Stencil work decomposition: one thread owns (site, direction) and keeps the two link
+// matrices it needs, U_d(x) and U_d(x-d), in registers while it walks over a block of EB
+// eigenvectors, so link traffic is amortised EB-fold and every field element is streamed.
+#include "edk_common.cuh"
+
+namespace edk {
+
+__device__ __forceinline__ cplx ldg(const cplx* p) { return __ldg(p); }
+
+// acc += a * b
+__device__ __forceinline__ void cfma(cplx& acc, const cplx a, const cplx b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+// acc -= conj(a) * b
+__device__ __forceinline__ void cfnma_conj(cplx& acc, const cplx a, const cplx b) {
+    acc.x = fma(-a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += conj(a) * b
+__device__ __forceinline__ void cfma_conj(cplx& acc, const cplx a, const cplx b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(-a.y, b.x, acc.y);
+}
+
+__device__ __forceinline__ void site_coords(int site, const Geom& g, int& x, int& y, int& z) {
+    x = site % g.Lx;
+    int r = site / g.Lx;
+    y = r % g.Ly;
+    z = r / g.Ly;
+}
+// neighbour of (x,y,z) one step along direction d (0=x,1=y,2=z), sign = +1/-1, periodic
+__device__ __forceinline__ int neighbour(int x, int y, int z, int d, int sign, const Geom& g) {
+    if (d == 0) x = (x + sign + g.Lx) % g.Lx;
+    if (d == 1) y = (y + sign + g.Ly) % g.Ly;
+    if (d == 2) z = (z + sign + g.Lz) % g.Lz;
+    return (z * g.Ly + y) * g.Lx + x;
+}
+
+// ---------------------------------------------------------------------------------------
+// prepare
+// ---------------------------------------------------------------------------------------
+__global__ void round_eigvecs_kernel(const void* __restrict__ in, int is_c8, cplx* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (is_c8) {
+        const float2* p = (const float2*)in;
+        for (; i < n; i += stride) {
+            float2 v = __ldg(p + i);
+            out[i] = make_double2((double)v.x, (double)v.y);
+        }
+    } else {
+        const double2* p = (const double2*)in;
+        for (; i < n; i += stride) {
+            double2 v = __ldg(p + i);
+            // round-to-nearest-even double -> float -> double: numpy's complex128 -> complex64 assignment
+            out[i] = make_double2((double)__double2float_rn(v.x), (double)__double2float_rn(v.y));
+        }
+    }
+}
+
+cudaError_t launch_round_eigvecs(const void* V_in, int is_c8, cplx* W0, size_t n_cplx, cudaStream_t s) {
+    int block = 256;
+    size_t want = (n_cplx + block - 1) / block;
+    int grid = (int)(want < (size_t)148 * 16 ? (want ? want : 1) : (size_t)148 * 16);
+    round_eigvecs_kernel<<<grid, block, 0, s>>>(V_in, is_c8, W0, n_cplx);
+    return cudaGetLastError();
+}
+
+__global__ void reorder_links_kernel(const cplx* __restrict__ in, int layout, cplx* __restrict__ out, int V) {
+    // out[d][site][m], m = 3*a + b
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)3 * V * 9;
+    if (i >= n) return;
+    int m = (int)(i % 9);
+    size_t r = i / 9;
+    int site = (int)(r % V);
+    int d = (int)(r / V);
+    size_t src = (layout == EDK_LINKS_FILE_T) ? (((size_t)site * 4 + d) * 9 + m) : i;
+    out[i] = __ldg(in + src);
+}
+
+cudaError_t launch_reorder_links(const cplx* U_in, int layout, cplx* U_out, Geom g, cudaStream_t s) {
+    size_t n = (size_t)3 * g.V * 9;
+    int block = 256;
+    reorder_links_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(U_in, layout, U_out, g.V);
+    return cudaGetLastError();
+}
+
+__global__ void phase_table_kernel(cplx* __restrict__ phase, const int* __restrict__ mom3, int nmom, Geom g) {
+    int site = blockIdx.x * blockDim.x + threadIdx.x;
+    int ip = blockIdx.y;
+    if (site >= g.Vpad) return;
+    cplx v = make_double2(0.0, 0.0);  // padding sites contribute nothing
+    if (site < g.V) {
+        int x, y, z;
+        site_coords(site, g, x, y, z);
+        long long px = mom3[3 * ip + 0], py = mom3[3 * ip + 1], pz = mom3[3 * ip + 2];
+        // reduce each p*x mod L in integers so the argument of sincospi stays in [0, 6)
+        long long rx = ((px * x) % g.Lx + g.Lx) % g.Lx;
+        long long ry = ((py * y) % g.Ly + g.Ly) % g.Ly;
+        long long rz = ((pz * z) % g.Lz + g.Lz) % g.Lz;
+        double turns = (double)rx / (double)g.Lx + (double)ry / (double)g.Ly + (double)rz / (double)g.Lz;
+        double sn, cs;
+        sincospi(2.0 * turns, &sn, &cs);
+        v = make_double2(cs, sn);
+    }
+    phase[(size_t)ip * g.Vpad + site] = v;
+}
+
+cudaError_t launch_phase_table(cplx* phase, const int* mom3_dev, int nmom, Geom g, cudaStream_t s) {
+    dim3 block(256), grid((g.Vpad + 255) / 256, nmom);
+    phase_table_kernel<<<grid, block, 0, s>>>(phase, mom3_dev, nmom, g);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// nabla3: out_d = nabla_d W  for d = x, y, z
+// ---------------------------------------------------------------------------------------
+constexpr int NABLA_SITES = 128;  // sites per CTA (threadIdx.x), threadIdx.y = direction
+constexpr int NABLA_EB = 8;       // eigenvectors per CTA
+
+__global__ void __launch_bounds__(NABLA_SITES * 3)
+nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restrict__ o1, cplx* __restrict__ o2,
+              const cplx* __restrict__ links, Geom g, int Ne) {
+    const int site = blockIdx.x * NABLA_SITES + threadIdx.x;
+    const int d = threadIdx.y;
+    if (site >= g.V) return;
+    int x, y, z;
+    site_coords(site, g, x, y, z);
+    const int sf = neighbour(x, y, z, d, +1, g);
+    const int sb = neighbour(x, y, z, d, -1, g);
+
+    cplx U[9], Ub[9];
+    const cplx* pu = links + ((size_t)d * g.V + site) * 9;
+    const cplx* pb = links + ((size_t)d * g.V + sb) * 9;
+#pragma unroll
+    for (int m = 0; m < 9; ++m) {
+        U[m] = ldg(pu + m);
+        Ub[m] = ldg(pb + m);
+    }
+    cplx* out = d == 0 ? o0 : (d == 1 ? o1 : o2);
+    const int e0 = blockIdx.y * NABLA_EB;
+    const int e1 = min(e0 + NABLA_EB, Ne);
+    const size_t fs = (size_t)g.V * 3;
+    for (int e = e0; e < e1; ++e) {
+        const cplx* We = W + (size_t)e * fs;
+        cplx wf[3], wb[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            wf[c] = ldg(We + (size_t)sf * 3 + c);
+            wb[c] = ldg(We + (size_t)sb * 3 + c);
+        }
+        cplx r[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            r[a] = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                cfma(r[a], U[3 * a + b], wf[b]);         // U_d(x) W(x+d)
+                cfnma_conj(r[a], Ub[3 * b + a], wb[b]);  // - U_d(x-d)^dagger W(x-d)
+            }
+        }
+        cplx* po = out + (size_t)e * fs + (size_t)site * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) po[a] = r[a];
+    }
+}
+
+cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
+                          cudaStream_t s) {
+    dim3 block(NABLA_SITES, 3);
+    dim3 grid((g.V + NABLA_SITES - 1) / NABLA_SITES, (Ne + NABLA_EB - 1) / NABLA_EB);
+    nabla3_kernel<<<grid, block, 0, s>>>(W_in, out_x, out_y, out_z, links, g, Ne);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// displacement step: six lines in, six lines out, plus their mean
+//   line d   (d<3): F_d^k(x) = U_d(x)        F_d^{k-1}(x+d)
+//   line 5-d      : B_d^k(x) = U_d(x-d)^dag  B_d^{k-1}(x-d)
+// ---------------------------------------------------------------------------------------
+constexpr int DISP_SITES = 64;
+constexpr int DISP_EB = 8;
+
+__global__ void __launch_bounds__(DISP_SITES * 6)
+displace_step6_kernel(Ptr6 p, cplx* __restrict__ mean_out, const cplx* __restrict__ links, Geom g, int Ne) {
+    __shared__ cplx red[6][DISP_SITES][3];
+    const int site = blockIdx.x * DISP_SITES + threadIdx.x;
+    const int line = threadIdx.y;
+    const bool fwd = line < 3;
+    const int d = fwd ? line : 5 - line;
+    const bool active = site < g.V;
+    int x = 0, y = 0, z = 0, sn = 0;
+    cplx U[9];
+    if (active) {
+        site_coords(site, g, x, y, z);
+        sn = neighbour(x, y, z, d, fwd ? +1 : -1, g);
+        const cplx* pu = links + ((size_t)d * g.V + (fwd ? site : sn)) * 9;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) U[m] = ldg(pu + m);
+    }
+    const cplx* src = p.src[line];
+    cplx* dst = p.dst[line];
+    const int e0 = blockIdx.y * DISP_EB;
+    const int e1 = min(e0 + DISP_EB, Ne);
+    const size_t fs = (size_t)g.V * 3;
+    const int tid = threadIdx.y * DISP_SITES + threadIdx.x;
+    for (int e = e0; e < e1; ++e) {
+        cplx r[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) r[a] = make_double2(0.0, 0.0);
+        if (active) {
+            cplx w[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) w[c] = ldg(src + (size_t)e * fs + (size_t)sn * 3 + c);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    if (fwd)
+                        cfma(r[a], U[3 * a + b], w[b]);
+                    else
+                        cfma_conj(r[a], U[3 * b + a], w[b]);
+                }
+            }
+            cplx* po = dst + (size_t)e * fs + (size_t)site * 3;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) po[a] = r[a];
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) red[line][threadIdx.x][a] = r[a];
+        __syncthreads();
+        if (tid < DISP_SITES * 3) {
+            const int sl = tid / 3, a = tid % 3;
+            const int so = blockIdx.x * DISP_SITES + sl;
+            if (so < g.V) {
+                cplx acc = red[0][sl][a];
+#pragma unroll
+                for (int l = 1; l < 6; ++l) {
+                    acc.x += red[l][sl][a].x;
+                    acc.y += red[l][sl][a].y;
+                }
+                mean_out[(size_t)e * fs + (size_t)so * 3 + a] = make_double2(acc.x / 6.0, acc.y / 6.0);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_displace_step6(Ptr6 p, cplx* mean_out, const cplx* links, Geom g, int Ne, cudaStream_t s) {
+    dim3 block(DISP_SITES, 6);
+    dim3 grid((g.V + DISP_SITES - 1) / DISP_SITES, (Ne + DISP_EB - 1) / DISP_EB);
+    displace_step6_kernel<<<grid, block, 0, s>>>(p, mean_out, links, g, Ne);
+    return cudaGetLastError();
+}
+
+}  // namespace edk

@@ -1,0 +1,145 @@
+"""Host logic shared by the two elemental generators: input handles, per-timeslice staging,
+the generator-owned result buffer, batch/sharded iteration."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .. import _capi
+from ..constant import Nc, Nd
+from ..engine import ElementalEngine
+
+
+class _TimesliceGenerator:
+    _mode: int = None
+
+    def _setup(self, latt_size, gauge_field, eigenvector, order: int, momentum_list, device):
+        Lx, Ly, Lz, Lt = (int(v) for v in latt_size)
+        self.latt_size = latt_size
+        self.gauge_field = gauge_field
+        self.eigenvector = eigenvector
+        self.momentum_list = momentum_list
+        self.num_momentum = len(momentum_list)
+        self.Ne = eigenvector.Ne
+        self._U = None
+        self._gauge_field_data = None
+        self._gauge_field_path = None
+        self._eigenvector_data = None
+        # device workspace + kernels; raises if the CUDA library or a GPU is missing
+        self._engine = ElementalEngine((Lx, Ly, Lz), self.Ne, self._mode, order, list(momentum_list), device)
+        # generator-owned, page-locked result buffer: calc() returns it and overwrites it next call
+        # (reference: elemental.py:56,295,338), so `data[t] = gen.calc(t)` works unchanged
+        self._VPV_pinned = _capi.PinnedBuffer(self._engine.out_shape, np.complex128)
+        self._VPV = self._VPV_pinned.array
+        self._V_pinned = None
+
+    # ---- load(key): reference elemental.py:102-105 / displacement_elemental.py:73-76 -------------
+    def load(self, key: str):
+        data = self.gauge_field.load(key)
+        U = data[:]
+        torch = self._engine.torch
+        if isinstance(U, torch.Tensor):
+            self._U = U
+        else:
+            U = np.asarray(U)
+            if U.ndim != 7 or U.shape[4:] != (Nd, Nc, Nc):
+                raise ValueError(f"gauge field must be [Lt, Lz, Ly, Lx, {Nd}, {Nc}, {Nc}], got {U.shape}")
+            Lx, Ly, Lz, Lt = (int(v) for v in self.latt_size)
+            if U.shape[:4] != (Lt, Lz, Ly, Lx):
+                raise ValueError(f"gauge field shape {U.shape[:4]} does not match latt_size {self.latt_size}")
+            # keep file order [Lt][Lz][Ly][Lx][4][3][3]: one timeslice is one contiguous block;
+            # the time links are dropped on the device (the reference's [:Nd-1] view)
+            self._U = np.ascontiguousarray(U, dtype="<c16")
+        self._gauge_field_path = getattr(data, "file", None)
+        self._gauge_field_data = self._gauge_field_path
+        self._eigenvector_data = self.eigenvector.load(key)
+
+    # ---- one timeslice of inputs -----------------------------------------------------------------
+    def _eigvecs_of(self, t: int):
+        """[Ne, Lz, Ly, Lx, Nc] of timeslice t in ONE read when the handle allows it, else the
+        reference's per-eigenvector loop (elemental.py:297-298)."""
+        ev = self._eigenvector_data
+        Lx, Ly, Lz, Lt = (int(v) for v in self.latt_size)
+        shape = (self.Ne, Lz, Ly, Lx, Nc)
+        torch = self._engine.torch
+        if isinstance(ev, torch.Tensor):
+            return ev[t, : self.Ne].reshape(shape).contiguous()
+        block = None
+        try:
+            block = np.asarray(ev[t])
+        except Exception:
+            block = None
+        if block is None or block.ndim < 2 or block.shape[0] < self.Ne:
+            block = np.stack([np.asarray(ev[t, e]) for e in range(self.Ne)])
+        block = block[: self.Ne].reshape(shape)
+        if block.dtype == np.complex64 or block.dtype == np.dtype(">c8"):
+            return np.ascontiguousarray(block, dtype="<c8")
+        return np.ascontiguousarray(block, dtype="<c16")
+
+    def _check_loaded(self, t):
+        if self._U is None or self._eigenvector_data is None:
+            raise RuntimeError("call load(key) before calc(t)")
+        Lt = int(self.latt_size[3])
+        if not 0 <= t < Lt:
+            raise IndexError(f"timeslice {t} out of range [0, {Lt})")
+
+    # ---- calc(t): reference elemental.py:290-338 / displacement_elemental.py:78-96 ---------------
+    def calc(self, t: int) -> np.ndarray:
+        """Elementals of timeslice t, shape (Nop, Nmom, Ne, Ne) complex128, in the generator's own
+        (page-locked) buffer: copy it before the next call, as with the reference."""
+        self._check_loaded(t)
+        eng = self._engine
+        torch = eng.torch
+        V_t = self._eigvecs_of(t)
+        if isinstance(self._U, torch.Tensor) or isinstance(V_t, torch.Tensor):
+            out = self.calc_device(t)
+            self._VPV[...] = out.cpu().numpy()
+            return self._VPV
+        eng.calc_host(self._U[t], _capi.LINKS_FILE_T, V_t, self._VPV)
+        return self._VPV
+
+    def calc_device(self, t: int, out=None):
+        """Same, result left on the GPU as a torch complex128 tensor (new tensor unless `out`)."""
+        self._check_loaded(t)
+        eng = self._engine
+        torch = eng.torch
+        U_t = self._U[t]
+        if not isinstance(U_t, torch.Tensor):
+            U_t = torch.from_numpy(U_t).to(eng.device, non_blocking=False)
+        V_t = self._eigvecs_of(t)
+        if not isinstance(V_t, torch.Tensor):
+            V_t = torch.from_numpy(V_t).to(eng.device)
+        eng.set_links(U_t.contiguous(), _capi.LINKS_FILE_T)
+        eng.set_eigvecs(V_t.contiguous())
+        return eng.calc(out)
+
+    # ---- batch / sharded form (each rank owns a contiguous t-range) -------------------
+    def calc_range(self, t0: int, t1: int) -> np.ndarray:
+        """(t1-t0, Nop, Nmom, Ne, Ne) for t in [t0, t1)."""
+        out = np.empty((t1 - t0,) + self._engine.out_shape, np.complex128)
+        for i, t in enumerate(range(t0, t1)):
+            out[i] = self.calc(t)
+        return out
+
+    def calc_all(self, group=None, dst: Optional[int] = 0):
+        """All Lt timeslices, sharded over the ranks of `group` (default: the world group if
+        torch.distributed is initialised, else this process alone) and gathered with one
+        collective.  Returns [Lt, Nop, Nmom, Ne, Ne] on rank `dst` (every rank if dst is None)."""
+        from ..sharding import gather_timeslices, timeslice_range, world
+
+        rank, size = world(group)
+        Lt = int(self.latt_size[3])
+        t0, t1 = timeslice_range(Lt, rank, size)
+        torch = self._engine.torch
+        local = torch.empty((t1 - t0,) + self._engine.out_shape, dtype=torch.complex128, device=self._engine.device)
+        for i, t in enumerate(range(t0, t1)):
+            self.calc_device(t, out=local[i])
+        return gather_timeslices(local, Lt, group=group, dst=dst)
+
+    # ---- gauge preprocessing hooks of the reference classes (not built yet) --------
+    def stout_smear(self, nstep, rho):
+        raise NotImplementedError("stout smearing is outside the round-1 hot path (SURVEY.md section 8f, N2)")
+
+    def project_SU3(self):
+        raise NotImplementedError("SU(3) projection is outside the round-1 hot path (SURVEY.md section 8f, N2)")

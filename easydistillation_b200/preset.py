@@ -1,0 +1,168 @@
+"""Typed data handles the generators accept (duck-typed like the reference's
+lattice/preset.py:44-204: an object with `.load(key)` that returns something indexable,
+plus `.Ne` for eigenvectors).
+
+Only what the elemental path touches is here: in-memory handles for synthetic / already
+loaded data, and numpy-memmap readers/writers for the raw-binary gauge field, the `.npy`
+eigenvector file and the `.npy` elemental file ([Nop, Nmom, Lt, Ne, Ne] complex128,
+tests/test_elemental.py:47 and lattice/data.py:26 of the reference).  The reference's own
+handle objects (GaugeFieldIldg, EigenvectorTimeSlice, ...) work unchanged as inputs.
+"""
+from __future__ import annotations
+
+from time import perf_counter
+from typing import List, Sequence
+
+import numpy as np
+
+
+class FileMetaData:
+    def __init__(self, shape: Sequence[int], dtype: str = "<c16", extra=None):
+        self.shape = list(shape)
+        self.dtype = dtype
+        self.extra = extra
+
+
+class ArrayData:
+    """Indexable view with the bookkeeping attributes of the reference's FileData
+    (lattice/filedata/abstract.py:11-20): `.file`, `.shape`, `.dtype`, I/O counters."""
+
+    def __init__(self, array, file: str = "<memory>"):
+        self._a = array
+        self.file = file
+        self.shape = list(array.shape)
+        self.dtype = array.dtype.str
+        self.time_in_sec = 0.0
+        self.size_in_byte = 0
+
+    def __getitem__(self, key):
+        s = perf_counter()
+        ret = np.ascontiguousarray(self._a[key])
+        self.time_in_sec += perf_counter() - s
+        self.size_in_byte += ret.nbytes
+        return ret
+
+
+class GaugeField:
+    def __init__(self, elem: FileMetaData) -> None:
+        self.elem = elem
+
+
+class Eigenvector:
+    def __init__(self, elem: FileMetaData, eigenNum: int) -> None:
+        self.elem = elem
+        self.Ne = eigenNum
+
+
+class Elemental:
+    def __init__(self, elem: FileMetaData, eigenNum: int) -> None:
+        self.elem = elem
+        self.Ne = eigenNum
+
+
+# ---------------------------------------------------------------------------------------------
+# in-memory handles
+# ---------------------------------------------------------------------------------------------
+class GaugeFieldHostmem(GaugeField):
+    """A whole configuration already in host memory: [Lt, Lz, Ly, Lx, Nd, Nc, Nc] complex128."""
+
+    def __init__(self, host_ndarray: np.ndarray) -> None:
+        if host_ndarray.ndim != 7 or host_ndarray.shape[-3:] != (4, 3, 3):
+            raise ValueError(f"gauge field must be [Lt, Lz, Ly, Lx, 4, 3, 3], got {host_ndarray.shape}")
+        super().__init__(FileMetaData(host_ndarray.shape, host_ndarray.dtype.str))
+        self.data = ArrayData(host_ndarray)
+
+    def load(self, key: str = None):
+        return self.data
+
+
+class EigenvectorHostmem(Eigenvector):
+    """Eigenvectors already in host memory: [Lt, Ne, Lz, Ly, Lx, Nc], complex64 or complex128
+    (cf. lattice/preset.py:77-89)."""
+
+    def __init__(self, host_ndarray: np.ndarray, totNe: int = None) -> None:
+        if host_ndarray.ndim != 6 or host_ndarray.shape[-1] != 3:
+            raise ValueError(f"eigenvectors must be [Lt, Ne, Lz, Ly, Lx, 3], got {host_ndarray.shape}")
+        Ne = host_ndarray.shape[1] if totNe is None else totNe
+        if Ne > host_ndarray.shape[1]:
+            raise ValueError("totNe exceeds the number of stored eigenvectors")
+        super().__init__(FileMetaData(host_ndarray.shape, host_ndarray.dtype.str), Ne)
+        self.data = ArrayData(host_ndarray)
+
+    def load(self, key: str = None):
+        return self.data
+
+
+# ---------------------------------------------------------------------------------------------
+# file handles (numpy memmap; one open per load, not one per eigenvector)
+# ---------------------------------------------------------------------------------------------
+class _KeyedFile:
+    def __init__(self, prefix: str, suffix: str):
+        self.prefix = prefix
+        self.suffix = suffix
+        self.file = None
+        self.data = None
+
+    def _name(self, key: str) -> str:
+        return f"{self.prefix}{key}{self.suffix}"
+
+
+class GaugeFieldBinary(_KeyedFile, GaugeField):
+    """Raw binary [Lt, Lz, Ly, Lx, Nd, Nc, Nc] (lattice/preset.py:162-170)."""
+
+    def __init__(self, prefix: str, suffix: str, shape: List[int], dtype: str = "<c16") -> None:
+        _KeyedFile.__init__(self, prefix, ".dat" if suffix is None else suffix)
+        GaugeField.__init__(self, FileMetaData(shape, dtype, 0))
+
+    def load(self, key: str):
+        name = self._name(key)
+        if self.file != name:
+            mm = np.memmap(name, dtype=self.elem.dtype, mode="r", shape=tuple(self.elem.shape))
+            self.file, self.data = name, ArrayData(mm, name)
+        return self.data
+
+
+class GaugeFieldNpy(_KeyedFile, GaugeField):
+    def __init__(self, prefix: str, suffix: str, shape: List[int] = None) -> None:
+        _KeyedFile.__init__(self, prefix, ".npy" if suffix is None else suffix)
+        GaugeField.__init__(self, FileMetaData(shape or [], "<c16", 0))
+
+    def load(self, key: str):
+        name = self._name(key)
+        if self.file != name:
+            self.file, self.data = name, ArrayData(np.load(name, mmap_mode="r"), name)
+        return self.data
+
+
+class EigenvectorNpy(_KeyedFile, Eigenvector):
+    """`.npy` [Lt, Ne, Lz, Ly, Lx, Nc] (lattice/preset.py:66-74; shape/dtype come from the header)."""
+
+    def __init__(self, prefix: str, suffix: str, shape: List[int] = None, totNe: int = 70) -> None:
+        _KeyedFile.__init__(self, prefix, ".lime.npy" if suffix is None else suffix)
+        Eigenvector.__init__(self, FileMetaData(shape or [], "<c16", 2), totNe)
+
+    def load(self, key: str):
+        name = self._name(key)
+        if self.file != name:
+            self.file, self.data = name, ArrayData(np.load(name, mmap_mode="r"), name)
+        return self.data
+
+
+class ElementalNpy(_KeyedFile, Elemental):
+    """`.npy` [Nop, Nmom, Lt, Ne, Ne] (lattice/preset.py:173-181)."""
+
+    def __init__(self, prefix: str, suffix: str, shape: List[int] = None, totNe: int = 70) -> None:
+        _KeyedFile.__init__(self, prefix, ".stout.n20.f0.12.nev70.meson.npy" if suffix is None else suffix)
+        Elemental.__init__(self, FileMetaData(shape or [], "<c16", 0), totNe)
+
+    def load(self, key: str):
+        name = self._name(key)
+        if self.file != name:
+            self.file, self.data = name, ArrayData(np.load(name, mmap_mode="r"), name)
+        return self.data
+
+    def create(self, key: str, shape: Sequence[int]) -> np.memmap:
+        """Pre-sized writable file so every timeslice (or rank) can drop its slab in place."""
+        name = self._name(key)
+        self.file = self.data = None
+        return np.lib.format.open_memmap(name, mode="w+", dtype="<c16", shape=tuple(int(s) for s in shape))

@@ -1,0 +1,146 @@
+/*
+ * edk.h - C ABI of the B200 elemental-distillation kernels (libedk_sm100a.so).
+ *
+ * This is the drop-in boundary for ONE path of IHEP-LQCD/EasyDistillation:
+ * per-timeslice elemental generation.  The reference has no FFI for it (the
+ * path is pure numpy/cupy behind two Python classes), so every entry point
+ * cites the reference interface it stands in for; `INTEGRATION.md` shows the
+ * ctypes stub a reference maintainer would add.  Paths are relative to the
+ * reference root.
+ *
+ * Conventions
+ *   - complex128 = two doubles (re, im); complex64 = two floats.
+ *   - all arrays are C-contiguous, slowest index first.
+ *   - "device" pointers are CUDA device pointers on the handle's device,
+ *     "host" pointers are ordinary (ideally page-locked) host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns EDK_OK (0) or a negative error; edk_last_error()
+ *     gives the message of the calling thread's last failure.
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef EDK_H
+#define EDK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDK_OK 0
+#define EDK_ERR_ARG -1    /* bad argument (-> ValueError on the Python side) */
+#define EDK_ERR_CUDA -2   /* CUDA runtime / launch failure                  */
+#define EDK_ERR_STATE -3  /* call order violated (inputs not set)           */
+#define EDK_ERR_NOMEM -4  /* workspace does not fit                         */
+
+#define EDK_MODE_DERIVATIVE 0   /* ElementalGenerator              */
+#define EDK_MODE_DISPLACEMENT 1 /* DisplacementElementalGenerator  */
+
+/* link layouts accepted by edk_set_links / edk_calc_host */
+#define EDK_LINKS_DIR_MAJOR 0 /* [3][Lz][Ly][Lx][3][3]   = the reference's U[:, t] made contiguous            */
+#define EDK_LINKS_FILE_T 1    /* [Lz][Ly][Lx][4][3][3]   = one timeslice of the file order, time links skipped */
+
+typedef struct edk_handle edk_handle;
+
+/* library ABI version (bumped on any signature change) */
+int edk_version(void);
+const char* edk_last_error(void);
+
+/*
+ * Constructor.  Replaces the numerical part of
+ *   ElementalGenerator.__init__            lattice/generator/elemental.py:17-59
+ *   DisplacementElementalGenerator.__init__ lattice/generator/displacement_elemental.py:12-51
+ * mode/order: EDK_MODE_DERIVATIVE with order = num_nabla (0..3), or
+ *             EDK_MODE_DISPLACEMENT with order = distance (>= 0).
+ * mom3: nmom integer triples (px,py,pz); the phase is exp(+2 pi i p.x/L)
+ *       (lattice/insertion/phase.py:11-13,41-46).
+ * Allocates the workspace (derived fields, phase tables, partial sums) on `device`.
+ */
+int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, const int* mom3, int device,
+               edk_handle** out);
+int edk_destroy(edk_handle* h);
+
+/*
+ * MomentumPhase.get for a list of momenta (lattice/insertion/phase.py:41-46):
+ * out_dev[ip][z][y][x] = exp(+2 pi i (px x/Lx + py y/Ly + pz z/Lz)), complex128, no handle needed.
+ */
+int edk_phase_table(int Lx, int Ly, int Lz, int nmom, const int* mom3, void* out_dev, int device, void* stream);
+
+/* number of operators in the output: (3^(num_nabla+1)-1)/2 or distance+1 (elemental.py:48, displacement_elemental.py:45) */
+int edk_num_operators(const edk_handle* h);
+/* bytes of one timeslice result [Nop][Nmom][Ne][Ne] complex128 */
+size_t edk_output_bytes(const edk_handle* h);
+size_t edk_workspace_bytes(const edk_handle* h);
+
+/*
+ * Inputs of one timeslice, device pointers.  Replace `U[:, t]` (elemental.py:103,320)
+ * and the per-eigenvector staging loop `V[e] = eigenvector[t, e]` (elemental.py:297-298,
+ * displacement_elemental.py:88-89).  Eigenvectors are [Ne][Lz][Ly][Lx][3]; is_c8 = 1 for
+ * complex64 input, 0 for complex128 input, which is value-rounded through complex64 on
+ * the device exactly as the reference's complex64 `_V` buffer does (elemental.py:55).
+ */
+int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream);
+int edk_set_eigvecs(edk_handle* h, const void* V_dev, int is_c8, void* stream);
+
+/* optional real [Ne][Ne] "blending" matrix multiplied into every output block
+ * (stocastic_coeff, elemental.py:61-100,331-337); NULL clears it. Device pointer, copied. */
+int edk_set_blending(edk_handle* h, const double* coeff_dev, void* stream);
+
+/*
+ * calc(t): elemental.py:290-338 / displacement_elemental.py:78-96.
+ * Writes [Nop][Nmom][Ne][Ne] complex128 to out_dev. Asynchronous on `stream`.
+ */
+int edk_calc(edk_handle* h, void* out_dev, void* stream);
+
+/*
+ * Same with HOST buffers: copies links (layout as above) and eigenvectors to the
+ * device, runs calc, copies the result back, and synchronises `stream` before
+ * returning.  This is the call `bench.py`'s end-to-end figure times.
+ */
+int edk_calc_host(edk_handle* h, const void* U_host, int layout, const void* V_host, int is_c8, void* out_host,
+                  void* stream);
+
+/* page-locked host memory for the buffers above (cudaHostAlloc / cudaFreeHost) */
+int edk_host_alloc(void** p, size_t bytes);
+int edk_host_free(void* p);
+
+/*
+ * Measurement hooks.  With profiling on, every kernel class of the next edk_calc is
+ * bracketed by CUDA events on the launching stream; edk_get_profile synchronises
+ * and returns the milliseconds and launch counts of the LAST calc.
+ *   ms[0] prepare (complex64 rounding / link reorder)   ms[1] stencil (nabla or displacement step)
+ *   ms[2] contraction (DMMA)                            ms[3] combine / reduce
+ * n_launch[i] likewise.
+ */
+int edk_set_profiling(edk_handle* h, int on);
+int edk_get_profile(edk_handle* h, double ms[4], int n_launch[4]);
+/* kernels launched by this handle since creation */
+long long edk_launch_count(const edk_handle* h);
+
+/*
+ * Test hooks (used by tests/ only).
+ * edk_debug_field: copy derived field `idx` ([Ne][Lz][Ly][Lx][3] complex128) of the last calc
+ *   to dst_dev.  Derivative mode: idx = (3^len-1)/2 + base-3 value of the direction sequence
+ *   in application order (0 = W0, 1..3 = nabla_a W0, 4+3a+b = nabla_b nabla_a W0).
+ *   Displacement mode: idx = k -> D_k.
+ * edk_debug_phase: copy the phase table of momentum ip ([Lz][Ly][Lx] complex128).
+ * edk_debug_use_naive_gram: 1 = run the scalar one-thread-per-output contraction instead of
+ *   the DMMA kernel (cross-check only; never enabled by the product path).
+ * edk_debug_gram_config: force the DMMA tile variant (m-frags per warp) and split-K factor; 0 = auto.
+ */
+int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream);
+int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream);
+int edk_debug_use_naive_gram(edk_handle* h, int on);
+int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit);
+
+/*
+ * Stand-alone micro-benchmarks (bench.py's roofline denominators): sustained
+ * DMMA.8x8x4 and DFMA throughput of the device in TFLOP/s, measured with CUDA events.
+ */
+int edk_microbench_fp64(int device, double* dmma_tflops, double* dfma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDK_H */

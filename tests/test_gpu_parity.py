@@ -1,0 +1,347 @@
+"""GPU parity: the sm_100a path (through the public classes / the C ABI) against
+ (1) golden outputs of the unmodified reference (tests/golden, made by oracle/make_golden.py),
+ (2) the numpy oracle on seeded synthetic inputs, including ragged / odd sizes,
+ (3) size-independent properties at BASELINE.json sizes.
+Tolerance: 1e-10 relative (Frobenius) per (operator, momentum) block, as north_star states."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def edb():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import easydistillation_b200 as m
+
+    return m
+
+
+def _orc():
+    from oracle import elemental_oracle as orc
+
+    return orc
+
+
+def _blocks_close(got, ref, tol=TOL, what=""):
+    """Per (operator, momentum) block Frobenius error <= tol * block norm.  Blocks that vanish
+    analytically (e.g. p_z = 1 second derivatives on an L_z = 2 lattice) are measured against
+    1e-4 of the largest block instead of their own rounding-noise norm."""
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    norms = np.sqrt((np.abs(ref) ** 2).sum(axis=(-1, -2)))
+    floor = 1e-4 * norms.max()
+    worst = 0.0
+    for a in range(ref.shape[0]):
+        for p in range(ref.shape[1]):
+            worst = max(worst, float(np.linalg.norm(got[a, p] - ref[a, p]) / max(norms[a, p], floor)))
+    assert worst < tol, f"{what}: worst block error {worst:.3e}"
+    assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref)), what
+    return worst
+
+
+def _golden_case(name):
+    g = load_golden(name)
+    latt = [int(v) for v in g["latt_size"]]
+    moms = [tuple(int(v) for v in p) for p in g["momentum_list"]]
+    return g, latt, moms
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) reference golden vectors
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["deriv_weak_4x4x4x2", "deriv_random_4x6x8x1", "deriv_n1_random_6x4x2x1"])
+def test_derivative_elementals_match_reference_golden(edb, name):
+    g, latt, moms = _golden_case(name)
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]),
+                                 int(g["num_nabla"]), moms)
+    assert gen.num_derivative == g["E"].shape[1] and gen.num_momentum == len(moms) and gen.Ne == int(g["Ne"])
+    gen.load("cfg")
+    data = np.zeros((latt[3],) + g["E"].shape[1:], "<c16")
+    for t in range(latt[3]):
+        data[t] = gen.calc(t)  # same idiom as the reference's test script
+    for t in range(latt[3]):
+        _blocks_close(data[t], g["E"][t], what=f"{name} t={t}")
+    # complex128 input goes through the device-side complex64 rounding and must agree too
+    gen2 = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]),
+                                  edb.EigenvectorHostmem(g["V"].astype(np.complex128)), int(g["num_nabla"]), moms)
+    gen2.load("cfg")
+    _blocks_close(gen2.calc(0), g["E"][0], what=name + " c16 input")
+
+
+@pytest.mark.parametrize("name", ["disp_weak_4x4x4x2", "disp_random_4x6x8x1"])
+def test_displacement_elementals_match_reference_golden(edb, name):
+    g, latt, moms = _golden_case(name)
+    gen = edb.DisplacementElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]),
+                                             int(g["distance"]), moms)
+    assert gen.distance == int(g["distance"])
+    gen.load("cfg")
+    for t in range(latt[3]):
+        _blocks_close(np.array(gen.calc(t)), g["E"][t], what=f"{name} t={t}")
+
+
+def test_blending_matches_reference_golden(edb):
+    g, latt, moms = _golden_case("deriv_blend_4x4x4x1")
+    dil = ([int(v) for v in g["dilution_tot"]], [int(v) for v in g["dilution_used"]])
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]),
+                                 int(g["num_nabla"]), moms, dil, True)
+    assert gen.stocastic_coeff.shape == (6, 6)
+    gen.load("cfg")
+    _blocks_close(np.array(gen.calc(0)), g["E"][0], what="blending")
+    with pytest.raises(ValueError):
+        edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]), 1, moms, None, True)
+
+
+def test_calc_returns_generator_owned_buffer_and_checks_state(edb):
+    g, latt, moms = _golden_case("deriv_weak_4x4x4x2")
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]), 1, moms[:2])
+    with pytest.raises(RuntimeError):
+        gen.calc(0)
+    gen.load("cfg")
+    a = gen.calc(0)
+    first = a.copy()
+    b = gen.calc(1)
+    assert a is b and not np.array_equal(first, b)  # overwritten, like the reference's _VPV
+    with pytest.raises(IndexError):
+        gen.calc(latt[3])
+    with pytest.raises(NotImplementedError):
+        gen.stout_smear(1, 0.1)
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) oracle on synthetic inputs: kernels one by one, then edge shapes
+# ---------------------------------------------------------------------------------------------
+def test_phase_table_matches_oracle(edb):
+    import torch
+
+    orc = _orc()
+    latt = [6, 4, 10, 1]
+    mp = edb.MomentumPhase(latt)
+    for p in [(0, 0, 0), (1, 0, 0), (0, -1, 2), (3, 2, 1), (-7, 11, 5)]:
+        got = mp.get(p).cpu().numpy()
+        assert got.shape == (10, 4, 6)
+        assert np.max(np.abs(got - orc.momentum_phase(latt, p))) < 1e-14
+    assert mp.get((1, 0, 0)) is mp.get((1, 0, 0))
+    g = load_golden("insertion_maps")
+    mp = edb.MomentumPhase([int(v) for v in g["phase_latt"]])
+    for p, ref in zip(g["phase_moms"], g["phases"]):
+        assert np.max(np.abs(mp.get(tuple(int(v) for v in p)).cpu().numpy() - ref)) < 1e-14
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("latt,Ne", [([4, 4, 4, 1], 5), ([6, 2, 4, 1], 3), ([3, 5, 7, 1], 4), ([8, 8, 8, 1], 9)])
+def test_stencil_fields_match_oracle(edb, latt, Ne):
+    """Every derived field W[seq] (bit-for-bit the same formula, so ~1e-15)."""
+    import torch
+
+    from easydistillation_b200 import _capi
+    from easydistillation_b200.engine import ElementalEngine
+
+    orc = _orc()
+    U_file = orc.synthetic_links(latt, 0)
+    V = orc.synthetic_eigvecs(latt, Ne, 0)
+    U = orc.links_file_to_spatial(U_file)
+    eng = ElementalEngine(latt[:3], Ne, _capi.MODE_DERIVATIVE, 2, [(0, 0, 0)])
+    eng.set_links(torch.from_numpy(U_file).cuda(), _capi.LINKS_FILE_T)
+    eng.set_eigvecs(torch.from_numpy(V).cuda())
+    eng.calc()
+    W0 = orc.round_through_c8(V).astype(np.complex128)
+    assert np.array_equal(eng.debug_field(0).cpu().numpy(), W0)  # rounding is exact
+    for a in range(3):
+        W1 = orc.covariant_hop(W0, U, a)
+        assert rel_err(eng.debug_field(1 + a).cpu().numpy(), W1) < 1e-14
+        for b in range(3):
+            W2 = orc.covariant_hop(W1, U, b)
+            assert rel_err(eng.debug_field(4 + 3 * a + b).cpu().numpy(), W2) < 1e-14
+    # direction-major link layout gives the same fields
+    eng.set_links(torch.from_numpy(np.ascontiguousarray(U)).cuda(), _capi.LINKS_DIR_MAJOR)
+    eng.calc()
+    assert rel_err(eng.debug_field(2).cpu().numpy(), orc.covariant_hop(W0, U, 1)) < 1e-14
+
+
+def test_displacement_fields_match_oracle(edb):
+    import torch
+
+    from easydistillation_b200 import _capi
+    from easydistillation_b200.engine import ElementalEngine
+
+    orc = _orc()
+    latt, Ne, dist = [4, 6, 2, 1], 5, 4
+    U_file = orc.synthetic_links(latt, 1)
+    V = orc.synthetic_eigvecs(latt, Ne, 1)
+    eng = ElementalEngine(latt[:3], Ne, _capi.MODE_DISPLACEMENT, dist, [(0, 0, 0)])
+    eng.set_links(torch.from_numpy(U_file).cuda(), _capi.LINKS_FILE_T)
+    eng.set_eigvecs(torch.from_numpy(V).cuda())
+    eng.calc()
+    for k, Dk in enumerate(orc.displacement_fields(V, orc.links_file_to_spatial(U_file), dist)):
+        assert rel_err(eng.debug_field(k).cpu().numpy(), np.asarray(Dk, np.complex128)) < 1e-14, k
+
+
+@pytest.mark.parametrize(
+    "latt,Ne,nabla,nmom",
+    [
+        ([4, 4, 4, 1], 1, 2, 1),     # single eigenvector
+        ([4, 4, 4, 1], 3, 0, 2),     # no derivative
+        ([3, 5, 7, 1], 7, 2, 5),     # V = 105: not a multiple of the 8-site k stage, ragged Ne
+        ([2, 2, 2, 1], 13, 1, 3),    # tiny volume, Ne not a multiple of 4
+        ([8, 4, 6, 1], 21, 2, 4),    # several m-fragments with a ragged last one
+        ([4, 4, 4, 1], 110, 1, 2),   # two row tiles (Ne > 104)
+        ([4, 4, 2, 1], 6, 3, 2),     # third-order derivatives (40 operators)
+    ],
+)
+def test_derivative_elementals_match_oracle_edge_shapes(edb, latt, Ne, nabla, nmom):
+    orc = _orc()
+    moms = orc.momentum_set(33)[::7][:nmom] if nmom > 1 else [(1, -1, 2)]
+    U_file = orc.synthetic_links(latt, 2)[None]
+    V = orc.synthetic_eigvecs(latt, Ne, 2)[None]
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), nabla, moms)
+    gen.load("x")
+    got = np.array(gen.calc(0))
+    U = orc.links_file_to_spatial(U_file[0])
+    if nabla <= 2:
+        ref = orc.elemental_timeslice_closed_form(V[0], U, latt, nabla, moms)
+    else:
+        ref = orc.elemental_timeslice(V[0], U, latt, nabla, moms)
+    _blocks_close(got, ref, what=f"{latt} Ne={Ne} nabla={nabla}")
+
+
+def test_dmma_tile_variants_and_split_k_agree_with_scalar_kernel(edb):
+    """Every instantiated tile height and several split-K factors against the scalar
+    one-thread-per-output contraction and the oracle."""
+    import torch
+
+    from easydistillation_b200 import _capi
+    from easydistillation_b200.engine import ElementalEngine
+
+    orc = _orc()
+    latt, Ne = [4, 6, 8, 1], 30
+    moms = orc.momentum_set(9)
+    U_file = orc.synthetic_links(latt, 5)
+    V = orc.synthetic_eigvecs(latt, Ne, 5)
+    ref = orc.elemental_timeslice_closed_form(V, orc.links_file_to_spatial(U_file), latt, 2, moms)
+    eng = ElementalEngine(latt[:3], Ne, _capi.MODE_DERIVATIVE, 2, moms)
+    eng.set_links(torch.from_numpy(U_file).cuda(), _capi.LINKS_FILE_T)
+    eng.set_eigvecs(torch.from_numpy(V).cuda())
+    eng.debug_use_naive_gram(True)
+    naive = eng.calc().cpu().numpy()
+    _blocks_close(naive, ref, what="scalar kernel")
+    eng.debug_use_naive_gram(False)
+    for mfrag in (2, 4, 5, 7, 9, 10, 11, 13):
+        for ksplit in (1, 3):
+            eng.debug_gram_config(mfrag, ksplit)
+            got = eng.calc().cpu().numpy()
+            _blocks_close(got, ref, what=f"mfrag={mfrag} ksplit={ksplit}")
+            _blocks_close(got, naive, what=f"mfrag={mfrag} ksplit={ksplit} vs scalar")
+    eng.debug_gram_config(0, 24)
+    _blocks_close(eng.calc().cpu().numpy(), ref, what="ksplit=24")
+    with pytest.raises(ValueError):
+        eng.debug_gram_config(6, 1)
+
+
+def test_displacement_matches_oracle_ragged(edb):
+    orc = _orc()
+    latt, Ne, dist = [3, 4, 5, 1], 11, 3
+    moms = [(0, 0, 0), (1, 2, -1), (0, -1, 0)]
+    U_file = orc.synthetic_links(latt, 9)[None]
+    V = orc.synthetic_eigvecs(latt, Ne, 9)[None]
+    gen = edb.DisplacementElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), dist, moms)
+    gen.load("x")
+    ref = orc.displacement_timeslice(V[0], orc.links_file_to_spatial(U_file[0]), latt, dist, moms)
+    _blocks_close(np.array(gen.calc(0)), ref, what="displacement ragged")
+    gen0 = edb.DisplacementElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), 0, moms)
+    gen0.load("x")
+    _blocks_close(np.array(gen0.calc(0)), ref[:1], what="distance 0")
+
+
+def test_file_handles_and_elemental_npy_roundtrip(edb, tmp_path):
+    """Inputs through file handles, output saved in the reference's [Nop,Nmom,Lt,Ne,Ne] layout."""
+    g, latt, moms = _golden_case("deriv_weak_4x4x4x2")
+    prefix = str(tmp_path) + "/"
+    g["U"].astype("<c16").tofile(prefix + "weak.dat")
+    np.save(prefix + "weak.eigenvector.npy", g["V"].astype("<c16"))
+    Lx, Ly, Lz, Lt = latt
+    gauge = edb.GaugeFieldBinary(prefix, ".dat", [Lt, Lz, Ly, Lx, 4, 3, 3], "<c16")
+    evec = edb.EigenvectorNpy(prefix, ".eigenvector.npy", [Lt, 8, Lz, Ly, Lx, 3], 8)
+    gen = edb.ElementalGenerator(latt, gauge, evec, 2, moms)
+    gen.load("weak")
+    data = gen.calc_range(0, Lt)
+    el = edb.ElementalNpy(prefix, ".elemental.npy", [13, len(moms), Lt, 8, 8], 8)
+    mm = el.create("weak", [13, len(moms), Lt, 8, 8])
+    mm[...] = data.transpose(1, 2, 0, 3, 4)
+    mm.flush()
+    back = el.load("weak")[:]
+    _blocks_close(back[:, :, 1], g["E"][1], what="npy roundtrip")
+    # calc_all without torch.distributed = all timeslices on this GPU
+    full = gen.calc_all()
+    assert tuple(full.shape) == (Lt, 13, len(moms), 8, 8)
+    _blocks_close(full[0].cpu().numpy(), g["E"][0], what="calc_all")
+
+
+# ---------------------------------------------------------------------------------------------
+# (3) BASELINE.json sizes: direct oracle where it takes seconds, properties beyond
+# ---------------------------------------------------------------------------------------------
+def test_config2_shape_against_oracle(edb):
+    """16^3, Ne=100, num_nabla=1, 9 momenta: one timeslice against the closed-form oracle."""
+    orc = _orc()
+    latt, Ne = [16, 16, 16, 1], 100
+    moms = orc.momentum_set(9)
+    U_file = orc.synthetic_links(latt, 0)[None]
+    V = orc.synthetic_eigvecs(latt, Ne, 0)[None].astype(np.complex64)
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), 1, moms)
+    gen.load("x")
+    got = np.array(gen.calc(0))
+    ref = orc.elemental_timeslice_closed_form(V[0], orc.links_file_to_spatial(U_file[0]), latt, 1, moms)
+    _blocks_close(got, ref, what="config 2")
+
+
+def test_config3_shape_properties(edb):
+    """24^3, Ne=100, num_nabla=2, 33 momenta: too slow for the full oracle, so check
+    (a) Hermiticity  E[0,p]^dag = E[0,-p],  E[a,p]^dag = -E[a,-p],  E[(a,b),p]^dag = E[(b,a),-p];
+    (b) p = 0, n = 0 block is the Gram matrix of unit-norm vectors (diagonal 1 to c8 accuracy);
+    (c) a random sub-block of every operator against the oracle run on 6 of the 100 vectors."""
+    orc = _orc()
+    latt, Ne = [24, 24, 24, 1], 100
+    moms = orc.momentum_set(33)
+    U_file = orc.synthetic_links(latt, 0)[None]
+    V = orc.synthetic_eigvecs(latt, Ne, 0)[None].astype(np.complex64)
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), 2, moms)
+    gen.load("x")
+    E = np.array(gen.calc(0))
+    neg = [moms.index(tuple(-c for c in p)) for p in moms]
+    for ip in range(len(moms)):
+        assert rel_err(E[0, ip].conj().T, E[0, neg[ip]]) < TOL
+        for a in range(3):
+            assert rel_err(-E[1 + a, ip].conj().T, E[1 + a, neg[ip]]) < TOL
+            for b in range(3):
+                assert rel_err(E[4 + 3 * a + b, ip].conj().T, E[4 + 3 * b + a, neg[ip]]) < TOL
+    assert np.max(np.abs(np.diag(E[0, 0]) - 1.0)) < 1e-6
+    sel = [3, 17, 42, 64, 65, 99]
+    ref = orc.elemental_timeslice_closed_form(V[0][sel], orc.links_file_to_spatial(U_file[0]), latt, 2, moms)
+    _blocks_close(E[:, :, sel][:, :, :, sel], ref, what="config 3 sub-block")
+
+
+def test_linearity_and_scaling_property(edb):
+    """E is sesquilinear in the eigenvectors: scaling vector f by c scales column f by c and row f by conj(c)
+    (powers of two keep the complex64 staging exact)."""
+    orc = _orc()
+    latt, Ne = [8, 8, 8, 1], 12
+    moms = orc.momentum_set(5)
+    U_file = orc.synthetic_links(latt, 4)[None]
+    V = orc.synthetic_eigvecs(latt, Ne, 4)[None].astype(np.complex64)
+    V2 = V.copy()
+    V2[0, 5] *= 4j
+    outs = []
+    for vv in (V, V2):
+        gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(vv), 2, moms)
+        gen.load("x")
+        outs.append(np.array(gen.calc(0)))
+    expect = outs[0].copy()
+    expect[:, :, :, 5] *= 4j
+    expect[:, :, 5, :] *= -4j
+    _blocks_close(outs[1], expect, what="sesquilinearity")

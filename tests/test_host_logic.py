@@ -1,0 +1,157 @@
+"""CPU-only checks: C-ABI surface, host-side logic, sharding over gloo (no kernels are run)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import REPO, load_golden
+
+import easydistillation_b200 as edb
+from easydistillation_b200 import _capi
+from easydistillation_b200.generator.elemental import blending_matrix
+from easydistillation_b200.insertion.derivative import derivative, num_derivative
+from easydistillation_b200.sharding import timeslice_range
+
+
+def _header_symbols():
+    text = open(os.path.join(REPO, "include", "edk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(edk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from easydistillation_b200.build import build
+
+    build()
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    names = _header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/edk.h but not exported"
+    assert sorted(_capi.SIGNATURES) == names, "ctypes table and header disagree"
+    lib.edk_version.restype = ctypes.c_int
+    assert lib.edk_version() == 1
+
+
+def test_library_is_sm100a_dmma():
+    """The shipped cubin is sm_100a and the contraction really is DMMA (FP64 tensor pipe)."""
+    out = subprocess.run(["cuobjdump", "-lelf", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("DMMA.8x8x4") >= 312
+
+
+def test_missing_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    U = np.zeros((1, 2, 2, 2, 4, 3, 3), np.complex128)
+    V = np.zeros((1, 2, 2, 2, 2, 3), np.complex128)
+    with pytest.raises(_capi.EdkError):
+        edb.ElementalGenerator([2, 2, 2, 1], edb.GaugeFieldHostmem(U), edb.EigenvectorHostmem(V), 1)
+    with pytest.raises(_capi.EdkError):
+        edb.MomentumPhase([2, 2, 2, 1]).get((0, 0, 1))
+
+
+def test_derivative_map_matches_reference_golden():
+    g = load_golden("insertion_maps")
+    for n, row in enumerate(g["derivative_tuples"]):
+        assert derivative(n) == tuple(int(v) for v in row if v >= 0)
+    assert [num_derivative(n) for n in range(4)] == [1, 4, 13, 40]
+    with pytest.raises(ValueError):
+        derivative(-1)
+
+
+def test_blending_matrix_matches_reference_output():
+    # printed by the reference for dilution=([10, 7], [4, 2]) when the golden was generated
+    c = blending_matrix(6, ([10, 7], [4, 2]))
+    assert c[0, 0] == 2.5 and c[0, 1] == 7.5 and c[0, 4] == 8.75 and c[4, 4] == 3.5 and c[4, 5] == 21.0
+    assert np.array_equal(c, c.T)
+    with pytest.raises(AssertionError):
+        blending_matrix(5, ([10, 7], [4, 2]))
+    from oracle.elemental_oracle import blending_matrix as ob
+
+    assert np.array_equal(ob(6, ([10, 7], [4, 2])), c)
+    assert np.array_equal(ob(6, ([9, 9, 9], 2)), blending_matrix(6, ([9, 9, 9], 2)))
+
+
+def test_timeslice_ranges_partition():
+    for Lt in (1, 7, 8, 96, 128):
+        for size in (1, 2, 3, 4, 8):
+            got = [timeslice_range(Lt, r, size) for r in range(size)]
+            assert got[0][0] == 0 and got[-1][1] == Lt
+            assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+            lens = [b - a for a, b in got]
+            assert max(lens) - min(lens) <= 1
+
+
+def test_presets_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    U = (rng.standard_normal((2, 2, 2, 2, 4, 3, 3)) + 0j).astype("<c16")
+    V = (rng.standard_normal((2, 3, 2, 2, 2, 3)) + 0j).astype("<c16")
+    prefix = str(tmp_path) + "/"
+    U.tofile(prefix + "c.dat")
+    np.save(prefix + "c.npy", U)
+    np.save(prefix + "c.evec.npy", V)
+    g = edb.GaugeFieldBinary(prefix, ".dat", list(U.shape), "<c16").load("c")
+    assert np.array_equal(g[:], U) and g.file.endswith("c.dat")
+    assert np.array_equal(edb.GaugeFieldNpy(prefix, ".npy").load("c")[1], U[1])
+    ev = edb.EigenvectorNpy(prefix, ".evec.npy", list(V.shape), 3)
+    assert ev.Ne == 3 and np.array_equal(ev.load("c")[1, 2], V[1, 2])
+    el = edb.ElementalNpy(prefix, ".elemental.npy", [4, 1, 2, 3, 3], 3)
+    mm = el.create("c", [4, 1, 2, 3, 3])
+    mm[:, :, 1] = 2.0 + 1j
+    mm.flush()
+    back = el.load("c")[:]
+    assert back.shape == (4, 1, 2, 3, 3) and back[0, 0, 1, 0, 0] == 2.0 + 1j and back[0, 0, 0, 0, 0] == 0
+    with pytest.raises(ValueError):
+        edb.GaugeFieldHostmem(np.zeros((2, 2, 2, 2, 3, 3, 3)))
+    with pytest.raises(ValueError):
+        edb.EigenvectorHostmem(np.zeros((2, 3, 2, 2, 2, 3)), totNe=5)
+
+
+GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["EDB_REPO"])
+from easydistillation_b200.sharding import gather_timeslices, timeslice_range, world
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["EDB_PORT"],
+                        rank=int(os.environ["EDB_RANK"]), world_size=2)
+rank, size = world()
+Lt = 5
+t0, t1 = timeslice_range(Lt, rank, size)
+full = (torch.arange(Lt * 6, dtype=torch.float64).reshape(Lt, 3, 2) * (1 + 0.5j)).to(torch.complex128)
+local = full[t0:t1].clone()
+got = gather_timeslices(local, Lt, dst=0)
+if rank == 0:
+    assert got.shape == full.shape and torch.equal(got, full), "gather to rank 0"
+else:
+    assert got is None
+got = gather_timeslices(local, Lt, dst=None)
+assert torch.equal(got, full), "all-gather"
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_gather_timeslices_gloo_world2(tmp_path):
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, EDB_REPO=REPO, EDB_PORT=str(port), EDB_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK {r}" in o, o
