@@ -41,7 +41,7 @@ struct edk_handle {
     cplx* fields = nullptr;   // nfield fields
     int nfield = 0;
     cplx* lines = nullptr;    // displacement: 12 line buffers (ping-pong)
-    cplx* phase = nullptr;    // [nmom][Vpad]
+    cplx* phase = nullptr;    // [2][nmom][Vpad]: phase and -i*phase
     cplx* partial = nullptr;  // [ksplit][njobs][nmom][Ne][Ne]
     double* coeff = nullptr;  // [Ne][Ne] or null
     bool have_coeff = false;
@@ -387,12 +387,12 @@ int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, co
     EDK_ALLOC(h->links, (size_t)3 * h->g.V * 9 * sizeof(cplx));
     EDK_ALLOC(h->fields, (size_t)h->nfield * h->field_cplx * sizeof(cplx));
     if (mode == EDK_MODE_DISPLACEMENT && order >= 1) EDK_ALLOC(h->lines, (size_t)12 * h->field_cplx * sizeof(cplx));
-    EDK_ALLOC(h->phase, (size_t)nmom * h->g.Vpad * sizeof(cplx));
+    EDK_ALLOC(h->phase, (size_t)2 * nmom * h->g.Vpad * sizeof(cplx));
     EDK_ALLOC(h->coeff, (size_t)Ne * Ne * sizeof(double));
     int* mom_dev = nullptr;
     EDK_ALLOC(mom_dev, (size_t)nmom * 3 * sizeof(int));
     cudaError_t e = cudaMemcpy(mom_dev, mom3, (size_t)nmom * 3 * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_phase_table(h->phase, mom_dev, nmom, h->g, 0);
+    if (e == cudaSuccess) e = launch_phase_table(h->phase, h->phase + (size_t)nmom * h->g.Vpad, mom_dev, nmom, h->g, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(mom_dev);
     ws -= (size_t)nmom * 3 * sizeof(int);
@@ -463,7 +463,7 @@ int edk_phase_table(int Lx, int Ly, int Lz, int nmom, const int* mom3, void* out
     EDK_CUDA_TRY(cudaMalloc(&mom_dev, (size_t)nmom * 3 * sizeof(int)));
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemcpyAsync(mom_dev, mom3, (size_t)nmom * 3 * sizeof(int), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = launch_phase_table((cplx*)out_dev, mom_dev, nmom, g, s);
+    if (e == cudaSuccess) e = launch_phase_table((cplx*)out_dev, nullptr, mom_dev, nmom, g, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     cudaFree(mom_dev);
     if (e != cudaSuccess) {

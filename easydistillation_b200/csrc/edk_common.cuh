@@ -54,7 +54,7 @@ struct GramParams {
     int ksplit;   // split-K factor
     int n_mt;     // tiles along e (rows)
     int n_nt;     // tiles along the flattened (f-fragment, momentum) axis
-    const cplx* phase;  // [nmom][Vpad]
+    const cplx* phase;  // [2][nmom][Vpad]: phase, then -i*phase
     cplx* partial;      // [ksplit][njobs][nmom][Ne][Ne]
 };
 
@@ -70,7 +70,7 @@ struct CombineOp {
 // prepare
 cudaError_t launch_round_eigvecs(const void* V_in, int is_c8, cplx* W0, size_t n_cplx, cudaStream_t s);
 cudaError_t launch_reorder_links(const cplx* U_in, int layout, cplx* U_out, Geom g, cudaStream_t s);
-cudaError_t launch_phase_table(cplx* phase, const int* mom3_dev, int nmom, Geom g, cudaStream_t s);
+cudaError_t launch_phase_table(cplx* phase, cplx* rot, const int* mom3_dev, int nmom, Geom g, cudaStream_t s);
 // stencil
 cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
                           cudaStream_t s);

@@ -11,7 +11,8 @@
 //                  column (f,re): (Pr | Pi)      column (f,im): (Pi | -Pr)
 //   so that  C[e][(f,re)] += Lr*Pr + Li*Pi = Re(conj(L) P),  C[e][(f,im)] += Lr*Pi - Li*Pr = Im(conj(L) P)
 //   and the accumulator fragment (2 doubles per lane) is one complex128 in natural (re, im) order.
-//   The phase multiply is fused into the B-fragment build: 4 FP64 ops per 2*MF MMAs.
+//   The phase multiply is fused into the B-fragment build: 4 FP64 ops per 2*MF MMAs; the
+//   (f,im) columns read a pre-rotated table -i*phase, so there is no select or negation.
 //
 // CTA tile: 8*MF rows (all warps share them) x 16 "n-fragments"; an n-fragment is 4 consecutive
 // f at one momentum, n-fragments are flattened f-fragment-major so one CTA needs few rows of R.
@@ -36,7 +37,7 @@ struct GramSmem {
     static constexpr int ROWS_A = 8 * MF;
     static constexpr int A_BYTES = GRAM_KG * ROWS_A * 64;
     static constexpr int B_BYTES = GRAM_KG * GRAM_BROWS * 64;
-    static constexpr int PH_BYTES = GRAM_NT * 8 * 16;
+    static constexpr int PH_BYTES = 2 * GRAM_NT * 8 * 16;  // phase and -i*phase
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + PH_BYTES;
     static constexpr int JOB_OFF = GRAM_STAGES * STAGE_BYTES;
     static constexpr int TOTAL = JOB_OFF + (int)sizeof(GramJob);
@@ -58,10 +59,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, 
                  : "d"(a), "d"(b));
 }
 
+// sign flip on the integer pipe: the FP64 pipe is the one the DMMAs need
+__device__ __forceinline__ double flip_sign(double x) {
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
 template <int MF>
 __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramParams P) {
     using S = GramSmem<MF>;
     constexpr int ROWS_A = S::ROWS_A;
+    constexpr int AJ = (ROWS_A + 31) / 32;  // loader passes over the rows of A
     extern __shared__ __align__(128) unsigned char smem[];
     GramJob* sjob = reinterpret_cast<GramJob*>(smem + S::JOB_OFF);
 
@@ -102,7 +109,9 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
         my_p[n] = nf - my_ffrag[n] * nmom;
         my_boff[n] = (uint32_t)(((4 * (my_ffrag[n] - ff0) + (g >> 1)) * 4 + kk) * 16);
     }
-    const bool part_im = (g & 1) != 0;
+    // columns (f, im) of the B operand are the components of (-i * phase) * R: those lanes read
+    // the second (pre-rotated) phase tile, so the fragment build has no select and no negation
+    const uint32_t my_phoff = (uint32_t)(((g & 1) * GRAM_NT + warp * GRAM_NF) * 8 * 16);
 
     // ---- k range of this split --------------------------------------------------------------
     const int T_all = nseg * P.ksteps;
@@ -110,38 +119,75 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
     const int T1 = (int)(((long long)T_all * (split + 1)) / P.ksplit);
     const int T = T1 - T0;
 
+    // ---- loader state: everything that does not depend on the stage --------------------------
+    // thread -> (row lrow + 32 j, 16-byte chunk lkq + 8 m) of a 24-chunk (8-site) row segment:
+    // 8 consecutive threads fetch one full 128-byte line of a row.
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
     const int row0 = mt * ROWS_A;
+    const int lrow = tid >> 3, lkq = tid & 7;
+    const uint32_t a_dst0 = (uint32_t)(((lkq >> 2) * ROWS_A + lrow) * 64 + (lkq & 3) * 16);
+    const uint32_t b_dst0 = (uint32_t)(S::A_BYTES + ((lkq >> 2) * GRAM_BROWS + lrow) * 64 + (lkq & 3) * 16);
+    const size_t a_goff = (size_t)(row0 + lrow) * P.Kc + lkq;
+    const size_t b_goff = (size_t)(4 * ff0 + lrow) * P.Kc + lkq;
+    const size_t rstride = (size_t)32 * P.Kc;
+    unsigned a_issue = 0, a_ok = 0, b_issue = 0, b_ok = 0;  // bit j: row pass j exists / is inside the matrix
+#pragma unroll
+    for (int j = 0; j < AJ; ++j) {
+        if (lrow + 32 * j < ROWS_A) a_issue |= 1u << j;
+        if (row0 + lrow + 32 * j < Ne) a_ok |= 1u << j;
+    }
+#pragma unroll
+    for (int j = 0; j < GRAM_BROWS / 32; ++j) {
+        if (lrow + 32 * j < nrows_b) b_issue |= 1u << j;
+        if (4 * ff0 + lrow + 32 * j < Ne) b_ok |= 1u << j;
+    }
+    // phase tiles: threads 0..127 fetch phase, 128..255 fetch -i*phase, 16 n-fragments x 8 sites each
+    const cplx* ph_src;
+    {
+        const int t2 = tid & (GRAM_NT * 8 - 1);
+        const int nf = min(nflat0 + (t2 >> 3), N_flat - 1);
+        ph_src = P.phase + ((size_t)(tid >> 7) * nmom + (nf % nmom)) * P.Vpad + (t2 & 7);
+    }
+    const uint32_t ph_dst0 = (uint32_t)(S::A_BYTES + S::B_BYTES + tid * 16);
 
-    auto issue_stage = [&](int it) {
-        const int buf = it % GRAM_STAGES;
-        const int flat = T0 + it;
-        const int seg = flat / P.ksteps;
-        const int kstep = flat - seg * P.ksteps;
-        const int kbase = kstep * 24;
-        const cplx* Lp = sjob->L[seg];
-        const cplx* Rp = sjob->R[seg];
-        const uint32_t a_s = smem_base + buf * S::STAGE_BYTES;
-        const uint32_t b_s = a_s + S::A_BYTES;
-        const uint32_t p_s = b_s + S::B_BYTES;
-        for (int c = tid; c < ROWS_A * 24; c += GRAM_NTHREADS) {
-            const int row = c / 24, kc = c - row * 24;
-            const bool ok = (row0 + row < Ne) && (kbase + kc < P.Kc);
-            const cplx* src = ok ? Lp + (size_t)(row0 + row) * P.Kc + kbase + kc : Lp;
-            cp_async16(a_s + (uint32_t)((((kc >> 2) * ROWS_A + row) * 4 + (kc & 3)) * 16), src, ok);
+    int ld_seg = T0 / P.ksteps;             // segment / k-step of the NEXT stage to be issued
+    int ld_kstep = T0 - ld_seg * P.ksteps;
+    auto issue_stage = [&](int buf) {
+        const int kbase = ld_kstep * 24;
+        const cplx* Lp = sjob->L[ld_seg];
+        const cplx* Rp = sjob->R[ld_seg];
+        const uint32_t st = smem_base + buf * S::STAGE_BYTES;
+        bool kok[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) kok[m] = kbase + lkq + 8 * m < P.Kc;
+        const cplx* ap = Lp + a_goff + kbase;
+#pragma unroll
+        for (int j = 0; j < AJ; ++j) {
+            if (a_issue >> j & 1) {
+                const bool rok = a_ok >> j & 1;
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const bool ok = rok && kok[m];
+                    cp_async16(st + a_dst0 + (uint32_t)(m * 2 * ROWS_A * 64 + j * 32 * 64), ok ? ap + j * rstride + 8 * m : Lp, ok);
+                }
+            }
         }
-        for (int c = tid; c < nrows_b * 24; c += GRAM_NTHREADS) {
-            const int row = c / 24, kc = c - row * 24;
-            const int f = 4 * ff0 + row;
-            const bool ok = (f < Ne) && (kbase + kc < P.Kc);
-            const cplx* src = ok ? Rp + (size_t)f * P.Kc + kbase + kc : Rp;
-            cp_async16(b_s + (uint32_t)((((kc >> 2) * GRAM_BROWS + row) * 4 + (kc & 3)) * 16), src, ok);
+        const cplx* bp = Rp + b_goff + kbase;
+#pragma unroll
+        for (int j = 0; j < GRAM_BROWS / 32; ++j) {
+            if (b_issue >> j & 1) {
+                const bool rok = b_ok >> j & 1;
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const bool ok = rok && kok[m];
+                    cp_async16(st + b_dst0 + (uint32_t)(m * 2 * GRAM_BROWS * 64 + j * 32 * 64), ok ? bp + j * rstride + 8 * m : Rp, ok);
+                }
+            }
         }
-        if (tid < GRAM_NT * 8) {
-            const int nl = tid >> 3, s = tid & 7;
-            const int nf = min(nflat0 + nl, N_flat - 1);
-            const int p = nf % nmom;
-            cp_async16(p_s + (uint32_t)(tid * 16), P.phase + (size_t)p * P.Vpad + kstep * 8 + s, true);
+        cp_async16(st + ph_dst0, ph_src + ld_kstep * 8, true);
+        if (++ld_kstep == P.ksteps) {
+            ld_kstep = 0;
+            ++ld_seg;
         }
     };
 
@@ -158,49 +204,99 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
         cp_async_commit();
     }
 
+    int cs_seg = T0 / P.ksteps;             // segment / k-step of the stage being computed
+    int cs_kstep = T0 - cs_seg * P.ksteps;
+    int buf = 0;
     for (int it = 0; it < T; ++it) {
         cp_async_wait<GRAM_STAGES - 2>();
         __syncthreads();
-        if (it + GRAM_STAGES - 1 < T) issue_stage(it + GRAM_STAGES - 1);
-        cp_async_commit();
-
-        const int seg = (T0 + it) / P.ksteps;
-        const int sgn = sjob->sign[seg];
+        {
+            int nb = buf + GRAM_STAGES - 1;
+            if (nb >= GRAM_STAGES) nb -= GRAM_STAGES;
+            if (it + GRAM_STAGES - 1 < T) issue_stage(nb);
+            cp_async_commit();
+        }
+        const int sgn = sjob->sign[cs_seg];
+        if (++cs_kstep == P.ksteps) {
+            cs_kstep = 0;
+            ++cs_seg;
+        }
         if (sgn != cur_sign) {  // uniform: fold the segment sign by flipping the running sum
 #pragma unroll
             for (int i = 0; i < MF; ++i)
 #pragma unroll
                 for (int n = 0; n < GRAM_NF; ++n) {
-                    acc[i][n][0] = -acc[i][n][0];
-                    acc[i][n][1] = -acc[i][n][1];
+                    acc[i][n][0] = flip_sign(acc[i][n][0]);
+                    acc[i][n][1] = flip_sign(acc[i][n][1]);
                 }
             cur_sign = sgn;
         }
 
-        const unsigned char* stage = smem + (it % GRAM_STAGES) * S::STAGE_BYTES;
+        const unsigned char* stage = smem + buf * S::STAGE_BYTES;
         const unsigned char* a_s = stage + lane * 16;
         const unsigned char* b_s = stage + S::A_BYTES;
-        const unsigned char* p_s = b_s + S::B_BYTES + (warp * GRAM_NF) * 8 * 16;
+        const unsigned char* p_s = b_s + S::B_BYTES + my_phoff;
+        if (++buf == GRAM_STAGES) buf = 0;
+
+        // B fragments of k-group kg: P' = phase' * R with phase' = phase (re columns) or -i*phase
+        // (im columns); b1 = Re P' pairs with Re L, b2 = Im P' pairs with Im L.
+        cplx rr[GRAM_NF], pp[GRAM_NF];
+        double b1[GRAM_NF], b2[GRAM_NF];
+#pragma unroll
+        for (int n = 0; n < GRAM_NF; ++n) {
+            rr[n] = *reinterpret_cast<const cplx*>(b_s + my_boff[n]);
+            pp[n] = *reinterpret_cast<const cplx*>(p_s + (n * 8 + kk / 3) * 16);
+        }
+#pragma unroll
+        for (int n = 0; n < GRAM_NF; ++n) {
+            b1[n] = fma(pp[n].x, rr[n].x, -(pp[n].y * rr[n].y));
+            b2[n] = fma(pp[n].x, rr[n].y, pp[n].y * rr[n].x);
+        }
 #pragma unroll
         for (int kg = 0; kg < GRAM_KG; ++kg) {
-            double b1[GRAM_NF], b2[GRAM_NF];
+            // raw operands of the next k-group are fetched now and multiplied in the shadow of the MMAs
+            if (kg + 1 < GRAM_KG) {
 #pragma unroll
-            for (int n = 0; n < GRAM_NF; ++n) {
-                const cplx r = *reinterpret_cast<const cplx*>(b_s + kg * (GRAM_BROWS * 64) + my_boff[n]);
-                const int site = (4 * kg + kk) / 3;
-                const cplx ph = *reinterpret_cast<const cplx*>(p_s + (n * 8 + site) * 16);
-                const double pr = fma(ph.x, r.x, -(ph.y * r.y));
-                const double pi = fma(ph.x, r.y, ph.y * r.x);
-                b1[n] = part_im ? pi : pr;
-                b2[n] = part_im ? -pr : pi;
+                for (int n = 0; n < GRAM_NF; ++n) {
+                    rr[n] = *reinterpret_cast<const cplx*>(b_s + (kg + 1) * (GRAM_BROWS * 64) + my_boff[n]);
+                    pp[n] = *reinterpret_cast<const cplx*>(p_s + (n * 8 + (4 * (kg + 1) + kk) / 3) * 16);
+                }
             }
+            double nb1[GRAM_NF], nb2[GRAM_NF];
+            // m-fragments in groups of <= 5: both MMAs of an accumulator are >= 2*group MMAs apart
+            constexpr int GRP = 5;
 #pragma unroll
-            for (int i = 0; i < MF; ++i) {
-                const cplx a = *reinterpret_cast<const cplx*>(a_s + (kg * ROWS_A + 8 * i) * 64);
+            for (int i0 = 0; i0 < MF; i0 += GRP) {
+                cplx a[GRP];
 #pragma unroll
-                for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i][n][0], acc[i][n][1], a.x, b1[n]);
+                for (int ii = 0; ii < GRP; ++ii)
+                    if (i0 + ii < MF) a[ii] = *reinterpret_cast<const cplx*>(a_s + (kg * ROWS_A + 8 * (i0 + ii)) * 64);
 #pragma unroll
-                for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i][n][0], acc[i][n][1], a.y, b2[n]);
+                for (int ii = 0; ii < GRP; ++ii)
+                    if (i0 + ii < MF) {
+#pragma unroll
+                        for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i0 + ii][n][0], acc[i0 + ii][n][1], a[ii].x, b1[n]);
+                    }
+                if (i0 == 0 && kg + 1 < GRAM_KG) {
+#pragma unroll
+                    for (int n = 0; n < GRAM_NF; ++n) {
+                        nb1[n] = fma(pp[n].x, rr[n].x, -(pp[n].y * rr[n].y));
+                        nb2[n] = fma(pp[n].x, rr[n].y, pp[n].y * rr[n].x);
+                    }
+                }
+#pragma unroll
+                for (int ii = 0; ii < GRP; ++ii)
+                    if (i0 + ii < MF) {
+#pragma unroll
+                        for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i0 + ii][n][0], acc[i0 + ii][n][1], a[ii].y, b2[n]);
+                    }
+            }
+            if (kg + 1 < GRAM_KG) {
+#pragma unroll
+                for (int n = 0; n < GRAM_NF; ++n) {
+                    b1[n] = nb1[n];
+                    b2[n] = nb2[n];
+                }
             }
         }
     }
