@@ -33,8 +33,15 @@ using namespace edk;
 
 struct edk_handle {
     Geom g;
-    int Ne, mode, order, nmom, device;
+    int Ne, mode, order, nmom, device;  // nmom = momenta the caller asked for (output)
     int nop;
+    // internal momentum list: the caller's momenta first, then any missing negatives when the
+    // Hermitian pairing G(L,R,p)^dagger = G(R,L,-p) is used to halve the number of contracted pairs
+    int nmom_int = 0;
+    bool symmetric = false;
+    int sym_request = -1;  // -1 auto, 0 off, 1 on (test hook)
+    std::vector<int> mom_user, mom_int, negidx;
+    int* negidx_dev = nullptr;
     size_t field_cplx;  // Ne * V * 3
     // device buffers
     cplx* links = nullptr;    // [3][V][9]
@@ -59,7 +66,7 @@ struct edk_handle {
     cplx* stage_out = nullptr;
     // state
     bool links_set = false, evecs_set = false;
-    size_t ws_bytes = 0;
+    size_t ws_bytes = 0, cfg_bytes = 0;
     long long launches = 0;
     // profiling
     bool profiling = false;
@@ -141,9 +148,13 @@ int pow3sum(int n) {  // (3^(n+1)-1)/2
 }
 
 // Build the job list of the derivative elementals (elemental.py:299-329).
-// Every output operator is a signed sum over left/right splits of G(L, R); (L, R) pairs that
-// occur in more than one operator (e.g. (nabla_a W0, nabla_b W0) for num_nabla = 2) become
-// shared single-segment jobs so no pair is contracted twice: 34 instead of 43 pair-GEMMs.
+// Every output operator is a signed sum over left/right splits of G(L, R).
+//  * plain mode: (L, R) pairs that occur in more than one operator (e.g. (nabla_a W0, nabla_b W0)
+//    for num_nabla = 2) become shared single-segment jobs, the others are fused into one
+//    multi-segment job per operator: 34 instead of the reference's 43 pair-GEMMs.
+//  * symmetric mode: G(L,R,p)^dagger = G(R,L,-p), so only pairs with L >= R are contracted (19 for
+//    num_nabla = 2, 4 for num_nabla = 1) and the combine step reads the conjugate transpose at -p
+//    for the others.  Needs -p in the (internal) momentum list for every p.
 void build_derivative_jobs(edk_handle* h) {
     struct Term {
         int L, R, sign;
@@ -162,65 +173,69 @@ void build_derivative_jobs(edk_handle* h) {
             ++uses[{t.L, t.R}];
         }
     }
-    std::map<std::pair<int, int>, int> shared_job;
     h->jobs_host.clear();
     h->ops_host.assign(h->nop, CombineOp{});
-    // private multi-segment jobs first (longest first helps the tail of the grid)
-    struct Pending {
-        int op;
-        GramJob job;
-    };
-    std::vector<Pending> priv;
-    for (int n = 0; n < h->nop; ++n) {
-        GramJob j{};
-        for (const Term& t : per_op[n]) {
-            if (uses[{t.L, t.R}] > 1) continue;
-            j.sign[j.nseg] = t.sign;
-            j.L[j.nseg] = h->field(t.L);
-            j.R[j.nseg] = h->field(t.R);
-            ++j.nseg;
-        }
-        if (j.nseg) priv.push_back({n, j});
-    }
-    std::stable_sort(priv.begin(), priv.end(), [](const Pending& a, const Pending& b) { return a.job.nseg > b.job.nseg; });
-    for (const Pending& p : priv) {
-        CombineOp& o = h->ops_host[p.op];
-        o.job[o.nterm] = (int)h->jobs_host.size();
-        o.weight[o.nterm] = 1.0;
+    auto add_term = [](CombineOp& o, int jid, double w, int herm) {
+        for (int k = 0; k < o.nterm; ++k)
+            if (o.job[k] == jid && o.herm[k] == herm) {
+                o.weight[k] += w;
+                return;
+            }
+        o.job[o.nterm] = jid;
+        o.weight[o.nterm] = w;
+        o.herm[o.nterm] = herm;
         ++o.nterm;
-        h->jobs_host.push_back(p.job);
-    }
-    for (int n = 0; n < h->nop; ++n) {
-        for (const Term& t : per_op[n]) {
-            if (uses[{t.L, t.R}] <= 1) continue;
-            auto key = std::make_pair(t.L, t.R);
-            auto it = shared_job.find(key);
-            int jid;
-            if (it == shared_job.end()) {
-                GramJob j{};
-                j.nseg = 1;
-                j.sign[0] = 1;
-                j.L[0] = h->field(t.L);
-                j.R[0] = h->field(t.R);
-                jid = (int)h->jobs_host.size();
-                h->jobs_host.push_back(j);
-                shared_job[key] = jid;
-            } else {
-                jid = it->second;
+    };
+    std::map<std::pair<int, int>, int> shared_job;
+    auto single_job = [&](int L, int R) {
+        auto key = std::make_pair(L, R);
+        auto it = shared_job.find(key);
+        if (it != shared_job.end()) return it->second;
+        GramJob j{};
+        j.nseg = 1;
+        j.sign[0] = 1;
+        j.L[0] = h->field(L);
+        j.R[0] = h->field(R);
+        const int jid = (int)h->jobs_host.size();
+        h->jobs_host.push_back(j);
+        shared_job[key] = jid;
+        return jid;
+    };
+    if (h->symmetric) {
+        for (int n = 0; n < h->nop; ++n)
+            for (const Term& t : per_op[n]) {
+                if (t.L >= t.R)
+                    add_term(h->ops_host[n], single_job(t.L, t.R), t.sign, 0);
+                else
+                    add_term(h->ops_host[n], single_job(t.R, t.L), t.sign, 1);
             }
-            CombineOp& o = h->ops_host[n];
-            bool merged = false;
-            for (int k = 0; k < o.nterm; ++k)
-                if (o.job[k] == jid) {
-                    o.weight[k] += t.sign;
-                    merged = true;
-                }
-            if (!merged) {
-                o.job[o.nterm] = jid;
-                o.weight[o.nterm] = t.sign;
-                ++o.nterm;
+    } else {
+        // private multi-segment jobs first (longest first helps the tail of the grid)
+        struct Pending {
+            int op;
+            GramJob job;
+        };
+        std::vector<Pending> priv;
+        for (int n = 0; n < h->nop; ++n) {
+            GramJob j{};
+            for (const Term& t : per_op[n]) {
+                if (uses[{t.L, t.R}] > 1) continue;
+                j.sign[j.nseg] = t.sign;
+                j.L[j.nseg] = h->field(t.L);
+                j.R[j.nseg] = h->field(t.R);
+                ++j.nseg;
             }
+            if (j.nseg) priv.push_back({n, j});
         }
+        std::stable_sort(priv.begin(), priv.end(),
+                         [](const Pending& a, const Pending& b) { return a.job.nseg > b.job.nseg; });
+        for (const Pending& p : priv) {
+            add_term(h->ops_host[p.op], (int)h->jobs_host.size(), 1.0, 0);
+            h->jobs_host.push_back(p.job);
+        }
+        for (int n = 0; n < h->nop; ++n)
+            for (const Term& t : per_op[n])
+                if (uses[{t.L, t.R}] > 1) add_term(h->ops_host[n], single_job(t.L, t.R), t.sign, 0);
     }
     // stencil schedule: every field of length < order spawns its three children
     h->hops.clear();
@@ -237,6 +252,26 @@ void build_derivative_jobs(edk_handle* h) {
         const int child0 = off + p + 3 * v;
         h->hops.push_back({f, child0});
     }
+}
+
+// number of pair-GEMMs (segments) the two modes need, to decide which is cheaper
+void count_pairs(int order, int& plain, int& sym) {
+    std::map<std::pair<int, int>, int> a, b;
+    const int nop = pow3sum(order);
+    for (int n = 0; n < nop; ++n) {
+        std::vector<int> dirs = derivative_tuple(n);
+        const int len = (int)dirs.size();
+        for (int pick = 0; pick < (1 << len); ++pick) {
+            std::vector<int> right, left;
+            for (int i = 0; i < len; ++i) ((pick >> i) & 1 ? right : left).push_back(dirs[i]);
+            std::reverse(left.begin(), left.end());
+            const int L = seq_index(left), R = seq_index(right);
+            a[{L, R}] = 1;
+            b[{std::max(L, R), std::min(L, R)}] = 1;
+        }
+    }
+    plain = (int)a.size();
+    sym = (int)b.size();
 }
 
 void build_displacement_jobs(edk_handle* h) {
@@ -260,7 +295,7 @@ void pick_gram_config(edk_handle* h) {
     const int rows = gram_rows_per_tile(h->mfrag);
     const int n_mt = (h->Ne + rows - 1) / rows;
     const int nfrag_f = (h->Ne + 3) / 4;
-    const int n_nt = (nfrag_f * h->nmom + gram_nfrag_per_tile() - 1) / gram_nfrag_per_tile();
+    const int n_nt = (nfrag_f * h->nmom_int + gram_nfrag_per_tile() - 1) / gram_nfrag_per_tile();
     const long long tiles = (long long)h->njobs * n_mt * n_nt;
     const int ksteps = h->g.Vpad / 8;
     int ks = 1;
@@ -277,11 +312,96 @@ void pick_gram_config(edk_handle* h) {
 }
 
 int ensure_partial(edk_handle* h) {
-    const size_t need = (size_t)h->ksplit * h->njobs * h->nmom * h->Ne * h->Ne * sizeof(cplx);
+    const size_t need = (size_t)h->ksplit * h->njobs * h->nmom_int * h->Ne * h->Ne * sizeof(cplx);
     static_assert(sizeof(cplx) == 16, "complex128");
     if (h->partial) EDK_CUDA_TRY(cudaFree(h->partial));
     h->partial = nullptr;
     EDK_CUDA_TRY(cudaMalloc(&h->partial, need));
+    return EDK_OK;
+}
+
+// (Re)build everything that depends on the momentum list and on the pairing mode:
+// internal momentum list, phase tables, contraction jobs, combine recipe, partial-sum buffer.
+int configure(edk_handle* h) {
+    const int nmom = h->nmom;
+    h->mom_int = h->mom_user;
+    h->symmetric = false;
+    if (h->mode == EDK_MODE_DERIVATIVE && h->order >= 1 && h->sym_request != 0) {
+        std::vector<int> ext = h->mom_user;
+        auto find = [&](int px, int py, int pz) {
+            for (size_t i = 0; i < ext.size() / 3; ++i)
+                if (ext[3 * i] == px && ext[3 * i + 1] == py && ext[3 * i + 2] == pz) return (int)i;
+            return -1;
+        };
+        for (int i = 0; i < nmom; ++i) {
+            const int px = -h->mom_user[3 * i], py = -h->mom_user[3 * i + 1], pz = -h->mom_user[3 * i + 2];
+            if (find(px, py, pz) < 0) {
+                ext.push_back(px);
+                ext.push_back(py);
+                ext.push_back(pz);
+            }
+        }
+        int plain = 0, sym = 0;
+        count_pairs(h->order, plain, sym);
+        const long long cost_sym = (long long)sym * (long long)(ext.size() / 3);
+        const long long cost_plain = (long long)plain * nmom;
+        if (h->sym_request == 1 || cost_sym < cost_plain) {
+            h->symmetric = true;
+            h->mom_int = ext;
+        }
+    }
+    h->nmom_int = (int)h->mom_int.size() / 3;
+    h->negidx.assign(h->nmom_int, -1);
+    for (int i = 0; i < h->nmom_int; ++i)
+        for (int j = 0; j < h->nmom_int; ++j)
+            if (h->mom_int[3 * j] == -h->mom_int[3 * i] && h->mom_int[3 * j + 1] == -h->mom_int[3 * i + 1] &&
+                h->mom_int[3 * j + 2] == -h->mom_int[3 * i + 2]) {
+                h->negidx[i] = j;
+                break;
+            }
+    if (h->mode == EDK_MODE_DERIVATIVE)
+        build_derivative_jobs(h);
+    else
+        build_displacement_jobs(h);
+    h->njobs = (int)h->jobs_host.size();
+
+    cudaFree(h->phase);
+    cudaFree(h->jobs_dev);
+    cudaFree(h->ops_dev);
+    cudaFree(h->negidx_dev);
+    cudaFree(h->partial);
+    h->phase = nullptr;
+    h->jobs_dev = nullptr;
+    h->ops_dev = nullptr;
+    h->negidx_dev = nullptr;
+    h->partial = nullptr;
+    const size_t nm = (size_t)h->nmom_int;
+    int* mom_dev = nullptr;
+    EDK_CUDA_TRY(cudaMalloc(&h->phase, 2 * nm * h->g.Vpad * sizeof(cplx)));
+    EDK_CUDA_TRY(cudaMalloc(&mom_dev, nm * 3 * sizeof(int)));
+    cudaError_t e = cudaMemcpy(mom_dev, h->mom_int.data(), nm * 3 * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_phase_table(h->phase, h->phase + nm * h->g.Vpad, mom_dev, h->nmom_int, h->g, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(mom_dev);
+    if (e != cudaSuccess) {
+        set_error("phase table failed: %s", cudaGetErrorString(e));
+        return EDK_ERR_CUDA;
+    }
+    h->launches += 1;
+    EDK_CUDA_TRY(cudaMalloc(&h->jobs_dev, h->jobs_host.size() * sizeof(GramJob)));
+    EDK_CUDA_TRY(cudaMalloc(&h->ops_dev, h->ops_host.size() * sizeof(CombineOp)));
+    EDK_CUDA_TRY(cudaMalloc(&h->negidx_dev, nm * sizeof(int)));
+    EDK_CUDA_TRY(cudaMemcpy(h->jobs_dev, h->jobs_host.data(), h->jobs_host.size() * sizeof(GramJob), cudaMemcpyHostToDevice));
+    EDK_CUDA_TRY(cudaMemcpy(h->ops_dev, h->ops_host.data(), h->ops_host.size() * sizeof(CombineOp), cudaMemcpyHostToDevice));
+    EDK_CUDA_TRY(cudaMemcpy(h->negidx_dev, h->negidx.data(), nm * sizeof(int), cudaMemcpyHostToDevice));
+    pick_gram_config(h);
+    const size_t partial_bytes = (size_t)h->ksplit * h->njobs * nm * h->Ne * h->Ne * sizeof(cplx);
+    cudaError_t pe = cudaMalloc(&h->partial, partial_bytes);
+    if (pe != cudaSuccess) {
+        set_error("cudaMalloc of %zu bytes (partial sums) failed: %s", partial_bytes, cudaGetErrorString(pe));
+        return pe == cudaErrorMemoryAllocation ? EDK_ERR_NOMEM : EDK_ERR_CUDA;
+    }
+    h->cfg_bytes = 2 * nm * h->g.Vpad * sizeof(cplx) + partial_bytes;
     return EDK_OK;
 }
 
@@ -290,7 +410,7 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     P.jobs = h->jobs_dev;
     P.njobs = h->njobs;
     P.Ne = h->Ne;
-    P.nmom = h->nmom;
+    P.nmom = h->nmom_int;
     P.Kc = 3 * h->g.V;
     P.ksteps = h->g.Vpad / 8;
     P.Vpad = h->g.Vpad;
@@ -298,7 +418,7 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     const int rows = gram_rows_per_tile(h->mfrag);
     P.n_mt = (h->Ne + rows - 1) / rows;
     const int nfrag_f = (h->Ne + 3) / 4;
-    P.n_nt = (nfrag_f * h->nmom + gram_nfrag_per_tile() - 1) / gram_nfrag_per_tile();
+    P.n_nt = (nfrag_f * h->nmom_int + gram_nfrag_per_tile() - 1) / gram_nfrag_per_tile();
     P.phase = h->phase;
     P.partial = h->partial;
     {
@@ -307,8 +427,8 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     }
     {
         PhaseTimer t(h, s, PH_COMBINE, 1);
-        EDK_CUDA_TRY(launch_combine(h->ops_dev, h->nop, h->partial, h->njobs, P.ksplit, h->nmom, h->Ne,
-                                    h->have_coeff ? h->coeff : nullptr, out, s));
+        EDK_CUDA_TRY(launch_combine(h->ops_dev, h->nop, h->partial, h->njobs, P.ksplit, h->nmom_int, h->nmom, h->negidx_dev,
+                                    h->Ne, h->have_coeff ? h->coeff : nullptr, out, s));
     }
     return EDK_OK;
 }
@@ -387,39 +507,15 @@ int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, co
     EDK_ALLOC(h->links, (size_t)3 * h->g.V * 9 * sizeof(cplx));
     EDK_ALLOC(h->fields, (size_t)h->nfield * h->field_cplx * sizeof(cplx));
     if (mode == EDK_MODE_DISPLACEMENT && order >= 1) EDK_ALLOC(h->lines, (size_t)12 * h->field_cplx * sizeof(cplx));
-    EDK_ALLOC(h->phase, (size_t)2 * nmom * h->g.Vpad * sizeof(cplx));
     EDK_ALLOC(h->coeff, (size_t)Ne * Ne * sizeof(double));
-    int* mom_dev = nullptr;
-    EDK_ALLOC(mom_dev, (size_t)nmom * 3 * sizeof(int));
-    cudaError_t e = cudaMemcpy(mom_dev, mom3, (size_t)nmom * 3 * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_phase_table(h->phase, h->phase + (size_t)nmom * h->g.Vpad, mom_dev, nmom, h->g, 0);
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    cudaFree(mom_dev);
-    ws -= (size_t)nmom * 3 * sizeof(int);
-    if (e != cudaSuccess) {
-        set_error("edk_create: phase table failed: %s", cudaGetErrorString(e));
-        edk_destroy(h);
-        return EDK_ERR_CUDA;
+    h->mom_user.assign(mom3, mom3 + 3 * (size_t)nmom);
+    {
+        const int rc = configure(h);
+        if (rc != EDK_OK) {
+            edk_destroy(h);
+            return rc;
+        }
     }
-    h->launches += 1;
-    if (mode == EDK_MODE_DERIVATIVE)
-        build_derivative_jobs(h);
-    else
-        build_displacement_jobs(h);
-    h->njobs = (int)h->jobs_host.size();
-    EDK_ALLOC(h->jobs_dev, h->jobs_host.size() * sizeof(GramJob));
-    EDK_ALLOC(h->ops_dev, h->ops_host.size() * sizeof(CombineOp));
-    e = cudaMemcpy(h->jobs_dev, h->jobs_host.data(), h->jobs_host.size() * sizeof(GramJob), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess)
-        e = cudaMemcpy(h->ops_dev, h->ops_host.data(), h->ops_host.size() * sizeof(CombineOp), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        set_error("edk_create: job upload failed: %s", cudaGetErrorString(e));
-        edk_destroy(h);
-        return EDK_ERR_CUDA;
-    }
-    pick_gram_config(h);
-    const size_t partial_bytes = (size_t)h->ksplit * h->njobs * nmom * Ne * Ne * sizeof(cplx);
-    EDK_ALLOC(h->partial, partial_bytes);
 #undef EDK_ALLOC
     h->ws_bytes = ws;
     *out = h;
@@ -437,6 +533,7 @@ int edk_destroy(edk_handle* h) {
     cudaFree(h->coeff);
     cudaFree(h->jobs_dev);
     cudaFree(h->ops_dev);
+    cudaFree(h->negidx_dev);
     cudaFree(h->stage_U);
     cudaFree(h->stage_V);
     cudaFree(h->stage_out);
@@ -477,7 +574,7 @@ int edk_num_operators(const edk_handle* h) { return h ? h->nop : EDK_ERR_ARG; }
 size_t edk_output_bytes(const edk_handle* h) {
     return h ? (size_t)h->nop * h->nmom * h->Ne * h->Ne * sizeof(cplx) : 0;
 }
-size_t edk_workspace_bytes(const edk_handle* h) { return h ? h->ws_bytes : 0; }
+size_t edk_workspace_bytes(const edk_handle* h) { return h ? h->ws_bytes + h->cfg_bytes : 0; }
 
 int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream) {
     if (!h || !U_dev || (layout != EDK_LINKS_DIR_MAJOR && layout != EDK_LINKS_FILE_T)) {
@@ -664,6 +761,31 @@ int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit) {
     h->force_ksplit = ksplit;
     pick_gram_config(h);
     return ensure_partial(h);
+}
+
+int edk_debug_symmetry(edk_handle* h, int mode) {
+    if (!h || mode < -1 || mode > 1) return EDK_ERR_ARG;
+    EDK_CUDA_TRY(cudaSetDevice(h->device));
+    EDK_CUDA_TRY(cudaDeviceSynchronize());
+    h->sym_request = mode;
+    return configure(h);
+}
+
+int edk_query(const edk_handle* h, int what) {
+    if (!h) return EDK_ERR_ARG;
+    switch (what) {
+        case 0: return h->symmetric ? 1 : 0;
+        case 1: return h->nmom_int;
+        case 2: {
+            int segs = 0;
+            for (const auto& j : h->jobs_host) segs += j.nseg;
+            return segs;
+        }
+        case 3: return h->ksplit;
+        case 4: return h->mfrag;
+        case 5: return h->njobs;
+        default: return EDK_ERR_ARG;
+    }
 }
 
 int edk_microbench_fp64(int device, double* dmma_tflops, double* dfma_tflops) {

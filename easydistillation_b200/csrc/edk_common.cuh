@@ -58,11 +58,14 @@ struct GramParams {
     cplx* partial;      // [ksplit][njobs][nmom][Ne][Ne]
 };
 
-// Output operator n = coeff * sum_terms weight * sum_split partial[split][job]
+// Output operator n at momentum p = coeff * sum_terms weight * sum_split X, with
+//   X = partial[split][job][p]                        (herm = 0)
+//   X = partial[split][job][index of -p]^dagger        (herm = 1: G(L,R,p) = G(R,L,-p)^dagger)
 #define EDK_MAX_TERMS 8
 struct CombineOp {
     int nterm;
     int job[EDK_MAX_TERMS];
+    int herm[EDK_MAX_TERMS];
     double weight[EDK_MAX_TERMS];
 };
 
@@ -87,8 +90,8 @@ cudaError_t launch_gram_naive(const GramParams& P, cudaStream_t s);
 int gram_pick_mfrag(int Ne);
 int gram_rows_per_tile(int mfrag);
 int gram_nfrag_per_tile();
-cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom, int Ne,
-                           const double* coeff, cplx* out, cudaStream_t s);
+cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom_int,
+                           int nmom_out, const int* negidx, int Ne, const double* coeff, cplx* out, cudaStream_t s);
 // microbench
 cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops);
 

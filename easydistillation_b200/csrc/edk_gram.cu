@@ -403,39 +403,49 @@ cudaError_t launch_gram_naive(const GramParams& P, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------
-// combine: out[op] = coeff * sum_terms w * sum_split partial[split][job]
+// combine: out[op][p] = coeff * sum_terms w * sum_split (partial[job][p]  or  partial[job][-p]^dagger)
+// (the caller's momenta are the first nmom_out entries of the internal list of nmom_int)
 // ---------------------------------------------------------------------------------------
 __global__ void combine_kernel(const CombineOp* __restrict__ ops, int nop, const cplx* __restrict__ partial, int njobs,
-                               int ksplit, int nmom, int Ne, const double* __restrict__ coeff, cplx* __restrict__ out) {
-    const size_t per_op = (size_t)nmom * Ne * Ne;
+                               int ksplit, int nmom_int, int nmom_out, const int* __restrict__ negidx, int Ne,
+                               const double* __restrict__ coeff, cplx* __restrict__ out) {
+    const size_t mat = (size_t)Ne * Ne;
+    const size_t per_op = (size_t)nmom_out * mat;
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= per_op * nop) return;
     const int op = (int)(idx / per_op);
-    const size_t r = idx - (size_t)op * per_op;
-    const CombineOp o = ops[op];
+    size_t r = idx - (size_t)op * per_op;
+    const int p = (int)(r / mat);
+    r -= (size_t)p * mat;
+    const int e = (int)(r / Ne), f = (int)(r - (size_t)e * Ne);
+    const CombineOp& o = ops[op];
+    const size_t per_job = (size_t)nmom_int * mat;
     double sr = 0.0, si = 0.0;
     for (int t = 0; t < o.nterm; ++t) {
+        const bool herm = o.herm[t] != 0;
+        const size_t off = herm ? (size_t)negidx[p] * mat + (size_t)f * Ne + e : (size_t)p * mat + r;
         double tr = 0.0, ti = 0.0;
         for (int s = 0; s < ksplit; ++s) {
-            const cplx v = partial[((size_t)s * njobs + o.job[t]) * per_op + r];
+            const cplx v = partial[((size_t)s * njobs + o.job[t]) * per_job + off];
             tr += v.x;
             ti += v.y;
         }
         sr = fma(o.weight[t], tr, sr);
-        si = fma(o.weight[t], ti, si);
+        si = fma(herm ? -o.weight[t] : o.weight[t], ti, si);
     }
     if (coeff != nullptr) {
-        const double c = coeff[r % ((size_t)Ne * Ne)];
+        const double c = coeff[r];
         sr *= c;
         si *= c;
     }
     out[idx] = make_double2(sr, si);
 }
 
-cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom, int Ne,
-                           const double* coeff, cplx* out, cudaStream_t s) {
-    const size_t n = (size_t)nop * nmom * Ne * Ne;
-    combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ops_dev, nop, partial, njobs, ksplit, nmom, Ne, coeff, out);
+cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom_int,
+                           int nmom_out, const int* negidx, int Ne, const double* coeff, cplx* out, cudaStream_t s) {
+    const size_t n = (size_t)nop * nmom_out * Ne * Ne;
+    combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ops_dev, nop, partial, njobs, ksplit, nmom_int, nmom_out, negidx,
+                                                               Ne, coeff, out);
     return cudaGetLastError();
 }
 

@@ -157,6 +157,15 @@ class ElementalEngine:
     def debug_gram_config(self, mfrag: int = 0, ksplit: int = 0):
         _capi.check(self.lib.edk_debug_gram_config(self.h, mfrag, ksplit), "edk_debug_gram_config")
 
+    def debug_symmetry(self, mode: int):
+        """-1 auto, 0 off, 1 force the Hermitian pairing of (left, right) field pairs."""
+        _capi.check(self.lib.edk_debug_symmetry(self.h, int(mode)), "edk_debug_symmetry")
+
+    def query(self):
+        q = lambda w: int(self.lib.edk_query(self.h, w))  # noqa: E731
+        return {"hermitian_pairing": bool(q(0)), "internal_momenta": q(1), "pair_gemms_per_momentum": q(2),
+                "ksplit": q(3), "mfrag": q(4), "jobs": q(5)}
+
 
 def microbench_fp64(device: int = 0):
     """(DMMA TFLOP/s, DFMA TFLOP/s) sustained on `device`."""

@@ -128,11 +128,17 @@ long long edk_launch_count(const edk_handle* h);
  * edk_debug_use_naive_gram: 1 = run the scalar one-thread-per-output contraction instead of
  *   the DMMA kernel (cross-check only; never enabled by the product path).
  * edk_debug_gram_config: force the DMMA tile variant (m-frags per warp) and split-K factor; 0 = auto.
+ * edk_debug_symmetry: -1 = auto (default), 0 = contract every (left, right) pair directly,
+ *   1 = force the Hermitian pairing G(L,R,p)^dagger = G(R,L,-p) (missing -p are added internally).
+ * edk_query: what = 0 pairing in use (0/1), 1 internal momentum count, 2 pair-GEMMs per momentum,
+ *   3 split-K factor, 4 m-fragments per tile, 5 contraction jobs.
  */
 int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream);
 int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream);
 int edk_debug_use_naive_gram(edk_handle* h, int on);
 int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit);
+int edk_debug_symmetry(edk_handle* h, int mode);
+int edk_query(const edk_handle* h, int what);
 
 /*
  * Stand-alone micro-benchmarks (bench.py's roofline denominators): sustained

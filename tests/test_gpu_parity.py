@@ -248,6 +248,40 @@ def test_dmma_tile_variants_and_split_k_agree_with_scalar_kernel(edb):
         eng.debug_gram_config(6, 1)
 
 
+@pytest.mark.parametrize("nabla", [1, 2, 3])
+def test_hermitian_pairing_and_direct_pairs_agree_with_oracle(edb, nabla):
+    """The contraction either runs every (left, right) pair (34 for num_nabla=2) or only the
+    canonical ones and reads G(R,L,-p)^dagger for the rest (19).  Both modes, on a momentum list
+    that is closed under negation and on one that is not (missing -p are added internally)."""
+    import torch
+
+    from easydistillation_b200 import _capi
+    from easydistillation_b200.engine import ElementalEngine
+
+    orc = _orc()
+    latt, Ne = ([4, 6, 8, 1], 10) if nabla < 3 else ([4, 4, 2, 1], 5)
+    U_file = orc.synthetic_links(latt, 6)
+    V = orc.synthetic_eigvecs(latt, Ne, 6)
+    U = orc.links_file_to_spatial(U_file)
+    expected_pairs = {1: (7, 4), 2: (34, 19)}
+    for moms in (orc.momentum_set(7), [(0, 0, 0), (1, 0, 0), (0, -1, 2), (1, 1, 1), (-1, -1, -1)]):
+        ref = orc.elemental_timeslice(V, U, latt, nabla, moms)
+        eng = ElementalEngine(latt[:3], Ne, _capi.MODE_DERIVATIVE, nabla, moms)
+        eng.set_links(torch.from_numpy(U_file).cuda(), _capi.LINKS_FILE_T)
+        eng.set_eigvecs(torch.from_numpy(V).cuda())
+        closed = set(moms) == {tuple(-c for c in p) for p in moms}
+        if closed:
+            assert eng.query()["hermitian_pairing"]  # auto mode picks the cheaper evaluation
+        for mode in (0, 1):
+            eng.debug_symmetry(mode)
+            q = eng.query()
+            assert q["hermitian_pairing"] == bool(mode)
+            if nabla in expected_pairs:
+                assert q["pair_gemms_per_momentum"] == expected_pairs[nabla][mode]
+            assert q["internal_momenta"] == (len(moms) if (closed or not mode) else len(moms) + 2)
+            _blocks_close(eng.calc().cpu().numpy(), ref, what=f"nabla={nabla} pairing={mode} closed={closed}")
+
+
 def test_displacement_matches_oracle_ragged(edb):
     orc = _orc()
     latt, Ne, dist = [3, 4, 5, 1], 11, 3
@@ -328,6 +362,10 @@ def test_config3_shape_properties(edb):
     sel = [3, 17, 42, 64, 65, 99]
     ref = orc.elemental_timeslice_closed_form(V[0][sel], orc.links_file_to_spatial(U_file[0]), latt, 2, moms)
     _blocks_close(E[:, :, sel][:, :, :, sel], ref, what="config 3 sub-block")
+    # (d) the two evaluation orders (Hermitian pairing on: 19 pair-GEMMs, off: 34) agree at full size
+    assert gen._engine.query()["hermitian_pairing"]
+    gen._engine.debug_symmetry(0)
+    _blocks_close(np.array(gen.calc(0)), E, tol=1e-11, what="config 3 direct pairs vs Hermitian pairing")
 
 
 def test_linearity_and_scaling_property(edb):
