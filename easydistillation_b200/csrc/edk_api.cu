@@ -8,6 +8,8 @@
 #include <utility>
 #include <vector>
 
+#include <cuda.h>
+
 #include "edk_common.cuh"
 
 namespace edk {
@@ -42,6 +44,11 @@ struct edk_handle {
     int sym_request = -1;  // -1 auto, 0 off, 1 on (test hook)
     std::vector<int> mom_user, mom_int, negidx;
     int* negidx_dev = nullptr;
+    // TMA-fed contraction (default); loader = 1 selects the cp.async kernel (A/B comparison hook)
+    GramTma tma{};
+    cplx* phase_tiles = nullptr;
+    bool tma_ready = false;
+    int loader = 0;
     size_t field_cplx;  // Ne * V * 3
     // device buffers
     cplx* links = nullptr;    // [3][V][9]
@@ -196,6 +203,8 @@ void build_derivative_jobs(edk_handle* h) {
         j.sign[0] = 1;
         j.L[0] = h->field(L);
         j.R[0] = h->field(R);
+        j.Lf[0] = L;
+        j.Rf[0] = R;
         const int jid = (int)h->jobs_host.size();
         h->jobs_host.push_back(j);
         shared_job[key] = jid;
@@ -223,6 +232,8 @@ void build_derivative_jobs(edk_handle* h) {
                 j.sign[j.nseg] = t.sign;
                 j.L[j.nseg] = h->field(t.L);
                 j.R[j.nseg] = h->field(t.R);
+                j.Lf[j.nseg] = t.L;
+                j.Rf[j.nseg] = t.R;
                 ++j.nseg;
             }
             if (j.nseg) priv.push_back({n, j});
@@ -283,6 +294,8 @@ void build_displacement_jobs(edk_handle* h) {
         j.sign[0] = 1;
         j.L[0] = h->field(0);
         j.R[0] = h->field(k);  // field k = D_k (field 0 = W0 = D_0)
+        j.Lf[0] = 0;
+        j.Rf[0] = k;
         h->ops_host[k].nterm = 1;
         h->ops_host[k].job[0] = k;
         h->ops_host[k].weight[0] = 1.0;
@@ -317,6 +330,55 @@ int ensure_partial(edk_handle* h) {
     if (h->partial) EDK_CUDA_TRY(cudaFree(h->partial));
     h->partial = nullptr;
     EDK_CUDA_TRY(cudaMalloc(&h->partial, need));
+    return EDK_OK;
+}
+
+// Tensor maps of the TMA-fed contraction: the field array as [nfield][Ne][2*Kc] doubles, boxes of
+// 8 doubles (4 complex k) x rows x 1 field.  cuTensorMapEncodeTiled comes from the driver through
+// the runtime's entry-point query, so the library does not link libcuda.
+int build_tma(edk_handle* h) {
+    h->tma_ready = false;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        EDK_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return EDK_ERR_CUDA;
+        }
+        encode = (EncodeFn)fn;
+    }
+    int rows = 0, nst = 0, bytes = 0;
+    if (gram_tma_plan(h->mfrag, h->nmom_int, h->Ne, &rows, &nst, &bytes) != 0) {
+        set_error("no shared-memory plan for the TMA contraction (mfrag %d)", h->mfrag);
+        return EDK_ERR_ARG;
+    }
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    const cuuint64_t Kd = (cuuint64_t)2 * 3 * h->g.V;
+    const cuuint64_t gdim[3] = {Kd, (cuuint64_t)h->Ne, (cuuint64_t)h->nfield};
+    const cuuint64_t gstr[2] = {Kd * 8, Kd * 8 * (cuuint64_t)h->Ne};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t boxA[3] = {8, (cuuint32_t)gram_rows_per_tile(h->mfrag), 1};
+    const cuuint32_t boxB[3] = {8, 8, 1};
+    CUresult r = encode((CUtensorMap*)h->tma.mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, boxA, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+        r = encode((CUtensorMap*)h->tma.mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, boxB, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return EDK_ERR_CUDA;
+    }
+    h->tma.phase_tiles = h->phase_tiles;
+    h->tma.brows_alloc = rows;
+    h->tma.nstages = nst;
+    h->tma_ready = true;
     return EDK_OK;
 }
 
@@ -366,6 +428,8 @@ int configure(edk_handle* h) {
     h->njobs = (int)h->jobs_host.size();
 
     cudaFree(h->phase);
+    cudaFree(h->phase_tiles);
+    h->phase_tiles = nullptr;
     cudaFree(h->jobs_dev);
     cudaFree(h->ops_dev);
     cudaFree(h->negidx_dev);
@@ -381,13 +445,15 @@ int configure(edk_handle* h) {
     EDK_CUDA_TRY(cudaMalloc(&mom_dev, nm * 3 * sizeof(int)));
     cudaError_t e = cudaMemcpy(mom_dev, h->mom_int.data(), nm * 3 * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = launch_phase_table(h->phase, h->phase + nm * h->g.Vpad, mom_dev, h->nmom_int, h->g, 0);
+    if (e == cudaSuccess) e = cudaMalloc(&h->phase_tiles, 2 * nm * h->g.Vpad * sizeof(cplx));
+    if (e == cudaSuccess) e = launch_phase_tiles(h->phase, h->phase_tiles, h->nmom_int, h->g.Vpad, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(mom_dev);
     if (e != cudaSuccess) {
         set_error("phase table failed: %s", cudaGetErrorString(e));
         return EDK_ERR_CUDA;
     }
-    h->launches += 1;
+    h->launches += 2;
     EDK_CUDA_TRY(cudaMalloc(&h->jobs_dev, h->jobs_host.size() * sizeof(GramJob)));
     EDK_CUDA_TRY(cudaMalloc(&h->ops_dev, h->ops_host.size() * sizeof(CombineOp)));
     EDK_CUDA_TRY(cudaMalloc(&h->negidx_dev, nm * sizeof(int)));
@@ -395,13 +461,17 @@ int configure(edk_handle* h) {
     EDK_CUDA_TRY(cudaMemcpy(h->ops_dev, h->ops_host.data(), h->ops_host.size() * sizeof(CombineOp), cudaMemcpyHostToDevice));
     EDK_CUDA_TRY(cudaMemcpy(h->negidx_dev, h->negidx.data(), nm * sizeof(int), cudaMemcpyHostToDevice));
     pick_gram_config(h);
+    {
+        const int rc = build_tma(h);
+        if (rc != EDK_OK) return rc;
+    }
     const size_t partial_bytes = (size_t)h->ksplit * h->njobs * nm * h->Ne * h->Ne * sizeof(cplx);
     cudaError_t pe = cudaMalloc(&h->partial, partial_bytes);
     if (pe != cudaSuccess) {
         set_error("cudaMalloc of %zu bytes (partial sums) failed: %s", partial_bytes, cudaGetErrorString(pe));
         return pe == cudaErrorMemoryAllocation ? EDK_ERR_NOMEM : EDK_ERR_CUDA;
     }
-    h->cfg_bytes = 2 * nm * h->g.Vpad * sizeof(cplx) + partial_bytes;
+    h->cfg_bytes = 4 * nm * h->g.Vpad * sizeof(cplx) + partial_bytes;
     return EDK_OK;
 }
 
@@ -423,7 +493,12 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     P.partial = h->partial;
     {
         PhaseTimer t(h, s, PH_GRAM, 1);
-        EDK_CUDA_TRY(h->naive ? launch_gram_naive(P, s) : launch_gram_dmma(P, h->mfrag, s));
+        if (h->naive)
+            EDK_CUDA_TRY(launch_gram_naive(P, s));
+        else if (h->loader == 0 && h->tma_ready)
+            EDK_CUDA_TRY(launch_gram_tma(P, h->tma, h->mfrag, s));
+        else
+            EDK_CUDA_TRY(launch_gram_dmma(P, h->mfrag, s));
     }
     {
         PhaseTimer t(h, s, PH_COMBINE, 1);
@@ -534,6 +609,7 @@ int edk_destroy(edk_handle* h) {
     cudaFree(h->jobs_dev);
     cudaFree(h->ops_dev);
     cudaFree(h->negidx_dev);
+    cudaFree(h->phase_tiles);
     cudaFree(h->stage_U);
     cudaFree(h->stage_V);
     cudaFree(h->stage_out);
@@ -760,7 +836,17 @@ int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit) {
     h->force_mfrag = mfrag;
     h->force_ksplit = ksplit;
     pick_gram_config(h);
+    {
+        const int rc = build_tma(h);
+        if (rc != EDK_OK) return rc;
+    }
     return ensure_partial(h);
+}
+
+int edk_debug_loader(edk_handle* h, int mode) {
+    if (!h || mode < 0 || mode > 1) return EDK_ERR_ARG;
+    h->loader = mode;
+    return EDK_OK;
 }
 
 int edk_debug_symmetry(edk_handle* h, int mode) {
@@ -784,6 +870,7 @@ int edk_query(const edk_handle* h, int what) {
         case 3: return h->ksplit;
         case 4: return h->mfrag;
         case 5: return h->njobs;
+        case 6: return (h->loader == 0 && h->tma_ready) ? h->tma.nstages : 0;
         default: return EDK_ERR_ARG;
     }
 }

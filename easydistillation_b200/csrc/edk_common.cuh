@@ -39,6 +39,8 @@ struct Geom {
 struct GramJob {
     int nseg;
     int sign[EDK_MAX_SEG];
+    int Lf[EDK_MAX_SEG];         // field indices (third TMA coordinate) of L and R
+    int Rf[EDK_MAX_SEG];
     const cplx* L[EDK_MAX_SEG];  // [Ne][3V]
     const cplx* R[EDK_MAX_SEG];  // [Ne][3V]
 };
@@ -56,6 +58,17 @@ struct GramParams {
     int n_nt;     // tiles along the flattened (f-fragment, momentum) axis
     const cplx* phase;  // [2][nmom][Vpad]: phase, then -i*phase
     cplx* partial;      // [ksplit][njobs][nmom][Ne][Ne]
+};
+
+// Extra launch state of the TMA-fed contraction: tensor maps over the field array viewed as
+// [nfield][Ne][2*Kc doubles] (box = 8 doubles x rows x 1 field) and the phase table re-tiled as
+// [kstep][2][nmom][8 sites] so that consecutive momenta of one 8-site stage are contiguous.
+struct GramTma {
+    alignas(64) unsigned char mapA[128];  // CUtensorMap, box rows = 8*mfrag
+    alignas(64) unsigned char mapB[128];  // CUtensorMap, box rows = 8
+    const cplx* phase_tiles;
+    int brows_alloc;  // rows of R kept per k-group in shared memory (multiple of 8, <= 64)
+    int nstages;      // depth of the full/empty ring
 };
 
 // Output operator n at momentum p = coeff * sum_terms weight * sum_split X, with
@@ -87,6 +100,9 @@ cudaError_t launch_displace_step6(Ptr6 p, cplx* mean_out, const cplx* links, Geo
 // contraction
 cudaError_t launch_gram_dmma(const GramParams& P, int mfrag, cudaStream_t s);
 cudaError_t launch_gram_naive(const GramParams& P, cudaStream_t s);
+cudaError_t launch_gram_tma(const GramParams& P, const GramTma& T, int mfrag, cudaStream_t s);
+cudaError_t launch_phase_tiles(const cplx* phase2, cplx* tiles, int nmom, int Vpad, cudaStream_t s);
+int gram_tma_plan(int mfrag, int nmom, int Ne, int* brows_alloc, int* nstages, int* smem_bytes);
 int gram_pick_mfrag(int Ne);
 int gram_rows_per_tile(int mfrag);
 int gram_nfrag_per_tile();

@@ -64,6 +64,81 @@ __device__ __forceinline__ double flip_sign(double x) {
     return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
 }
 
+// One pipeline stage (8 sites = 6 k-groups of 4 complex k) of one warp: 2*MF*NF DMMAs per k-group.
+//   a_s : this lane's slot in A[kg][row][4]  (+ (kg*ROWS_A + 8 i)*64 selects fragment i)
+//   b_s : B[kg][row][4], b_kg_stride bytes per k-group; my_boff = this lane's (row, k) offset
+//   p_s : this lane's phase tile [n-fragment][8 sites] (already offset to phase or -i*phase)
+template <int MF>
+__device__ __forceinline__ void gram_compute_stage(double (&acc)[MF][GRAM_NF][2], const unsigned char* a_s,
+                                                   const unsigned char* b_s, const int b_kg_stride,
+                                                   const unsigned char* p_s, const uint32_t (&my_boff)[GRAM_NF],
+                                                   const int kk) {
+    constexpr int ROWS_A = 8 * MF;
+    {
+        // B fragments of k-group kg: P' = phase' * R with phase' = phase (re columns) or -i*phase
+        // (im columns); b1 = Re P' pairs with Re L, b2 = Im P' pairs with Im L.
+        cplx rr[GRAM_NF], pp[GRAM_NF];
+        double b1[GRAM_NF], b2[GRAM_NF];
+#pragma unroll
+        for (int n = 0; n < GRAM_NF; ++n) {
+            rr[n] = *reinterpret_cast<const cplx*>(b_s + my_boff[n]);
+            pp[n] = *reinterpret_cast<const cplx*>(p_s + (n * 8 + kk / 3) * 16);
+        }
+#pragma unroll
+        for (int n = 0; n < GRAM_NF; ++n) {
+            b1[n] = fma(pp[n].x, rr[n].x, -(pp[n].y * rr[n].y));
+            b2[n] = fma(pp[n].x, rr[n].y, pp[n].y * rr[n].x);
+        }
+#pragma unroll
+        for (int kg = 0; kg < GRAM_KG; ++kg) {
+            // raw operands of the next k-group are fetched now and multiplied in the shadow of the MMAs
+            if (kg + 1 < GRAM_KG) {
+#pragma unroll
+                for (int n = 0; n < GRAM_NF; ++n) {
+                    rr[n] = *reinterpret_cast<const cplx*>(b_s + (kg + 1) * (b_kg_stride) + my_boff[n]);
+                    pp[n] = *reinterpret_cast<const cplx*>(p_s + (n * 8 + (4 * (kg + 1) + kk) / 3) * 16);
+                }
+            }
+            double nb1[GRAM_NF], nb2[GRAM_NF];
+            // m-fragments in groups of <= 5: both MMAs of an accumulator are >= 2*group MMAs apart
+            constexpr int GRP = 5;
+#pragma unroll
+            for (int i0 = 0; i0 < MF; i0 += GRP) {
+                cplx a[GRP];
+#pragma unroll
+                for (int ii = 0; ii < GRP; ++ii)
+                    if (i0 + ii < MF) a[ii] = *reinterpret_cast<const cplx*>(a_s + (kg * ROWS_A + 8 * (i0 + ii)) * 64);
+#pragma unroll
+                for (int ii = 0; ii < GRP; ++ii)
+                    if (i0 + ii < MF) {
+#pragma unroll
+                        for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i0 + ii][n][0], acc[i0 + ii][n][1], a[ii].x, b1[n]);
+                    }
+                if (i0 == 0 && kg + 1 < GRAM_KG) {
+#pragma unroll
+                    for (int n = 0; n < GRAM_NF; ++n) {
+                        nb1[n] = fma(pp[n].x, rr[n].x, -(pp[n].y * rr[n].y));
+                        nb2[n] = fma(pp[n].x, rr[n].y, pp[n].y * rr[n].x);
+                    }
+                }
+#pragma unroll
+                for (int ii = 0; ii < GRP; ++ii)
+                    if (i0 + ii < MF) {
+#pragma unroll
+                        for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i0 + ii][n][0], acc[i0 + ii][n][1], a[ii].y, b2[n]);
+                    }
+            }
+            if (kg + 1 < GRAM_KG) {
+#pragma unroll
+                for (int n = 0; n < GRAM_NF; ++n) {
+                    b1[n] = nb1[n];
+                    b2[n] = nb2[n];
+                }
+            }
+        }
+        }
+}
+
 template <int MF>
 __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramParams P) {
     using S = GramSmem<MF>;
@@ -238,67 +313,7 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
         const unsigned char* p_s = b_s + S::B_BYTES + my_phoff;
         if (++buf == GRAM_STAGES) buf = 0;
 
-        // B fragments of k-group kg: P' = phase' * R with phase' = phase (re columns) or -i*phase
-        // (im columns); b1 = Re P' pairs with Re L, b2 = Im P' pairs with Im L.
-        cplx rr[GRAM_NF], pp[GRAM_NF];
-        double b1[GRAM_NF], b2[GRAM_NF];
-#pragma unroll
-        for (int n = 0; n < GRAM_NF; ++n) {
-            rr[n] = *reinterpret_cast<const cplx*>(b_s + my_boff[n]);
-            pp[n] = *reinterpret_cast<const cplx*>(p_s + (n * 8 + kk / 3) * 16);
-        }
-#pragma unroll
-        for (int n = 0; n < GRAM_NF; ++n) {
-            b1[n] = fma(pp[n].x, rr[n].x, -(pp[n].y * rr[n].y));
-            b2[n] = fma(pp[n].x, rr[n].y, pp[n].y * rr[n].x);
-        }
-#pragma unroll
-        for (int kg = 0; kg < GRAM_KG; ++kg) {
-            // raw operands of the next k-group are fetched now and multiplied in the shadow of the MMAs
-            if (kg + 1 < GRAM_KG) {
-#pragma unroll
-                for (int n = 0; n < GRAM_NF; ++n) {
-                    rr[n] = *reinterpret_cast<const cplx*>(b_s + (kg + 1) * (GRAM_BROWS * 64) + my_boff[n]);
-                    pp[n] = *reinterpret_cast<const cplx*>(p_s + (n * 8 + (4 * (kg + 1) + kk) / 3) * 16);
-                }
-            }
-            double nb1[GRAM_NF], nb2[GRAM_NF];
-            // m-fragments in groups of <= 5: both MMAs of an accumulator are >= 2*group MMAs apart
-            constexpr int GRP = 5;
-#pragma unroll
-            for (int i0 = 0; i0 < MF; i0 += GRP) {
-                cplx a[GRP];
-#pragma unroll
-                for (int ii = 0; ii < GRP; ++ii)
-                    if (i0 + ii < MF) a[ii] = *reinterpret_cast<const cplx*>(a_s + (kg * ROWS_A + 8 * (i0 + ii)) * 64);
-#pragma unroll
-                for (int ii = 0; ii < GRP; ++ii)
-                    if (i0 + ii < MF) {
-#pragma unroll
-                        for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i0 + ii][n][0], acc[i0 + ii][n][1], a[ii].x, b1[n]);
-                    }
-                if (i0 == 0 && kg + 1 < GRAM_KG) {
-#pragma unroll
-                    for (int n = 0; n < GRAM_NF; ++n) {
-                        nb1[n] = fma(pp[n].x, rr[n].x, -(pp[n].y * rr[n].y));
-                        nb2[n] = fma(pp[n].x, rr[n].y, pp[n].y * rr[n].x);
-                    }
-                }
-#pragma unroll
-                for (int ii = 0; ii < GRP; ++ii)
-                    if (i0 + ii < MF) {
-#pragma unroll
-                        for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i0 + ii][n][0], acc[i0 + ii][n][1], a[ii].y, b2[n]);
-                    }
-            }
-            if (kg + 1 < GRAM_KG) {
-#pragma unroll
-                for (int n = 0; n < GRAM_NF; ++n) {
-                    b1[n] = nb1[n];
-                    b2[n] = nb2[n];
-                }
-            }
-        }
+        gram_compute_stage<MF>(acc, a_s, b_s, GRAM_BROWS * 64, p_s, my_boff, kk);
     }
     cp_async_wait<0>();
 
@@ -316,6 +331,304 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
             if (e < Ne) outp[(size_t)e * Ne + f] = make_double2(fs * acc[i][n][0], fs * acc[i][n][1]);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA-fed, warp-specialised variant: warps 0..7 only wait / MMA / release, warp 8 is the producer.
+//   producer : per stage 6 A boxes + 6*nbb B boxes (cp.async.bulk.tensor.3d over the field array
+//              viewed as [field][row][2K doubles], box = 8 doubles x rows) and the phase tile
+//              (cp.async.bulk runs of consecutive momenta), all completing on full[stage]
+//   consumers: mbarrier.try_wait(full) -> gram_compute_stage -> arrive(empty)
+// No CTA-wide barrier and no loader code in the MMA warps, so they drift apart instead of hitting
+// the same bubbles in lock-step.  Out-of-range rows / k are zero-filled by the TMA unit.
+// ---------------------------------------------------------------------------------------
+constexpr int GT_CONSUMERS = GRAM_NWARP;
+constexpr int GT_THREADS = (GT_CONSUMERS + 1) * 32;
+constexpr int GT_PH_BYTES = 2 * GRAM_NT * 8 * 16;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// A wait that cannot hang the GPU: a pipeline bug traps after ~1 s instead of spinning forever.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && spin >= 64) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > (1LL << 31)) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
+        "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int MF>
+__global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParams P, const __grid_constant__ GramTma Tm) {
+    constexpr int ROWS_A = 8 * MF;
+    constexpr int A_BYTES = GRAM_KG * ROWS_A * 64;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int nst = Tm.nstages;
+    const int b_kg_stride = Tm.brows_alloc * 64;
+    const int stage_bytes = A_BYTES + GRAM_KG * b_kg_stride + GT_PH_BYTES;
+    unsigned char* tail = smem + (size_t)nst * stage_bytes;
+    const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(tail);  // nst x 8 bytes
+    const uint32_t bar_empty = bar_full + 8 * nst;
+    GramJob* sjob = reinterpret_cast<GramJob*>(tail + 16 * 8);  // room for up to 8 stages of barriers
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, kk = lane & 3;
+
+    int bid = blockIdx.x;
+    const int nt = bid % P.n_nt;
+    bid /= P.n_nt;
+    const int mt = bid % P.n_mt;
+    const int job_id = bid / P.n_mt;
+    const int split = blockIdx.y;
+
+    if (tid < (int)(sizeof(GramJob) / sizeof(int))) {
+        reinterpret_cast<int*>(sjob)[tid] = reinterpret_cast<const int*>(P.jobs + job_id)[tid];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, GT_CONSUMERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int nseg = sjob->nseg;
+
+    const int Ne = P.Ne, nmom = P.nmom;
+    const int nfrag_f = (Ne + 3) >> 2;
+    const int N_flat = nfrag_f * nmom;
+    const int nflat0 = nt * GRAM_NT;
+    const int nflat_last = min(nflat0 + GRAM_NT, N_flat) - 1;
+    const int ff0 = nflat0 / nmom;
+    const int nrows_b = 4 * (nflat_last / nmom - ff0 + 1);
+    const int row0 = mt * ROWS_A;
+
+    const int T_all = nseg * P.ksteps;
+    const int T0 = (int)(((long long)T_all * split) / P.ksplit);
+    const int T1 = (int)(((long long)T_all * (split + 1)) / P.ksplit);
+    const int T = T1 - T0;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+
+    if (warp == GT_CONSUMERS) {
+        // ================================ producer warp ================================
+        const int nvalid = nflat_last - nflat0 + 1;  // n-fragments of this tile that exist
+        const int p0 = nflat0 - ff0 * nmom;
+        // phase tile = runs of consecutive momenta: slot s holds momentum (p0 + s) mod nmom
+        int nruns = 0;
+        for (int slot = 0, p = p0; slot < nvalid;) {
+            const int len = min(nvalid - slot, nmom - p);
+            ++nruns;
+            slot += len;
+            p = 0;
+        }
+        int run_slot = 0, run_p = 0, run_len = 0, run_tab = 0;
+        if (lane < 2 * nruns) {
+            run_tab = lane / nruns;
+            const int r = lane - run_tab * nruns;
+            int i = 0;
+            for (int slot = 0, p = p0; slot < nvalid; ++i) {
+                const int len = min(nvalid - slot, nmom - p);
+                if (i == r) {
+                    run_slot = slot;
+                    run_p = p;
+                    run_len = len;
+                }
+                slot += len;
+                p = 0;
+            }
+        }
+        const int nbb = (nrows_b + 7) >> 3;
+        const uint32_t tx_bytes = (uint32_t)(A_BYTES + GRAM_KG * nbb * 512 + 2 * nvalid * 128);
+        int seg = T0 / P.ksteps;
+        int kstep = T0 - seg * P.ksteps;
+        int s = 0;
+        uint32_t par = 1;  // the first pass over the ring finds every slot free
+        for (int it = 0; it < T; ++it) {
+            mbar_wait(bar_empty + 8 * s, par);
+            const uint32_t full = bar_full + 8 * s;
+            if (lane == 0) mbar_arrive_expect_tx(full, tx_bytes);
+            __syncwarp();
+            const uint32_t st = smem_base + (uint32_t)(s * stage_bytes);
+            const int kd = kstep * 48;  // first double of this stage's 24 complex k
+            if (lane < GRAM_KG) tma_load_3d(st + lane * (ROWS_A * 64), Tm.mapA, full, kd + 8 * lane, row0, sjob->Lf[seg]);
+            for (int i = lane; i < GRAM_KG * nbb; i += 32) {
+                const int kg = i / nbb, j = i - kg * nbb;
+                tma_load_3d(st + A_BYTES + kg * b_kg_stride + j * 512, Tm.mapB, full, kd + 8 * kg, 4 * ff0 + 8 * j, sjob->Rf[seg]);
+            }
+            if (lane < 2 * nruns) {
+                const cplx* src = Tm.phase_tiles + (((size_t)kstep * 2 + run_tab) * nmom + run_p) * 8;
+                bulk_load(st + A_BYTES + GRAM_KG * b_kg_stride + (run_tab * GRAM_NT + run_slot) * 128, src, run_len * 128, full);
+            }
+            if (++kstep == P.ksteps) {
+                kstep = 0;
+                ++seg;
+            }
+            if (++s == nst) {
+                s = 0;
+                par ^= 1;
+            }
+        }
+        return;
+    }
+
+    // ================================== consumer warps ==================================
+    int my_ffrag[GRAM_NF], my_p[GRAM_NF];
+    bool my_valid[GRAM_NF];
+    uint32_t my_boff[GRAM_NF];
+#pragma unroll
+    for (int n = 0; n < GRAM_NF; ++n) {
+        const int nf_raw = nflat0 + warp * GRAM_NF + n;
+        my_valid[n] = nf_raw < N_flat;
+        const int nf = min(nf_raw, N_flat - 1);
+        my_ffrag[n] = nf / nmom;
+        my_p[n] = nf - my_ffrag[n] * nmom;
+        my_boff[n] = (uint32_t)(((4 * (my_ffrag[n] - ff0) + (g >> 1)) * 4 + kk) * 16);
+    }
+    // slot of n-fragment nl in the phase tile is nl itself; n-fragments past the end of the tail
+    // tile read whatever the slot holds, their columns are never stored
+    const uint32_t my_phoff = (uint32_t)(((g & 1) * GRAM_NT + warp * GRAM_NF) * 8 * 16);
+
+    double acc[MF][GRAM_NF][2];
+#pragma unroll
+    for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int n = 0; n < GRAM_NF; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
+    int cur_sign = 1;
+    int cs_seg = T0 / P.ksteps;
+    int cs_kstep = T0 - cs_seg * P.ksteps;
+    int s = 0;
+    uint32_t par = 0;
+    for (int it = 0; it < T; ++it) {
+        const int sgn = sjob->sign[cs_seg];
+        if (++cs_kstep == P.ksteps) {
+            cs_kstep = 0;
+            ++cs_seg;
+        }
+        if (sgn != cur_sign) {
+#pragma unroll
+            for (int i = 0; i < MF; ++i)
+#pragma unroll
+                for (int n = 0; n < GRAM_NF; ++n) {
+                    acc[i][n][0] = flip_sign(acc[i][n][0]);
+                    acc[i][n][1] = flip_sign(acc[i][n][1]);
+                }
+            cur_sign = sgn;
+        }
+        mbar_wait(bar_full + 8 * s, par);
+        const unsigned char* stage = smem + (size_t)s * stage_bytes;
+        const unsigned char* b_s = stage + A_BYTES;
+        gram_compute_stage<MF>(acc, stage + lane * 16, b_s, b_kg_stride, b_s + GRAM_KG * b_kg_stride + my_phoff, my_boff, kk);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+        if (++s == nst) {
+            s = 0;
+            par ^= 1;
+        }
+    }
+
+    const double fs = (double)cur_sign;
+    cplx* outj = P.partial + ((size_t)split * P.njobs + job_id) * (size_t)nmom * Ne * Ne;
+#pragma unroll
+    for (int n = 0; n < GRAM_NF; ++n) {
+        const int f = 4 * my_ffrag[n] + kk;
+        if (!my_valid[n] || f >= Ne) continue;
+        cplx* outp = outj + (size_t)my_p[n] * Ne * Ne;
+#pragma unroll
+        for (int i = 0; i < MF; ++i) {
+            const int e = row0 + 8 * i + g;
+            if (e < Ne) outp[(size_t)e * Ne + f] = make_double2(fs * acc[i][n][0], fs * acc[i][n][1]);
+        }
+    }
+}
+
+// shared-memory plan of the TMA variant: rows of R per k-group, ring depth, total bytes
+int gram_tma_plan(int mfrag, int nmom, int Ne, int* brows_alloc, int* nstages, int* smem_bytes) {
+    const int nfrag_f = (Ne + 3) / 4;
+    int maxff = (GRAM_NT - 1) / nmom + 2;  // distinct f-fragments 16 consecutive n-fragments can touch
+    if (maxff > GRAM_NT) maxff = GRAM_NT;
+    if (maxff > nfrag_f) maxff = nfrag_f;
+    int rows = ((4 * maxff + 7) / 8) * 8;
+    if (rows > GRAM_BROWS) rows = GRAM_BROWS;
+    const int stage = GRAM_KG * 8 * mfrag * 64 + GRAM_KG * rows * 64 + GT_PH_BYTES;
+    const int tail = 16 * 8 + (int)sizeof(GramJob) + 64;
+    int nst = (227 * 1024 - tail) / stage;
+    if (nst > 8) nst = 8;
+    if (nst < 2) return -1;
+    *brows_alloc = rows;
+    *nstages = nst;
+    *smem_bytes = nst * stage + tail;
+    return 0;
+}
+
+template <int MF>
+static cudaError_t launch_gram_tma_mf(const GramParams& P, const GramTma& T, cudaStream_t s) {
+    int rows, nst, bytes;
+    if (gram_tma_plan(MF, P.nmom, P.Ne, &rows, &nst, &bytes) != 0 || rows != T.brows_alloc || nst != T.nstages)
+        return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)(P.njobs * P.n_mt * P.n_nt), (unsigned)P.ksplit);
+    gram_tma_kernel<MF><<<grid, GT_THREADS, bytes, s>>>(P, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gram_tma(const GramParams& P, const GramTma& T, int mfrag, cudaStream_t s) {
+    switch (mfrag) {
+        case 2: return launch_gram_tma_mf<2>(P, T, s);
+        case 4: return launch_gram_tma_mf<4>(P, T, s);
+        case 5: return launch_gram_tma_mf<5>(P, T, s);
+        case 7: return launch_gram_tma_mf<7>(P, T, s);
+        case 9: return launch_gram_tma_mf<9>(P, T, s);
+        case 10: return launch_gram_tma_mf<10>(P, T, s);
+        case 11: return launch_gram_tma_mf<11>(P, T, s);
+        case 13: return launch_gram_tma_mf<13>(P, T, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// phase[2][nmom][Vpad] -> tiles[kstep][2][nmom][8]
+__global__ void phase_tiles_kernel(const cplx* __restrict__ phase2, cplx* __restrict__ tiles, int nmom, int Vpad) {
+    const size_t n = (size_t)2 * nmom * Vpad;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int site = (int)(i % Vpad);
+    const size_t r = i / Vpad;  // tab * nmom + p
+    const int p = (int)(r % nmom), tab = (int)(r / nmom);
+    tiles[((((size_t)(site >> 3)) * 2 + tab) * nmom + p) * 8 + (site & 7)] = phase2[i];
+}
+
+cudaError_t launch_phase_tiles(const cplx* phase2, cplx* tiles, int nmom, int Vpad, cudaStream_t s) {
+    const size_t n = (size_t)2 * nmom * Vpad;
+    phase_tiles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(phase2, tiles, nmom, Vpad);
+    return cudaGetLastError();
 }
 
 // available tile heights (m-fragments of 8 rows per CTA)

@@ -161,10 +161,14 @@ class ElementalEngine:
         """-1 auto, 0 off, 1 force the Hermitian pairing of (left, right) field pairs."""
         _capi.check(self.lib.edk_debug_symmetry(self.h, int(mode)), "edk_debug_symmetry")
 
+    def debug_loader(self, mode: int):
+        """0 = TMA producer warp (default), 1 = cp.async loader inside the MMA warps."""
+        _capi.check(self.lib.edk_debug_loader(self.h, int(mode)), "edk_debug_loader")
+
     def query(self):
         q = lambda w: int(self.lib.edk_query(self.h, w))  # noqa: E731
         return {"hermitian_pairing": bool(q(0)), "internal_momenta": q(1), "pair_gemms_per_momentum": q(2),
-                "ksplit": q(3), "mfrag": q(4), "jobs": q(5)}
+                "ksplit": q(3), "mfrag": q(4), "jobs": q(5), "tma_stages": q(6)}
 
 
 def microbench_fp64(device: int = 0):
