@@ -127,6 +127,7 @@ def cpu_sample(name, W0=None, U=None, hop_frac=8):
     reference run."""
     from oracle import elemental_oracle as orc
 
+    use_all_host_cores()
     Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
     latt = [Lx, Ly, Lz, Lt]
     rng = np.random.default_rng(orc.SEED0)
@@ -154,14 +155,25 @@ def cpu_sample(name, W0=None, U=None, hop_frac=8):
     return 1.0 / T, sample
 
 
-def host_threads():
+def use_all_host_cores():
+    """Give the BLAS behind numpy every core this process may run on (torchrun exports
+    OMP_NUM_THREADS=1, which would otherwise cripple the CPU arm) and return the count in use."""
     try:
-        from threadpoolctl import threadpool_info
-
-        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-        return int(n)
+        want = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        want = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=want)
+        got = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return int(got)
+    except Exception:
+        return 1
+
+
+def host_threads():
+    return use_all_host_cores()
 
 
 def run_reference(args):
@@ -282,6 +294,8 @@ def run_native(args):
     scratch = torch.empty(eng.out_shape, dtype=torch.complex128, device=dev)
     for i in range(W):
         step(i, scratch)
+    if world > 1:  # first use of the collective sets up the NCCL channels: not part of a step
+        gather_timeslices(outs[:1], world, dst=0)
     barrier()
 
     # ---- device-resident throughput --------------------------------------------------------
@@ -374,7 +388,8 @@ def run_native(args):
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {
-                "kernel": "gram_dmma_kernel (momentum-phased contraction, DMMA.8x8x4)", "bound": "tensor",
+                "kernel": ("gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel")
+                          + " (momentum-phased contraction, DMMA.8x8x4, TMA producer warp + mbarrier ring)", "bound": "tensor",
                 "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
                 "traffic": None,
                 "peak_source": f"cuBLAS FP64 GEMM measured in this run (dgemm {gemm['dgemm']:.1f}, zgemm {gemm['zgemm']:.1f} TFLOP/s); "

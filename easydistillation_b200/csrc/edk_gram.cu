@@ -68,7 +68,9 @@ __device__ __forceinline__ double flip_sign(double x) {
 //   a_s : this lane's slot in A[kg][row][4]  (+ (kg*ROWS_A + 8 i)*64 selects fragment i)
 //   b_s : B[kg][row][4], b_kg_stride bytes per k-group; my_boff = this lane's (row, k) offset
 //   p_s : this lane's phase tile [n-fragment][8 sites] (already offset to phase or -i*phase)
-template <int MF>
+// MFL <= MF is the number of live m-fragments of this tile (row tiles are balanced, so the last
+// tiles of a column may own one fragment less; its MMAs are simply not issued).
+template <int MF, int MFL>
 __device__ __forceinline__ void gram_compute_stage(double (&acc)[MF][GRAM_NF][2], const unsigned char* a_s,
                                                    const unsigned char* b_s, const int b_kg_stride,
                                                    const unsigned char* p_s, const uint32_t (&my_boff)[GRAM_NF],
@@ -103,14 +105,14 @@ __device__ __forceinline__ void gram_compute_stage(double (&acc)[MF][GRAM_NF][2]
             // m-fragments in groups of <= 5: both MMAs of an accumulator are >= 2*group MMAs apart
             constexpr int GRP = 5;
 #pragma unroll
-            for (int i0 = 0; i0 < MF; i0 += GRP) {
+            for (int i0 = 0; i0 < MFL; i0 += GRP) {
                 cplx a[GRP];
 #pragma unroll
                 for (int ii = 0; ii < GRP; ++ii)
-                    if (i0 + ii < MF) a[ii] = *reinterpret_cast<const cplx*>(a_s + (kg * ROWS_A + 8 * (i0 + ii)) * 64);
+                    if (i0 + ii < MFL) a[ii] = *reinterpret_cast<const cplx*>(a_s + (kg * ROWS_A + 8 * (i0 + ii)) * 64);
 #pragma unroll
                 for (int ii = 0; ii < GRP; ++ii)
-                    if (i0 + ii < MF) {
+                    if (i0 + ii < MFL) {
 #pragma unroll
                         for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i0 + ii][n][0], acc[i0 + ii][n][1], a[ii].x, b1[n]);
                     }
@@ -123,7 +125,7 @@ __device__ __forceinline__ void gram_compute_stage(double (&acc)[MF][GRAM_NF][2]
                 }
 #pragma unroll
                 for (int ii = 0; ii < GRP; ++ii)
-                    if (i0 + ii < MF) {
+                    if (i0 + ii < MFL) {
 #pragma unroll
                         for (int n = 0; n < GRAM_NF; ++n) dmma884(acc[i0 + ii][n][0], acc[i0 + ii][n][1], a[ii].y, b2[n]);
                     }
@@ -137,6 +139,15 @@ __device__ __forceinline__ void gram_compute_stage(double (&acc)[MF][GRAM_NF][2]
             }
         }
         }
+}
+
+// Balanced row tiling: ceil(Ne/8) m-fragments over n_mt tiles, the first (frags % n_mt) tiles own
+// one fragment more.  Returns the first row of tile mt and its live fragment count.
+__device__ __forceinline__ int gram_row_tile(int Ne, int n_mt, int mt, int& mf_live) {
+    const int frags = (Ne + 7) >> 3;
+    const int q = frags / n_mt, r = frags - q * n_mt;
+    mf_live = q + (mt < r ? 1 : 0);
+    return 8 * (mt * q + min(mt, r));
 }
 
 template <int MF>
@@ -198,7 +209,8 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
     // thread -> (row lrow + 32 j, 16-byte chunk lkq + 8 m) of a 24-chunk (8-site) row segment:
     // 8 consecutive threads fetch one full 128-byte line of a row.
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
-    const int row0 = mt * ROWS_A;
+    int mf_live;
+    const int row0 = gram_row_tile(Ne, P.n_mt, mt, mf_live);
     const int lrow = tid >> 3, lkq = tid & 7;
     const uint32_t a_dst0 = (uint32_t)(((lkq >> 2) * ROWS_A + lrow) * 64 + (lkq & 3) * 16);
     const uint32_t b_dst0 = (uint32_t)(S::A_BYTES + ((lkq >> 2) * GRAM_BROWS + lrow) * 64 + (lkq & 3) * 16);
@@ -313,7 +325,7 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
         const unsigned char* p_s = b_s + S::B_BYTES + my_phoff;
         if (++buf == GRAM_STAGES) buf = 0;
 
-        gram_compute_stage<MF>(acc, a_s, b_s, GRAM_BROWS * 64, p_s, my_boff, kk);
+        gram_compute_stage<MF, MF>(acc, a_s, b_s, GRAM_BROWS * 64, p_s, my_boff, kk);
     }
     cp_async_wait<0>();
 
@@ -328,7 +340,7 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
 #pragma unroll
         for (int i = 0; i < MF; ++i) {
             const int e = row0 + 8 * i + g;
-            if (e < Ne) outp[(size_t)e * Ne + f] = make_double2(fs * acc[i][n][0], fs * acc[i][n][1]);
+            if (i < mf_live && e < Ne) outp[(size_t)e * Ne + f] = make_double2(fs * acc[i][n][0], fs * acc[i][n][1]);
         }
     }
 }
@@ -340,10 +352,13 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
 //              (cp.async.bulk runs of consecutive momenta), all completing on full[stage]
 //   consumers: mbarrier.try_wait(full) -> gram_compute_stage -> arrive(empty)
 // No CTA-wide barrier and no loader code in the MMA warps, so they drift apart instead of hitting
-// the same bubbles in lock-step.  Out-of-range rows / k are zero-filled by the TMA unit.
+// the same bubbles in lock-step.  Out-of-range rows / k are zero-filled by the TMA unit.  The
+// producer warpgroup gives its registers away (setmaxnreg), the MMA warps run with 232.
 // ---------------------------------------------------------------------------------------
-constexpr int GT_CONSUMERS = GRAM_NWARP;
-constexpr int GT_THREADS = (GT_CONSUMERS + 1) * 32;
+constexpr int GT_CONSUMERS = GRAM_NWARP;             // two consumer warpgroups
+constexpr int GT_THREADS = (GT_CONSUMERS + 4) * 32;  // + one producer warpgroup (one warp of it works)
+constexpr int GT_REGS_CONSUMER = 232;                // setmaxnreg: 256 x 232 + 128 x 40 <= 64 K registers
+constexpr int GT_REGS_PRODUCER = 40;
 constexpr int GT_PH_BYTES = 2 * GRAM_NT * 8 * 16;
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -429,7 +444,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     const int nflat_last = min(nflat0 + GRAM_NT, N_flat) - 1;
     const int ff0 = nflat0 / nmom;
     const int nrows_b = 4 * (nflat_last / nmom - ff0 + 1);
-    const int row0 = mt * ROWS_A;
+    int mf_live;
+    const int row0 = gram_row_tile(Ne, P.n_mt, mt, mf_live);
 
     const int T_all = nseg * P.ksteps;
     const int T0 = (int)(((long long)T_all * split) / P.ksplit);
@@ -437,8 +453,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     const int T = T1 - T0;
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 
-    if (warp == GT_CONSUMERS) {
-        // ================================ producer warp ================================
+    if (warp >= GT_CONSUMERS) {
+        // ================================ producer warpgroup ================================
+        // hands its registers to the MMA warpgroups; only its first warp issues copies
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(GT_REGS_PRODUCER));
+        if (warp != GT_CONSUMERS) return;
         const int nvalid = nflat_last - nflat0 + 1;  // n-fragments of this tile that exist
         const int p0 = nflat0 - ff0 * nmom;
         // phase tile = runs of consecutive momenta: slot s holds momentum (p0 + s) mod nmom
@@ -500,6 +519,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     }
 
     // ================================== consumer warps ==================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(GT_REGS_CONSUMER));
     int my_ffrag[GRAM_NF], my_p[GRAM_NF];
     bool my_valid[GRAM_NF];
     uint32_t my_boff[GRAM_NF];
@@ -545,7 +565,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
         mbar_wait(bar_full + 8 * s, par);
         const unsigned char* stage = smem + (size_t)s * stage_bytes;
         const unsigned char* b_s = stage + A_BYTES;
-        gram_compute_stage<MF>(acc, stage + lane * 16, b_s, b_kg_stride, b_s + GRAM_KG * b_kg_stride + my_phoff, my_boff, kk);
+        if (MF > 1 && mf_live == MF - 1)  // uniform per CTA
+            gram_compute_stage<MF, (MF > 1 ? MF - 1 : 1)>(acc, stage + lane * 16, b_s, b_kg_stride,
+                                                          b_s + GRAM_KG * b_kg_stride + my_phoff, my_boff, kk);
+        else
+            gram_compute_stage<MF, MF>(acc, stage + lane * 16, b_s, b_kg_stride, b_s + GRAM_KG * b_kg_stride + my_phoff,
+                                       my_boff, kk);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         if (++s == nst) {
@@ -564,7 +589,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
 #pragma unroll
         for (int i = 0; i < MF; ++i) {
             const int e = row0 + 8 * i + g;
-            if (e < Ne) outp[(size_t)e * Ne + f] = make_double2(fs * acc[i][n][0], fs * acc[i][n][1]);
+            if (i < mf_live && e < Ne) outp[(size_t)e * Ne + f] = make_double2(fs * acc[i][n][0], fs * acc[i][n][1]);
         }
     }
 }
@@ -802,7 +827,7 @@ cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const int blocks = 148 * 4, threads = 256;
+    const int blocks = 148 * 2, threads = 256;
     float ms = 0.f;
     // DMMA: per warp-iteration 16 MMAs x 512 flop
     const int it_mma = 20000;
