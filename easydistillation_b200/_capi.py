@@ -45,6 +45,7 @@ SIGNATURES = {
     "edk_debug_gram_config": (_i, [_vp, _i, _i]),
     "edk_debug_symmetry": (_i, [_vp, _i]),
     "edk_debug_loader": (_i, [_vp, _i]),
+    "edk_debug_algo": (_i, [_vp, _i]),
     "edk_query": (_i, [_vp, _i]),
     "edk_microbench_fp64": (_i, [_i, _dp, _dp]),
 }

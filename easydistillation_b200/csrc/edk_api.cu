@@ -49,6 +49,7 @@ struct edk_handle {
     cplx* phase_tiles = nullptr;
     bool tma_ready = false;
     int loader = 0;
+    int algo = 1;  // arithmetic of the TMA kernel: 1 = 3M (three real MMAs per complex block), 0 = 4M
     size_t field_cplx;  // Ne * V * 3
     // device buffers
     cplx* links = nullptr;    // [3][V][9]
@@ -303,12 +304,19 @@ void build_displacement_jobs(edk_handle* h) {
     }
 }
 
+int effective_algo(const edk_handle* h) { return (h->loader == 0 && !h->naive) ? h->algo : 0; }
+
+int count_n_tiles(const edk_handle* h, int algo) {
+    const int fw = gram_fwidth(algo), nt = gram_nfrag_per_tile(algo);
+    const int nfrag_f = (h->Ne + fw - 1) / fw;
+    return (nfrag_f * h->nmom_int + nt - 1) / nt;
+}
+
 void pick_gram_config(edk_handle* h) {
     h->mfrag = h->force_mfrag ? h->force_mfrag : gram_pick_mfrag(h->Ne);
     const int rows = gram_rows_per_tile(h->mfrag);
     const int n_mt = (h->Ne + rows - 1) / rows;
-    const int nfrag_f = (h->Ne + 3) / 4;
-    const int n_nt = (nfrag_f * h->nmom_int + gram_nfrag_per_tile() - 1) / gram_nfrag_per_tile();
+    const int n_nt = count_n_tiles(h, effective_algo(h));
     const long long tiles = (long long)h->njobs * n_mt * n_nt;
     const int ksteps = h->g.Vpad / 8;
     int ks = 1;
@@ -353,7 +361,7 @@ int build_tma(edk_handle* h) {
         encode = (EncodeFn)fn;
     }
     int rows = 0, nst = 0, bytes = 0;
-    if (gram_tma_plan(h->mfrag, h->nmom_int, h->Ne, &rows, &nst, &bytes) != 0) {
+    if (gram_tma_plan(h->algo, h->mfrag, h->nmom_int, h->Ne, &rows, &nst, &bytes) != 0) {
         set_error("no shared-memory plan for the TMA contraction (mfrag %d)", h->mfrag);
         return EDK_ERR_ARG;
     }
@@ -487,16 +495,16 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     P.ksplit = h->naive ? 1 : h->ksplit;
     const int rows = gram_rows_per_tile(h->mfrag);
     P.n_mt = (h->Ne + rows - 1) / rows;
-    const int nfrag_f = (h->Ne + 3) / 4;
-    P.n_nt = (nfrag_f * h->nmom_int + gram_nfrag_per_tile() - 1) / gram_nfrag_per_tile();
+    const bool use_tma = !h->naive && h->loader == 0 && h->tma_ready;
+    P.n_nt = count_n_tiles(h, use_tma ? h->algo : 0);
     P.phase = h->phase;
     P.partial = h->partial;
     {
         PhaseTimer t(h, s, PH_GRAM, 1);
         if (h->naive)
             EDK_CUDA_TRY(launch_gram_naive(P, s));
-        else if (h->loader == 0 && h->tma_ready)
-            EDK_CUDA_TRY(launch_gram_tma(P, h->tma, h->mfrag, s));
+        else if (use_tma)
+            EDK_CUDA_TRY(launch_gram_tma(P, h->tma, h->mfrag, h->algo, s));
         else
             EDK_CUDA_TRY(launch_gram_dmma(P, h->mfrag, s));
     }
@@ -846,7 +854,17 @@ int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit) {
 int edk_debug_loader(edk_handle* h, int mode) {
     if (!h || mode < 0 || mode > 1) return EDK_ERR_ARG;
     h->loader = mode;
-    return EDK_OK;
+    pick_gram_config(h);
+    return ensure_partial(h);
+}
+
+int edk_debug_algo(edk_handle* h, int algo) {
+    if (!h || algo < 0 || algo > 1) return EDK_ERR_ARG;
+    h->algo = algo;
+    pick_gram_config(h);
+    const int rc = build_tma(h);
+    if (rc != EDK_OK) return rc;
+    return ensure_partial(h);
 }
 
 int edk_debug_symmetry(edk_handle* h, int mode) {
@@ -871,6 +889,7 @@ int edk_query(const edk_handle* h, int what) {
         case 4: return h->mfrag;
         case 5: return h->njobs;
         case 6: return (h->loader == 0 && h->tma_ready) ? h->tma.nstages : 0;
+        case 7: return effective_algo(h) ? 3 : 4;
         default: return EDK_ERR_ARG;
     }
 }

@@ -100,12 +100,13 @@ cudaError_t launch_displace_step6(Ptr6 p, cplx* mean_out, const cplx* links, Geo
 // contraction
 cudaError_t launch_gram_dmma(const GramParams& P, int mfrag, cudaStream_t s);
 cudaError_t launch_gram_naive(const GramParams& P, cudaStream_t s);
-cudaError_t launch_gram_tma(const GramParams& P, const GramTma& T, int mfrag, cudaStream_t s);
+cudaError_t launch_gram_tma(const GramParams& P, const GramTma& T, int mfrag, int algo, cudaStream_t s);
 cudaError_t launch_phase_tiles(const cplx* phase2, cplx* tiles, int nmom, int Vpad, cudaStream_t s);
-int gram_tma_plan(int mfrag, int nmom, int Ne, int* brows_alloc, int* nstages, int* smem_bytes);
+int gram_tma_plan(int algo, int mfrag, int nmom, int Ne, int* brows_alloc, int* nstages, int* smem_bytes);
+int gram_fwidth(int algo);
 int gram_pick_mfrag(int Ne);
 int gram_rows_per_tile(int mfrag);
-int gram_nfrag_per_tile();
+int gram_nfrag_per_tile(int algo);
 cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom_int,
                            int nmom_out, const int* negidx, int Ne, const double* coeff, cplx* out, cudaStream_t s);
 // microbench

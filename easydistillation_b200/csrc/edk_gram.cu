@@ -359,7 +359,22 @@ constexpr int GT_CONSUMERS = GRAM_NWARP;             // two consumer warpgroups
 constexpr int GT_THREADS = (GT_CONSUMERS + 4) * 32;  // + one producer warpgroup (one warp of it works)
 constexpr int GT_REGS_CONSUMER = 232;                // setmaxnreg: 256 x 232 + 128 x 40 <= 64 K registers
 constexpr int GT_REGS_PRODUCER = 40;
-constexpr int GT_PH_BYTES = 2 * GRAM_NT * 8 * 16;
+
+// Column organisation of the two arithmetic variants.
+//   ALGO 0 ("4M"): an n-fragment is 4 complex f, its 8 MMA columns are (f, re|im); 2 n-fragments per
+//                  warp, 16 per CTA; phase tile holds phase and -i*phase.  4 real MMAs per complex block.
+//   ALGO 1 ("3M"): an n-fragment is 8 complex f = the 8 MMA columns; 1 per warp, 8 per CTA; three
+//                  accumulators T1 = Lr.Pr, T2 = Li.Pi, T3 = (Lr+Li).(Pi-Pr), combined in the epilogue as
+//                  Re = T1 + T2, Im = T3 + T1 - T2 (Gauss / 3M).  3 real MMAs per complex block.
+template <int ALGO>
+struct GtCols {
+    static constexpr int FW = ALGO ? 8 : 4;                 // complex f per n-fragment
+    static constexpr int NF = ALGO ? 1 : 2;                 // n-fragments per warp
+    static constexpr int NT = GT_CONSUMERS * NF;            // n-fragments per CTA
+    static constexpr int NTAB = ALGO ? 1 : 2;               // phase tables staged per stage
+    static constexpr int PH_BYTES = NTAB * NT * 8 * 16;
+    static constexpr int NACC = ALGO ? 3 : 2;               // accumulator fragments per (m-fragment, warp)
+};
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
@@ -400,14 +415,65 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  : "memory");
 }
 
-template <int MF>
+// 3M stage: same operand tiles as gram_compute_stage, three MMAs per (m-fragment, k-group).
+template <int MF, int MFL>
+__device__ __forceinline__ void gram_compute_stage_3m(double (&acc)[MF][3][2], const unsigned char* a_s,
+                                                      const unsigned char* b_s, const int b_kg_stride,
+                                                      const unsigned char* p_s, const uint32_t my_boff, const int kk) {
+    constexpr int ROWS_A = 8 * MF;
+    cplx rr = *reinterpret_cast<const cplx*>(b_s + my_boff);
+    cplx pp = *reinterpret_cast<const cplx*>(p_s + (kk / 3) * 16);
+    double pr = fma(pp.x, rr.x, -(pp.y * rr.y));
+    double pi = fma(pp.x, rr.y, pp.y * rr.x);
+    double pd = pi - pr;
+#pragma unroll
+    for (int kg = 0; kg < GRAM_KG; ++kg) {
+        if (kg + 1 < GRAM_KG) {
+            rr = *reinterpret_cast<const cplx*>(b_s + (kg + 1) * b_kg_stride + my_boff);
+            pp = *reinterpret_cast<const cplx*>(p_s + ((4 * (kg + 1) + kk) / 3) * 16);
+        }
+        double npr = 0.0, npi = 0.0, npd = 0.0;
+        constexpr int GRP = 4;
+#pragma unroll
+        for (int i0 = 0; i0 < MFL; i0 += GRP) {
+            cplx a[GRP];
+            double as[GRP];
+#pragma unroll
+            for (int ii = 0; ii < GRP; ++ii)
+                if (i0 + ii < MFL) {
+                    a[ii] = *reinterpret_cast<const cplx*>(a_s + (kg * ROWS_A + 8 * (i0 + ii)) * 64);
+                    as[ii] = a[ii].x + a[ii].y;
+                }
+#pragma unroll
+            for (int ii = 0; ii < GRP; ++ii)
+                if (i0 + ii < MFL) {
+                    dmma884(acc[i0 + ii][0][0], acc[i0 + ii][0][1], a[ii].x, pr);
+                    dmma884(acc[i0 + ii][1][0], acc[i0 + ii][1][1], a[ii].y, pi);
+                    dmma884(acc[i0 + ii][2][0], acc[i0 + ii][2][1], as[ii], pd);
+                }
+            if (i0 == 0 && kg + 1 < GRAM_KG) {
+                npr = fma(pp.x, rr.x, -(pp.y * rr.y));
+                npi = fma(pp.x, rr.y, pp.y * rr.x);
+                npd = npi - npr;
+            }
+        }
+        if (kg + 1 < GRAM_KG) {
+            pr = npr;
+            pi = npi;
+            pd = npd;
+        }
+    }
+}
+
+template <int MF, int ALGO>
 __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParams P, const __grid_constant__ GramTma Tm) {
+    using C = GtCols<ALGO>;
     constexpr int ROWS_A = 8 * MF;
     constexpr int A_BYTES = GRAM_KG * ROWS_A * 64;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int nst = Tm.nstages;
     const int b_kg_stride = Tm.brows_alloc * 64;
-    const int stage_bytes = A_BYTES + GRAM_KG * b_kg_stride + GT_PH_BYTES;
+    const int stage_bytes = A_BYTES + GRAM_KG * b_kg_stride + C::PH_BYTES;
     unsigned char* tail = smem + (size_t)nst * stage_bytes;
     const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(tail);  // nst x 8 bytes
     const uint32_t bar_empty = bar_full + 8 * nst;
@@ -438,12 +504,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     const int nseg = sjob->nseg;
 
     const int Ne = P.Ne, nmom = P.nmom;
-    const int nfrag_f = (Ne + 3) >> 2;
+    const int nfrag_f = (Ne + C::FW - 1) / C::FW;
     const int N_flat = nfrag_f * nmom;
-    const int nflat0 = nt * GRAM_NT;
-    const int nflat_last = min(nflat0 + GRAM_NT, N_flat) - 1;
+    const int nflat0 = nt * C::NT;
+    const int nflat_last = min(nflat0 + C::NT, N_flat) - 1;
     const int ff0 = nflat0 / nmom;
-    const int nrows_b = 4 * (nflat_last / nmom - ff0 + 1);
+    const int nrows_b = C::FW * (nflat_last / nmom - ff0 + 1);
     int mf_live;
     const int row0 = gram_row_tile(Ne, P.n_mt, mt, mf_live);
 
@@ -469,7 +535,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
             p = 0;
         }
         int run_slot = 0, run_p = 0, run_len = 0, run_tab = 0;
-        if (lane < 2 * nruns) {
+        if (lane < C::NTAB * nruns) {
             run_tab = lane / nruns;
             const int r = lane - run_tab * nruns;
             int i = 0;
@@ -485,7 +551,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
             }
         }
         const int nbb = (nrows_b + 7) >> 3;
-        const uint32_t tx_bytes = (uint32_t)(A_BYTES + GRAM_KG * nbb * 512 + 2 * nvalid * 128);
+        const uint32_t tx_bytes = (uint32_t)(A_BYTES + GRAM_KG * nbb * 512 + C::NTAB * nvalid * 128);
         int seg = T0 / P.ksteps;
         int kstep = T0 - seg * P.ksteps;
         int s = 0;
@@ -500,11 +566,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
             if (lane < GRAM_KG) tma_load_3d(st + lane * (ROWS_A * 64), Tm.mapA, full, kd + 8 * lane, row0, sjob->Lf[seg]);
             for (int i = lane; i < GRAM_KG * nbb; i += 32) {
                 const int kg = i / nbb, j = i - kg * nbb;
-                tma_load_3d(st + A_BYTES + kg * b_kg_stride + j * 512, Tm.mapB, full, kd + 8 * kg, 4 * ff0 + 8 * j, sjob->Rf[seg]);
+                tma_load_3d(st + A_BYTES + kg * b_kg_stride + j * 512, Tm.mapB, full, kd + 8 * kg, C::FW * ff0 + 8 * j,
+                            sjob->Rf[seg]);
             }
-            if (lane < 2 * nruns) {
+            if (lane < C::NTAB * nruns) {
+                // table 0 = phase, table 1 = -i*phase (global tile layout [kstep][2][nmom][8])
                 const cplx* src = Tm.phase_tiles + (((size_t)kstep * 2 + run_tab) * nmom + run_p) * 8;
-                bulk_load(st + A_BYTES + GRAM_KG * b_kg_stride + (run_tab * GRAM_NT + run_slot) * 128, src, run_len * 128, full);
+                bulk_load(st + A_BYTES + GRAM_KG * b_kg_stride + (run_tab * C::NT + run_slot) * 128, src, run_len * 128, full);
             }
             if (++kstep == P.ksteps) {
                 kstep = 0;
@@ -520,27 +588,28 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
 
     // ================================== consumer warps ==================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(GT_REGS_CONSUMER));
-    int my_ffrag[GRAM_NF], my_p[GRAM_NF];
-    bool my_valid[GRAM_NF];
-    uint32_t my_boff[GRAM_NF];
+    int my_ffrag[C::NF], my_p[C::NF];
+    bool my_valid[C::NF];
+    uint32_t my_boff[C::NF];
 #pragma unroll
-    for (int n = 0; n < GRAM_NF; ++n) {
-        const int nf_raw = nflat0 + warp * GRAM_NF + n;
+    for (int n = 0; n < C::NF; ++n) {
+        const int nf_raw = nflat0 + warp * C::NF + n;
         my_valid[n] = nf_raw < N_flat;
         const int nf = min(nf_raw, N_flat - 1);
         my_ffrag[n] = nf / nmom;
         my_p[n] = nf - my_ffrag[n] * nmom;
-        my_boff[n] = (uint32_t)(((4 * (my_ffrag[n] - ff0) + (g >> 1)) * 4 + kk) * 16);
+        const int brow = ALGO ? 8 * (my_ffrag[n] - ff0) + g : 4 * (my_ffrag[n] - ff0) + (g >> 1);
+        my_boff[n] = (uint32_t)((brow * 4 + kk) * 16);
     }
     // slot of n-fragment nl in the phase tile is nl itself; n-fragments past the end of the tail
     // tile read whatever the slot holds, their columns are never stored
-    const uint32_t my_phoff = (uint32_t)(((g & 1) * GRAM_NT + warp * GRAM_NF) * 8 * 16);
+    const uint32_t my_phoff = (uint32_t)(((ALGO ? 0 : (g & 1)) * C::NT + warp * C::NF) * 8 * 16);
 
-    double acc[MF][GRAM_NF][2];
+    double acc[MF][C::NACC][2];
 #pragma unroll
     for (int i = 0; i < MF; ++i)
 #pragma unroll
-        for (int n = 0; n < GRAM_NF; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
+        for (int n = 0; n < C::NACC; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
     int cur_sign = 1;
     int cs_seg = T0 / P.ksteps;
     int cs_kstep = T0 - cs_seg * P.ksteps;
@@ -556,7 +625,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
 #pragma unroll
             for (int i = 0; i < MF; ++i)
 #pragma unroll
-                for (int n = 0; n < GRAM_NF; ++n) {
+                for (int n = 0; n < C::NACC; ++n) {
                     acc[i][n][0] = flip_sign(acc[i][n][0]);
                     acc[i][n][1] = flip_sign(acc[i][n][1]);
                 }
@@ -565,12 +634,19 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
         mbar_wait(bar_full + 8 * s, par);
         const unsigned char* stage = smem + (size_t)s * stage_bytes;
         const unsigned char* b_s = stage + A_BYTES;
-        if (MF > 1 && mf_live == MF - 1)  // uniform per CTA
-            gram_compute_stage<MF, (MF > 1 ? MF - 1 : 1)>(acc, stage + lane * 16, b_s, b_kg_stride,
-                                                          b_s + GRAM_KG * b_kg_stride + my_phoff, my_boff, kk);
-        else
-            gram_compute_stage<MF, MF>(acc, stage + lane * 16, b_s, b_kg_stride, b_s + GRAM_KG * b_kg_stride + my_phoff,
-                                       my_boff, kk);
+        const unsigned char* p_s = b_s + GRAM_KG * b_kg_stride + my_phoff;
+        constexpr int MFM = MF > 1 ? MF - 1 : 1;
+        if constexpr (ALGO == 0) {
+            if (MF > 1 && mf_live == MF - 1)  // uniform per CTA
+                gram_compute_stage<MF, MFM>(acc, stage + lane * 16, b_s, b_kg_stride, p_s, my_boff, kk);
+            else
+                gram_compute_stage<MF, MF>(acc, stage + lane * 16, b_s, b_kg_stride, p_s, my_boff, kk);
+        } else {
+            if (MF > 1 && mf_live == MF - 1)
+                gram_compute_stage_3m<MF, MFM>(acc, stage + lane * 16, b_s, b_kg_stride, p_s, my_boff[0], kk);
+            else
+                gram_compute_stage_3m<MF, MF>(acc, stage + lane * 16, b_s, b_kg_stride, p_s, my_boff[0], kk);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         if (++s == nst) {
@@ -581,28 +657,52 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
 
     const double fs = (double)cur_sign;
     cplx* outj = P.partial + ((size_t)split * P.njobs + job_id) * (size_t)nmom * Ne * Ne;
+    if constexpr (ALGO == 0) {
+        // lane holds C[e = row0+8i+g][f = 4*ffrag+kk] = (re, im)
 #pragma unroll
-    for (int n = 0; n < GRAM_NF; ++n) {
-        const int f = 4 * my_ffrag[n] + kk;
-        if (!my_valid[n] || f >= Ne) continue;
-        cplx* outp = outj + (size_t)my_p[n] * Ne * Ne;
+        for (int n = 0; n < C::NF; ++n) {
+            const int f = 4 * my_ffrag[n] + kk;
+            if (!my_valid[n] || f >= Ne) continue;
+            cplx* outp = outj + (size_t)my_p[n] * Ne * Ne;
 #pragma unroll
-        for (int i = 0; i < MF; ++i) {
-            const int e = row0 + 8 * i + g;
-            if (i < mf_live && e < Ne) outp[(size_t)e * Ne + f] = make_double2(fs * acc[i][n][0], fs * acc[i][n][1]);
+            for (int i = 0; i < MF; ++i) {
+                const int e = row0 + 8 * i + g;
+                if (i < mf_live && e < Ne) outp[(size_t)e * Ne + f] = make_double2(fs * acc[i][n][0], fs * acc[i][n][1]);
+            }
+        }
+    } else {
+        // lane holds T1,T2,T3 of C[e = row0+8i+g][f = 8*ffrag + 2kk + {0,1}]
+        const int f = 8 * my_ffrag[0] + 2 * kk;
+        if (my_valid[0]) {
+            cplx* outp = outj + (size_t)my_p[0] * Ne * Ne;
+#pragma unroll
+            for (int i = 0; i < MF; ++i) {
+                const int e = row0 + 8 * i + g;
+                if (i < mf_live && e < Ne) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (f + c < Ne) {
+                            const double t1 = acc[i][0][c], t2 = acc[i][1][c], t3 = acc[i][2][c];
+                            outp[(size_t)e * Ne + f + c] = make_double2(fs * (t1 + t2), fs * (t3 + (t1 - t2)));
+                        }
+                    }
+                }
+            }
         }
     }
 }
 
 // shared-memory plan of the TMA variant: rows of R per k-group, ring depth, total bytes
-int gram_tma_plan(int mfrag, int nmom, int Ne, int* brows_alloc, int* nstages, int* smem_bytes) {
-    const int nfrag_f = (Ne + 3) / 4;
-    int maxff = (GRAM_NT - 1) / nmom + 2;  // distinct f-fragments 16 consecutive n-fragments can touch
-    if (maxff > GRAM_NT) maxff = GRAM_NT;
+int gram_tma_plan(int algo, int mfrag, int nmom, int Ne, int* brows_alloc, int* nstages, int* smem_bytes) {
+    const int FW = algo ? 8 : 4, NT = algo ? 8 : 16;
+    const int nfrag_f = (Ne + FW - 1) / FW;
+    int maxff = (NT - 1) / nmom + 2;  // distinct f-fragments NT consecutive n-fragments can touch
+    if (maxff > NT) maxff = NT;
     if (maxff > nfrag_f) maxff = nfrag_f;
-    int rows = ((4 * maxff + 7) / 8) * 8;
+    int rows = ((FW * maxff + 7) / 8) * 8;
     if (rows > GRAM_BROWS) rows = GRAM_BROWS;
-    const int stage = GRAM_KG * 8 * mfrag * 64 + GRAM_KG * rows * 64 + GT_PH_BYTES;
+    const int ph = (algo ? 1 : 2) * NT * 128;
+    const int stage = GRAM_KG * 8 * mfrag * 64 + GRAM_KG * rows * 64 + ph;
     const int tail = 16 * 8 + (int)sizeof(GramJob) + 64;
     int nst = (227 * 1024 - tail) / stage;
     if (nst > 8) nst = 8;
@@ -613,30 +713,36 @@ int gram_tma_plan(int mfrag, int nmom, int Ne, int* brows_alloc, int* nstages, i
     return 0;
 }
 
-template <int MF>
+int gram_nfrag_per_tile(int algo) { return algo ? 8 : 16; }
+int gram_fwidth(int algo) { return algo ? 8 : 4; }
+
+template <int MF, int ALGO>
 static cudaError_t launch_gram_tma_mf(const GramParams& P, const GramTma& T, cudaStream_t s) {
     int rows, nst, bytes;
-    if (gram_tma_plan(MF, P.nmom, P.Ne, &rows, &nst, &bytes) != 0 || rows != T.brows_alloc || nst != T.nstages)
+    if (gram_tma_plan(ALGO, MF, P.nmom, P.Ne, &rows, &nst, &bytes) != 0 || rows != T.brows_alloc || nst != T.nstages)
         return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<MF, ALGO>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)(P.njobs * P.n_mt * P.n_nt), (unsigned)P.ksplit);
-    gram_tma_kernel<MF><<<grid, GT_THREADS, bytes, s>>>(P, T);
+    gram_tma_kernel<MF, ALGO><<<grid, GT_THREADS, bytes, s>>>(P, T);
     return cudaGetLastError();
 }
 
-cudaError_t launch_gram_tma(const GramParams& P, const GramTma& T, int mfrag, cudaStream_t s) {
+cudaError_t launch_gram_tma(const GramParams& P, const GramTma& T, int mfrag, int algo, cudaStream_t s) {
+#define EDK_TMA_CASE(M) \
+    case M: return algo ? launch_gram_tma_mf<M, 1>(P, T, s) : launch_gram_tma_mf<M, 0>(P, T, s);
     switch (mfrag) {
-        case 2: return launch_gram_tma_mf<2>(P, T, s);
-        case 4: return launch_gram_tma_mf<4>(P, T, s);
-        case 5: return launch_gram_tma_mf<5>(P, T, s);
-        case 7: return launch_gram_tma_mf<7>(P, T, s);
-        case 9: return launch_gram_tma_mf<9>(P, T, s);
-        case 10: return launch_gram_tma_mf<10>(P, T, s);
-        case 11: return launch_gram_tma_mf<11>(P, T, s);
-        case 13: return launch_gram_tma_mf<13>(P, T, s);
+        EDK_TMA_CASE(2)
+        EDK_TMA_CASE(4)
+        EDK_TMA_CASE(5)
+        EDK_TMA_CASE(7)
+        EDK_TMA_CASE(9)
+        EDK_TMA_CASE(10)
+        EDK_TMA_CASE(11)
+        EDK_TMA_CASE(13)
         default: return cudaErrorInvalidValue;
     }
+#undef EDK_TMA_CASE
 }
 
 // phase[2][nmom][Vpad] -> tiles[kstep][2][nmom][8]
@@ -668,7 +774,6 @@ int gram_pick_mfrag(int Ne) {
     return GRAM_MAX_MF;
 }
 int gram_rows_per_tile(int mfrag) { return 8 * mfrag; }
-int gram_nfrag_per_tile() { return GRAM_NT; }
 
 template <int MF>
 static cudaError_t launch_gram_mf(const GramParams& P, cudaStream_t s) {

@@ -165,10 +165,15 @@ class ElementalEngine:
         """0 = TMA producer warp (default), 1 = cp.async loader inside the MMA warps."""
         _capi.check(self.lib.edk_debug_loader(self.h, int(mode)), "edk_debug_loader")
 
+    def debug_algo(self, algo: int):
+        """1 = 3M arithmetic (default), 0 = 4M, for the TMA kernel."""
+        _capi.check(self.lib.edk_debug_algo(self.h, int(algo)), "edk_debug_algo")
+
     def query(self):
         q = lambda w: int(self.lib.edk_query(self.h, w))  # noqa: E731
         return {"hermitian_pairing": bool(q(0)), "internal_momenta": q(1), "pair_gemms_per_momentum": q(2),
-                "ksplit": q(3), "mfrag": q(4), "jobs": q(5), "tma_stages": q(6)}
+                "ksplit": q(3), "mfrag": q(4), "jobs": q(5), "tma_stages": q(6),
+                "real_mma_per_complex_block": q(7)}
 
 
 def microbench_fp64(device: int = 0):

@@ -131,8 +131,11 @@ long long edk_launch_count(const edk_handle* h);
  * edk_debug_symmetry: -1 = auto (default), 0 = contract every (left, right) pair directly,
  *   1 = force the Hermitian pairing G(L,R,p)^dagger = G(R,L,-p) (missing -p are added internally).
  * edk_debug_loader: 0 = TMA producer warp + mbarrier ring (default), 1 = cp.async ring executed by the MMA warps.
+ * edk_debug_algo: arithmetic of the TMA kernel, 1 = 3M (default: Re = T1+T2, Im = T3+T1-T2 with
+ *   T1 = Lr.Pr, T2 = Li.Pi, T3 = (Lr+Li).(Pi-Pr): three real MMAs per complex block), 0 = 4M (four).
  * edk_query: what = 0 pairing in use (0/1), 1 internal momentum count, 2 pair-GEMMs per momentum,
- *   3 split-K factor, 4 m-fragments per tile, 5 contraction jobs, 6 TMA ring depth (0 = cp.async loader).
+ *   3 split-K factor, 4 m-fragments per tile, 5 contraction jobs, 6 TMA ring depth (0 = cp.async loader),
+ *   7 real MMAs per complex block (3 or 4).
  */
 int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream);
 int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream);
@@ -140,6 +143,7 @@ int edk_debug_use_naive_gram(edk_handle* h, int on);
 int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit);
 int edk_debug_symmetry(edk_handle* h, int mode);
 int edk_debug_loader(edk_handle* h, int mode);
+int edk_debug_algo(edk_handle* h, int algo);
 int edk_query(const edk_handle* h, int what);
 
 /*

@@ -236,17 +236,22 @@ def test_dmma_tile_variants_and_split_k_agree_with_scalar_kernel(edb):
     naive = eng.calc().cpu().numpy()
     _blocks_close(naive, ref, what="scalar kernel")
     eng.debug_use_naive_gram(False)
-    for loader in (0, 1):  # 0: TMA producer warp + mbarrier ring (product path), 1: cp.async ring
+    # product path = TMA producer warp + mbarrier ring with 3M arithmetic; the 4M arithmetic and
+    # the cp.async loader are kept as cross-checks
+    for loader, algo in ((0, 1), (0, 0), (1, 0)):
         eng.debug_loader(loader)
+        eng.debug_algo(algo)
         for mfrag in (2, 4, 5, 7, 9, 10, 11, 13):
             for ksplit in (1, 3):
                 eng.debug_gram_config(mfrag, ksplit)
-                assert (eng.query()["tma_stages"] >= 2) == (loader == 0)
+                q = eng.query()
+                assert (q["tma_stages"] >= 2) == (loader == 0)
+                assert q["real_mma_per_complex_block"] == (3 if algo else 4)
                 got = eng.calc().cpu().numpy()
-                _blocks_close(got, ref, what=f"loader={loader} mfrag={mfrag} ksplit={ksplit}")
-                _blocks_close(got, naive, what=f"loader={loader} mfrag={mfrag} ksplit={ksplit} vs scalar")
+                _blocks_close(got, ref, what=f"loader={loader} algo={algo} mfrag={mfrag} ksplit={ksplit}")
+                _blocks_close(got, naive, what=f"loader={loader} algo={algo} mfrag={mfrag} ksplit={ksplit} vs scalar")
         eng.debug_gram_config(0, 24)
-        _blocks_close(eng.calc().cpu().numpy(), ref, what=f"loader={loader} ksplit=24")
+        _blocks_close(eng.calc().cpu().numpy(), ref, what=f"loader={loader} algo={algo} ksplit=24")
     with pytest.raises(ValueError):
         eng.debug_gram_config(6, 1)
 
