@@ -42,8 +42,13 @@ struct edk_handle {
     int nmom_int = 0;
     bool symmetric = false;
     int sym_request = -1;  // -1 auto, 0 off, 1 on (test hook)
-    std::vector<int> mom_user, mom_int, negidx;
+    std::vector<int> mom_user, mom_int, negidx, pmap;
+    int n_half = 0;  // the first n_half internal momenta hold one of every +-p couple (pairing mode)
     int* negidx_dev = nullptr;
+    int* pmap_dev = nullptr;
+    int2* cta_map_dev = nullptr;
+    int ncta = 0;
+    bool cta_dirty = true;
     // TMA-fed contraction (default); loader = 1 selects the cp.async kernel (A/B comparison hook)
     GramTma tma{};
     cplx* phase_tiles = nullptr;
@@ -183,7 +188,7 @@ void build_derivative_jobs(edk_handle* h) {
     }
     h->jobs_host.clear();
     h->ops_host.assign(h->nop, CombineOp{});
-    auto add_term = [](CombineOp& o, int jid, double w, int herm) {
+    auto add_term = [](CombineOp& o, int jid, double w, int herm, int half) {
         for (int k = 0; k < o.nterm; ++k)
             if (o.job[k] == jid && o.herm[k] == herm) {
                 o.weight[k] += w;
@@ -192,6 +197,7 @@ void build_derivative_jobs(edk_handle* h) {
         o.job[o.nterm] = jid;
         o.weight[o.nterm] = w;
         o.herm[o.nterm] = herm;
+        o.half[o.nterm] = half;
         ++o.nterm;
     };
     std::map<std::pair<int, int>, int> shared_job;
@@ -201,6 +207,7 @@ void build_derivative_jobs(edk_handle* h) {
         if (it != shared_job.end()) return it->second;
         GramJob j{};
         j.nseg = 1;
+        j.nmom = (h->symmetric && L == R) ? h->n_half : h->nmom_int;
         j.sign[0] = 1;
         j.L[0] = h->field(L);
         j.R[0] = h->field(R);
@@ -215,9 +222,9 @@ void build_derivative_jobs(edk_handle* h) {
         for (int n = 0; n < h->nop; ++n)
             for (const Term& t : per_op[n]) {
                 if (t.L >= t.R)
-                    add_term(h->ops_host[n], single_job(t.L, t.R), t.sign, 0);
+                    add_term(h->ops_host[n], single_job(t.L, t.R), t.sign, 0, t.L == t.R);
                 else
-                    add_term(h->ops_host[n], single_job(t.R, t.L), t.sign, 1);
+                    add_term(h->ops_host[n], single_job(t.R, t.L), t.sign, 1, 0);
             }
     } else {
         // private multi-segment jobs first (longest first helps the tail of the grid)
@@ -228,6 +235,7 @@ void build_derivative_jobs(edk_handle* h) {
         std::vector<Pending> priv;
         for (int n = 0; n < h->nop; ++n) {
             GramJob j{};
+            j.nmom = h->nmom_int;
             for (const Term& t : per_op[n]) {
                 if (uses[{t.L, t.R}] > 1) continue;
                 j.sign[j.nseg] = t.sign;
@@ -242,12 +250,12 @@ void build_derivative_jobs(edk_handle* h) {
         std::stable_sort(priv.begin(), priv.end(),
                          [](const Pending& a, const Pending& b) { return a.job.nseg > b.job.nseg; });
         for (const Pending& p : priv) {
-            add_term(h->ops_host[p.op], (int)h->jobs_host.size(), 1.0, 0);
+            add_term(h->ops_host[p.op], (int)h->jobs_host.size(), 1.0, 0, 0);
             h->jobs_host.push_back(p.job);
         }
         for (int n = 0; n < h->nop; ++n)
             for (const Term& t : per_op[n])
-                if (uses[{t.L, t.R}] > 1) add_term(h->ops_host[n], single_job(t.L, t.R), t.sign, 0);
+                if (uses[{t.L, t.R}] > 1) add_term(h->ops_host[n], single_job(t.L, t.R), t.sign, 0, 0);
     }
     // stencil schedule: every field of length < order spawns its three children
     h->hops.clear();
@@ -292,6 +300,7 @@ void build_displacement_jobs(edk_handle* h) {
     for (int k = 0; k < h->nop; ++k) {
         GramJob j{};
         j.nseg = 1;
+        j.nmom = h->nmom_int;
         j.sign[0] = 1;
         j.L[0] = h->field(0);
         j.R[0] = h->field(k);  // field k = D_k (field 0 = W0 = D_0)
@@ -306,18 +315,40 @@ void build_displacement_jobs(edk_handle* h) {
 
 int effective_algo(const edk_handle* h) { return (h->loader == 0 && !h->naive) ? h->algo : 0; }
 
-int count_n_tiles(const edk_handle* h, int algo) {
+int count_n_tiles(const edk_handle* h, int algo, int nmom_job) {
     const int fw = gram_fwidth(algo), nt = gram_nfrag_per_tile(algo);
     const int nfrag_f = (h->Ne + fw - 1) / fw;
-    return (nfrag_f * h->nmom_int + nt - 1) / nt;
+    return (nfrag_f * nmom_job + nt - 1) / nt;
+}
+
+int row_tiles(const edk_handle* h) {
+    const int rows = gram_rows_per_tile(h->mfrag);
+    return (h->Ne + rows - 1) / rows;
+}
+
+// CTA -> (job, tile inside the job).  Jobs keep their order (longest first), tiles of one job are
+// contiguous with nt fastest, so CTAs that run together share the rows of L.
+int build_cta_map(edk_handle* h) {
+    const int algo = effective_algo(h);
+    const int n_mt = row_tiles(h);
+    std::vector<int2> map;
+    for (int j = 0; j < h->njobs; ++j) {
+        const int tiles = n_mt * count_n_tiles(h, algo, h->jobs_host[j].nmom);
+        for (int t = 0; t < tiles; ++t) map.push_back(make_int2(j, t));
+    }
+    h->ncta = (int)map.size();
+    cudaFree(h->cta_map_dev);
+    h->cta_map_dev = nullptr;
+    EDK_CUDA_TRY(cudaMalloc(&h->cta_map_dev, map.size() * sizeof(int2)));
+    EDK_CUDA_TRY(cudaMemcpy(h->cta_map_dev, map.data(), map.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    return EDK_OK;
 }
 
 void pick_gram_config(edk_handle* h) {
+    h->cta_dirty = true;
     h->mfrag = h->force_mfrag ? h->force_mfrag : gram_pick_mfrag(h->Ne);
-    const int rows = gram_rows_per_tile(h->mfrag);
-    const int n_mt = (h->Ne + rows - 1) / rows;
-    const int n_nt = count_n_tiles(h, effective_algo(h));
-    const long long tiles = (long long)h->njobs * n_mt * n_nt;
+    long long tiles = 0;
+    for (const auto& j : h->jobs_host) tiles += (long long)row_tiles(h) * count_n_tiles(h, effective_algo(h), j.nmom);
     const int ksteps = h->g.Vpad / 8;
     int ks = 1;
     if (!h->force_ksplit) {
@@ -396,16 +427,24 @@ int configure(edk_handle* h) {
     const int nmom = h->nmom;
     h->mom_int = h->mom_user;
     h->symmetric = false;
+    h->pmap.resize(nmom);
+    for (int i = 0; i < nmom; ++i) h->pmap[i] = i;
     if (h->mode == EDK_MODE_DERIVATIVE && h->order >= 1 && h->sym_request != 0) {
-        std::vector<int> ext = h->mom_user;
-        auto find = [&](int px, int py, int pz) {
-            for (size_t i = 0; i < ext.size() / 3; ++i)
-                if (ext[3 * i] == px && ext[3 * i + 1] == py && ext[3 * i + 2] == pz) return (int)i;
+        // distinct momenta of the caller plus any missing negatives
+        std::vector<int> ext;
+        auto find = [&](const std::vector<int>& v, int px, int py, int pz) {
+            for (size_t i = 0; i < v.size() / 3; ++i)
+                if (v[3 * i] == px && v[3 * i + 1] == py && v[3 * i + 2] == pz) return (int)i;
             return -1;
         };
         for (int i = 0; i < nmom; ++i) {
-            const int px = -h->mom_user[3 * i], py = -h->mom_user[3 * i + 1], pz = -h->mom_user[3 * i + 2];
-            if (find(px, py, pz) < 0) {
+            const int* m = &h->mom_user[3 * i];
+            if (find(ext, m[0], m[1], m[2]) < 0) ext.insert(ext.end(), m, m + 3);
+        }
+        const size_t nuser_distinct = ext.size() / 3;
+        for (size_t i = 0; i < nuser_distinct; ++i) {
+            const int px = -ext[3 * i], py = -ext[3 * i + 1], pz = -ext[3 * i + 2];
+            if (find(ext, px, py, pz) < 0) {
                 ext.push_back(px);
                 ext.push_back(py);
                 ext.push_back(pz);
@@ -417,10 +456,26 @@ int configure(edk_handle* h) {
         const long long cost_plain = (long long)plain * nmom;
         if (h->sym_request == 1 || cost_sym < cost_plain) {
             h->symmetric = true;
-            h->mom_int = ext;
+            // internal order: one representative of every {p, -p} couple first (self-conjugate p = 0
+            // included), then the partners, so that self pairs only contract the first half
+            std::vector<int> reps, partners;
+            for (size_t i = 0; i < ext.size() / 3; ++i) {
+                const int px = ext[3 * i], py = ext[3 * i + 1], pz = ext[3 * i + 2];
+                if (find(reps, px, py, pz) >= 0 || find(partners, px, py, pz) >= 0) continue;
+                reps.insert(reps.end(), {px, py, pz});
+                if (px != 0 || py != 0 || pz != 0) partners.insert(partners.end(), {-px, -py, -pz});
+            }
+            h->n_half = (int)reps.size() / 3;
+            h->mom_int = reps;
+            h->mom_int.insert(h->mom_int.end(), partners.begin(), partners.end());
+            for (int i = 0; i < nmom; ++i) {
+                const int* m = &h->mom_user[3 * i];
+                h->pmap[i] = find(h->mom_int, m[0], m[1], m[2]);
+            }
         }
     }
     h->nmom_int = (int)h->mom_int.size() / 3;
+    if (!h->symmetric) h->n_half = h->nmom_int;
     h->negidx.assign(h->nmom_int, -1);
     for (int i = 0; i < h->nmom_int; ++i)
         for (int j = 0; j < h->nmom_int; ++j)
@@ -429,6 +484,8 @@ int configure(edk_handle* h) {
                 h->negidx[i] = j;
                 break;
             }
+    if (!h->symmetric)
+        for (int i = 0; i < h->nmom_int; ++i) h->negidx[i] = i;  // never dereferenced meaningfully without pairing
     if (h->mode == EDK_MODE_DERIVATIVE)
         build_derivative_jobs(h);
     else
@@ -441,7 +498,9 @@ int configure(edk_handle* h) {
     cudaFree(h->jobs_dev);
     cudaFree(h->ops_dev);
     cudaFree(h->negidx_dev);
+    cudaFree(h->pmap_dev);
     cudaFree(h->partial);
+    h->pmap_dev = nullptr;
     h->phase = nullptr;
     h->jobs_dev = nullptr;
     h->ops_dev = nullptr;
@@ -468,6 +527,8 @@ int configure(edk_handle* h) {
     EDK_CUDA_TRY(cudaMemcpy(h->jobs_dev, h->jobs_host.data(), h->jobs_host.size() * sizeof(GramJob), cudaMemcpyHostToDevice));
     EDK_CUDA_TRY(cudaMemcpy(h->ops_dev, h->ops_host.data(), h->ops_host.size() * sizeof(CombineOp), cudaMemcpyHostToDevice));
     EDK_CUDA_TRY(cudaMemcpy(h->negidx_dev, h->negidx.data(), nm * sizeof(int), cudaMemcpyHostToDevice));
+    EDK_CUDA_TRY(cudaMalloc(&h->pmap_dev, (size_t)h->nmom * sizeof(int)));
+    EDK_CUDA_TRY(cudaMemcpy(h->pmap_dev, h->pmap.data(), (size_t)h->nmom * sizeof(int), cudaMemcpyHostToDevice));
     pick_gram_config(h);
     {
         const int rc = build_tma(h);
@@ -493,10 +554,16 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     P.ksteps = h->g.Vpad / 8;
     P.Vpad = h->g.Vpad;
     P.ksplit = h->naive ? 1 : h->ksplit;
-    const int rows = gram_rows_per_tile(h->mfrag);
-    P.n_mt = (h->Ne + rows - 1) / rows;
+    P.n_mt = row_tiles(h);
     const bool use_tma = !h->naive && h->loader == 0 && h->tma_ready;
-    P.n_nt = count_n_tiles(h, use_tma ? h->algo : 0);
+    P.n_nt = 0;
+    if (h->cta_dirty) {
+        const int rc = build_cta_map(h);
+        if (rc != EDK_OK) return rc;
+        h->cta_dirty = false;
+    }
+    P.cta_map = h->cta_map_dev;
+    P.ncta = h->ncta;
     P.phase = h->phase;
     P.partial = h->partial;
     {
@@ -510,8 +577,8 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     }
     {
         PhaseTimer t(h, s, PH_COMBINE, 1);
-        EDK_CUDA_TRY(launch_combine(h->ops_dev, h->nop, h->partial, h->njobs, P.ksplit, h->nmom_int, h->nmom, h->negidx_dev,
-                                    h->Ne, h->have_coeff ? h->coeff : nullptr, out, s));
+        EDK_CUDA_TRY(launch_combine(h->ops_dev, h->nop, h->partial, h->njobs, P.ksplit, h->nmom_int, h->nmom, h->pmap_dev,
+                                    h->negidx_dev, h->n_half, h->Ne, h->have_coeff ? h->coeff : nullptr, out, s));
     }
     return EDK_OK;
 }
@@ -617,6 +684,8 @@ int edk_destroy(edk_handle* h) {
     cudaFree(h->jobs_dev);
     cudaFree(h->ops_dev);
     cudaFree(h->negidx_dev);
+    cudaFree(h->pmap_dev);
+    cudaFree(h->cta_map_dev);
     cudaFree(h->phase_tiles);
     cudaFree(h->stage_U);
     cudaFree(h->stage_V);
@@ -826,6 +895,7 @@ int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream) {
 int edk_debug_use_naive_gram(edk_handle* h, int on) {
     if (!h) return EDK_ERR_ARG;
     h->naive = on != 0;
+    h->cta_dirty = true;
     return EDK_OK;
 }
 
@@ -890,6 +960,12 @@ int edk_query(const edk_handle* h, int what) {
         case 5: return h->njobs;
         case 6: return (h->loader == 0 && h->tma_ready) ? h->tma.nstages : 0;
         case 7: return effective_algo(h) ? 3 : 4;
+        case 8: {  // (pair, momentum) GEMMs actually contracted
+            int n = 0;
+            for (const auto& j : h->jobs_host) n += j.nseg * j.nmom;
+            return n;
+        }
+        case 9: return h->n_half;
         default: return EDK_ERR_ARG;
     }
 }

@@ -38,6 +38,7 @@ struct Geom {
 #define EDK_MAX_SEG 8
 struct GramJob {
     int nseg;
+    int nmom;                    // momenta contracted by this job: the first nmom of the internal list
     int sign[EDK_MAX_SEG];
     int Lf[EDK_MAX_SEG];         // field indices (third TMA coordinate) of L and R
     int Rf[EDK_MAX_SEG];
@@ -55,7 +56,9 @@ struct GramParams {
     int Vpad;     // row stride of the phase table
     int ksplit;   // split-K factor
     int n_mt;     // tiles along e (rows)
-    int n_nt;     // tiles along the flattened (f-fragment, momentum) axis
+    int n_nt;     // unused by the kernels (tiles per job vary with the job's momentum count)
+    int ncta;     // CTAs per split = entries of cta_map
+    const int2* cta_map;  // per CTA: (job, tile index inside the job = mt * n_nt(job) + nt)
     const cplx* phase;  // [2][nmom][Vpad]: phase, then -i*phase
     cplx* partial;      // [ksplit][njobs][nmom][Ne][Ne]
 };
@@ -75,10 +78,13 @@ struct GramTma {
 //   X = partial[split][job][p]                        (herm = 0)
 //   X = partial[split][job][index of -p]^dagger        (herm = 1: G(L,R,p) = G(R,L,-p)^dagger)
 #define EDK_MAX_TERMS 8
+//   half = 1: the job is a self pair (L == R) contracted only for the first n_half momenta of the
+//   internal list (one of every +-p couple); the other momenta are read as G(L,L,-p)^dagger.
 struct CombineOp {
     int nterm;
     int job[EDK_MAX_TERMS];
     int herm[EDK_MAX_TERMS];
+    int half[EDK_MAX_TERMS];
     double weight[EDK_MAX_TERMS];
 };
 
@@ -108,7 +114,8 @@ int gram_pick_mfrag(int Ne);
 int gram_rows_per_tile(int mfrag);
 int gram_nfrag_per_tile(int algo);
 cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom_int,
-                           int nmom_out, const int* negidx, int Ne, const double* coeff, cplx* out, cudaStream_t s);
+                           int nmom_out, const int* pmap, const int* negidx, int n_half, int Ne, const double* coeff, cplx* out,
+                           cudaStream_t s);
 // microbench
 cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops);
 

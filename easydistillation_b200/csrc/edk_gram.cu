@@ -162,11 +162,8 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, kk = lane & 3;
 
-    int bid = blockIdx.x;
-    const int nt = bid % P.n_nt;
-    bid /= P.n_nt;
-    const int mt = bid % P.n_mt;
-    const int job_id = bid / P.n_mt;
+    const int2 cta = P.cta_map[blockIdx.x];
+    const int job_id = cta.x;
     const int split = blockIdx.y;
 
     if (tid < (int)(sizeof(GramJob) / sizeof(int))) {
@@ -176,9 +173,11 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
     const int nseg = sjob->nseg;
 
     // ---- column bookkeeping -------------------------------------------------------------
-    const int Ne = P.Ne, nmom = P.nmom;
+    const int Ne = P.Ne, nmom = sjob->nmom;  // this job's momenta (a prefix of the internal list)
     const int nfrag_f = (Ne + 3) >> 2;
     const int N_flat = nfrag_f * nmom;
+    const int n_nt = (N_flat + GRAM_NT - 1) / GRAM_NT;
+    const int mt = cta.y / n_nt, nt = cta.y - mt * n_nt;
     const int nflat0 = nt * GRAM_NT;
     const int nflat_last = min(nflat0 + GRAM_NT, N_flat) - 1;
     const int ff0 = nflat0 / nmom;
@@ -233,7 +232,7 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
     {
         const int t2 = tid & (GRAM_NT * 8 - 1);
         const int nf = min(nflat0 + (t2 >> 3), N_flat - 1);
-        ph_src = P.phase + ((size_t)(tid >> 7) * nmom + (nf % nmom)) * P.Vpad + (t2 & 7);
+        ph_src = P.phase + ((size_t)(tid >> 7) * P.nmom + (nf % nmom)) * P.Vpad + (t2 & 7);
     }
     const uint32_t ph_dst0 = (uint32_t)(S::A_BYTES + S::B_BYTES + tid * 16);
 
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(GRAM_NTHREADS, 1) gram_dmma_kernel(const GramP
 
     // ---- epilogue: lane holds C[e = row0+8i+g][f = 4*ffrag+kk] = (re, im) ------------------------
     const double fs = (double)cur_sign;
-    cplx* outj = P.partial + ((size_t)split * P.njobs + job_id) * (size_t)nmom * Ne * Ne;
+    cplx* outj = P.partial + ((size_t)split * P.njobs + job_id) * (size_t)P.nmom * Ne * Ne;
 #pragma unroll
     for (int n = 0; n < GRAM_NF; ++n) {
         const int f = 4 * my_ffrag[n] + kk;
@@ -483,11 +482,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, kk = lane & 3;
 
-    int bid = blockIdx.x;
-    const int nt = bid % P.n_nt;
-    bid /= P.n_nt;
-    const int mt = bid % P.n_mt;
-    const int job_id = bid / P.n_mt;
+    const int2 cta = P.cta_map[blockIdx.x];
+    const int job_id = cta.x;
     const int split = blockIdx.y;
 
     if (tid < (int)(sizeof(GramJob) / sizeof(int))) {
@@ -503,9 +499,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     __syncthreads();
     const int nseg = sjob->nseg;
 
-    const int Ne = P.Ne, nmom = P.nmom;
+    const int Ne = P.Ne, nmom = sjob->nmom;  // this job's momenta (a prefix of the internal list)
     const int nfrag_f = (Ne + C::FW - 1) / C::FW;
     const int N_flat = nfrag_f * nmom;
+    const int n_nt = (N_flat + C::NT - 1) / C::NT;
+    const int mt = cta.y / n_nt, nt = cta.y - mt * n_nt;
     const int nflat0 = nt * C::NT;
     const int nflat_last = min(nflat0 + C::NT, N_flat) - 1;
     const int ff0 = nflat0 / nmom;
@@ -571,7 +569,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
             }
             if (lane < C::NTAB * nruns) {
                 // table 0 = phase, table 1 = -i*phase (global tile layout [kstep][2][nmom][8])
-                const cplx* src = Tm.phase_tiles + (((size_t)kstep * 2 + run_tab) * nmom + run_p) * 8;
+                const cplx* src = Tm.phase_tiles + (((size_t)kstep * 2 + run_tab) * P.nmom + run_p) * 8;
                 bulk_load(st + A_BYTES + GRAM_KG * b_kg_stride + (run_tab * C::NT + run_slot) * 128, src, run_len * 128, full);
             }
             if (++kstep == P.ksteps) {
@@ -656,7 +654,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     }
 
     const double fs = (double)cur_sign;
-    cplx* outj = P.partial + ((size_t)split * P.njobs + job_id) * (size_t)nmom * Ne * Ne;
+    cplx* outj = P.partial + ((size_t)split * P.njobs + job_id) * (size_t)P.nmom * Ne * Ne;
     if constexpr (ALGO == 0) {
         // lane holds C[e = row0+8i+g][f = 4*ffrag+kk] = (re, im)
 #pragma unroll
@@ -723,7 +721,7 @@ static cudaError_t launch_gram_tma_mf(const GramParams& P, const GramTma& T, cud
         return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<MF, ALGO>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)(P.njobs * P.n_mt * P.n_nt), (unsigned)P.ksplit);
+    dim3 grid((unsigned)P.ncta, (unsigned)P.ksplit);
     gram_tma_kernel<MF, ALGO><<<grid, GT_THREADS, bytes, s>>>(P, T);
     return cudaGetLastError();
 }
@@ -783,7 +781,7 @@ static cudaError_t launch_gram_mf(const GramParams& P, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
     (void)configured;
-    dim3 grid((unsigned)(P.njobs * P.n_mt * P.n_nt), (unsigned)P.ksplit);
+    dim3 grid((unsigned)P.ncta, (unsigned)P.ksplit);
     gram_dmma_kernel<MF><<<grid, GRAM_NTHREADS, S::TOTAL, s>>>(P);
     return cudaGetLastError();
 }
@@ -818,7 +816,7 @@ __global__ void gram_naive_kernel(const GramParams P) {
     const GramJob& job = P.jobs[job_id];
     double sr = 0.0, si = 0.0;
     const int V = P.Kc / 3;
-    for (int s = 0; s < job.nseg; ++s) {
+    for (int s = 0; s < (p < job.nmom ? job.nseg : 0); ++s) {
         const cplx* L = job.L[s] + (size_t)e * P.Kc;
         const cplx* R = job.R[s] + (size_t)f * P.Kc;
         double tr = 0.0, ti = 0.0;
@@ -850,23 +848,30 @@ cudaError_t launch_gram_naive(const GramParams& P, cudaStream_t s) {
 // (the caller's momenta are the first nmom_out entries of the internal list of nmom_int)
 // ---------------------------------------------------------------------------------------
 __global__ void combine_kernel(const CombineOp* __restrict__ ops, int nop, const cplx* __restrict__ partial, int njobs,
-                               int ksplit, int nmom_int, int nmom_out, const int* __restrict__ negidx, int Ne,
-                               const double* __restrict__ coeff, cplx* __restrict__ out) {
+                               int ksplit, int nmom_int, int nmom_out, const int* __restrict__ pmap,
+                               const int* __restrict__ negidx, int n_half, int Ne, const double* __restrict__ coeff,
+                               cplx* __restrict__ out) {
     const size_t mat = (size_t)Ne * Ne;
     const size_t per_op = (size_t)nmom_out * mat;
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= per_op * nop) return;
     const int op = (int)(idx / per_op);
     size_t r = idx - (size_t)op * per_op;
-    const int p = (int)(r / mat);
-    r -= (size_t)p * mat;
+    const int p_out = (int)(r / mat);
+    r -= (size_t)p_out * mat;
     const int e = (int)(r / Ne), f = (int)(r - (size_t)e * Ne);
+    const int p = pmap[p_out];  // internal index of the caller's momentum
     const CombineOp& o = ops[op];
     const size_t per_job = (size_t)nmom_int * mat;
     double sr = 0.0, si = 0.0;
     for (int t = 0; t < o.nterm; ++t) {
-        const bool herm = o.herm[t] != 0;
-        const size_t off = herm ? (size_t)negidx[p] * mat + (size_t)f * Ne + e : (size_t)p * mat + r;
+        bool herm = o.herm[t] != 0;
+        int q = herm ? negidx[p] : p;
+        if (o.half[t] && q >= n_half) {  // self pair kept for one momentum of each +-p couple only
+            q = negidx[q];
+            herm = !herm;
+        }
+        const size_t off = (size_t)q * mat + (herm ? (size_t)f * Ne + e : r);
         double tr = 0.0, ti = 0.0;
         for (int s = 0; s < ksplit; ++s) {
             const cplx v = partial[((size_t)s * njobs + o.job[t]) * per_job + off];
@@ -885,10 +890,11 @@ __global__ void combine_kernel(const CombineOp* __restrict__ ops, int nop, const
 }
 
 cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom_int,
-                           int nmom_out, const int* negidx, int Ne, const double* coeff, cplx* out, cudaStream_t s) {
+                           int nmom_out, const int* pmap, const int* negidx, int n_half, int Ne, const double* coeff, cplx* out,
+                           cudaStream_t s) {
     const size_t n = (size_t)nop * nmom_out * Ne * Ne;
-    combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ops_dev, nop, partial, njobs, ksplit, nmom_int, nmom_out, negidx,
-                                                               Ne, coeff, out);
+    combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ops_dev, nop, partial, njobs, ksplit, nmom_int, nmom_out, pmap,
+                                                               negidx, n_half, Ne, coeff, out);
     return cudaGetLastError();
 }
 

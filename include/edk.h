@@ -135,7 +135,8 @@ long long edk_launch_count(const edk_handle* h);
  *   T1 = Lr.Pr, T2 = Li.Pi, T3 = (Lr+Li).(Pi-Pr): three real MMAs per complex block), 0 = 4M (four).
  * edk_query: what = 0 pairing in use (0/1), 1 internal momentum count, 2 pair-GEMMs per momentum,
  *   3 split-K factor, 4 m-fragments per tile, 5 contraction jobs, 6 TMA ring depth (0 = cp.async loader),
- *   7 real MMAs per complex block (3 or 4).
+ *   7 real MMAs per complex block (3 or 4), 8 number of (pair, momentum) GEMMs contracted per timeslice
+ *   (self pairs L == R only run one momentum of every +-p couple), 9 size of that half set.
  */
 int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream);
 int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream);

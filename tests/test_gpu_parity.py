@@ -287,6 +287,9 @@ def test_hermitian_pairing_and_direct_pairs_agree_with_oracle(edb, nabla):
             if nabla in expected_pairs:
                 assert q["pair_gemms_per_momentum"] == expected_pairs[nabla][mode]
             assert q["internal_momenta"] == (len(moms) if (closed or not mode) else len(moms) + 2)
+            if mode and closed and nabla == 2:
+                # 4 self pairs run only p = 0 and one of each +-p couple (4 of 7 momenta)
+                assert q["half_set_momenta"] == 4 and q["pair_momentum_gemms"] == 15 * 7 + 4 * 4
             _blocks_close(eng.calc().cpu().numpy(), ref, what=f"nabla={nabla} pairing={mode} closed={closed}")
 
 
