@@ -150,14 +150,13 @@ cudaError_t launch_phase_table(cplx* phase, cplx* rot, const int* mom3_dev, int 
 constexpr int NABLA_SITES = 64;   // sites per CTA (threadIdx.x), threadIdx.y = direction
 constexpr int NABLA_THREADS = NABLA_SITES * 3;
 constexpr int NABLA_EB = 16;      // eigenvectors per CTA
-constexpr int NABLA_STAGES = 4;
-constexpr int NABLA_SMEM = NABLA_STAGES * 6 * NABLA_THREADS * (int)sizeof(cplx);
 
 __device__ __forceinline__ void cp_async_ca16(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
 }
 
-__global__ void __launch_bounds__(NABLA_THREADS, 2)
+template <int NABLA_STAGES, int MINB>
+__global__ void __launch_bounds__(NABLA_THREADS, MINB)
 nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restrict__ o1, cplx* __restrict__ o2,
               const cplx* __restrict__ links, Geom g, int Ne) {
     extern __shared__ __align__(16) unsigned char nabla_smem[];
@@ -230,18 +229,23 @@ nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restric
     }
 }
 
-cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
-                          cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(nabla3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NABLA_SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+template <int STAGES, int MINB>
+static cudaError_t launch_nabla3_v(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
+                                   cudaStream_t s) {
+    constexpr int SMEM = STAGES * 6 * NABLA_THREADS * (int)sizeof(cplx);
+    cudaError_t e = cudaFuncSetAttribute(nabla3_kernel<STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
     dim3 block(NABLA_SITES, 3);
     dim3 grid((g.V + NABLA_SITES - 1) / NABLA_SITES, (Ne + NABLA_EB - 1) / NABLA_EB);
-    nabla3_kernel<<<grid, block, NABLA_SMEM, s>>>(W_in, out_x, out_y, out_z, links, g, Ne);
+    nabla3_kernel<STAGES, MINB><<<grid, block, SMEM, s>>>(W_in, out_x, out_y, out_z, links, g, Ne);
     return cudaGetLastError();
+}
+
+cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
+                          cudaStream_t s) {
+    // measured on B200 (32^3, Ne=200): 4 stages x 2 CTAs/SM 3.99 TB/s; 3 stages 3.96; 2 stages 3.26;
+    // 6 stages 2.99 and 3 CTAs/SM 2.41 (their shared memory eats the L1 that serves the x/y reuse)
+    return launch_nabla3_v<4, 2>(W_in, out_x, out_y, out_z, links, g, Ne, s);
 }
 
 // ---------------------------------------------------------------------------------------
