@@ -31,6 +31,8 @@ SIGNATURES = {
     "edk_workspace_bytes": (_sz, [_vp]),
     "edk_set_links": (_i, [_vp, _vp, _i, _vp]),
     "edk_set_eigvecs": (_i, [_vp, _vp, _i, _vp]),
+    "edk_set_link_ops": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), _dp]),
+    "edk_debug_links": (_i, [_vp, _vp, _vp]),
     "edk_set_blending": (_i, [_vp, _vp, _vp]),
     "edk_calc": (_i, [_vp, _vp, _vp]),
     "edk_calc_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),

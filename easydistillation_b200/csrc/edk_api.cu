@@ -58,6 +58,13 @@ struct edk_handle {
     size_t field_cplx;  // Ne * V * 3
     // device buffers
     cplx* links = nullptr;    // [3][V][9]
+    cplx* links_tmp = nullptr;  // second buffer for the stout ping-pong (allocated on first use)
+    struct LinkOp {
+        int kind;  // 1 = stout(nstep, rho), 2 = project_SU3
+        int nstep;
+        double rho;
+    };
+    std::vector<LinkOp> link_ops;  // applied, in order, to every timeslice's links after upload
     cplx* fields = nullptr;   // nfield fields
     int nfield = 0;
     cplx* lines = nullptr;    // displacement: 12 line buffers (ping-pong)
@@ -676,6 +683,7 @@ int edk_destroy(edk_handle* h) {
     if (!h) return EDK_OK;
     cudaSetDevice(h->device);
     cudaFree(h->links);
+    cudaFree(h->links_tmp);
     cudaFree(h->fields);
     cudaFree(h->lines);
     cudaFree(h->phase);
@@ -735,9 +743,49 @@ int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream) {
         return EDK_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    PhaseTimer t(h, s, PH_PREP, 1);
-    EDK_CUDA_TRY(launch_reorder_links((const cplx*)U_dev, layout, h->links, h->g, s));
+    {
+        PhaseTimer t(h, s, PH_PREP, 1);
+        EDK_CUDA_TRY(launch_reorder_links((const cplx*)U_dev, layout, h->links, h->g, s));
+    }
+    for (const auto& op : h->link_ops) {
+        if (op.kind == 2) {
+            PhaseTimer t(h, s, PH_PREP, 1);
+            EDK_CUDA_TRY(launch_project_su3(h->links, h->g, s));
+        } else {
+            if (!h->links_tmp) EDK_CUDA_TRY(cudaMalloc(&h->links_tmp, (size_t)3 * h->g.V * 9 * sizeof(cplx)));
+            for (int i = 0; i < op.nstep; ++i) {
+                PhaseTimer t(h, s, PH_PREP, 1);
+                EDK_CUDA_TRY(launch_stout_step(h->links, h->links_tmp, op.rho, h->g, s));
+                std::swap(h->links, h->links_tmp);
+            }
+        }
+    }
     h->links_set = true;
+    return EDK_OK;
+}
+
+int edk_set_link_ops(edk_handle* h, int nops, const int* kinds, const int* nsteps, const double* rhos) {
+    if (!h || nops < 0 || (nops > 0 && (!kinds || !nsteps || !rhos))) {
+        set_error("edk_set_link_ops: bad argument");
+        return EDK_ERR_ARG;
+    }
+    std::vector<edk_handle::LinkOp> ops;
+    for (int i = 0; i < nops; ++i) {
+        if ((kinds[i] != 1 && kinds[i] != 2) || (kinds[i] == 1 && nsteps[i] < 0)) {
+            set_error("edk_set_link_ops: op %d is neither stout (1, nstep >= 0) nor project (2)", i);
+            return EDK_ERR_ARG;
+        }
+        ops.push_back({kinds[i], nsteps[i], rhos[i]});
+    }
+    h->link_ops = ops;
+    h->links_set = false;  // links already on the device were processed with the old list
+    return EDK_OK;
+}
+
+int edk_debug_links(edk_handle* h, void* dst_dev, void* stream) {
+    if (!h || !dst_dev) return EDK_ERR_ARG;
+    EDK_CUDA_TRY(cudaMemcpyAsync(dst_dev, h->links, (size_t)3 * h->g.V * 9 * sizeof(cplx), cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream));
     return EDK_OK;
 }
 

@@ -93,6 +93,20 @@ class ElementalEngine:
         _capi.check(self.lib.edk_set_eigvecs(self.h, _ptr(Vt), int(Vt.dtype == torch.complex64), self._stream()),
                     "edk_set_eigvecs")
 
+    def set_link_ops(self, ops):
+        """ops: list of ("stout", nstep, rho) / ("project",) applied to every timeslice's links."""
+        n = len(ops)
+        kinds = (C.c_int * max(n, 1))(*[1 if o[0] == "stout" else 2 for o in ops])
+        nsteps = (C.c_int * max(n, 1))(*[int(o[1]) if o[0] == "stout" else 0 for o in ops])
+        rhos = (C.c_double * max(n, 1))(*[float(o[2]) if o[0] == "stout" else 0.0 for o in ops])
+        _capi.check(self.lib.edk_set_link_ops(self.h, n, kinds, nsteps, rhos), "edk_set_link_ops")
+
+    def debug_links(self):
+        Lx, Ly, Lz = self.latt3
+        out = self.torch.empty((3, Lz, Ly, Lx, 3, 3), dtype=self.torch.complex128, device=self.device)
+        _capi.check(self.lib.edk_debug_links(self.h, _ptr(out), self._stream()), "edk_debug_links")
+        return out
+
     def set_blending(self, coeff):
         if coeff is None:
             _capi.check(self.lib.edk_set_blending(self.h, None, self._stream()))

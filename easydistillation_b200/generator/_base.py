@@ -33,9 +33,14 @@ class _TimesliceGenerator:
         self._VPV_pinned = _capi.PinnedBuffer(self._engine.out_shape, np.complex128)
         self._VPV = self._VPV_pinned.array
         self._V_pinned = None
+        self._pipeline = None
+        self._gauge_ops = []
 
     # ---- load(key): reference elemental.py:102-105 / displacement_elemental.py:73-76 -------------
     def load(self, key: str):
+        if self._gauge_ops:  # a freshly loaded configuration is unsmeared, as in the reference
+            self._gauge_ops = []
+            self._engine.set_link_ops([])
         data = self.gauge_field.load(key)
         U = data[:]
         torch = self._engine.torch
@@ -115,9 +120,23 @@ class _TimesliceGenerator:
         return eng.calc(out)
 
     # ---- batch / sharded form (each rank owns a contiguous t-range) -------------------
+    def _host_inputs(self) -> bool:
+        torch = self._engine.torch
+        return not isinstance(self._U, torch.Tensor) and not isinstance(self._eigenvector_data, torch.Tensor)
+
     def calc_range(self, t0: int, t1: int) -> np.ndarray:
-        """(t1-t0, Nop, Nmom, Ne, Ne) for t in [t0, t1)."""
-        out = np.empty((t1 - t0,) + self._engine.out_shape, np.complex128)
+        """(t1-t0, Nop, Nmom, Ne, Ne) for t in [t0, t1).  Host-resident inputs go through the
+        streamed pipeline: upload of t+1 and download of t-1 overlap the kernels of t."""
+        self._check_loaded(t0)
+        if t1 > t0:
+            self._check_loaded(t1 - 1)
+        out = np.empty((max(t1 - t0, 0),) + self._engine.out_shape, np.complex128)
+        if self._host_inputs():
+            from ..pipeline import TimeslicePipeline
+
+            if self._pipeline is None:
+                self._pipeline = TimeslicePipeline(self)
+            return self._pipeline.run_host(range(t0, t1), out)
         for i, t in enumerate(range(t0, t1)):
             out[i] = self.calc(t)
         return out
@@ -133,13 +152,31 @@ class _TimesliceGenerator:
         t0, t1 = timeslice_range(Lt, rank, size)
         torch = self._engine.torch
         local = torch.empty((t1 - t0,) + self._engine.out_shape, dtype=torch.complex128, device=self._engine.device)
-        for i, t in enumerate(range(t0, t1)):
-            self.calc_device(t, out=local[i])
+        if self._host_inputs():
+            from ..pipeline import TimeslicePipeline
+
+            if self._pipeline is None:
+                self._pipeline = TimeslicePipeline(self)
+            self._pipeline.run_device(range(t0, t1), local)
+        else:
+            for i, t in enumerate(range(t0, t1)):
+                self.calc_device(t, out=local[i])
         return gather_timeslices(local, Lt, group=group, dst=dst)
 
-    # ---- gauge preprocessing hooks of the reference classes (not built yet) --------
+    # ---- gauge preprocessing of the reference classes -----------------------------
+    # The reference rewrites the whole loaded configuration at once (elemental.py:107-117,264-277).
+    # Spatial smearing / projection never couple timeslices, so here the request is recorded and the
+    # sm_100a kernels process each timeslice's links on the device right after they are uploaded.
     def stout_smear(self, nstep, rho):
-        raise NotImplementedError("stout smearing is outside the round-1 hot path (SURVEY.md section 8f, N2)")
+        if self._U is None:
+            raise RuntimeError("call load(key) before stout_smear")
+        if nstep < 0:
+            raise ValueError("nstep must be >= 0")
+        self._gauge_ops.append(("stout", int(nstep), float(rho)))
+        self._engine.set_link_ops(self._gauge_ops)
 
     def project_SU3(self):
-        raise NotImplementedError("SU(3) projection is outside the round-1 hot path (SURVEY.md section 8f, N2)")
+        if self._U is None:
+            raise RuntimeError("call load(key) before project_SU3")
+        self._gauge_ops.append(("project",))
+        self._engine.set_link_ops(self._gauge_ops)

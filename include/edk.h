@@ -83,6 +83,17 @@ size_t edk_workspace_bytes(const edk_handle* h);
 int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream);
 int edk_set_eigvecs(edk_handle* h, const void* V_dev, int is_c8, void* stream);
 
+/*
+ * Gauge preprocessing of the reference classes, applied on the device to the links of every
+ * timeslice right after edk_set_links / inside edk_calc_host, in the order given:
+ *   kinds[i] = 1: stout_smear(nsteps[i], rhos[i])  spatial links only, 3-d staples
+ *                 (lattice/generator/elemental.py:175-277, lattice/generator/stout_smear.cu:159-245)
+ *   kinds[i] = 2: project_SU3()                    X <- (X + X^-dagger)/2 to 1e-15 (elemental.py:107-117)
+ * nops = 0 clears the list.  (Spatial smearing never couples timeslices, so per-timeslice
+ * application equals the reference's whole-configuration call after load().)
+ */
+int edk_set_link_ops(edk_handle* h, int nops, const int* kinds, const int* nsteps, const double* rhos);
+
 /* optional real [Ne][Ne] "blending" matrix multiplied into every output block
  * (stocastic_coeff, elemental.py:61-100,331-337); NULL clears it. Device pointer, copied. */
 int edk_set_blending(edk_handle* h, const double* coeff_dev, void* stream);
@@ -140,6 +151,7 @@ long long edk_launch_count(const edk_handle* h);
  */
 int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream);
 int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream);
+int edk_debug_links(edk_handle* h, void* dst_dev, void* stream); /* processed links [3][Lz][Ly][Lx][3][3] */
 int edk_debug_use_naive_gram(edk_handle* h, int on);
 int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit);
 int edk_debug_symmetry(edk_handle* h, int mode);

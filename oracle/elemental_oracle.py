@@ -219,6 +219,76 @@ def displacement_timeslice(V_t, U_t, latt_size, distance, momentum_list):
 
 
 # --------------------------------------------------------------------------
+# gauge preprocessing of the generator classes
+# --------------------------------------------------------------------------
+def _shift(A, d, step):
+    """A(x + step*d) for a one-timeslice array [Lz, Ly, Lx, ...]; d = 0(x), 1(y), 2(z)."""
+    return np.roll(A, -step, 2 - d)
+
+
+def _dag(A):
+    return np.conj(np.swapaxes(A, -1, -2))
+
+
+def exp_i_traceless_hermitian(Q):
+    """exp(iQ) for traceless Hermitian 3x3 Q by Cayley-Hamilton (Morningstar-Peardon), with the
+    same branch handling as lattice/generator/elemental.py:200-238 (c0 -> |c0| plus conjugation)."""
+    Q2 = Q @ Q
+    c0 = np.trace(Q @ Q2, axis1=-2, axis2=-1).real / 3
+    c1 = np.trace(Q2, axis1=-2, axis2=-1).real / 2
+    c0_max = 2 * (c1 / 3) ** 1.5
+    neg = c0 < 0
+    theta = np.arccos(np.abs(c0) / c0_max)
+    u = np.sqrt(c1 / 3) * np.cos(theta / 3)
+    w = np.sqrt(c1) * np.sin(theta / 3)
+    u2, w2 = u * u, w * w
+    xi0 = 1 - w2 / 6 * (1 - w2 / 20 * (1 - w2 / 42 * (1 - w2 / 72)))
+    big = np.abs(w) > 0.05
+    xi0[big] = np.sin(w[big]) / w[big]
+    e2, em = np.exp(2j * u), np.exp(-1j * u)
+    den = 1 / (9 * u2 - w2)
+    f0 = ((u2 - w2) * e2 + em * (8 * u2 * np.cos(w) + 2j * u * (3 * u2 + w2) * xi0)) * den
+    f1 = (2 * u * e2 - em * (2 * u * np.cos(w) - 1j * (3 * u2 - w2) * xi0)) * den
+    f2 = (e2 - em * (np.cos(w) + 3j * u * xi0)) * den
+    f0 = np.where(neg, np.conj(f0), f0)
+    f1 = np.where(neg, -np.conj(f1), f1)
+    f2 = np.where(neg, np.conj(f2), f2)
+    return f0[..., None, None] * np.eye(3) + f1[..., None, None] * Q + f2[..., None, None] * Q2
+
+
+def stout_smear_timeslice(U_t, nstep, rho):
+    """Spatial stout smearing of one timeslice U_t[d, z, y, x, a, b] (elemental.py:175-241; the
+    three spatial directions never couple different timeslices)."""
+    U = np.array(U_t, dtype=np.complex128)
+    for _ in range(nstep):
+        new = np.empty_like(U)
+        for mu in range(3):
+            C = np.zeros_like(U[mu])
+            for nu in range(3):
+                if nu == mu:
+                    continue
+                C += U[nu] @ _shift(U[mu], nu, 1) @ _dag(_shift(U[nu], mu, 1))
+                C += _dag(_shift(U[nu], nu, -1)) @ _shift(U[mu], nu, -1) @ _shift(_shift(U[nu], nu, -1), mu, 1)
+            Om = rho * C @ _dag(U[mu])
+            Q = 0.5j * (_dag(Om) - Om)
+            Q = Q - np.trace(Q, axis1=-2, axis2=-1)[..., None, None] * np.eye(3) / 3
+            new[mu] = exp_i_traceless_hermitian(Q) @ U[mu]
+        U = new
+    return U
+
+
+def project_su3_timeslice(U_t, max_iter=100):
+    """X <- (X + X^-dagger)/2 until X is unitary to 1e-15 (elemental.py:107-117)."""
+    U = np.array(U_t, dtype=np.complex128)
+    for _ in range(max_iter):
+        Uinv = np.linalg.inv(U)
+        if np.max(np.abs(U - _dag(Uinv))) <= 1e-15 and np.max(np.abs(U @ _dag(U) - np.eye(3))) <= 1e-15:
+            break
+        U = 0.5 * (U + _dag(Uinv))
+    return U
+
+
+# --------------------------------------------------------------------------
 # synthetic inputs (SURVEY 8d): seeded, shared by tests and bench
 # --------------------------------------------------------------------------
 SEED0 = 20261017

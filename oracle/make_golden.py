@@ -40,7 +40,8 @@ def import_reference():
     return lattice
 
 
-def run_reference(lattice, latt_size, Ne, U_file, V_file, *, num_nabla=None, distance=None, momentum_list, dilution=None):
+def run_reference(lattice, latt_size, Ne, U_file, V_file, *, num_nabla=None, distance=None, momentum_list, dilution=None,
+                  gauge_ops=(), return_links=False):
     """U_file [Lt,Lz,Ly,Lx,4,3,3] c16, V_file [Lt,Ne,Lz,Ly,Lx,3] c16 -> [Lt,Nop,Nmom,Ne,Ne]."""
     Lx, Ly, Lz, Lt = latt_size
     with tempfile.TemporaryDirectory() as tmp:
@@ -57,10 +58,16 @@ def run_reference(lattice, latt_size, Ne, U_file, V_file, *, num_nabla=None, dis
         else:
             gen = lattice.DisplacementElementalGenerator(latt_size, gauge, evec, distance, momentum_list)
         gen.load("cfg")
+        for op in gauge_ops:  # the gauge preprocessing methods of the reference classes
+            if op[0] == "stout":
+                gen.stout_smear(op[1], op[2])
+            else:
+                gen.project_SU3()
+        links = np.array(gen._U, copy=True) if return_links else None
         out = []
         for t in range(Lt):
             out.append(np.array(gen.calc(t), copy=True))
-    return np.stack(out)
+    return (np.stack(out), links) if return_links else np.stack(out)
 
 
 def main():
@@ -103,6 +110,26 @@ def main():
             **meta,
         )
         print(f"{name}: U{U_file.shape} V{V_file.shape} -> E{ref.shape}  |E|={np.linalg.norm(ref):.6e}")
+
+    # gauge preprocessing: stout smearing and the unitarity projection, on a weak
+    # field and on a slightly non-unitary one; the processed links are stored next to the elementals
+    rng = np.random.default_rng(orc.SEED0 + 99)
+    latt, Ne = [4, 4, 6, 2], 5
+    Lx, Ly, Lz, Lt = latt
+    moms = [(0, 0, 0), (1, 0, -1)]
+    U_file = np.stack([orc.synthetic_links(latt, t, "weak") for t in range(Lt)])
+    V_file = np.stack([orc.synthetic_eigvecs(latt, Ne, t) for t in range(Lt)])
+    noisy = U_file + 1e-3 * (rng.standard_normal(U_file.shape) + 1j * rng.standard_normal(U_file.shape))
+    for name, Uin, ops in (("gauge_stout_4x4x6x2", U_file, [("stout", 3, 0.1)]),
+                           ("gauge_project_4x4x6x2", noisy, [("project",)]),
+                           ("gauge_project_stout_4x4x6x2", noisy, [("project",), ("stout", 2, 0.125)])):
+        E, links = run_reference(lattice, latt, Ne, Uin, V_file, num_nabla=1, momentum_list=moms, gauge_ops=ops,
+                                 return_links=True)
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), U=Uin.astype("<c16"), V=V_file.astype("<c8"), E=E.astype("<c16"),
+                            links=links.astype("<c16"), latt_size=np.array(latt), Ne=Ne, momentum_list=np.array(moms), num_nabla=1,
+                            ops=np.array([[1 if o[0] == "stout" else 2, o[1] if len(o) > 1 else 0] for o in ops]),
+                            rhos=np.array([o[2] if len(o) > 2 else 0.0 for o in ops]))
+        print(f"{name}: links{links.shape} E{E.shape} |E|={np.linalg.norm(E):.6e}")
 
     # index-map and phase goldens straight from the reference's insertion module
     from lattice.insertion.derivative import derivative

@@ -98,6 +98,52 @@ def test_blending_matches_reference_golden(edb):
         edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]), 1, moms, None, True)
 
 
+@pytest.mark.parametrize("name", ["gauge_stout_4x4x6x2", "gauge_project_4x4x6x2", "gauge_project_stout_4x4x6x2"])
+def test_gauge_preprocessing_matches_reference_golden(edb, name):
+    """stout_smear(nstep, rho) / project_SU3() of the generator classes (the reference's only CUDA
+    kernel is the stout step): processed links and the elementals computed on them."""
+    g, latt, moms = _golden_case(name)
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]), int(g["num_nabla"]), moms)
+    gen.load("cfg")
+    for (kind, nstep), rho in zip(g["ops"], g["rhos"]):
+        if kind == 1:
+            gen.stout_smear(int(nstep), float(rho))
+        else:
+            gen.project_SU3()
+    for t in range(latt[3]):
+        E = np.array(gen.calc(t))
+        links = gen._engine.debug_links().cpu().numpy()
+        assert rel_err(links, g["links"][:, t]) < 1e-12, (name, t)
+        _blocks_close(E, g["E"][t], what=f"{name} t={t}")
+    # the displacement generator shares the preprocessing
+    dgen = edb.DisplacementElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]), 1, moms)
+    dgen.load("cfg")
+    for (kind, nstep), rho in zip(g["ops"], g["rhos"]):
+        dgen.stout_smear(int(nstep), float(rho)) if kind == 1 else dgen.project_SU3()
+    dgen.calc(1)
+    assert rel_err(dgen._engine.debug_links().cpu().numpy(), g["links"][:, 1]) < 1e-12
+    # load() starts again from the unprocessed configuration
+    gen.load("cfg")
+    gen.calc(0)
+    raw = np.moveaxis(g["U"][0], 3, 0)[:3]
+    assert rel_err(gen._engine.debug_links().cpu().numpy(), raw) == 0.0
+
+
+def test_stout_on_unit_links_is_identity(edb):
+    """Q = 0: the reference divides 0/0 here, the kernel leaves the links unchanged."""
+    orc = _orc()
+    latt, Ne = [4, 4, 4, 1], 3
+    U = np.zeros((1, 4, 4, 4, 4, 3, 3), np.complex128)
+    U[...] = np.eye(3)
+    V = orc.synthetic_eigvecs(latt, Ne, 0)[None]
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U), edb.EigenvectorHostmem(V), 1, [(0, 0, 0)])
+    gen.load("x")
+    gen.stout_smear(2, 0.1)
+    E = np.array(gen.calc(0))
+    assert np.all(np.isfinite(E))
+    assert np.array_equal(gen._engine.debug_links().cpu().numpy(), np.moveaxis(U[0], 3, 0)[:3])
+
+
 def test_calc_returns_generator_owned_buffer_and_checks_state(edb):
     g, latt, moms = _golden_case("deriv_weak_4x4x4x2")
     gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]), 1, moms[:2])
@@ -110,8 +156,9 @@ def test_calc_returns_generator_owned_buffer_and_checks_state(edb):
     assert a is b and not np.array_equal(first, b)  # overwritten, like the reference's _VPV
     with pytest.raises(IndexError):
         gen.calc(latt[3])
-    with pytest.raises(NotImplementedError):
-        gen.stout_smear(1, 0.1)
+    fresh = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]), 0, moms[:1])
+    with pytest.raises(RuntimeError):
+        fresh.stout_smear(1, 0.1)  # nothing loaded yet
 
 
 # ---------------------------------------------------------------------------------------------
@@ -330,6 +377,30 @@ def test_file_handles_and_elemental_npy_roundtrip(edb, tmp_path):
     full = gen.calc_all()
     assert tuple(full.shape) == (Lt, 13, len(moms), 8, 8)
     _blocks_close(full[0].cpu().numpy(), g["E"][0], what="calc_all")
+
+
+def test_streamed_pipeline_matches_per_timeslice_calls(edb):
+    """calc_range / calc_all overlap upload, kernels and download over double buffers: five
+    timeslices so every buffer is reused, complex128 and complex64 eigenvector sources."""
+    orc = _orc()
+    latt, Ne = [4, 4, 6, 5], 7
+    moms = orc.momentum_set(7)
+    U = np.stack([orc.synthetic_links(latt, t, "weak") for t in range(latt[3])])
+    V = np.stack([orc.synthetic_eigvecs(latt, Ne, t) for t in range(latt[3])])
+    for Vsrc in (V, V.astype(np.complex64)):
+        gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U), edb.EigenvectorHostmem(Vsrc), 2, moms)
+        gen.load("x")
+        single = np.stack([np.array(gen.calc(t)) for t in range(latt[3])])
+        ranged = gen.calc_range(0, latt[3])
+        assert np.array_equal(ranged, single)  # same kernels, same order: bit-identical
+        assert np.array_equal(gen.calc_range(1, 4), single[1:4])
+        full = gen.calc_all().cpu().numpy()
+        assert np.array_equal(full, single)
+        ref = orc.elemental_timeslice_closed_form(V[3], orc.links_file_to_spatial(U[3]), latt, 2, moms)
+        _blocks_close(ranged[3], ref, what="pipeline t=3")
+    dgen = edb.DisplacementElementalGenerator(latt, edb.GaugeFieldHostmem(U), edb.EigenvectorHostmem(V), 2, moms[:2])
+    dgen.load("x")
+    assert np.array_equal(dgen.calc_range(0, 3), np.stack([np.array(dgen.calc(t)) for t in range(3)]))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -107,3 +107,29 @@ def test_synthetic_inputs_are_seeded_and_unitary():
     m33 = orc.momentum_set(33)
     assert len(m33) == 33 and m33[0] == (0, 0, 0) and max(sum(c * c for c in p) for p in m33) == 4
     assert set(m33) == {tuple(-c for c in p) for p in m33}
+
+
+GAUGE_CASES = ["gauge_stout_4x4x6x2", "gauge_project_4x4x6x2", "gauge_project_stout_4x4x6x2"]
+
+
+def apply_gauge_ops(g, U_t):
+    """Replay the recorded gauge preprocessing (1 = stout(nstep, rho), 2 = project) with the oracle."""
+    for (kind, nstep), rho in zip(g["ops"], g["rhos"]):
+        U_t = orc.stout_smear_timeslice(U_t, int(nstep), float(rho)) if kind == 1 else orc.project_su3_timeslice(U_t)
+    return U_t
+
+
+@pytest.mark.parametrize("name", GAUGE_CASES)
+def test_gauge_preprocessing_matches_reference(name):
+    """stout_smear / project_SU3 of the reference classes: processed links and the elementals on them."""
+    g = load_golden(name)
+    latt = [int(v) for v in g["latt_size"]]
+    moms = [tuple(int(v) for v in p) for p in g["momentum_list"]]
+    for t in range(latt[3]):
+        U_t = apply_gauge_ops(g, orc.links_file_to_spatial(g["U"][t]))
+        assert rel_err(U_t, g["links"][:, t]) < 1e-13, (name, t)
+        E = orc.elemental_timeslice_closed_form(g["V"][t], U_t, latt, int(g["num_nabla"]), moms)
+        assert rel_err(E, g["E"][t]) < TOL
+    # smeared / projected links are unitary
+    eye = U_t @ np.conj(np.swapaxes(U_t, -1, -2))
+    assert np.max(np.abs(eye - np.eye(3))) < 1e-13
