@@ -321,27 +321,47 @@ def run_native(args):
     value = world * K / (ms_max * 1e-3)
     del gathered
 
-    # ---- end to end through the host-buffer C-ABI call ------------------------------------------
+    # everything that needs the first handle, then free its 14 GB workspace for the end-to-end leg
+    q = eng.query()
+    workspace_mb = eng.workspace_bytes / 1e6
+    W0_host = eng.debug_field(0).cpu().numpy() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     U0, v0 = inputs[0]
-    U_host = torch.empty(U0.shape, dtype=U0.dtype, pin_memory=True).copy_(U0)
-    V_host = torch.empty(v0.shape, dtype=v0.dtype, pin_memory=True).copy_(v0)
-    out_host = _capi.PinnedBuffer(eng.out_shape, np.complex128)
-    U_np, V_np = U_host.numpy(), V_host.numpy().reshape(eng.field_shape)
-    for _ in range(min(W, 1)):
-        eng.calc_host(U_np, _capi.LINKS_FILE_T, V_np, out_host.array)
+    U_sp_host = None
+    if W0_host is not None:
+        U_sp_host = np.ascontiguousarray(np.moveaxis(U0.cpu().numpy().reshape(Lz, Ly, Lx, 4, 3, 3), 3, 0)[:3])
+    dmma_tf, dfma_tf = microbench_fp64(local) if rank == 0 else (0.0, 0.0)
+    eng.close()
+    del eng, outs, scratch
+
+    # ---- end to end through the public class API: host arrays in, numpy out ---------------------
+    # ElementalGenerator.calc_range streams the timeslices: pinned staging + H2D of t+1 and D2H of
+    # t-1 overlap the kernels of t (easydistillation_b200/pipeline.py); every step uploads its links
+    # and eigenvectors and downloads its result.
+    import easydistillation_b200 as edb
+
+    U_host = np.stack([inputs[i % 2][0].cpu().numpy().reshape(Lz, Ly, Lx, 4, 3, 3) for i in range(K)])
+    V_host = np.stack([inputs[i % 2][1].cpu().numpy().reshape(Ne, Lz, Ly, Lx, 3) for i in range(K)])
+    del inputs
+    torch.cuda.empty_cache()
+    gen = edb.ElementalGenerator([Lx, Ly, Lz, K], edb.GaugeFieldHostmem(U_host), edb.EigenvectorHostmem(V_host), nabla, moms,
+                                 device=local)
+    gen.load("bench")
+    gen.calc_range(0, min(K, 2))  # warm-up: allocates the staging buffers
+    pipe = gen._pipeline
+    h2d0, d2h0 = pipe.h2d_bytes, pipe.d2h_bytes
     barrier()
     e0.record()
-    for _ in range(K):
-        eng.calc_host(U_np, _capi.LINKS_FILE_T, V_np, out_host.array)
+    res = gen.calc_range(0, K)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * K / (float(t.item()) * 1e-3)
-    h2d = U_np.nbytes + V_np.nbytes
-    d2h = out_host.nbytes
-    checksum = float(np.abs(out_host.array[0, 0]).sum())
+    h2d = (pipe.h2d_bytes - h2d0) // K
+    d2h = (pipe.d2h_bytes - d2h0) // K
+    checksum = float(np.abs(res[0, 0, 0]).sum())
+    del res
 
     line = None
     if rank == 0:
@@ -357,9 +377,7 @@ def run_native(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         gemm = fp64_gemm_peak(torch, dev)
-        dmma_tf, dfma_tf = microbench_fp64(local)
         fp64_peak = max(gemm.values())
-        q = eng.query()
         # flops the kernel EXECUTES: 2 x (real MMAs per complex block) x Ne^2 x 3V per (pair, momentum).
         # Algorithmic savings make this smaller than SURVEY 8d's count (8 Ne^2 3V x 34 pairs x Nmom): the
         # Hermitian pairing contracts 19 pairs (self pairs only for one momentum of each +-p couple), and
@@ -373,10 +391,8 @@ def run_native(args):
         st_bytes_launch = 4 * Ne * V * 48.0 + 3 * V * 144.0
         st_gbs = st_bytes_launch / (st_ms * 1e-3) / 1e9 if prof["stencil"]["launches"] else None
         cpu_val, cpu_smp = (None, "skipped (--no-cpu-baseline)")
-        if not args.no_cpu_baseline and world == 1:
-            W0 = eng.debug_field(0).cpu().numpy()
-            U_sp = np.ascontiguousarray(np.moveaxis(U0.cpu().numpy().reshape(Lz, Ly, Lx, 4, 3, 3), 3, 0)[:3])
-            cpu_val, cpu_smp = cpu_sample(name, W0.astype(np.complex64), U_sp)
+        if W0_host is not None:
+            cpu_val, cpu_smp = cpu_sample(name, W0_host.astype(np.complex64), U_sp_host)
         line = {
             "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
@@ -384,11 +400,12 @@ def run_native(args):
             "config": {
                 "workload": workload_desc(name), "lattice": [Lx, Ly, Lz], "Ne": Ne, "num_nabla": nabla, "momenta": nmom,
                 "sharding": f"timeslices, {K} per rank, {world} rank(s)" + (", NCCL gather to rank 0 inside the timed region" if world > 1 else ""),
-                "l2": f"step inputs+fields ({(v0.numel() * 8 + Ne * V * 48 * SRC_OUT[nabla][1]) / 1e6:.0f} MB) exceed the 126 MB L2; two input sets alternated",
-                "dmma_tile": {"mfrag": "auto", "workspace_MB": eng.workspace_bytes / 1e6},
+                "l2": f"step inputs+fields ({(Ne * V * 3 * 8 + Ne * V * 48 * SRC_OUT[nabla][1]) / 1e6:.0f} MB) exceed the 126 MB L2; two input sets alternated",
+                "workspace_MB": workspace_mb,
             },
             "e2e": {"value": e2e_value, "unit": "timeslices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "edk_calc_host (host pinned links+eigenvectors in, result out)", "checksum": checksum},
+                    "api": "ElementalGenerator.calc_range over host arrays (streamed: pinned staging, H2D/D2H overlapped with the kernels)",
+                    "checksum": checksum},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {
