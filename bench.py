@@ -40,19 +40,31 @@ HOPS_REFERENCE = {0: 0, 1: 6, 2: 78}     # single-direction _nD applications per
 SRC_OUT = {0: (0, 0), 1: (1, 3), 2: (4, 12)}  # stencil source / output fields per timeslice
 
 
-def workload_desc(name):
+def workload_desc(name, distance=None):
     Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    if distance is not None:
+        return (f"{name}: {Lx}x{Ly}x{Lz}x{Lt} synthetic gauge field, Ne={Ne}, distance={distance}, {nmom} momenta, "
+                "DisplacementElementalGenerator, one timeslice per step")
     return (f"{name}: {Lx}x{Ly}x{Lz}x{Lt} synthetic gauge field, Ne={Ne}, num_nabla={nabla}, {nmom} momenta, "
             "ElementalGenerator, one timeslice per step")
 
 
-def algorithmic(name):
+def algorithmic(name, distance=None):
+    """contraction flops per timeslice and bytes of ONE stencil launch."""
     Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
     V = Lx * Ly * Lz
+    if distance is not None:
+        return 8.0 * Ne * Ne * 3 * V * nmom * (distance + 1), 13 * Ne * V * 48.0 + 3 * V * 144.0
     flops = 8.0 * Ne * Ne * 3 * V * nmom * PAIRS_DISTINCT[nabla]
-    nsrc, nout = SRC_OUT[nabla]
-    stencil_bytes = (nsrc + nout) * Ne * V * 48.0 + nsrc * 3 * V * 144.0
-    return flops, stencil_bytes
+    return flops, 4 * Ne * V * 48.0 + 3 * V * 144.0
+
+
+def measured_traffic(kernel, name):
+    """DRAM bytes per launch from the committed ncu --set full captures (profiles/traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(REPO, "profiles", "traffic.json")))[kernel][name]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def momentum_set(count):
@@ -155,6 +167,36 @@ def cpu_sample(name, W0=None, U=None, hop_frac=8):
     return 1.0 / T, sample
 
 
+def cpu_sample_displacement(name, distance, W0=None, U=None, hop_frac=8):
+    """Reference composition for the displacement generator (displacement_elemental.py:78-96):
+    per timeslice `distance` line-extension steps (_D) and (distance+1) x Nmom einsums."""
+    from oracle import elemental_oracle as orc
+
+    use_all_host_cores()
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    latt = [Lx, Ly, Lz, Lt]
+    rng = np.random.default_rng(orc.SEED0)
+    if W0 is None:
+        W0 = (rng.standard_normal((Ne, Lz, Ly, Lx, 3)) + 1j * rng.standard_normal((Ne, Lz, Ly, Lx, 3))).astype(np.complex64)
+    if U is None:
+        U = orc.links_file_to_spatial(orc.synthetic_links(latt, 0))
+    ne_hop = max(1, Ne // hop_frac)
+    list(orc.displacement_fields(W0[:ne_hop], U, 1))
+    t0 = time.perf_counter()
+    D1 = list(orc.displacement_fields(W0[:ne_hop], U, 1))[1]
+    t_step = (time.perf_counter() - t0) * (Ne / ne_hop)
+    right = np.ascontiguousarray(np.broadcast_to(D1[:1], W0.shape)) if ne_hop < Ne else D1
+    phase = orc.momentum_phase(latt, (0, 0, 1))
+    orc.gram(W0, right, phase)
+    t0 = time.perf_counter()
+    orc.gram(W0, right, phase)
+    t_pair = time.perf_counter() - t0
+    T = distance * t_step + (distance + 1) * nmom * t_pair
+    sample = (f"1 _D step on {ne_hop}/{Ne} eigenvectors (scaled x{Ne / ne_hop:.0f}) = {t_step:.2f}s, 1 (distance, momentum) "
+              f"einsum at full size = {t_pair:.2f}s; composed {distance} steps + {distance + 1}x{nmom} einsums = {T:.1f}s per timeslice")
+    return 1.0 / T, sample
+
+
 def use_all_host_cores():
     """Give the BLAS behind numpy every core this process may run on (torchrun exports
     OMP_NUM_THREADS=1, which would otherwise cripple the CPU arm) and return the count in use."""
@@ -185,8 +227,9 @@ def run_reference(args):
     name = args.workload
     vals = []
     sample = ""
+    dist_ = args.distance if args.generator == "displacement" else None
     for i in range(args.warmup + args.steps):
-        v, sample = cpu_sample(name)
+        v, sample = cpu_sample(name) if dist_ is None else cpu_sample_displacement(name, dist_)
         if i >= args.warmup:
             vals.append(v)
     value = float(len(vals) / sum(1.0 / v for v in vals))
@@ -195,7 +238,7 @@ def run_reference(args):
         "impl": "reference", "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
-        "config": {"workload": workload_desc(name)},
+        "config": {"workload": workload_desc(name, dist_)},
         "cpu_baseline": {"value": value, "unit": "timeslices/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "timeslices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -274,7 +317,11 @@ def run_native(args):
     V = Lx * Ly * Lz
     K, W = args.steps, args.warmup
     moms = momentum_set(nmom)
-    eng = ElementalEngine((Lx, Ly, Lz), Ne, _capi.MODE_DERIVATIVE, nabla, moms, device=local)
+    dist_ = args.distance if args.generator == "displacement" else None
+    if dist_ is None:
+        eng = ElementalEngine((Lx, Ly, Lz), Ne, _capi.MODE_DERIVATIVE, nabla, moms, device=local)
+    else:
+        eng = ElementalEngine((Lx, Ly, Lz), Ne, _capi.MODE_DISPLACEMENT, dist_, moms, device=local)
 
     # two resident input sets, alternated, each far larger than L2 at the graded workloads
     inputs = [synth_device_inputs(torch, dev, name, 1000 * rank + i) for i in range(2)]
@@ -343,8 +390,12 @@ def run_native(args):
     V_host = np.stack([inputs[i % 2][1].cpu().numpy().reshape(Ne, Lz, Ly, Lx, 3) for i in range(K)])
     del inputs
     torch.cuda.empty_cache()
-    gen = edb.ElementalGenerator([Lx, Ly, Lz, K], edb.GaugeFieldHostmem(U_host), edb.EigenvectorHostmem(V_host), nabla, moms,
-                                 device=local)
+    if dist_ is None:
+        gen = edb.ElementalGenerator([Lx, Ly, Lz, K], edb.GaugeFieldHostmem(U_host), edb.EigenvectorHostmem(V_host), nabla, moms,
+                                     device=local)
+    else:
+        gen = edb.DisplacementElementalGenerator([Lx, Ly, Lz, K], edb.GaugeFieldHostmem(U_host), edb.EigenvectorHostmem(V_host),
+                                                 dist_, moms, device=local)
     gen.load("bench")
     gen.calc_range(0, min(K, 2))  # warm-up: allocates the staging buffers
     pipe = gen._pipeline
@@ -365,7 +416,7 @@ def run_native(args):
 
     line = None
     if rank == 0:
-        flops, st_bytes = algorithmic(name)
+        flops, st_bytes_launch = algorithmic(name, dist_)
         gram_ms = prof["contraction"]["ms"] / max(1, prof["contraction"]["launches"])
         st_launch = max(1, prof["stencil"]["launches"])
         st_ms = prof["stencil"]["ms"] / st_launch
@@ -387,20 +438,24 @@ def run_native(args):
         exec_flops = 2.0 * q["real_mma_per_complex_block"] * Ne * Ne * 3 * V * q["pair_momentum_gemms"]
         achieved_tf = exec_flops / (gram_ms * 1e-3) / 1e12
         survey_tf = flops / (gram_ms * 1e-3) / 1e12
-        # stencil: bytes of ONE nabla3 launch (1 source, 3 outputs, links once)
-        st_bytes_launch = 4 * Ne * V * 48.0 + 3 * V * 144.0
+        # stencil: bytes of ONE launch (nabla3: 1 source, 3 outputs, links once; displacement step: 6 in, 6 + mean out)
         st_gbs = st_bytes_launch / (st_ms * 1e-3) / 1e9 if prof["stencil"]["launches"] else None
         cpu_val, cpu_smp = (None, "skipped (--no-cpu-baseline)")
-        if W0_host is not None:
+        if W0_host is not None and dist_ is None:
             cpu_val, cpu_smp = cpu_sample(name, W0_host.astype(np.complex64), U_sp_host)
+        elif W0_host is not None:
+            cpu_val, cpu_smp = cpu_sample_displacement(name, dist_, W0_host.astype(np.complex64), U_sp_host)
+        gram_name = "gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel"
+        st_name = "nabla3_kernel" if dist_ is None else "displace_step6_kernel"
         line = {
             "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
             "config": {
-                "workload": workload_desc(name), "lattice": [Lx, Ly, Lz], "Ne": Ne, "num_nabla": nabla, "momenta": nmom,
+                "workload": workload_desc(name, dist_), "lattice": [Lx, Ly, Lz], "Ne": Ne,
+                **({"num_nabla": nabla} if dist_ is None else {"distance": dist_}), "momenta": nmom,
                 "sharding": f"timeslices, {K} per rank, {world} rank(s)" + (", NCCL gather to rank 0 inside the timed region" if world > 1 else ""),
-                "l2": f"step inputs+fields ({(Ne * V * 3 * 8 + Ne * V * 48 * SRC_OUT[nabla][1]) / 1e6:.0f} MB) exceed the 126 MB L2; two input sets alternated",
+                "l2": f"step inputs+fields ({(Ne * V * 3 * 8 + Ne * V * 48 * (SRC_OUT[nabla][1] if dist_ is None else 12)) / 1e6:.0f} MB) exceed the 126 MB L2; two input sets alternated",
                 "workspace_MB": workspace_mb,
             },
             "e2e": {"value": e2e_value, "unit": "timeslices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -409,10 +464,10 @@ def run_native(args):
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {
-                "kernel": ("gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel")
-                          + " (momentum-phased contraction, DMMA.8x8x4, TMA producer warp + mbarrier ring)", "bound": "tensor",
+                "kernel": gram_name + " (momentum-phased contraction, DMMA.8x8x4, TMA producer warp + mbarrier ring)",
+                "bound": "tensor",
                 "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-                "traffic": None,
+                "traffic": measured_traffic(gram_name, name if dist_ is None else name + "_displacement"),
                 "peak_source": f"cuBLAS FP64 GEMM measured in this run (dgemm {gemm['dgemm']:.1f}, zgemm {gemm['zgemm']:.1f} TFLOP/s); "
                                f"DMMA issue-rate microbench {dmma_tf:.1f}, DFMA {dfma_tf:.1f} TFLOP/s; nominal 37-40",
                 "algorithmic_flops_per_launch": exec_flops, "ms_per_launch": gram_ms,
@@ -423,9 +478,10 @@ def run_native(args):
                 "share_of_step": prof["contraction"]["ms"] / ms,
             },
             "roofline_stencil": {
-                "kernel": "nabla3_kernel (covariant central differences, 3 directions per pass)", "bound": "hbm",
+                "kernel": st_name + (" (covariant central differences, 3 directions per pass)" if dist_ is None
+                                     else " (six straight Wilson lines extended by one link + their mean)"), "bound": "hbm",
                 "achieved": st_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (st_gbs / hbm_peak) if st_gbs else None,
-                "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_launch": st_bytes_launch,
+                "traffic": measured_traffic(st_name, name if dist_ is None else name + "_displacement"), "peak_source": hbm_src, "algorithmic_bytes_per_launch": st_bytes_launch,
                 "ms_per_launch": st_ms, "launches_per_step": st_launch / K,
                 "share_of_step": prof["stencil"]["ms"] / ms,
             },
@@ -447,6 +503,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=os.environ.get("EDK_BENCH_WORKLOAD", "config5"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generator", default="derivative", choices=["derivative", "displacement"],
+                    help="ElementalGenerator (default, the graded workload) or DisplacementElementalGenerator")
+    ap.add_argument("--distance", type=int, default=2, help="displacement generator: number of link steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

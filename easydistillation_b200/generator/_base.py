@@ -141,6 +141,27 @@ class _TimesliceGenerator:
             out[i] = self.calc(t)
         return out
 
+    def calc_to_file(self, elemental, key: str, t_range: Optional[Tuple[int, int]] = None, dtype: str = "<c16"):
+        """Write the elemental file of configuration `key` in the reference's layout
+        [Nop, Nmom, Lt, Ne, Ne] (tests/test_elemental.py:47, read back by ElementalNpy / lattice/data.py:26).
+
+        `elemental` is an ElementalNpy-like handle with `create(key, shape, dtype)`; the file is
+        pre-sized once and every timeslice drops its slab in place as soon as its download has
+        finished, while the next timeslices are still being computed.  `t_range=(t0, t1)` writes
+        only that slab (one rank of a sharded run; ranks share the file), `dtype="<c8"` down-casts
+        to the complex64 the reference declares for stored elementals (preset.py:176)."""
+        Lt = int(self.latt_size[3])
+        t0, t1 = (0, Lt) if t_range is None else t_range
+        shape = (self._engine.out_shape[0], self._engine.out_shape[1], Lt, self.Ne, self.Ne)
+        mm = elemental.create(key, shape, dtype) if (t_range is None or t0 == 0) else elemental.open_rw(key, shape, dtype)
+        chunk = 4  # timeslices per streamed batch: bounds the host buffer
+        for a in range(t0, t1, chunk):
+            b = min(a + chunk, t1)
+            block = self.calc_range(a, b)  # [b-a, Nop, Nmom, Ne, Ne]
+            mm[:, :, a:b] = block.transpose(1, 2, 0, 3, 4)
+        mm.flush()
+        return mm
+
     def calc_all(self, group=None, dst: Optional[int] = 0):
         """All Lt timeslices, sharded over the ranks of `group` (default: the world group if
         torch.distributed is initialised, else this process alone) and gathered with one

@@ -161,8 +161,16 @@ class ElementalNpy(_KeyedFile, Elemental):
             self.file, self.data = name, ArrayData(np.load(name, mmap_mode="r"), name)
         return self.data
 
-    def create(self, key: str, shape: Sequence[int]) -> np.memmap:
+    def create(self, key: str, shape: Sequence[int], dtype: str = "<c16") -> np.memmap:
         """Pre-sized writable file so every timeslice (or rank) can drop its slab in place."""
         name = self._name(key)
         self.file = self.data = None
-        return np.lib.format.open_memmap(name, mode="w+", dtype="<c16", shape=tuple(int(s) for s in shape))
+        return np.lib.format.open_memmap(name, mode="w+", dtype=dtype, shape=tuple(int(s) for s in shape))
+
+    def open_rw(self, key: str, shape: Sequence[int], dtype: str = "<c16") -> np.memmap:
+        """Re-open a file made by `create` for in-place writes (another rank's timeslice slab)."""
+        mm = np.lib.format.open_memmap(self._name(key), mode="r+")
+        if tuple(mm.shape) != tuple(int(s) for s in shape) or mm.dtype != np.dtype(dtype):
+            raise ValueError(f"{self._name(key)} has shape {mm.shape} / dtype {mm.dtype}, expected {tuple(shape)} / {dtype}")
+        self.file = self.data = None
+        return mm

@@ -373,6 +373,18 @@ def test_file_handles_and_elemental_npy_roundtrip(edb, tmp_path):
     mm.flush()
     back = el.load("weak")[:]
     _blocks_close(back[:, :, 1], g["E"][1], what="npy roundtrip")
+    # streamed writer: whole file, then the same file written as two rank slabs, and a complex64 down-cast
+    el2 = edb.ElementalNpy(prefix, ".elemental2.npy", None, 8)
+    gen.calc_to_file(el2, "weak")
+    assert np.array_equal(el2.load("weak")[:], back)
+    el3 = edb.ElementalNpy(prefix, ".elemental3.npy", None, 8)
+    gen.calc_to_file(el3, "weak", t_range=(0, 1))
+    gen.calc_to_file(el3, "weak", t_range=(1, Lt))
+    assert np.array_equal(el3.load("weak")[:], back)
+    el4 = edb.ElementalNpy(prefix, ".elemental4.npy", None, 8)
+    gen.calc_to_file(el4, "weak", dtype="<c8")
+    got8 = el4.load("weak")[:]
+    assert got8.dtype == np.complex64 and np.array_equal(got8, back.astype(np.complex64))
     # calc_all without torch.distributed = all timeslices on this GPU
     full = gen.calc_all()
     assert tuple(full.shape) == (Lt, 13, len(moms), 8, 8)

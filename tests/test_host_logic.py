@@ -155,3 +155,25 @@ def test_gather_timeslices_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK {r}" in o, o
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU oracle port on a bounded sample) on the smallest workload."""
+    import json
+
+    for extra in ([], ["--generator", "displacement"]):
+        out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                              "--steps", "1", "--warmup", "0"] + extra, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["metric"] == "elemental_timeslices_per_sec"
+        assert line["unit"] == "timeslices/s" and line["higher_is_better"] is True and line["value"] > 0
+        assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+        assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+        assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+        assert "workload" in line["config"]
+    # non-zero ranks of a torchrun launch print nothing and exit 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                          "--steps", "1", "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
