@@ -563,7 +563,6 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     P.ksplit = h->naive ? 1 : h->ksplit;
     P.n_mt = row_tiles(h);
     const bool use_tma = !h->naive && h->loader == 0 && h->tma_ready;
-    P.n_nt = 0;
     if (h->cta_dirty) {
         const int rc = build_cta_map(h);
         if (rc != EDK_OK) return rc;

@@ -55,8 +55,7 @@ struct GramParams {
     int ksteps;   // Vpad/8 : stages of 8 sites (24 complex) per segment
     int Vpad;     // row stride of the phase table
     int ksplit;   // split-K factor
-    int n_mt;     // tiles along e (rows)
-    int n_nt;     // unused by the kernels (tiles per job vary with the job's momentum count)
+    int n_mt;     // tiles along e (rows); tiles along the flattened (f-fragment, momentum) axis depend on the job
     int ncta;     // CTAs per split = entries of cta_map
     const int2* cta_map;  // per CTA: (job, tile index inside the job = mt * n_nt(job) + nt)
     const cplx* phase;  // [2][nmom][Vpad]: phase, then -i*phase
@@ -96,8 +95,6 @@ cudaError_t launch_phase_table(cplx* phase, cplx* rot, const int* mom3_dev, int 
 // stencil
 cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
                           cudaStream_t s);
-cudaError_t launch_displace_step(const cplx* const* src6, cplx* const* dst6, const cplx* links, Geom g, int Ne,
-                                 cudaStream_t s);
 struct Ptr6 {
     const cplx* src[6];
     cplx* dst[6];

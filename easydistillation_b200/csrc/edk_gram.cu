@@ -3,22 +3,33 @@
 //   G[p][e][f] = sum_seg sign_seg * sum_{x,c} conj(L_seg[e][x][c]) * phase_p(x) * R_seg[f][x][c]
 //   (reference: the einsum "zyx,ezyxc,fzyxc->ef" of lattice/generator/elemental.py:322-329 and
 //    lattice/generator/displacement_elemental.py:94-95, with the left/right split sum of
-//    elemental.py:309-321 folded into the K loop as signed segments)
+//    elemental.py:309-321 folded into job lists, see edk_api.cu)
 //
-// Mapping onto real m8n8k4 MMAs (tcgen05 has no f64 kind; mma.sync -> SASS DMMA.8x8x4):
+// tcgen05 has no f64 kind, so the FP64 tensor path is mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4.
+// Kernels in this file:
+//   gram_tma_kernel<MF, ALGO>  product path: TMA producer warp + mbarrier full/empty ring, 8 MMA
+//                              warps; ALGO 1 = 3M arithmetic (3 real MMAs per complex block),
+//                              ALGO 0 = 4M (cross-check)
+//   gram_dmma_kernel<MF>       earlier variant: cp.async ring issued by the MMA warps themselves, 4M
+//                              (A/B cross-check, selected by edk_debug_loader)
+//   gram_naive_kernel          one thread per output element (tests only)
+//   combine_kernel             split-K sum, +-weights, Hermitian / half-set reads, blending matrix
+//
+// 4M mapping onto real m8n8k4 MMAs:
 //   A operand  = rows e of L, k-slots hold Re L (first MMA) or Im L (second MMA) of 4 complex k,
 //   B operand  = columns (f, re|im), k-slots hold the matching part of P = phase * R:
 //                  column (f,re): (Pr | Pi)      column (f,im): (Pi | -Pr)
 //   so that  C[e][(f,re)] += Lr*Pr + Li*Pi = Re(conj(L) P),  C[e][(f,im)] += Lr*Pi - Li*Pr = Im(conj(L) P)
 //   and the accumulator fragment (2 doubles per lane) is one complex128 in natural (re, im) order.
-//   The phase multiply is fused into the B-fragment build: 4 FP64 ops per 2*MF MMAs; the
-//   (f,im) columns read a pre-rotated table -i*phase, so there is no select or negation.
+//   The (f,im) columns read a pre-rotated table -i*phase, so there is no select or negation.
+// 3M mapping: B columns are 8 complex f; T1 += Lr*Pr, T2 += Li*Pi, T3 += (Lr+Li)*(Pi-Pr);
+//   Re = T1 + T2, Im = T3 + T1 - T2 in the epilogue.
+// In both, the phase multiply is fused into the B-fragment build (a few FP64 ops per 2-3*MF MMAs).
 //
-// CTA tile: 8*MF rows (all warps share them) x 16 "n-fragments"; an n-fragment is 4 consecutive
-// f at one momentum, n-fragments are flattened f-fragment-major so one CTA needs few rows of R.
-// Shared memory per stage (8 sites = 24 complex k): A [6 kgroups][8*MF rows][4 complex] so a
+// Shared memory per stage (8 sites = 24 complex k): A [6 k-groups][8*MF rows][4 complex] so a
 // warp's fragment load is 512 contiguous bytes (bank-conflict free LDS.128), B likewise, plus the
-// 16 x 8 phase entries.  3-stage cp.async pipeline, one __syncthreads per stage.
+// phase tile [n-fragment][8 sites].  All warps of a CTA share the 8*MF rows of L, so no B value is
+// built twice; n-fragments (4 or 8 consecutive f at one momentum) are flattened f-fragment-major.
 #include "edk_common.cuh"
 
 namespace edk {
