@@ -112,6 +112,7 @@ int gram_tma_plan(int algo, int mfrag, int nmom, int Ne, int* brows_alloc, int* 
 int gram_fwidth(int algo);
 int gram_pick_mfrag(int Ne);
 int gram_rows_per_tile(int mfrag);
+bool gram_mfrag_available(int mfrag);
 int gram_nfrag_per_tile(int algo);
 cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom_int,
                            int nmom_out, const int* pmap, const int* negidx, int n_half, int Ne, const double* coeff, cplx* out,

@@ -741,14 +741,8 @@ cudaError_t launch_gram_tma(const GramParams& P, const GramTma& T, int mfrag, in
 #define EDK_TMA_CASE(M) \
     case M: return algo ? launch_gram_tma_mf<M, 1>(P, T, s) : launch_gram_tma_mf<M, 0>(P, T, s);
     switch (mfrag) {
-        EDK_TMA_CASE(2)
-        EDK_TMA_CASE(4)
-        EDK_TMA_CASE(5)
-        EDK_TMA_CASE(7)
-        EDK_TMA_CASE(9)
-        EDK_TMA_CASE(10)
-        EDK_TMA_CASE(11)
-        EDK_TMA_CASE(13)
+        EDK_TMA_CASE(2) EDK_TMA_CASE(3) EDK_TMA_CASE(4) EDK_TMA_CASE(5) EDK_TMA_CASE(6) EDK_TMA_CASE(7)
+        EDK_TMA_CASE(8) EDK_TMA_CASE(9) EDK_TMA_CASE(10) EDK_TMA_CASE(11) EDK_TMA_CASE(12) EDK_TMA_CASE(13)
         default: return cudaErrorInvalidValue;
     }
 #undef EDK_TMA_CASE
@@ -772,7 +766,7 @@ cudaError_t launch_phase_tiles(const cplx* phase2, cplx* tiles, int nmom, int Vp
 }
 
 // available tile heights (m-fragments of 8 rows per CTA)
-static const int kMfragAvail[] = {2, 4, 5, 7, 9, 10, 11, 13};
+static const int kMfragAvail[] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13};
 
 int gram_pick_mfrag(int Ne) {
     const int frags = (Ne + 7) / 8;
@@ -798,17 +792,20 @@ static cudaError_t launch_gram_mf(const GramParams& P, cudaStream_t s) {
 }
 
 cudaError_t launch_gram_dmma(const GramParams& P, int mfrag, cudaStream_t s) {
+#define EDK_DMMA_CASE(M) \
+    case M: return launch_gram_mf<M>(P, s);
     switch (mfrag) {
-        case 2: return launch_gram_mf<2>(P, s);
-        case 4: return launch_gram_mf<4>(P, s);
-        case 5: return launch_gram_mf<5>(P, s);
-        case 7: return launch_gram_mf<7>(P, s);
-        case 9: return launch_gram_mf<9>(P, s);
-        case 10: return launch_gram_mf<10>(P, s);
-        case 11: return launch_gram_mf<11>(P, s);
-        case 13: return launch_gram_mf<13>(P, s);
+        EDK_DMMA_CASE(2) EDK_DMMA_CASE(3) EDK_DMMA_CASE(4) EDK_DMMA_CASE(5) EDK_DMMA_CASE(6) EDK_DMMA_CASE(7)
+        EDK_DMMA_CASE(8) EDK_DMMA_CASE(9) EDK_DMMA_CASE(10) EDK_DMMA_CASE(11) EDK_DMMA_CASE(12) EDK_DMMA_CASE(13)
         default: return cudaErrorInvalidValue;
     }
+#undef EDK_DMMA_CASE
+}
+
+bool gram_mfrag_available(int mfrag) {
+    for (int v : kMfragAvail)
+        if (v == mfrag) return true;
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------
