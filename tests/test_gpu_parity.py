@@ -462,6 +462,37 @@ def test_config3_shape_properties(edb):
     _blocks_close(np.array(gen.calc(0)), E, tol=1e-11, what="config 3 direct pairs vs Hermitian pairing")
 
 
+def test_config4_shape_properties(edb):
+    """32^3, Ne=200, num_nabla=2, 33 momenta (BASELINE config 4, the production tile shapes: two row
+    tiles of 13 + 12 fragments, 24-wave grids).  The full oracle would take ~50 min here, so:
+    (a) the product path (TMA, 3M, Hermitian pairing + half-set self pairs) against the same
+        timeslice evaluated with every pair contracted directly in 4M arithmetic (34 x 33 GEMMs),
+    (b) a 5-vector sub-block of every operator against the oracle,
+    (c) unit Gram diagonal at p = 0."""
+    import torch
+
+    orc = _orc()
+    latt, Ne = [32, 32, 32, 1], 200
+    moms = orc.momentum_set(33)
+    U_file = orc.synthetic_links(latt, 0)[None]
+    V = orc.synthetic_eigvecs(latt, Ne, 0)[None].astype(np.complex64)
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), 2, moms)
+    gen.load("x")
+    E = np.array(gen.calc(0))
+    q = gen._engine.query()
+    assert q["hermitian_pairing"] and q["real_mma_per_complex_block"] == 3 and q["pair_momentum_gemms"] == 15 * 33 + 4 * 17
+    gen._engine.debug_symmetry(0)
+    gen._engine.debug_algo(0)
+    assert gen._engine.query()["pair_momentum_gemms"] == 34 * 33
+    _blocks_close(np.array(gen.calc(0)), E, tol=1e-11, what="config 4: direct pairs / 4M vs pairing / 3M")
+    sel = [0, 57, 103, 104, 199]
+    ref = orc.elemental_timeslice_closed_form(V[0][sel], orc.links_file_to_spatial(U_file[0]), latt, 2, moms)
+    _blocks_close(E[:, :, sel][:, :, :, sel], ref, what="config 4 sub-block")
+    assert np.max(np.abs(np.diag(E[0, 0]) - 1.0)) < 1e-6
+    del gen
+    torch.cuda.empty_cache()
+
+
 def test_linearity_and_scaling_property(edb):
     """E is sesquilinear in the eigenvectors: scaling vector f by c scales column f by c and row f by conj(c)
     (powers of two keep the complex64 staging exact)."""
