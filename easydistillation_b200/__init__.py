@@ -2,7 +2,7 @@
 path of IHEP-LQCD/EasyDistillation behind the reference's own class API, running on
 hand-written sm_100a kernels (libedk_sm100a.so).  See DESIGN.md."""
 from .constant import Nc, Nd, Ns
-from .generator import DisplacementElementalGenerator, ElementalGenerator
+from .generator import DisplacementElementalGenerator, ElementalGenerator, Laplacian
 from .insertion.derivative import derivative
 from .insertion.phase import MomentumPhase
 from .preset import (
@@ -15,7 +15,7 @@ from .preset import (
 )
 
 __all__ = [
-    "ElementalGenerator", "DisplacementElementalGenerator", "MomentumPhase", "derivative",
+    "ElementalGenerator", "DisplacementElementalGenerator", "Laplacian", "MomentumPhase", "derivative",
     "GaugeFieldBinary", "GaugeFieldNpy", "GaugeFieldHostmem", "EigenvectorNpy", "EigenvectorHostmem",
     "ElementalNpy", "Nc", "Ns", "Nd",
 ]

@@ -36,6 +36,7 @@ SIGNATURES = {
     "edk_set_blending": (_i, [_vp, _vp, _vp]),
     "edk_calc": (_i, [_vp, _vp, _vp]),
     "edk_calc_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "edk_laplacian": (_i, [_vp, _vp, _vp, _i, _vp]),
     "edk_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "edk_host_free": (_i, [_vp]),
     "edk_set_profiling": (_i, [_vp, _i]),

@@ -846,6 +846,22 @@ int edk_calc(edk_handle* h, void* out_dev, void* stream) {
     return run_gram_and_combine(h, (cplx*)out_dev, s);
 }
 
+int edk_laplacian(edk_handle* h, const void* F_dev, void* out_dev, int nvec, void* stream) {
+    if (!h || !F_dev || !out_dev || nvec < 1 || F_dev == out_dev) {
+        set_error("edk_laplacian: bad argument (in-place application is not supported)");
+        return EDK_ERR_ARG;
+    }
+    if (!h->links_set) {
+        set_error("edk_laplacian: the links of the timeslice must be set first");
+        return EDK_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    EDK_CUDA_TRY(cudaSetDevice(h->device));
+    PhaseTimer t(h, s, PH_STENCIL, 1);
+    EDK_CUDA_TRY(launch_laplacian((const cplx*)F_dev, (cplx*)out_dev, h->links, h->g, nvec, s));
+    return EDK_OK;
+}
+
 int edk_calc_host(edk_handle* h, const void* U_host, int layout, const void* V_host, int is_c8, void* out_host,
                   void* stream) {
     if (!h || !U_host || !V_host || !out_host) {
@@ -948,15 +964,9 @@ int edk_debug_use_naive_gram(edk_handle* h, int on) {
 
 int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit) {
     if (!h || mfrag < 0 || ksplit < 0) return EDK_ERR_ARG;
-    if (mfrag) {
-        const int rows = gram_rows_per_tile(mfrag);
-        (void)rows;
-        bool ok = false;
-        for (int v : {2, 4, 5, 7, 9, 10, 11, 13}) ok |= (v == mfrag);
-        if (!ok) {
-            set_error("edk_debug_gram_config: mfrag %d not instantiated", mfrag);
-            return EDK_ERR_ARG;
-        }
+    if (mfrag && !gram_mfrag_available(mfrag)) {
+        set_error("edk_debug_gram_config: mfrag %d not instantiated (2..13)", mfrag);
+        return EDK_ERR_ARG;
     }
     h->force_mfrag = mfrag;
     h->force_ksplit = ksplit;

@@ -100,6 +100,7 @@ struct Ptr6 {
     cplx* dst[6];
 };
 cudaError_t launch_displace_step6(Ptr6 p, cplx* mean_out, const cplx* links, Geom g, int Ne, cudaStream_t s);
+cudaError_t launch_laplacian(const cplx* F, cplx* out, const cplx* links, Geom g, int nvec, cudaStream_t s);
 // gauge preprocessing
 cudaError_t launch_stout_step(const cplx* Uin, cplx* Uout, double rho, Geom g, cudaStream_t s);
 cudaError_t launch_project_su3(cplx* U, Geom g, cudaStream_t s);

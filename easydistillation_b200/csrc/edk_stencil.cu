@@ -328,4 +328,84 @@ cudaError_t launch_displace_step6(Ptr6 p, cplx* mean_out, const cplx* links, Geo
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// Laplacian of the eigensolver (lattice/generator/eigenvector.py:11-26):
+//   (L F)(x) = 6 F(x) - sum_d [ U_d(x) F(x+d) + U_d(x-d)^dagger F(x-d) ]
+// Same decomposition as nabla3 (thread = (site, direction), links in registers across a block of
+// vectors); the three hop sums are reduced through shared memory.  96 B of field traffic per
+// (vector, site).
+// ---------------------------------------------------------------------------------------
+constexpr int LAP_SITES = 64;
+constexpr int LAP_EB = 16;
+
+__global__ void __launch_bounds__(LAP_SITES * 3)
+laplacian_kernel(const cplx* __restrict__ F, cplx* __restrict__ out, const cplx* __restrict__ links, Geom g, int nvec) {
+    __shared__ cplx red[3][LAP_SITES][3];
+    const int site = blockIdx.x * LAP_SITES + threadIdx.x;
+    const int d = threadIdx.y;
+    const bool active = site < g.V;
+    int sf = 0, sb = 0;
+    cplx U[9], Ub[9];
+    if (active) {
+        int x, y, z;
+        site_coords(site, g, x, y, z);
+        sf = neighbour(x, y, z, d, +1, g);
+        sb = neighbour(x, y, z, d, -1, g);
+        const cplx* pu = links + ((size_t)d * g.V + site) * 9;
+        const cplx* pl = links + ((size_t)d * g.V + sb) * 9;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) {
+            U[m] = ldg(pu + m);
+            Ub[m] = ldg(pl + m);
+        }
+    }
+    const int e0 = blockIdx.y * LAP_EB;
+    const int e1 = min(e0 + LAP_EB, nvec);
+    const size_t fs = (size_t)g.V * 3;
+    const int tid = threadIdx.y * LAP_SITES + threadIdx.x;
+    for (int e = e0; e < e1; ++e) {
+        cplx r[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) r[a] = make_double2(0.0, 0.0);
+        if (active) {
+            const cplx* Fe = F + (size_t)e * fs;
+            cplx wf[3], wb[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                wf[c] = ldg(Fe + (size_t)sf * 3 + c);
+                wb[c] = ldg(Fe + (size_t)sb * 3 + c);
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    cfma(r[a], U[3 * a + b], wf[b]);
+                    cfma_conj(r[a], Ub[3 * b + a], wb[b]);
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) red[d][threadIdx.x][a] = r[a];
+        __syncthreads();
+        if (tid < LAP_SITES * 3) {
+            const int sl = tid / 3, a = tid % 3;
+            const int so = blockIdx.x * LAP_SITES + sl;
+            if (so < g.V) {
+                const size_t idx = (size_t)e * fs + (size_t)so * 3 + a;
+                const cplx f = ldg(F + idx);
+                const double hx = red[0][sl][a].x + red[1][sl][a].x + red[2][sl][a].x;
+                const double hy = red[0][sl][a].y + red[1][sl][a].y + red[2][sl][a].y;
+                out[idx] = make_double2(6.0 * f.x - hx, 6.0 * f.y - hy);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_laplacian(const cplx* F, cplx* out, const cplx* links, Geom g, int nvec, cudaStream_t s) {
+    dim3 block(LAP_SITES, 3);
+    dim3 grid((g.V + LAP_SITES - 1) / LAP_SITES, (nvec + LAP_EB - 1) / LAP_EB);
+    laplacian_kernel<<<grid, block, 0, s>>>(F, out, links, g, nvec);
+    return cudaGetLastError();
+}
+
 }  // namespace edk

@@ -127,6 +127,18 @@ class ElementalEngine:
         _capi.check(self.lib.edk_calc(self.h, _ptr(out), self._stream()), "edk_calc")
         return out
 
+    def laplacian(self, F, out=None):
+        """out[v] = (6 - hops) F[v] on the current links; F [nvec, Lz, Ly, Lx, 3] complex128 on the device."""
+        torch = self.torch
+        Lx, Ly, Lz = self.latt3
+        if F.dtype != torch.complex128 or F.dim() != 5 or tuple(F.shape[1:]) != (Lz, Ly, Lx, 3) or not F.is_contiguous() \
+                or F.device != self.device:
+            raise ValueError(f"F must be a contiguous complex128 tensor [nvec, {Lz}, {Ly}, {Lx}, 3] on {self.device}")
+        if out is None:
+            out = torch.empty_like(F)
+        _capi.check(self.lib.edk_laplacian(self.h, _ptr(F), _ptr(out), int(F.shape[0]), self._stream()), "edk_laplacian")
+        return out
+
     # -- host-buffer path (what the generators' calc(t) and bench e2e use) ------------------
     def calc_host(self, U_host: np.ndarray, layout: int, V_host: np.ndarray, out_host: np.ndarray):
         V = self.latt3[0] * self.latt3[1] * self.latt3[2]

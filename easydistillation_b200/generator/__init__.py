@@ -1,2 +1,3 @@
 from .elemental import ElementalGenerator
 from .displacement_elemental import DisplacementElementalGenerator
+from .laplacian import Laplacian

@@ -61,6 +61,16 @@ class _TimesliceGenerator:
         self._eigenvector_data = self.eigenvector.load(key)
 
     # ---- one timeslice of inputs -----------------------------------------------------------------
+    def _eigvecs_view(self, t: int):
+        """Zero-copy view of timeslice t's eigenvectors when the handle wraps a host array (our
+        ArrayData), else None: lets the streamed pipeline copy source -> pinned staging once."""
+        a = getattr(self._eigenvector_data, "_a", None)
+        if not isinstance(a, np.ndarray) or a.ndim < 3 or a.dtype not in (np.dtype("<c8"), np.dtype("<c16")):
+            return None
+        Lx, Ly, Lz, Lt = (int(v) for v in self.latt_size)
+        blk = a[t][: self.Ne]
+        return blk.reshape((self.Ne, Lz, Ly, Lx, Nc)) if blk.flags.c_contiguous else None
+
     def _eigvecs_of(self, t: int):
         """[Ne, Lz, Ly, Lx, Nc] of timeslice t in ONE read when the handle allows it, else the
         reference's per-eigenvector loop (elemental.py:297-298)."""

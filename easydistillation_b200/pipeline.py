@@ -41,7 +41,9 @@ class TimeslicePipeline:
         if self.ev_h2d[b] is not None:
             self.ev_h2d[b].synchronize()  # the previous upload from this staging slot has left the host
         U_t = gen._U[t]
-        V_t = gen._eigvecs_of(t)
+        V_t = gen._eigvecs_view(t)
+        if V_t is None:
+            V_t = gen._eigvecs_of(t)
         if isinstance(U_t, torch.Tensor) or isinstance(V_t, torch.Tensor):
             raise TypeError("the streamed pipeline is for host-resident inputs")
         np.copyto(self.U_pin[b].numpy().reshape(U_t.shape), U_t)

@@ -112,6 +112,14 @@ int edk_calc(edk_handle* h, void* out_dev, void* stream);
 int edk_calc_host(edk_handle* h, const void* U_host, int layout, const void* V_host, int is_c8, void* out_host,
                   void* stream);
 
+/*
+ * The eigensolver's operator on the same links (lattice/generator/eigenvector.py:11-26, `_Laplacian`):
+ *   out[v] = 6 F[v] - sum_d [ U_d(x) F[v](x+d) + U_d(x-d)^dagger F[v](x-d) ],  v < nvec,
+ * F and out are [nvec][Lz][Ly][Lx][3] complex128 device arrays (vector index slowest; the reference keeps
+ * it fastest), out != F.  Uses the links of the last edk_set_links, gauge preprocessing included.
+ */
+int edk_laplacian(edk_handle* h, const void* F_dev, void* out_dev, int nvec, void* stream);
+
 /* page-locked host memory for the buffers above (cudaHostAlloc / cudaFreeHost) */
 int edk_host_alloc(void** p, size_t bytes);
 int edk_host_free(void* p);

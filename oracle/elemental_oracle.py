@@ -19,6 +19,8 @@ Reference lines each function follows (relative to the reference root):
   elemental_timeslice   lattice/generator/elemental.py:290-338
   blending_matrix       lattice/generator/elemental.py:61-100
   displacement_*        lattice/generator/displacement_elemental.py:53-96
+  stout_smear_timeslice lattice/generator/elemental.py:175-241 (project_su3_timeslice :107-117)
+  laplacian             lattice/generator/eigenvector.py:11-26
 
 Array conventions (same as the reference): links `U[d, z, y, x, a, b]` for the
 three spatial directions d = 0(x), 1(y), 2(z) of ONE timeslice, eigenvectors
@@ -286,6 +288,17 @@ def project_su3_timeslice(U_t, max_iter=100):
             break
         U = 0.5 * (U + _dag(Uinv))
     return U
+
+
+def laplacian(V, U_t):
+    """Gauge-covariant 3-d Laplacian of the eigensolver (lattice/generator/eigenvector.py:11-26):
+    (L V)(x) = 6 V(x) - sum_d [ U_d(x) V(x+d) + U_d(x-d)^dagger V(x-d) ], V[e, z, y, x, c]."""
+    out = 6.0 * V.astype(np.complex128)
+    for d in range(3):
+        axis = 3 - d
+        out -= np.einsum("zyxab,ezyxb->ezyxa", U_t[d], np.roll(V, -1, axis), optimize=True)
+        out -= np.roll(np.einsum("zyxba,ezyxb->ezyxa", U_t[d].conj(), V, optimize=True), 1, axis)
+    return out
 
 
 # --------------------------------------------------------------------------

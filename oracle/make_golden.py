@@ -131,6 +131,21 @@ def main():
                             rhos=np.array([o[2] if len(o) > 2 else 0.0 for o in ops]))
         print(f"{name}: links{links.shape} E{E.shape} |E|={np.linalg.norm(E):.6e}")
 
+    # the eigensolver's Laplacian, called exactly as eigenvector.py:243-250 does:
+    # F is [Lz*Ly*Lx*Nc, nvec] (vector index fastest), U and U_dag are [3, Lz, Ly, Lx, 3, 3]
+    from lattice.generator.eigenvector import _Laplacian
+
+    latt = [4, 6, 8, 1]
+    Lx, Ly, Lz, Lt = latt
+    U_sp = orc.links_file_to_spatial(orc.synthetic_links(latt, 3))
+    F = orc.synthetic_eigvecs(latt, 5, 3)                                    # [e, z, y, x, c]
+    F_ref = np.ascontiguousarray(np.moveaxis(F, 0, -1)).reshape(Lz * Ly * Lx * 3, 5)
+    LF = _Laplacian(F_ref, U_sp, U_sp.transpose(0, 1, 2, 3, 5, 4).conj(), latt)
+    LF = np.moveaxis(LF.reshape(Lz, Ly, Lx, 3, 5), -1, 0)
+    np.savez_compressed(os.path.join(outdir, "laplacian_4x6x8.npz"), U_file=orc.synthetic_links(latt, 3), F=F, LF=LF,
+                        latt_size=np.array(latt))
+    print(f"laplacian_4x6x8: F{F.shape} -> LF{LF.shape} |LF|={np.linalg.norm(LF):.6e}")
+
     # index-map and phase goldens straight from the reference's insertion module
     from lattice.insertion.derivative import derivative
     from lattice.insertion.phase import MomentumPhase

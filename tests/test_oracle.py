@@ -133,3 +133,13 @@ def test_gauge_preprocessing_matches_reference(name):
     # smeared / projected links are unitary
     eye = U_t @ np.conj(np.swapaxes(U_t, -1, -2))
     assert np.max(np.abs(eye - np.eye(3))) < 1e-13
+
+
+def test_laplacian_matches_reference():
+    g = load_golden("laplacian_4x6x8")
+    U = orc.links_file_to_spatial(g["U_file"])
+    assert rel_err(orc.laplacian(g["F"], U), g["LF"]) < 1e-14
+    # Hermitian and positive semi-definite
+    F = g["F"]
+    M = np.einsum("ezyxc,fzyxc->ef", F.conj(), orc.laplacian(F, U))
+    assert rel_err(M.conj().T, M) < 1e-13 and np.linalg.eigvalsh(0.5 * (M + M.conj().T)).min() > -1e-12
