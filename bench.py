@@ -400,7 +400,11 @@ def run_native(args):
 
     U_two = [inputs[i][0].cpu().numpy().reshape(Lz, Ly, Lx, 4, 3, 3) for i in range(2)]
     U_host = np.stack([U_two[i % 2] for i in range(K)])
-    evec = CyclicEigenvectors([inputs[i][1].cpu().numpy().reshape(Ne, Lz, Ly, Lx, 3) for i in range(2)])
+    V_two = [inputs[i][1].cpu().numpy().reshape(Ne, Lz, Ly, Lx, 3) for i in range(2)]
+    if K * V_two[0].nbytes <= 8 << 30:  # small enough to hold K timeslices: the ordinary in-memory handle
+        evec = edb.EigenvectorHostmem(np.stack([V_two[i % 2] for i in range(K)]))
+    else:
+        evec = CyclicEigenvectors(V_two)
     del inputs, U0, v0
     torch.cuda.empty_cache()
     if dist_ is None:

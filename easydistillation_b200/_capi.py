@@ -39,6 +39,8 @@ SIGNATURES = {
     "edk_laplacian": (_i, [_vp, _vp, _vp, _i, _vp]),
     "edk_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "edk_host_free": (_i, [_vp]),
+    "edk_host_register": (_i, [_vp, _sz]),
+    "edk_host_unregister": (_i, [_vp]),
     "edk_set_profiling": (_i, [_vp, _i]),
     "edk_get_profile": (_i, [_vp, _dp, C.POINTER(_i)]),
     "edk_launch_count": (C.c_longlong, [_vp]),

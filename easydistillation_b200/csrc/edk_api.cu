@@ -910,6 +910,26 @@ int edk_host_free(void* p) {
     return EDK_OK;
 }
 
+int edk_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return EDK_ERR_ARG;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // not sticky: e.g. file-backed or already registered ranges; the caller stages instead
+        set_error("cudaHostRegister failed: %s", cudaGetErrorString(e));
+        return EDK_ERR_CUDA;
+    }
+    return EDK_OK;
+}
+int edk_host_unregister(void* p) {
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostUnregister failed: %s", cudaGetErrorString(e));
+        return EDK_ERR_CUDA;
+    }
+    return EDK_OK;
+}
+
 int edk_set_profiling(edk_handle* h, int on) {
     if (!h) return EDK_ERR_ARG;
     h->profiling = on != 0;

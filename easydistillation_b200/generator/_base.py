@@ -38,6 +38,9 @@ class _TimesliceGenerator:
 
     # ---- load(key): reference elemental.py:102-105 / displacement_elemental.py:73-76 -------------
     def load(self, key: str):
+        if self._pipeline is not None:  # staging / page-locking is tied to the arrays of one configuration
+            self._pipeline.close()
+            self._pipeline = None
         if self._gauge_ops:  # a freshly loaded configuration is unsmeared, as in the reference
             self._gauge_ops = []
             self._engine.set_link_ops([])

@@ -5,6 +5,7 @@ Ne separate open+mmap+copy calls per timeslice and a blocking upload (elemental.
 filedata/ndarray.py:17-47)."""
 from __future__ import annotations
 
+import ctypes as C
 from typing import Iterable
 
 import numpy as np
@@ -33,6 +34,32 @@ class TimeslicePipeline:
         self.ev_consumed = [None, None]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        # In-memory sources are page-locked in place (cudaHostRegister) so their timeslices go to the
+        # device by DMA straight from where they are; files / foreign handles go through the staging copy.
+        self._registered = []
+        self._U_direct = self._register(gen._U)
+        ev = getattr(gen._eigenvector_data, "_a", None)
+        self._V_direct = self._register(ev) if gen._eigvecs_view(0) is not None else False
+
+    def _register(self, a) -> bool:
+        if not isinstance(a, np.ndarray) or isinstance(a, np.memmap) or not a.flags.c_contiguous or a.nbytes == 0:
+            return False
+        if not a.flags.writeable or _capi.lib().edk_host_register(C.c_void_p(a.ctypes.data), a.nbytes) != _capi.EDK_OK:
+            return False
+        self._registered.append(a)
+        return True
+
+    def close(self):
+        for a in self._registered:
+            _capi.lib().edk_host_unregister(C.c_void_p(a.ctypes.data))
+        self._registered = []
+
+    def __del__(self):
+        try:
+            self.torch.cuda.synchronize(self.eng.device)
+            self.close()
+        except Exception:
+            pass
 
     def _stage(self, b: int, t: int):
         """Host side of one timeslice: source handles -> pinned staging -> async upload."""
@@ -46,21 +73,30 @@ class TimeslicePipeline:
             V_t = gen._eigvecs_of(t)
         if isinstance(U_t, torch.Tensor) or isinstance(V_t, torch.Tensor):
             raise TypeError("the streamed pipeline is for host-resident inputs")
-        np.copyto(self.U_pin[b].numpy().reshape(U_t.shape), U_t)
         tdt = torch.complex64 if V_t.dtype == np.complex64 else torch.complex128
-        if self.V_pin[b] is None or self.V_pin[b].dtype != tdt:
-            self.V_pin[b] = torch.empty(V_t.shape, dtype=tdt, pin_memory=True)
+        if self.V_dev[b] is None or self.V_dev[b].dtype != tdt:
             self.V_dev[b] = torch.empty(V_t.shape, dtype=tdt, device=self.eng.device)
-        np.copyto(self.V_pin[b].numpy(), V_t)
+        if self._U_direct:
+            U_src = torch.from_numpy(U_t).reshape(self.U_dev[b].shape)
+        else:
+            np.copyto(self.U_pin[b].numpy().reshape(U_t.shape), U_t)
+            U_src = self.U_pin[b]
+        if self._V_direct:
+            V_src = torch.from_numpy(V_t)
+        else:
+            if self.V_pin[b] is None or self.V_pin[b].dtype != tdt:
+                self.V_pin[b] = torch.empty(V_t.shape, dtype=tdt, pin_memory=True)
+            np.copyto(self.V_pin[b].numpy(), V_t)
+            V_src = self.V_pin[b]
         with torch.cuda.stream(self.copy_stream):
             if self.ev_consumed[b] is not None:
                 self.copy_stream.wait_event(self.ev_consumed[b])  # device slot free again
-            self.U_dev[b].copy_(self.U_pin[b], non_blocking=True)
-            self.V_dev[b].copy_(self.V_pin[b], non_blocking=True)
+            self.U_dev[b].copy_(U_src, non_blocking=True)
+            self.V_dev[b].copy_(V_src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
             self.ev_h2d[b] = ev
-        self.h2d_bytes += self.U_pin[b].numel() * 16 + self.V_pin[b].numel() * self.V_pin[b].element_size()
+        self.h2d_bytes += self.U_dev[b].numel() * 16 + self.V_dev[b].numel() * self.V_dev[b].element_size()
 
     def _compute(self, b: int, out):
         torch = self.torch

@@ -123,6 +123,10 @@ int edk_laplacian(edk_handle* h, const void* F_dev, void* out_dev, int nvec, voi
 /* page-locked host memory for the buffers above (cudaHostAlloc / cudaFreeHost) */
 int edk_host_alloc(void** p, size_t bytes);
 int edk_host_free(void* p);
+/* page-lock an existing host range in place (cudaHostRegister) so its timeslices can be uploaded by DMA
+ * without a staging copy; fails harmlessly (EDK_ERR_CUDA) for ranges that cannot be locked */
+int edk_host_register(void* p, size_t bytes);
+int edk_host_unregister(void* p);
 
 /*
  * Measurement hooks.  With profiling on, every kernel class of the next edk_calc is
