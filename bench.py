@@ -228,8 +228,15 @@ def run_reference(args):
     vals = []
     sample = ""
     dist_ = args.distance if args.generator == "displacement" else None
+    # synthetic inputs are made once; every step then times the same bounded sample of the workload
+    from oracle import elemental_oracle as orc
+
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    rng = np.random.default_rng(orc.SEED0)
+    W0 = (rng.standard_normal((Ne, Lz, Ly, Lx, 3)) + 1j * rng.standard_normal((Ne, Lz, Ly, Lx, 3))).astype(np.complex64)
+    U = orc.links_file_to_spatial(orc.synthetic_links([Lx, Ly, Lz, Lt], 0))
     for i in range(args.warmup + args.steps):
-        v, sample = cpu_sample(name) if dist_ is None else cpu_sample_displacement(name, dist_)
+        v, sample = cpu_sample(name, W0, U) if dist_ is None else cpu_sample_displacement(name, dist_, W0, U)
         if i >= args.warmup:
             vals.append(v)
     value = float(len(vals) / sum(1.0 / v for v in vals))
