@@ -12,8 +12,8 @@
 // colour), links [3][Lz][Ly][Lx][3][3] complex128 (144 B per site and direction).
 //
 // Stencil work decomposition: one thread owns (site, direction) and keeps the two link
-// matrices it needs, U_d(x) and U_d(x-d), in registers while it walks over a block of EB
-// eigenvectors, so link traffic is amortised EB-fold and every field element is streamed.
+// matrices it needs, U_d(x) and U_d(x-d), in registers while it walks over a chunk of
+// eigenvectors, so link traffic is amortised over the chunk and every field element is streamed.
 #include "edk_common.cuh"
 
 namespace edk {
@@ -140,112 +140,128 @@ cudaError_t launch_phase_table(cplx* phase, cplx* rot, const int* mom3_dev, int 
 // nabla3: out_d = nabla_d W  for d = x, y, z
 //
 // HBM-bound (192 B of field traffic per (eigenvector, site), 216 DFMA).  One thread owns
-// (site, direction): U_d(x) and U_d(x-d) stay in registers for a block of NABLA_EB
-// eigenvectors.  The two neighbour colour vectors of eigenvector e+1..e+3 are already in flight
-// while e is computed: each thread stages them with 16-byte cp.async into its own shared-memory
-// slots (a 4-deep ring, SoA so that a warp's LDS.128 is conflict-free); the slots are
-// thread-private, so the pipeline needs no block barrier.  L1 keeps the x/y neighbour reuse,
-// L2 the z reuse, so DRAM traffic stays at the algorithmic minimum (ncu: 1.03x).
+// (site, direction): U_d(x) and U_d(x-d) stay in registers while it walks over a chunk of ~50
+// eigenvectors (the 288 B of links per thread cost 54 B per (e, site) at 16 eigenvectors per CTA
+// and 17 B at 50: measured 3.94 -> 4.35 TB/s).  The neighbour colour vectors of the next two
+// eigenvectors are prefetched straight into registers (two independent LDG batches in flight per
+// thread); L1 serves the x/y neighbour reuse, L2 the z reuse.  A warp = 32 consecutive sites of
+// one direction, so its results are 1536 contiguous bytes: they are staged through warp-private
+// shared memory and every STG.128 writes 512 contiguous bytes (full sectors) instead of 16-byte
+// pieces strided by 48 bytes.
+// Measured alternatives (32^3 / 48^3, Ne=200): 4-deep cp.async ring in shared memory 3.94 TB/s at
+// 16 eigenvectors per CTA (3 stages 3.96, 2 stages 3.26, 6 stages 2.99, 3 CTAs/SM 2.41: shared
+// memory eats the L1 that serves the reuse); eigenvector chunk as the fast CTA index 3.69; CTAs
+// grouped per wave 3.84; links pinned in L2 (access-policy window) no change.
 // ---------------------------------------------------------------------------------------
-constexpr int NABLA_SITES = 64;   // sites per CTA (threadIdx.x), threadIdx.y = direction
+constexpr int NABLA_SITES = 64;  // sites per CTA (threadIdx.x), threadIdx.y = direction
 constexpr int NABLA_THREADS = NABLA_SITES * 3;
-constexpr int NABLA_EB = 16;      // eigenvectors per CTA
 
-__device__ __forceinline__ void cp_async_ca16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
-}
-
-template <int NABLA_STAGES, int MINB>
-__global__ void __launch_bounds__(NABLA_THREADS, MINB)
+__global__ void __launch_bounds__(NABLA_THREADS, 2)
 nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restrict__ o1, cplx* __restrict__ o2,
-              const cplx* __restrict__ links, Geom g, int Ne) {
-    extern __shared__ __align__(16) unsigned char nabla_smem[];
+              const cplx* __restrict__ links, Geom g, int Ne, int chunk) {
+    __shared__ cplx stage[NABLA_THREADS / 32][96];
     const int site = blockIdx.x * NABLA_SITES + threadIdx.x;
     const int d = threadIdx.y;
-    if (site >= g.V) return;  // no block-wide barrier below
-    const int tid = threadIdx.y * NABLA_SITES + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    cplx* my_stage = stage[(threadIdx.y * NABLA_SITES + threadIdx.x) >> 5];
+    const int warp_site0 = blockIdx.x * NABLA_SITES + (threadIdx.x & ~31);
+    const int warp_sites = min(32, g.V - warp_site0);
+    if (warp_sites <= 0) return;    // whole warp past the end of the volume (no block barrier below)
+    const bool active = site < g.V;  // lanes past the end only help with the coalesced stores
     int x, y, z;
-    site_coords(site, g, x, y, z);
+    site_coords(active ? site : 0, g, x, y, z);
     const int sf = neighbour(x, y, z, d, +1, g);
     const int sb = neighbour(x, y, z, d, -1, g);
-
-    const int e0 = blockIdx.y * NABLA_EB;
-    const int e1 = min(e0 + NABLA_EB, Ne);
+    const int e0 = blockIdx.y * chunk;
+    const int e1 = min(e0 + chunk, Ne);
     const size_t fs = (size_t)g.V * 3;
-    const cplx* pf = W + (size_t)e0 * fs + (size_t)sf * 3;
-    const cplx* pb = W + (size_t)e0 * fs + (size_t)sb * 3;
-    // slot j of stage s of this thread: ((s*6 + j) * NABLA_THREADS + tid) * 16 bytes
-    const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(nabla_smem) + tid * 16;
-    auto issue = [&](int e) {
-        const uint32_t dst = slot0 + (uint32_t)(((e - e0) % NABLA_STAGES) * 6 * NABLA_THREADS * 16);
-        const size_t off = (size_t)(e - e0) * fs;
+    const cplx* pf = W + (size_t)sf * 3;
+    const cplx* pb = W + (size_t)sb * 3;
+
+    cplx fa[3], ba[3], fb[3], bb[3];
+    auto fetch = [&](int e, cplx (&f)[3], cplx (&b)[3]) {
+        if (e < e1 && active) {
+            const size_t off = (size_t)e * fs;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            cp_async_ca16(dst + c * (NABLA_THREADS * 16), pf + off + c);
-            cp_async_ca16(dst + (3 + c) * (NABLA_THREADS * 16), pb + off + c);
+            for (int c = 0; c < 3; ++c) {
+                f[c] = ldg(pf + off + c);
+                b[c] = ldg(pb + off + c);
+            }
         }
     };
-#pragma unroll
-    for (int s = 0; s < NABLA_STAGES - 1; ++s) {
-        if (e0 + s < e1) issue(e0 + s);
-        asm volatile("cp.async.commit_group;\n" ::);
-    }
+    fetch(e0, fa, ba);
+    fetch(e0 + 1, fb, bb);
 
     cplx U[9], Ub[9];
-    const cplx* pu = links + ((size_t)d * g.V + site) * 9;
+    const cplx* pu = links + ((size_t)d * g.V + (active ? site : 0)) * 9;
     const cplx* pl = links + ((size_t)d * g.V + sb) * 9;
 #pragma unroll
     for (int m = 0; m < 9; ++m) {
         U[m] = ldg(pu + m);
         Ub[m] = ldg(pl + m);
     }
-    cplx* out = (d == 0 ? o0 : (d == 1 ? o1 : o2)) + (size_t)site * 3;
-
-    for (int e = e0; e < e1; ++e) {
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(NABLA_STAGES - 2));
-        const unsigned char* st = nabla_smem + ((e - e0) % NABLA_STAGES) * 6 * NABLA_THREADS * 16 + tid * 16;
-        cplx wf[3], wb[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            wf[c] = *reinterpret_cast<const cplx*>(st + c * (NABLA_THREADS * 16));
-            wb[c] = *reinterpret_cast<const cplx*>(st + (3 + c) * (NABLA_THREADS * 16));
-        }
-        // refill the slot that was read one iteration ago (its loads above are complete)
-        if (e + NABLA_STAGES - 1 < e1) issue(e + NABLA_STAGES - 1);
-        asm volatile("cp.async.commit_group;\n" ::);
+    cplx* out = (d == 0 ? o0 : (d == 1 ? o1 : o2)) + (size_t)warp_site0 * 3;  // the warp's block
+    const int warp_cplx = warp_sites * 3;
+    auto apply = [&](int e, const cplx (&f)[3], const cplx (&b)[3]) {
         cplx r[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             r[a] = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                cfma(r[a], U[3 * a + b], wf[b]);         // U_d(x) W(x+d)
-                cfnma_conj(r[a], Ub[3 * b + a], wb[b]);  // - U_d(x-d)^dagger W(x-d)
+            for (int c = 0; c < 3; ++c) {
+                cfma(r[a], U[3 * a + c], f[c]);         // U_d(x) W(x+d)
+                cfnma_conj(r[a], Ub[3 * c + a], b[c]);  // - U_d(x-d)^dagger W(x-d)
             }
         }
+        __syncwarp();  // the previous round's reads of the staging block are done
+#pragma unroll
+        for (int a = 0; a < 3; ++a) my_stage[lane * 3 + a] = r[a];
+        __syncwarp();
         cplx* po = out + (size_t)e * fs;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) po[a] = r[a];
+        for (int j = 0; j < 3; ++j)
+            if (j * 32 + lane < warp_cplx) po[j * 32 + lane] = my_stage[j * 32 + lane];
+    };
+    for (int e = e0; e < e1; e += 2) {
+        cplx f0[3], b0[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            f0[c] = fa[c];
+            b0[c] = ba[c];
+        }
+        fetch(e + 2, fa, ba);
+        apply(e, f0, b0);
+        if (e + 1 < e1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                f0[c] = fb[c];
+                b0[c] = bb[c];
+            }
+            fetch(e + 3, fb, bb);
+            apply(e + 1, f0, b0);
+        }
     }
 }
 
-template <int STAGES, int MINB>
-static cudaError_t launch_nabla3_v(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
-                                   cudaStream_t s) {
-    constexpr int SMEM = STAGES * 6 * NABLA_THREADS * (int)sizeof(cplx);
-    cudaError_t e = cudaFuncSetAttribute(nabla3_kernel<STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return e;
-    dim3 block(NABLA_SITES, 3);
-    dim3 grid((g.V + NABLA_SITES - 1) / NABLA_SITES, (Ne + NABLA_EB - 1) / NABLA_EB);
-    nabla3_kernel<STAGES, MINB><<<grid, block, SMEM, s>>>(W_in, out_x, out_y, out_z, links, g, Ne);
-    return cudaGetLastError();
+// eigenvectors per CTA: ~56 at most, balanced over the chunks, but never so few CTAs that the
+// 148 SMs (2 CTAs each) see less than ~3 waves
+static int stencil_chunk(int V, int sites_per_cta, int Ne) {
+    const int nblk = (V + sites_per_cta - 1) / sites_per_cta;
+    int nchunk = (Ne + 55) / 56;
+    const int want = (3 * 296 + nblk - 1) / nblk;
+    if (nchunk < want) nchunk = want;
+    if (nchunk > (Ne + 7) / 8) nchunk = (Ne + 7) / 8;
+    if (nchunk < 1) nchunk = 1;
+    return (Ne + nchunk - 1) / nchunk;
 }
 
 cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
                           cudaStream_t s) {
-    // measured on B200 (32^3, Ne=200): 4 stages x 2 CTAs/SM 3.99 TB/s; 3 stages 3.96; 2 stages 3.26;
-    // 6 stages 2.99 and 3 CTAs/SM 2.41 (their shared memory eats the L1 that serves the x/y reuse)
-    return launch_nabla3_v<4, 2>(W_in, out_x, out_y, out_z, links, g, Ne, s);
+    const int chunk = stencil_chunk(g.V, NABLA_SITES, Ne);
+    dim3 block(NABLA_SITES, 3);
+    dim3 grid((g.V + NABLA_SITES - 1) / NABLA_SITES, (Ne + chunk - 1) / chunk);
+    nabla3_kernel<<<grid, block, 0, s>>>(W_in, out_x, out_y, out_z, links, g, Ne, chunk);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -254,10 +270,9 @@ cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_
 //   line 5-d      : B_d^k(x) = U_d(x-d)^dag  B_d^{k-1}(x-d)
 // ---------------------------------------------------------------------------------------
 constexpr int DISP_SITES = 64;
-constexpr int DISP_EB = 8;
 
 __global__ void __launch_bounds__(DISP_SITES * 6)
-displace_step6_kernel(Ptr6 p, cplx* __restrict__ mean_out, const cplx* __restrict__ links, Geom g, int Ne) {
+displace_step6_kernel(Ptr6 p, cplx* __restrict__ mean_out, const cplx* __restrict__ links, Geom g, int Ne, int chunk) {
     __shared__ cplx red[6][DISP_SITES][3];
     const int site = blockIdx.x * DISP_SITES + threadIdx.x;
     const int line = threadIdx.y;
@@ -275,8 +290,8 @@ displace_step6_kernel(Ptr6 p, cplx* __restrict__ mean_out, const cplx* __restric
     }
     const cplx* src = p.src[line];
     cplx* dst = p.dst[line];
-    const int e0 = blockIdx.y * DISP_EB;
-    const int e1 = min(e0 + DISP_EB, Ne);
+    const int e0 = blockIdx.y * chunk;
+    const int e1 = min(e0 + chunk, Ne);
     const size_t fs = (size_t)g.V * 3;
     const int tid = threadIdx.y * DISP_SITES + threadIdx.x;
     for (int e = e0; e < e1; ++e) {
@@ -322,9 +337,10 @@ displace_step6_kernel(Ptr6 p, cplx* __restrict__ mean_out, const cplx* __restric
 }
 
 cudaError_t launch_displace_step6(Ptr6 p, cplx* mean_out, const cplx* links, Geom g, int Ne, cudaStream_t s) {
+    const int chunk = stencil_chunk(g.V, DISP_SITES, Ne);
     dim3 block(DISP_SITES, 6);
-    dim3 grid((g.V + DISP_SITES - 1) / DISP_SITES, (Ne + DISP_EB - 1) / DISP_EB);
-    displace_step6_kernel<<<grid, block, 0, s>>>(p, mean_out, links, g, Ne);
+    dim3 grid((g.V + DISP_SITES - 1) / DISP_SITES, (Ne + chunk - 1) / chunk);
+    displace_step6_kernel<<<grid, block, 0, s>>>(p, mean_out, links, g, Ne, chunk);
     return cudaGetLastError();
 }
 
