@@ -26,6 +26,7 @@ SIGNATURES = {
     "edk_create": (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_vp)]),
     "edk_destroy": (_i, [_vp]),
     "edk_phase_table": (_i, [_i, _i, _i, _i, C.POINTER(_i), _vp, _i, _vp]),
+    "edk_plan": (_i, [_i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i)]),
     "edk_num_operators": (_i, [_vp]),
     "edk_output_bytes": (_sz, [_vp]),
     "edk_workspace_bytes": (_sz, [_vp]),
@@ -90,6 +91,20 @@ def check(rc: int, what: str = "edk"):
     if rc == EDK_ERR_NOMEM:
         raise MemoryError(f"{what}: {msg}")
     raise EdkError(f"{what} failed ({rc}): {msg}")
+
+
+def plan(mode: int, order: int, momentum_list, sym_request: int = -1) -> dict:
+    """Host-only contraction plan (edk_plan): pairing decision, momentum counts, pair-GEMM counts."""
+    import numpy as np
+
+    mom = np.ascontiguousarray(np.asarray(momentum_list, dtype=np.int32).reshape(-1, 3))
+    out = (C.c_int * 8)()
+    check(lib().edk_plan(mode, order, mom.shape[0], mom.ctypes.data_as(C.POINTER(C.c_int)), sym_request, out), "edk_plan")
+    keys = ("hermitian_pairing", "internal_momenta", "half_set_momenta", "pairs_direct", "pairs_paired",
+            "pair_momentum_gemms", "operators", "self_pairs")
+    d = dict(zip(keys, list(out)))
+    d["hermitian_pairing"] = bool(d["hermitian_pairing"])
+    return d
 
 
 def require_cuda():

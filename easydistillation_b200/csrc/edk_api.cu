@@ -282,7 +282,7 @@ void build_derivative_jobs(edk_handle* h) {
 }
 
 // number of pair-GEMMs (segments) the two modes need, to decide which is cheaper
-void count_pairs(int order, int& plain, int& sym) {
+void count_pairs(int order, int& plain, int& sym, int* self_pairs = nullptr) {
     std::map<std::pair<int, int>, int> a, b;
     const int nop = pow3sum(order);
     for (int n = 0; n < nop; ++n) {
@@ -299,6 +299,10 @@ void count_pairs(int order, int& plain, int& sym) {
     }
     plain = (int)a.size();
     sym = (int)b.size();
+    if (self_pairs) {
+        *self_pairs = 0;
+        for (const auto& kv : b) *self_pairs += kv.first.first == kv.first.second;
+    }
 }
 
 void build_displacement_jobs(edk_handle* h) {
@@ -428,43 +432,44 @@ int build_tma(edk_handle* h) {
     return EDK_OK;
 }
 
-// (Re)build everything that depends on the momentum list and on the pairing mode:
-// internal momentum list, phase tables, contraction jobs, combine recipe, partial-sum buffer.
-int configure(edk_handle* h) {
-    const int nmom = h->nmom;
-    h->mom_int = h->mom_user;
-    h->symmetric = false;
-    h->pmap.resize(nmom);
-    for (int i = 0; i < nmom; ++i) h->pmap[i] = i;
-    if (h->mode == EDK_MODE_DERIVATIVE && h->order >= 1 && h->sym_request != 0) {
-        // distinct momenta of the caller plus any missing negatives
-        std::vector<int> ext;
-        auto find = [&](const std::vector<int>& v, int px, int py, int pz) {
-            for (size_t i = 0; i < v.size() / 3; ++i)
-                if (v[3 * i] == px && v[3 * i + 1] == py && v[3 * i + 2] == pz) return (int)i;
-            return -1;
-        };
+// Momentum bookkeeping of the contraction, pure host logic (unit-tested on CPU through edk_plan):
+// whether the Hermitian pairing pays, the internal momentum list (the caller's distinct momenta plus
+// missing negatives, one representative of every {p, -p} couple first), the index of -p for every
+// internal p, the caller's -> internal map and the size of the half set the self pairs contract.
+struct MomentumPlan {
+    bool symmetric = false;
+    std::vector<int> mom_int, negidx, pmap;
+    int n_half = 0;
+};
+
+MomentumPlan plan_momenta(int mode, int order, int sym_request, const std::vector<int>& mom_user) {
+    MomentumPlan P;
+    const int nmom = (int)mom_user.size() / 3;
+    P.mom_int = mom_user;
+    P.pmap.resize(nmom);
+    for (int i = 0; i < nmom; ++i) P.pmap[i] = i;
+    auto find = [](const std::vector<int>& v, int px, int py, int pz) {
+        for (size_t i = 0; i < v.size() / 3; ++i)
+            if (v[3 * i] == px && v[3 * i + 1] == py && v[3 * i + 2] == pz) return (int)i;
+        return -1;
+    };
+    if (mode == EDK_MODE_DERIVATIVE && order >= 1 && sym_request != 0) {
+        std::vector<int> ext;  // distinct momenta of the caller plus any missing negatives
         for (int i = 0; i < nmom; ++i) {
-            const int* m = &h->mom_user[3 * i];
+            const int* m = &mom_user[3 * i];
             if (find(ext, m[0], m[1], m[2]) < 0) ext.insert(ext.end(), m, m + 3);
         }
         const size_t nuser_distinct = ext.size() / 3;
         for (size_t i = 0; i < nuser_distinct; ++i) {
             const int px = -ext[3 * i], py = -ext[3 * i + 1], pz = -ext[3 * i + 2];
-            if (find(ext, px, py, pz) < 0) {
-                ext.push_back(px);
-                ext.push_back(py);
-                ext.push_back(pz);
-            }
+            if (find(ext, px, py, pz) < 0) ext.insert(ext.end(), {px, py, pz});
         }
         int plain = 0, sym = 0;
-        count_pairs(h->order, plain, sym);
+        count_pairs(order, plain, sym);
         const long long cost_sym = (long long)sym * (long long)(ext.size() / 3);
         const long long cost_plain = (long long)plain * nmom;
-        if (h->sym_request == 1 || cost_sym < cost_plain) {
-            h->symmetric = true;
-            // internal order: one representative of every {p, -p} couple first (self-conjugate p = 0
-            // included), then the partners, so that self pairs only contract the first half
+        if (sym_request == 1 || cost_sym < cost_plain) {
+            P.symmetric = true;
             std::vector<int> reps, partners;
             for (size_t i = 0; i < ext.size() / 3; ++i) {
                 const int px = ext[3 * i], py = ext[3 * i + 1], pz = ext[3 * i + 2];
@@ -472,27 +477,38 @@ int configure(edk_handle* h) {
                 reps.insert(reps.end(), {px, py, pz});
                 if (px != 0 || py != 0 || pz != 0) partners.insert(partners.end(), {-px, -py, -pz});
             }
-            h->n_half = (int)reps.size() / 3;
-            h->mom_int = reps;
-            h->mom_int.insert(h->mom_int.end(), partners.begin(), partners.end());
+            P.n_half = (int)reps.size() / 3;
+            P.mom_int = reps;
+            P.mom_int.insert(P.mom_int.end(), partners.begin(), partners.end());
             for (int i = 0; i < nmom; ++i) {
-                const int* m = &h->mom_user[3 * i];
-                h->pmap[i] = find(h->mom_int, m[0], m[1], m[2]);
+                const int* m = &mom_user[3 * i];
+                P.pmap[i] = find(P.mom_int, m[0], m[1], m[2]);
             }
         }
     }
+    const int nint = (int)P.mom_int.size() / 3;
+    if (!P.symmetric) P.n_half = nint;
+    P.negidx.assign(nint, -1);
+    for (int i = 0; i < nint; ++i) {
+        if (!P.symmetric) {
+            P.negidx[i] = i;  // never used without the pairing
+            continue;
+        }
+        P.negidx[i] = find(P.mom_int, -P.mom_int[3 * i], -P.mom_int[3 * i + 1], -P.mom_int[3 * i + 2]);
+    }
+    return P;
+}
+
+// (Re)build everything that depends on the momentum list and on the pairing mode:
+// internal momentum list, phase tables, contraction jobs, combine recipe, partial-sum buffer.
+int configure(edk_handle* h) {
+    const MomentumPlan plan = plan_momenta(h->mode, h->order, h->sym_request, h->mom_user);
+    h->symmetric = plan.symmetric;
+    h->mom_int = plan.mom_int;
+    h->negidx = plan.negidx;
+    h->pmap = plan.pmap;
+    h->n_half = plan.n_half;
     h->nmom_int = (int)h->mom_int.size() / 3;
-    if (!h->symmetric) h->n_half = h->nmom_int;
-    h->negidx.assign(h->nmom_int, -1);
-    for (int i = 0; i < h->nmom_int; ++i)
-        for (int j = 0; j < h->nmom_int; ++j)
-            if (h->mom_int[3 * j] == -h->mom_int[3 * i] && h->mom_int[3 * j + 1] == -h->mom_int[3 * i + 1] &&
-                h->mom_int[3 * j + 2] == -h->mom_int[3 * i + 2]) {
-                h->negidx[i] = j;
-                break;
-            }
-    if (!h->symmetric)
-        for (int i = 0; i < h->nmom_int; ++i) h->negidx[i] = i;  // never dereferenced meaningfully without pairing
     if (h->mode == EDK_MODE_DERIVATIVE)
         build_derivative_jobs(h);
     else
@@ -727,6 +743,31 @@ int edk_phase_table(int Lx, int Ly, int Lz, int nmom, const int* mom3, void* out
         set_error("edk_phase_table: %s", cudaGetErrorString(e));
         return EDK_ERR_CUDA;
     }
+    return EDK_OK;
+}
+
+int edk_plan(int mode, int order, int nmom, const int* mom3, int sym_request, int out[8]) {
+    if (nmom < 1 || !mom3 || !out || order < 0 || (mode != EDK_MODE_DERIVATIVE && mode != EDK_MODE_DISPLACEMENT) ||
+        (mode == EDK_MODE_DERIVATIVE && order > 3)) {
+        set_error("edk_plan: bad argument");
+        return EDK_ERR_ARG;
+    }
+    const std::vector<int> user(mom3, mom3 + 3 * (size_t)nmom);
+    const MomentumPlan P = plan_momenta(mode, order, sym_request, user);
+    const int nint = (int)P.mom_int.size() / 3;
+    int plain = 1, sym = 1, self = 0;
+    if (mode == EDK_MODE_DERIVATIVE)
+        count_pairs(order, plain, sym, &self);
+    else
+        plain = sym = order + 1;
+    out[0] = P.symmetric ? 1 : 0;
+    out[1] = nint;
+    out[2] = P.n_half;
+    out[3] = plain;
+    out[4] = sym;
+    out[5] = P.symmetric ? (sym - self) * nint + self * P.n_half : plain * nint;  // (pair, momentum) GEMMs per timeslice
+    out[6] = mode == EDK_MODE_DERIVATIVE ? pow3sum(order) : order + 1;            // operators in the output
+    out[7] = self;
     return EDK_OK;
 }
 

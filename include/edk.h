@@ -67,6 +67,16 @@ int edk_destroy(edk_handle* h);
  */
 int edk_phase_table(int Lx, int Ly, int Lz, int nmom, const int* mom3, void* out_dev, int device, void* stream);
 
+/*
+ * Contraction plan for a momentum list, pure host logic (no device needed): out[0] Hermitian pairing
+ * G(L,R,p)^dagger = G(R,L,-p) used (sym_request: -1 auto by cost, 0 never, 1 always), out[1] internal momenta
+ * (the caller's plus missing negatives), out[2] half set contracted by self pairs L == R, out[3]/out[4] distinct
+ * (left, right) pairs without / with the pairing (34 / 19 for num_nabla = 2; the reference runs 43,
+ * lattice/generator/elemental.py:309-329), out[5] (pair, momentum) GEMMs per timeslice, out[6] output operators,
+ * out[7] self pairs.
+ */
+int edk_plan(int mode, int order, int nmom, const int* mom3, int sym_request, int out[8]);
+
 /* number of operators in the output: (3^(num_nabla+1)-1)/2 or distance+1 (elemental.py:48, displacement_elemental.py:45) */
 int edk_num_operators(const edk_handle* h);
 /* bytes of one timeslice result [Nop][Nmom][Ne][Ne] complex128 */

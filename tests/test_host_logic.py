@@ -177,3 +177,32 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "tiny",
                           "--steps", "1", "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_contraction_plan_host_logic():
+    """edk_plan: pairing decision and pair / momentum counts (pure host code of the library)."""
+    from oracle.elemental_oracle import momentum_set
+
+    m33, m9 = momentum_set(33), momentum_set(9)
+    p = _capi.plan(_capi.MODE_DERIVATIVE, 2, m33)
+    assert p == {"hermitian_pairing": True, "internal_momenta": 33, "half_set_momenta": 17, "pairs_direct": 34,
+                 "pairs_paired": 19, "pair_momentum_gemms": 15 * 33 + 4 * 17, "operators": 13, "self_pairs": 4}
+    # the reference contracts 43 pairs x 33 momenta = 1419 for the same timeslice
+    assert _capi.plan(_capi.MODE_DERIVATIVE, 2, m33, 0)["pair_momentum_gemms"] == 34 * 33
+    p = _capi.plan(_capi.MODE_DERIVATIVE, 1, m9)  # 9 momenta are not closed under negation: 2 are added
+    assert p["hermitian_pairing"] and p["internal_momenta"] == 11 and p["pairs_direct"] == 7 and p["pairs_paired"] == 4
+    assert p["half_set_momenta"] == 6 and p["pair_momentum_gemms"] == 3 * 11 + 1 * 6 and p["operators"] == 4
+    # a list with no negatives at all: closing it doubles the momenta, 19 * 8 > 34 * 4, so pairing does not pay
+    one_sided = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0)]
+    p = _capi.plan(_capi.MODE_DERIVATIVE, 2, one_sided)
+    assert not p["hermitian_pairing"] and p["internal_momenta"] == 4 and p["pair_momentum_gemms"] == 34 * 4
+    assert not _capi.plan(_capi.MODE_DERIVATIVE, 1, one_sided)["hermitian_pairing"]  # 4 * 8 > 7 * 4
+    p = _capi.plan(_capi.MODE_DERIVATIVE, 2, one_sided, 1)  # forced
+    assert p["hermitian_pairing"] and p["internal_momenta"] == 8 and p["half_set_momenta"] == 4
+    # no derivative / displacement: nothing to pair
+    assert not _capi.plan(_capi.MODE_DERIVATIVE, 0, m33)["hermitian_pairing"]
+    p = _capi.plan(_capi.MODE_DISPLACEMENT, 8, m9)
+    assert not p["hermitian_pairing"] and p["operators"] == 9 and p["pair_momentum_gemms"] == 9 * 9
+    assert _capi.plan(_capi.MODE_DERIVATIVE, 3, m33)["operators"] == 40
+    with pytest.raises(ValueError):
+        _capi.plan(_capi.MODE_DERIVATIVE, 4, m9)
