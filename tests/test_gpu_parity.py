@@ -391,6 +391,35 @@ def test_file_handles_and_elemental_npy_roundtrip(edb, tmp_path):
     _blocks_close(full[0].cpu().numpy(), g["E"][0], what="calc_all")
 
 
+def test_device_resident_inputs(edb):
+    """the generators also take torch CUDA tensors (a handle whose load() returns a tensor)."""
+    import torch
+
+    g, latt, moms = _golden_case("deriv_weak_4x4x4x2")
+
+    class TensorHandle:
+        def __init__(self, tensor, Ne=None):
+            self.tensor, self.Ne = tensor, Ne
+
+        def load(self, key):
+            return self.tensor
+
+    U_dev = torch.from_numpy(g["U"]).cuda()
+    V_dev = torch.from_numpy(g["V"]).cuda()
+    for gauge, evec in ((TensorHandle(U_dev), TensorHandle(V_dev, 8)),                       # both on the device
+                        (edb.GaugeFieldHostmem(g["U"]), TensorHandle(V_dev, 8)),             # mixed
+                        (TensorHandle(U_dev), edb.EigenvectorHostmem(g["V"]))):
+        gen = edb.ElementalGenerator(latt, gauge, evec, 2, moms)
+        gen.load("cfg")
+        _blocks_close(np.array(gen.calc(1)), g["E"][1], what="device-resident inputs, calc")
+        out = gen.calc_device(0)
+        assert out.is_cuda
+        _blocks_close(out.cpu().numpy(), g["E"][0], what="device-resident inputs, calc_device")
+        full = gen.calc_all()
+        _blocks_close(full[1].cpu().numpy(), g["E"][1], what="device-resident inputs, calc_all")
+        _blocks_close(gen.calc_range(0, 2)[0], g["E"][0], what="device-resident inputs, calc_range")
+
+
 def test_laplacian_matches_reference_golden(edb):
     """The eigensolver's operator on the same links and stencil machinery."""
     import torch
