@@ -56,7 +56,17 @@ def algorithmic(name, distance=None):
     if distance is not None:
         return 8.0 * Ne * Ne * 3 * V * nmom * (distance + 1), 13 * Ne * V * 48.0 + 3 * V * 144.0
     flops = 8.0 * Ne * Ne * 3 * V * nmom * PAIRS_DISTINCT[nabla]
+    # nabla3 launch: 1 field in, 3 fields out, links once (SURVEY 8d) ...
     return flops, 4 * Ne * V * 48.0 + 3 * V * 144.0
+
+
+def stencil_bytes_moved(name, distance=None):
+    """... plus what this build's nabla3 additionally has to write: the Re+Im plane of each output
+    field (8 B per element), which the 3M contraction reads as its third A operand."""
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    V = Lx * Ly * Lz
+    base = algorithmic(name, distance)[1]
+    return base if distance is not None else base + 3 * Ne * V * 24.0
 
 
 def measured_traffic(kernel, name):
@@ -461,7 +471,9 @@ def run_native(args):
         achieved_tf = exec_flops / (gram_ms * 1e-3) / 1e12
         survey_tf = flops / (gram_ms * 1e-3) / 1e12
         # stencil: bytes of ONE launch (nabla3: 1 source, 3 outputs, links once; displacement step: 6 in, 6 + mean out)
-        st_gbs = st_bytes_launch / (st_ms * 1e-3) / 1e9 if prof["stencil"]["launches"] else None
+        st_moved = stencil_bytes_moved(name, dist_)
+        st_gbs = st_moved / (st_ms * 1e-3) / 1e9 if prof["stencil"]["launches"] else None
+        st_survey_gbs = st_bytes_launch / (st_ms * 1e-3) / 1e9 if prof["stencil"]["launches"] else None
         cpu_val, cpu_smp = (None, "skipped (--no-cpu-baseline)")
         if W0_host is not None and dist_ is None:
             cpu_val, cpu_smp = cpu_sample(name, W0_host.astype(np.complex64), U_sp_host)

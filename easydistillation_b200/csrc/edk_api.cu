@@ -66,6 +66,7 @@ struct edk_handle {
     };
     std::vector<LinkOp> link_ops;  // applied, in order, to every timeslice's links after upload
     cplx* fields = nullptr;   // nfield fields
+    double* fsum = nullptr;   // Re + Im of every field element, [nfield][Ne][3V]: the 3M contraction's third A operand
     int nfield = 0;
     cplx* lines = nullptr;    // displacement: 12 line buffers (ping-pong)
     cplx* phase = nullptr;    // [2][nmom][Vpad]: phase and -i*phase
@@ -99,6 +100,8 @@ struct edk_handle {
     std::vector<CombineOp> ops_host;
 
     cplx* field(int i) const { return fields + (size_t)i * field_cplx; }
+    size_t sum_row = 0;       // doubles per eigenvector row of a sum plane: 3V rounded up to even (16-byte TMA strides)
+    double* field_sum(int i) const { return fsum + (size_t)i * Ne * sum_row; }
 };
 
 namespace {
@@ -421,6 +424,15 @@ int build_tma(edk_handle* h) {
         r = encode((CUtensorMap*)h->tma.mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, boxB, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+        const cuuint64_t Ks = (cuuint64_t)3 * h->g.V;
+        const cuuint64_t sdim[3] = {Ks, (cuuint64_t)h->Ne, (cuuint64_t)(h->mode == EDK_MODE_DERIVATIVE ? h->nfield : 1)};
+        const cuuint64_t sstr[2] = {(cuuint64_t)h->sum_row * 8, (cuuint64_t)h->sum_row * 8 * (cuuint64_t)h->Ne};
+        const cuuint32_t boxS[3] = {4, (cuuint32_t)gram_rows_per_tile(h->mfrag), 1};
+        r = encode((CUtensorMap*)h->tma.mapS, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fsum, sdim, sstr, boxS, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return EDK_ERR_CUDA;
@@ -678,6 +690,9 @@ int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, co
     } while (0)
     EDK_ALLOC(h->links, (size_t)3 * h->g.V * 9 * sizeof(cplx));
     EDK_ALLOC(h->fields, (size_t)h->nfield * h->field_cplx * sizeof(cplx));
+    // displacement mode only ever has W0 on the left of a pair, so only its plane is needed
+    h->sum_row = ((size_t)3 * h->g.V + 1) & ~(size_t)1;
+    EDK_ALLOC(h->fsum, (size_t)(mode == EDK_MODE_DERIVATIVE ? h->nfield : 1) * Ne * h->sum_row * sizeof(double));
     if (mode == EDK_MODE_DISPLACEMENT && order >= 1) EDK_ALLOC(h->lines, (size_t)12 * h->field_cplx * sizeof(cplx));
     EDK_ALLOC(h->coeff, (size_t)Ne * Ne * sizeof(double));
     h->mom_user.assign(mom3, mom3 + 3 * (size_t)nmom);
@@ -700,6 +715,7 @@ int edk_destroy(edk_handle* h) {
     cudaFree(h->links);
     cudaFree(h->links_tmp);
     cudaFree(h->fields);
+    cudaFree(h->fsum);
     cudaFree(h->lines);
     cudaFree(h->phase);
     cudaFree(h->partial);
@@ -836,7 +852,8 @@ int edk_set_eigvecs(edk_handle* h, const void* V_dev, int is_c8, void* stream) {
     }
     cudaStream_t s = (cudaStream_t)stream;
     PhaseTimer t(h, s, PH_PREP, 1);
-    EDK_CUDA_TRY(launch_round_eigvecs(V_dev, is_c8 ? 1 : 0, h->field(0), h->field_cplx, s));
+    EDK_CUDA_TRY(launch_round_eigvecs(V_dev, is_c8 ? 1 : 0, h->field(0), h->field_sum(0), h->field_cplx, (size_t)3 * h->g.V,
+                                      h->sum_row, s));
     h->evecs_set = true;
     return EDK_OK;
 }
@@ -871,7 +888,8 @@ int edk_calc(edk_handle* h, void* out_dev, void* stream) {
         for (const auto& hop : h->hops) {
             PhaseTimer t(h, s, PH_STENCIL, 1);
             EDK_CUDA_TRY(launch_nabla3(h->field(hop.first), h->field(hop.second), h->field(hop.second + 1),
-                                       h->field(hop.second + 2), h->links, h->g, h->Ne, s));
+                                       h->field(hop.second + 2), h->field_sum(hop.second), h->field_sum(hop.second + 1),
+                                       h->field_sum(hop.second + 2), h->sum_row, h->links, h->g, h->Ne, s));
         }
     } else {
         for (int k = 1; k <= h->order; ++k) {

@@ -68,6 +68,7 @@ struct GramParams {
 struct GramTma {
     alignas(64) unsigned char mapA[128];  // CUtensorMap, box rows = 8*mfrag
     alignas(64) unsigned char mapB[128];  // CUtensorMap, box rows = 8
+    alignas(64) unsigned char mapS[128];  // CUtensorMap over the Re+Im planes [nfield][Ne][Kc doubles], box 4 x 8*mfrag x 1
     const cplx* phase_tiles;
     int brows_alloc;  // rows of R kept per k-group in shared memory (multiple of 8, <= 64)
     int nstages;      // depth of the full/empty ring
@@ -89,12 +90,13 @@ struct CombineOp {
 
 // ---- launchers (defined in the .cu files) -------------------------------------------------
 // prepare
-cudaError_t launch_round_eigvecs(const void* V_in, int is_c8, cplx* W0, size_t n_cplx, cudaStream_t s);
+cudaError_t launch_round_eigvecs(const void* V_in, int is_c8, cplx* W0, double* W0_sum, size_t n_cplx, size_t row,
+                                 size_t sum_row, cudaStream_t s);
 cudaError_t launch_reorder_links(const cplx* U_in, int layout, cplx* U_out, Geom g, cudaStream_t s);
 cudaError_t launch_phase_table(cplx* phase, cplx* rot, const int* mom3_dev, int nmom, Geom g, cudaStream_t s);
 // stencil
-cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
-                          cudaStream_t s);
+cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, double* sum_x, double* sum_y, double* sum_z,
+                          size_t sum_row, const cplx* links, Geom g, int Ne, cudaStream_t s);
 struct Ptr6 {
     const cplx* src[6];
     cplx* dst[6];

@@ -384,6 +384,7 @@ struct GtCols {
     static constexpr int NTAB = ALGO ? 1 : 2;               // phase tables staged per stage
     static constexpr int PH_BYTES = NTAB * NT * 8 * 16;
     static constexpr int NACC = ALGO ? 3 : 2;               // accumulator fragments per (m-fragment, warp)
+    static constexpr int LS_PER_ROW = ALGO ? 32 : 0;        // bytes per (row, k-group) of the Re+Im plane
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -425,11 +426,14 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  : "memory");
 }
 
-// 3M stage: same operand tiles as gram_compute_stage, three MMAs per (m-fragment, k-group).
+// 3M stage: same operand tiles as gram_compute_stage plus the plane Ls = Re L + Im L that the
+// field-producing kernels wrote and the producer fetched as a third box (ls_s = this lane's slot
+// in Ls[kg][row][4]); three MMAs per (m-fragment, k-group), no FP64 add in the MMA warps.
 template <int MF, int MFL>
 __device__ __forceinline__ void gram_compute_stage_3m(double (&acc)[MF][3][2], const unsigned char* a_s,
-                                                      const unsigned char* b_s, const int b_kg_stride,
-                                                      const unsigned char* p_s, const uint32_t my_boff, const int kk) {
+                                                      const unsigned char* ls_s, const unsigned char* b_s,
+                                                      const int b_kg_stride, const unsigned char* p_s,
+                                                      const uint32_t my_boff, const int kk) {
     constexpr int ROWS_A = 8 * MF;
     cplx rr = *reinterpret_cast<const cplx*>(b_s + my_boff);
     cplx pp = *reinterpret_cast<const cplx*>(p_s + (kk / 3) * 16);
@@ -452,7 +456,7 @@ __device__ __forceinline__ void gram_compute_stage_3m(double (&acc)[MF][3][2], c
             for (int ii = 0; ii < GRP; ++ii)
                 if (i0 + ii < MFL) {
                     a[ii] = *reinterpret_cast<const cplx*>(a_s + (kg * ROWS_A + 8 * (i0 + ii)) * 64);
-                    as[ii] = a[ii].x + a[ii].y;
+                    as[ii] = *reinterpret_cast<const double*>(ls_s + (kg * ROWS_A + 8 * (i0 + ii)) * 32);
                 }
 #pragma unroll
             for (int ii = 0; ii < GRP; ++ii)
@@ -483,7 +487,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     extern __shared__ __align__(1024) unsigned char smem[];
     const int nst = Tm.nstages;
     const int b_kg_stride = Tm.brows_alloc * 64;
-    const int stage_bytes = A_BYTES + GRAM_KG * b_kg_stride + C::PH_BYTES;
+    constexpr int LS_BYTES = GRAM_KG * ROWS_A * C::LS_PER_ROW;
+    const int ls_off = A_BYTES + GRAM_KG * b_kg_stride + C::PH_BYTES;  // stage = A | B | phase tile(s) | Ls plane (3M)
+    const int stage_bytes = ls_off + LS_BYTES;
     unsigned char* tail = smem + (size_t)nst * stage_bytes;
     const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(tail);  // nst x 8 bytes
     const uint32_t bar_empty = bar_full + 8 * nst;
@@ -560,7 +566,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
             }
         }
         const int nbb = (nrows_b + 7) >> 3;
-        const uint32_t tx_bytes = (uint32_t)(A_BYTES + GRAM_KG * nbb * 512 + C::NTAB * nvalid * 128);
+        const uint32_t tx_bytes = (uint32_t)(A_BYTES + LS_BYTES + GRAM_KG * nbb * 512 + C::NTAB * nvalid * 128);
         int seg = T0 / P.ksteps;
         int kstep = T0 - seg * P.ksteps;
         int s = 0;
@@ -573,6 +579,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
             const uint32_t st = smem_base + (uint32_t)(s * stage_bytes);
             const int kd = kstep * 48;  // first double of this stage's 24 complex k
             if (lane < GRAM_KG) tma_load_3d(st + lane * (ROWS_A * 64), Tm.mapA, full, kd + 8 * lane, row0, sjob->Lf[seg]);
+            if (ALGO == 1 && lane >= 8 && lane < 8 + GRAM_KG)
+                tma_load_3d(st + ls_off + (lane - 8) * (ROWS_A * 32), Tm.mapS, full, kstep * 24 + 4 * (lane - 8), row0,
+                            sjob->Lf[seg]);
             for (int i = lane; i < GRAM_KG * nbb; i += 32) {
                 const int kg = i / nbb, j = i - kg * nbb;
                 tma_load_3d(st + A_BYTES + kg * b_kg_stride + j * 512, Tm.mapB, full, kd + 8 * kg, C::FW * ff0 + 8 * j,
@@ -652,9 +661,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
                 gram_compute_stage<MF, MF>(acc, stage + lane * 16, b_s, b_kg_stride, p_s, my_boff, kk);
         } else {
             if (MF > 1 && mf_live == MF - 1)
-                gram_compute_stage_3m<MF, MFM>(acc, stage + lane * 16, b_s, b_kg_stride, p_s, my_boff[0], kk);
+                gram_compute_stage_3m<MF, MFM>(acc, stage + lane * 16, stage + ls_off + lane * 8, b_s, b_kg_stride, p_s,
+                                               my_boff[0], kk);
             else
-                gram_compute_stage_3m<MF, MF>(acc, stage + lane * 16, b_s, b_kg_stride, p_s, my_boff[0], kk);
+                gram_compute_stage_3m<MF, MF>(acc, stage + lane * 16, stage + ls_off + lane * 8, b_s, b_kg_stride, p_s,
+                                              my_boff[0], kk);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
@@ -711,7 +722,7 @@ int gram_tma_plan(int algo, int mfrag, int nmom, int Ne, int* brows_alloc, int* 
     int rows = ((FW * maxff + 7) / 8) * 8;
     if (rows > GRAM_BROWS) rows = GRAM_BROWS;
     const int ph = (algo ? 1 : 2) * NT * 128;
-    const int stage = GRAM_KG * 8 * mfrag * 64 + GRAM_KG * rows * 64 + ph;
+    const int stage = GRAM_KG * 8 * mfrag * 64 + GRAM_KG * rows * 64 + ph + (algo ? GRAM_KG * 8 * mfrag * 32 : 0);
     const int tail = 16 * 8 + (int)sizeof(GramJob) + 64;
     int nst = (227 * 1024 - tail) / stage;
     if (nst > 8) nst = 8;

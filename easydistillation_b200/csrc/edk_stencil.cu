@@ -59,7 +59,10 @@ __device__ __forceinline__ int neighbour(int x, int y, int z, int d, int sign, c
 // ---------------------------------------------------------------------------------------
 // prepare
 // ---------------------------------------------------------------------------------------
-__global__ void round_eigvecs_kernel(const void* __restrict__ in, int is_c8, cplx* __restrict__ out, size_t n) {
+// `sum` receives Re + Im of every element: the A-side operand Lr + Li of the 3M contraction
+// (rows of `sum` are padded to an even number of doubles so that a TMA tensor map can describe them)
+__global__ void round_eigvecs_kernel(const void* __restrict__ in, int is_c8, cplx* __restrict__ out,
+                                     double* __restrict__ sum, size_t n, size_t row, size_t sum_row) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     if (is_c8) {
@@ -67,22 +70,26 @@ __global__ void round_eigvecs_kernel(const void* __restrict__ in, int is_c8, cpl
         for (; i < n; i += stride) {
             float2 v = __ldg(p + i);
             out[i] = make_double2((double)v.x, (double)v.y);
+            sum[(i / row) * sum_row + i % row] = (double)v.x + (double)v.y;
         }
     } else {
         const double2* p = (const double2*)in;
         for (; i < n; i += stride) {
             double2 v = __ldg(p + i);
             // round-to-nearest-even double -> float -> double: numpy's complex128 -> complex64 assignment
-            out[i] = make_double2((double)__double2float_rn(v.x), (double)__double2float_rn(v.y));
+            const double re = (double)__double2float_rn(v.x), im = (double)__double2float_rn(v.y);
+            out[i] = make_double2(re, im);
+            sum[(i / row) * sum_row + i % row] = re + im;
         }
     }
 }
 
-cudaError_t launch_round_eigvecs(const void* V_in, int is_c8, cplx* W0, size_t n_cplx, cudaStream_t s) {
+cudaError_t launch_round_eigvecs(const void* V_in, int is_c8, cplx* W0, double* W0_sum, size_t n_cplx, size_t row,
+                                 size_t sum_row, cudaStream_t s) {
     int block = 256;
     size_t want = (n_cplx + block - 1) / block;
     int grid = (int)(want < (size_t)148 * 16 ? (want ? want : 1) : (size_t)148 * 16);
-    round_eigvecs_kernel<<<grid, block, 0, s>>>(V_in, is_c8, W0, n_cplx);
+    round_eigvecs_kernel<<<grid, block, 0, s>>>(V_in, is_c8, W0, W0_sum, n_cplx, row, sum_row);
     return cudaGetLastError();
 }
 
@@ -158,6 +165,7 @@ constexpr int NABLA_THREADS = NABLA_SITES * 3;
 
 __global__ void __launch_bounds__(NABLA_THREADS, 2)
 nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restrict__ o1, cplx* __restrict__ o2,
+              double* __restrict__ s0, double* __restrict__ s1, double* __restrict__ s2, size_t sum_row,
               const cplx* __restrict__ links, Geom g, int Ne, int chunk) {
     __shared__ cplx stage[NABLA_THREADS / 32][96];
     const int site = blockIdx.x * NABLA_SITES + threadIdx.x;
@@ -201,6 +209,7 @@ nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restric
         Ub[m] = ldg(pl + m);
     }
     cplx* out = (d == 0 ? o0 : (d == 1 ? o1 : o2)) + (size_t)warp_site0 * 3;  // the warp's block
+    double* outs = (d == 0 ? s0 : (d == 1 ? s1 : s2)) + (size_t)warp_site0 * 3;  // its Re + Im plane
     const int warp_cplx = warp_sites * 3;
     auto apply = [&](int e, const cplx (&f)[3], const cplx (&b)[3]) {
         cplx r[3];
@@ -218,9 +227,14 @@ nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restric
         for (int a = 0; a < 3; ++a) my_stage[lane * 3 + a] = r[a];
         __syncwarp();
         cplx* po = out + (size_t)e * fs;
+        double* ps = outs + (size_t)e * sum_row;
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            if (j * 32 + lane < warp_cplx) po[j * 32 + lane] = my_stage[j * 32 + lane];
+            if (j * 32 + lane < warp_cplx) {
+                const cplx v = my_stage[j * 32 + lane];
+                po[j * 32 + lane] = v;
+                ps[j * 32 + lane] = v.x + v.y;
+            }
     };
     for (int e = e0; e < e1; e += 2) {
         cplx f0[3], b0[3];
@@ -255,12 +269,12 @@ static int stencil_chunk(int V, int sites_per_cta, int Ne) {
     return (Ne + nchunk - 1) / nchunk;
 }
 
-cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, const cplx* links, Geom g, int Ne,
-                          cudaStream_t s) {
+cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, double* sum_x, double* sum_y, double* sum_z,
+                          size_t sum_row, const cplx* links, Geom g, int Ne, cudaStream_t s) {
     const int chunk = stencil_chunk(g.V, NABLA_SITES, Ne);
     dim3 block(NABLA_SITES, 3);
     dim3 grid((g.V + NABLA_SITES - 1) / NABLA_SITES, (Ne + chunk - 1) / chunk);
-    nabla3_kernel<<<grid, block, 0, s>>>(W_in, out_x, out_y, out_z, links, g, Ne, chunk);
+    nabla3_kernel<<<grid, block, 0, s>>>(W_in, out_x, out_y, out_z, sum_x, sum_y, sum_z, sum_row, links, g, Ne, chunk);
     return cudaGetLastError();
 }
 
