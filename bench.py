@@ -515,7 +515,10 @@ def run_native(args):
                 "kernel": st_name + (" (covariant central differences, 3 directions per pass)" if dist_ is None
                                      else " (six straight Wilson lines extended by one link + their mean)"), "bound": "hbm",
                 "achieved": st_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (st_gbs / hbm_peak) if st_gbs else None,
-                "traffic": measured_traffic(st_name, name if dist_ is None else name + "_displacement"), "peak_source": hbm_src, "algorithmic_bytes_per_launch": st_bytes_launch,
+                "traffic": measured_traffic(st_name, name if dist_ is None else name + "_displacement"), "peak_source": hbm_src, "algorithmic_bytes_per_launch": st_moved,
+                "survey_bytes_per_launch": st_bytes_launch, "survey_equivalent_gbs": st_survey_gbs,
+                "note": "algorithmic bytes = 1 field in + 3 fields out + links (SURVEY 8d) + the 3 Re+Im planes (8 B per element) "
+                        "this build's stencil writes for the 3M contraction; survey_equivalent_gbs counts SURVEY's bytes only",
                 "ms_per_launch": st_ms, "launches_per_step": st_launch / K,
                 "share_of_step": prof["stencil"]["ms"] / ms,
             },
