@@ -340,6 +340,10 @@ def run_native(args):
     else:
         eng = ElementalEngine((Lx, Ly, Lz), Ne, _capi.MODE_DISPLACEMENT, dist_, moms, device=local)
 
+    if os.environ.get("EDK_BENCH_GRAM"):  # tuning hook: "mfrag,ksplit" (0 = auto)
+        mf, ks = (int(v) for v in os.environ["EDK_BENCH_GRAM"].split(","))
+        eng.debug_gram_config(mf, ks)
+
     # two resident input sets, alternated, each far larger than L2 at the graded workloads
     inputs = [synth_device_inputs(torch, dev, name, 1000 * rank + i) for i in range(2)]
     outs = torch.empty((K,) + eng.out_shape, dtype=torch.complex128, device=dev)

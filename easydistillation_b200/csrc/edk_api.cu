@@ -369,6 +369,9 @@ void pick_gram_config(edk_handle* h) {
         // fill the 148 SMs at least ~4 times over, but keep >= 16 stages per CTA
         const long long want = 148LL * 4;
         if (tiles < want) ks = (int)((want + tiles - 1) / tiles);
+        // CTAs that share row tiles drift apart over very long K ranges and lose their L2 sharing:
+        // measured at 48^3 (13824 stages) 1424 -> 1390 ms with 4 K-segments; 32^3 (4096) is best unsplit
+        ks = std::max(ks, (ksteps + 4095) / 4096);
         ks = std::min(ks, std::max(1, ksteps / 16));
         ks = std::min(ks, 64);
     } else {
