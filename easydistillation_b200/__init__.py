@@ -8,14 +8,17 @@ from .insertion.phase import MomentumPhase
 from .preset import (
     EigenvectorHostmem,
     EigenvectorNpy,
+    EigenvectorTimeSlice,
     ElementalNpy,
     GaugeFieldBinary,
     GaugeFieldHostmem,
+    GaugeFieldIldg,
     GaugeFieldNpy,
 )
 
 __all__ = [
     "ElementalGenerator", "DisplacementElementalGenerator", "Laplacian", "MomentumPhase", "derivative",
-    "GaugeFieldBinary", "GaugeFieldNpy", "GaugeFieldHostmem", "EigenvectorNpy", "EigenvectorHostmem",
+    "GaugeFieldBinary", "GaugeFieldNpy", "GaugeFieldHostmem", "GaugeFieldIldg", "EigenvectorNpy", "EigenvectorHostmem",
+    "EigenvectorTimeSlice",
     "ElementalNpy", "Nc", "Ns", "Nd",
 ]

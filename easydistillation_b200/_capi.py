@@ -17,6 +17,17 @@ MODE_DERIVATIVE = 0
 MODE_DISPLACEMENT = 1
 LINKS_DIR_MAJOR = 0
 LINKS_FILE_T = 1
+LINKS_BIG_ENDIAN = 0x100  # OR-ed into the layout: raw big-endian file payload, swapped on the device
+EIGVECS_C8 = 1
+EIGVECS_BIG_ENDIAN = 2
+
+
+def raw_view(a):
+    """(little-endian-typed view of the same bytes, big_endian?) of a numpy complex array: big-endian
+    file payloads go to the device as they are and are byte-swapped there."""
+    if a.dtype.byteorder == ">":
+        return a.view(a.dtype.newbyteorder("<")), True
+    return a, False
 
 # every symbol include/edk.h declares: (restype, argtypes)
 _vp, _i, _sz, _dp = C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_double)

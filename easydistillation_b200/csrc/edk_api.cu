@@ -797,6 +797,8 @@ size_t edk_output_bytes(const edk_handle* h) {
 size_t edk_workspace_bytes(const edk_handle* h) { return h ? h->ws_bytes + h->cfg_bytes : 0; }
 
 int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream) {
+    const int big_endian = (layout & EDK_LINKS_BIG_ENDIAN) ? 1 : 0;
+    layout &= ~EDK_LINKS_BIG_ENDIAN;
     if (!h || !U_dev || (layout != EDK_LINKS_DIR_MAJOR && layout != EDK_LINKS_FILE_T)) {
         set_error("edk_set_links: bad argument");
         return EDK_ERR_ARG;
@@ -804,7 +806,7 @@ int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     {
         PhaseTimer t(h, s, PH_PREP, 1);
-        EDK_CUDA_TRY(launch_reorder_links((const cplx*)U_dev, layout, h->links, h->g, s));
+        EDK_CUDA_TRY(launch_reorder_links((const cplx*)U_dev, layout, big_endian, h->links, h->g, s));
     }
     for (const auto& op : h->link_ops) {
         if (op.kind == 2) {
@@ -849,13 +851,13 @@ int edk_debug_links(edk_handle* h, void* dst_dev, void* stream) {
 }
 
 int edk_set_eigvecs(edk_handle* h, const void* V_dev, int is_c8, void* stream) {
-    if (!h || !V_dev) {
+    if (!h || !V_dev || (is_c8 & ~(EDK_EIGVECS_C8 | EDK_EIGVECS_BIG_ENDIAN))) {
         set_error("edk_set_eigvecs: bad argument");
         return EDK_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
     PhaseTimer t(h, s, PH_PREP, 1);
-    EDK_CUDA_TRY(launch_round_eigvecs(V_dev, is_c8 ? 1 : 0, h->field(0), h->field_sum(0), h->field_cplx, (size_t)3 * h->g.V,
+    EDK_CUDA_TRY(launch_round_eigvecs(V_dev, is_c8, h->field(0), h->field_sum(0), h->field_cplx, (size_t)3 * h->g.V,
                                       h->sum_row, s));
     h->evecs_set = true;
     return EDK_OK;
@@ -932,8 +934,8 @@ int edk_calc_host(edk_handle* h, const void* U_host, int layout, const void* V_h
     }
     cudaStream_t s = (cudaStream_t)stream;
     EDK_CUDA_TRY(cudaSetDevice(h->device));
-    const size_t ub = (size_t)(layout == EDK_LINKS_FILE_T ? 4 : 3) * h->g.V * 9 * sizeof(cplx);
-    const size_t vb = h->field_cplx * (is_c8 ? 8 : 16);
+    const size_t ub = (size_t)((layout & ~EDK_LINKS_BIG_ENDIAN) == EDK_LINKS_FILE_T ? 4 : 3) * h->g.V * 9 * sizeof(cplx);
+    const size_t vb = h->field_cplx * ((is_c8 & EDK_EIGVECS_C8) ? 8 : 16);
     if (h->stage_U_bytes < ub) {
         cudaFree(h->stage_U);
         h->stage_U = nullptr;

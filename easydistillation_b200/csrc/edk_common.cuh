@@ -90,9 +90,9 @@ struct CombineOp {
 
 // ---- launchers (defined in the .cu files) -------------------------------------------------
 // prepare
-cudaError_t launch_round_eigvecs(const void* V_in, int is_c8, cplx* W0, double* W0_sum, size_t n_cplx, size_t row,
+cudaError_t launch_round_eigvecs(const void* V_in, int flags, cplx* W0, double* W0_sum, size_t n_cplx, size_t row,
                                  size_t sum_row, cudaStream_t s);
-cudaError_t launch_reorder_links(const cplx* U_in, int layout, cplx* U_out, Geom g, cudaStream_t s);
+cudaError_t launch_reorder_links(const cplx* U_in, int layout, int big_endian, cplx* U_out, Geom g, cudaStream_t s);
 cudaError_t launch_phase_table(cplx* phase, cplx* rot, const int* mom3_dev, int nmom, Geom g, cudaStream_t s);
 // stencil
 cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_z, double* sum_x, double* sum_y, double* sum_z,

@@ -61,39 +61,58 @@ __device__ __forceinline__ int neighbour(int x, int y, int z, int d, int sign, c
 // ---------------------------------------------------------------------------------------
 // `sum` receives Re + Im of every element: the A-side operand Lr + Li of the 3M contraction
 // (rows of `sum` are padded to an even number of doubles so that a TMA tensor map can describe them)
-__global__ void round_eigvecs_kernel(const void* __restrict__ in, int is_c8, cplx* __restrict__ out,
-                                     double* __restrict__ sum, size_t n, size_t row, size_t sum_row) {
+// byte-order reversal of one IEEE word: big-endian file payloads (ILDG links, QDP eigenvector records:
+// filedata/ildg.py:70, filedata/timeslice.py:96 convert them on the host) are swapped as they are read
+__device__ __forceinline__ float bswap_f32(float v) { return __uint_as_float(__byte_perm(__float_as_uint(v), 0, 0x0123)); }
+__device__ __forceinline__ double bswap_f64(double v) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    return __hiloint2double((int)__byte_perm(lo, 0, 0x0123), (int)__byte_perm(hi, 0, 0x0123));
+}
+
+template <bool C8, bool BE>
+__global__ void round_eigvecs_kernel(const void* __restrict__ in, cplx* __restrict__ out, double* __restrict__ sum, size_t n,
+                                     size_t row, size_t sum_row) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    if (is_c8) {
-        const float2* p = (const float2*)in;
-        for (; i < n; i += stride) {
-            float2 v = __ldg(p + i);
-            out[i] = make_double2((double)v.x, (double)v.y);
-            sum[(i / row) * sum_row + i % row] = (double)v.x + (double)v.y;
-        }
-    } else {
-        const double2* p = (const double2*)in;
-        for (; i < n; i += stride) {
-            double2 v = __ldg(p + i);
+    for (; i < n; i += stride) {
+        double re, im;
+        if (C8) {
+            float2 v = __ldg((const float2*)in + i);
+            if (BE) {
+                v.x = bswap_f32(v.x);
+                v.y = bswap_f32(v.y);
+            }
+            re = (double)v.x;
+            im = (double)v.y;
+        } else {
+            double2 v = __ldg((const double2*)in + i);
+            if (BE) {
+                v.x = bswap_f64(v.x);
+                v.y = bswap_f64(v.y);
+            }
             // round-to-nearest-even double -> float -> double: numpy's complex128 -> complex64 assignment
-            const double re = (double)__double2float_rn(v.x), im = (double)__double2float_rn(v.y);
-            out[i] = make_double2(re, im);
-            sum[(i / row) * sum_row + i % row] = re + im;
+            re = (double)__double2float_rn(v.x);
+            im = (double)__double2float_rn(v.y);
         }
+        out[i] = make_double2(re, im);
+        sum[(i / row) * sum_row + i % row] = re + im;
     }
 }
 
-cudaError_t launch_round_eigvecs(const void* V_in, int is_c8, cplx* W0, double* W0_sum, size_t n_cplx, size_t row,
+cudaError_t launch_round_eigvecs(const void* V_in, int flags, cplx* W0, double* W0_sum, size_t n_cplx, size_t row,
                                  size_t sum_row, cudaStream_t s) {
     int block = 256;
     size_t want = (n_cplx + block - 1) / block;
     int grid = (int)(want < (size_t)148 * 16 ? (want ? want : 1) : (size_t)148 * 16);
-    round_eigvecs_kernel<<<grid, block, 0, s>>>(V_in, is_c8, W0, W0_sum, n_cplx, row, sum_row);
+    const bool c8 = flags & EDK_EIGVECS_C8, be = flags & EDK_EIGVECS_BIG_ENDIAN;
+    if (c8 && be) round_eigvecs_kernel<true, true><<<grid, block, 0, s>>>(V_in, W0, W0_sum, n_cplx, row, sum_row);
+    else if (c8) round_eigvecs_kernel<true, false><<<grid, block, 0, s>>>(V_in, W0, W0_sum, n_cplx, row, sum_row);
+    else if (be) round_eigvecs_kernel<false, true><<<grid, block, 0, s>>>(V_in, W0, W0_sum, n_cplx, row, sum_row);
+    else round_eigvecs_kernel<false, false><<<grid, block, 0, s>>>(V_in, W0, W0_sum, n_cplx, row, sum_row);
     return cudaGetLastError();
 }
 
-__global__ void reorder_links_kernel(const cplx* __restrict__ in, int layout, cplx* __restrict__ out, int V) {
+__global__ void reorder_links_kernel(const cplx* __restrict__ in, int layout, int big_endian, cplx* __restrict__ out, int V) {
     // out[d][site][m], m = 3*a + b
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t n = (size_t)3 * V * 9;
@@ -103,13 +122,18 @@ __global__ void reorder_links_kernel(const cplx* __restrict__ in, int layout, cp
     int site = (int)(r % V);
     int d = (int)(r / V);
     size_t src = (layout == EDK_LINKS_FILE_T) ? (((size_t)site * 4 + d) * 9 + m) : i;
-    out[i] = __ldg(in + src);
+    cplx v = __ldg(in + src);
+    if (big_endian) {
+        v.x = bswap_f64(v.x);
+        v.y = bswap_f64(v.y);
+    }
+    out[i] = v;
 }
 
-cudaError_t launch_reorder_links(const cplx* U_in, int layout, cplx* U_out, Geom g, cudaStream_t s) {
+cudaError_t launch_reorder_links(const cplx* U_in, int layout, int big_endian, cplx* U_out, Geom g, cudaStream_t s) {
     size_t n = (size_t)3 * g.V * 9;
     int block = 256;
-    reorder_links_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(U_in, layout, U_out, g.V);
+    reorder_links_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(U_in, layout, big_endian, U_out, g.V);
     return cudaGetLastError();
 }
 

@@ -79,19 +79,20 @@ class ElementalEngine:
     def set_links(self, U, layout: int):
         torch = self.torch
         V = self.latt3[0] * self.latt3[1] * self.latt3[2]
-        ndir = 4 if layout == _capi.LINKS_FILE_T else 3
+        ndir = 4 if (layout & ~_capi.LINKS_BIG_ENDIAN) == _capi.LINKS_FILE_T else 3
         if U.dtype != torch.complex128 or U.numel() != ndir * V * 9 or not U.is_contiguous() or U.device != self.device:
             raise ValueError(f"links must be a contiguous complex128 tensor of {ndir}*V*9 elements on {self.device}")
         _capi.check(self.lib.edk_set_links(self.h, _ptr(U), layout, self._stream()), "edk_set_links")
 
-    def set_eigvecs(self, Vt):
+    def set_eigvecs(self, Vt, big_endian: bool = False):
+        """`big_endian`: the tensor holds the raw bytes of a big-endian file record."""
         torch = self.torch
         if Vt.dtype not in (torch.complex64, torch.complex128):
             raise ValueError("eigenvectors must be complex64 or complex128")
         if Vt.numel() != int(np.prod(self.field_shape)) or not Vt.is_contiguous() or Vt.device != self.device:
             raise ValueError(f"eigenvectors must be a contiguous tensor of shape {self.field_shape} on {self.device}")
-        _capi.check(self.lib.edk_set_eigvecs(self.h, _ptr(Vt), int(Vt.dtype == torch.complex64), self._stream()),
-                    "edk_set_eigvecs")
+        flags = (_capi.EIGVECS_C8 if Vt.dtype == torch.complex64 else 0) | (_capi.EIGVECS_BIG_ENDIAN if big_endian else 0)
+        _capi.check(self.lib.edk_set_eigvecs(self.h, _ptr(Vt), flags, self._stream()), "edk_set_eigvecs")
 
     def set_link_ops(self, ops):
         """ops: list of ("stout", nstep, rho) / ("project",) applied to every timeslice's links."""
@@ -141,8 +142,13 @@ class ElementalEngine:
 
     # -- host-buffer path (what the generators' calc(t) and bench e2e use) ------------------
     def calc_host(self, U_host: np.ndarray, layout: int, V_host: np.ndarray, out_host: np.ndarray):
+        """Big-endian numpy arrays (`>c16` links, `>c8`/`>c16` eigenvectors: raw file payloads) are
+        uploaded as they are and byte-swapped by the kernels that read them."""
+        U_host, u_be = _capi.raw_view(U_host)
+        V_host, v_be = _capi.raw_view(V_host)
+        layout = (layout & ~_capi.LINKS_BIG_ENDIAN) | (_capi.LINKS_BIG_ENDIAN if u_be or layout & _capi.LINKS_BIG_ENDIAN else 0)
         V = self.latt3[0] * self.latt3[1] * self.latt3[2]
-        ndir = 4 if layout == _capi.LINKS_FILE_T else 3
+        ndir = 4 if (layout & ~_capi.LINKS_BIG_ENDIAN) == _capi.LINKS_FILE_T else 3
         if U_host.dtype != np.complex128 or U_host.size != ndir * V * 9 or not U_host.flags.c_contiguous:
             raise ValueError(f"links must be C-contiguous complex128 with {ndir}*V*9 elements")
         if V_host.dtype not in (np.complex64, np.complex128) or V_host.size != int(np.prod(self.field_shape)) \
@@ -150,8 +156,9 @@ class ElementalEngine:
             raise ValueError(f"eigenvectors must be C-contiguous complex64/128 of shape {self.field_shape}")
         if out_host.dtype != np.complex128 or out_host.shape != self.out_shape or not out_host.flags.c_contiguous:
             raise ValueError(f"out must be C-contiguous complex128 of shape {self.out_shape}")
-        rc = self.lib.edk_calc_host(self.h, _np_ptr(U_host), layout, _np_ptr(V_host), int(V_host.dtype == np.complex64),
-                                    _np_ptr(out_host), self._stream())
+        vflags = (_capi.EIGVECS_C8 if V_host.dtype == np.complex64 else 0) | (_capi.EIGVECS_BIG_ENDIAN if v_be else 0)
+        rc = self.lib.edk_calc_host(self.h, _np_ptr(U_host), layout, _np_ptr(V_host), vflags, _np_ptr(out_host),
+                                    self._stream())
         _capi.check(rc, "edk_calc_host")
         return out_host
 

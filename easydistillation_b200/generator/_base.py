@@ -11,6 +11,10 @@ from ..constant import Nc, Nd
 from ..engine import ElementalEngine
 
 
+_RAW_C16 = (np.dtype("<c16"), np.dtype(">c16"))
+_RAW_EIGVECS = (np.dtype("<c8"), np.dtype("<c16"), np.dtype(">c8"), np.dtype(">c16"))
+
+
 class _TimesliceGenerator:
     _mode: int = None
 
@@ -51,14 +55,17 @@ class _TimesliceGenerator:
             self._U = U
         else:
             U = np.asarray(U)
+            Lx, Ly, Lz, Lt = (int(v) for v in self.latt_size)
+            if U.ndim == 5 and U.shape == (Lt, Lz * Ly * Lx, Nd, Nc, Nc):  # the flattened default shape of preset.py:142,152
+                U = U.reshape(Lt, Lz, Ly, Lx, Nd, Nc, Nc)
             if U.ndim != 7 or U.shape[4:] != (Nd, Nc, Nc):
                 raise ValueError(f"gauge field must be [Lt, Lz, Ly, Lx, {Nd}, {Nc}, {Nc}], got {U.shape}")
-            Lx, Ly, Lz, Lt = (int(v) for v in self.latt_size)
             if U.shape[:4] != (Lt, Lz, Ly, Lx):
                 raise ValueError(f"gauge field shape {U.shape[:4]} does not match latt_size {self.latt_size}")
             # keep file order [Lt][Lz][Ly][Lx][4][3][3]: one timeslice is one contiguous block;
-            # the time links are dropped on the device (the reference's [:Nd-1] view)
-            self._U = np.ascontiguousarray(U, dtype="<c16")
+            # the time links are dropped on the device (the reference's [:Nd-1] view).  A big-endian
+            # payload (ILDG) stays as read: the device swaps the bytes (filedata/ildg.py:70 does it here)
+            self._U = np.ascontiguousarray(U) if U.dtype in _RAW_C16 else np.ascontiguousarray(U, dtype="<c16")
         self._gauge_field_path = getattr(data, "file", None)
         self._gauge_field_data = self._gauge_field_path
         self._eigenvector_data = self.eigenvector.load(key)
@@ -68,7 +75,7 @@ class _TimesliceGenerator:
         """Zero-copy view of timeslice t's eigenvectors when the handle wraps a host array (our
         ArrayData), else None: lets the streamed pipeline copy source -> pinned staging once."""
         a = getattr(self._eigenvector_data, "_a", None)
-        if not isinstance(a, np.ndarray) or a.ndim < 3 or a.dtype not in (np.dtype("<c8"), np.dtype("<c16")):
+        if not isinstance(a, np.ndarray) or a.ndim < 3 or a.dtype not in _RAW_EIGVECS:
             return None
         Lx, Ly, Lz, Lt = (int(v) for v in self.latt_size)
         blk = a[t][: self.Ne]
@@ -91,8 +98,8 @@ class _TimesliceGenerator:
         if block is None or block.ndim < 2 or block.shape[0] < self.Ne:
             block = np.stack([np.asarray(ev[t, e]) for e in range(self.Ne)])
         block = block[: self.Ne].reshape(shape)
-        if block.dtype == np.complex64 or block.dtype == np.dtype(">c8"):
-            return np.ascontiguousarray(block, dtype="<c8")
+        if block.dtype in _RAW_EIGVECS:  # big-endian records (QDP timeslice files) are swapped on the device
+            return np.ascontiguousarray(block)
         return np.ascontiguousarray(block, dtype="<c16")
 
     def _check_loaded(self, t):
@@ -122,14 +129,16 @@ class _TimesliceGenerator:
         self._check_loaded(t)
         eng = self._engine
         torch = eng.torch
-        U_t = self._U[t]
+        U_t, u_be = self._U[t], False
         if not isinstance(U_t, torch.Tensor):
-            U_t = torch.from_numpy(U_t).to(eng.device, non_blocking=False)
-        V_t = self._eigvecs_of(t)
+            U_t, u_be = _capi.raw_view(U_t)
+            U_t = torch.from_numpy(U_t if U_t.flags.writeable else U_t.copy()).to(eng.device, non_blocking=False)
+        V_t, v_be = self._eigvecs_of(t), False
         if not isinstance(V_t, torch.Tensor):
-            V_t = torch.from_numpy(V_t).to(eng.device)
-        eng.set_links(U_t.contiguous(), _capi.LINKS_FILE_T)
-        eng.set_eigvecs(V_t.contiguous())
+            V_t, v_be = _capi.raw_view(V_t)
+            V_t = torch.from_numpy(V_t if V_t.flags.writeable else V_t.copy()).to(eng.device)
+        eng.set_links(U_t.contiguous(), _capi.LINKS_FILE_T | (_capi.LINKS_BIG_ENDIAN if u_be else 0))
+        eng.set_eigvecs(V_t.contiguous(), big_endian=v_be)
         return eng.calc(out)
 
     # ---- batch / sharded form (each rank owns a contiguous t-range) -------------------

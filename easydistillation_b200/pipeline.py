@@ -32,6 +32,8 @@ class TimeslicePipeline:
         self.V_dev = [None, None]
         self.ev_h2d = [None, None]
         self.ev_consumed = [None, None]
+        self.U_be = [False, False]  # slot holds a raw big-endian payload (swapped by the kernels that read it)
+        self.V_be = [False, False]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         # In-memory sources are page-locked in place (cudaHostRegister) so their timeslices go to the
@@ -73,6 +75,8 @@ class TimeslicePipeline:
             V_t = gen._eigvecs_of(t)
         if isinstance(U_t, torch.Tensor) or isinstance(V_t, torch.Tensor):
             raise TypeError("the streamed pipeline is for host-resident inputs")
+        U_t, self.U_be[b] = _capi.raw_view(U_t)
+        V_t, self.V_be[b] = _capi.raw_view(V_t)
         tdt = torch.complex64 if V_t.dtype == np.complex64 else torch.complex128
         if self.V_dev[b] is None or self.V_dev[b].dtype != tdt:
             self.V_dev[b] = torch.empty(V_t.shape, dtype=tdt, device=self.eng.device)
@@ -102,8 +106,8 @@ class TimeslicePipeline:
         torch = self.torch
         cur = torch.cuda.current_stream(self.eng.device)
         cur.wait_event(self.ev_h2d[b])
-        self.eng.set_links(self.U_dev[b], _capi.LINKS_FILE_T)
-        self.eng.set_eigvecs(self.V_dev[b])
+        self.eng.set_links(self.U_dev[b], _capi.LINKS_FILE_T | (_capi.LINKS_BIG_ENDIAN if self.U_be[b] else 0))
+        self.eng.set_eigvecs(self.V_dev[b], big_endian=self.V_be[b])
         ev = torch.cuda.Event()
         ev.record(cur)
         self.ev_consumed[b] = ev

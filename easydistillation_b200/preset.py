@@ -5,8 +5,10 @@ plus `.Ne` for eigenvectors).
 Only what the elemental path touches is here: in-memory handles for synthetic / already
 loaded data, and numpy-memmap readers/writers for the raw-binary gauge field, the `.npy`
 eigenvector file and the `.npy` elemental file ([Nop, Nmom, Lt, Ne, Ne] complex128,
-tests/test_elemental.py:47 and lattice/data.py:26 of the reference).  The reference's own
-handle objects (GaugeFieldIldg, EigenvectorTimeSlice, ...) work unchanged as inputs.
+tests/test_elemental.py:47 and lattice/data.py:26 of the reference), and readers of the two
+big-endian production formats (ILDG gauge fields, QDP timeslice eigenvectors) that keep the file's
+byte order so the device does the conversion.  The reference's own handle objects
+(GaugeFieldIldg, EigenvectorTimeSlice, ...) work unchanged as inputs too.
 """
 from __future__ import annotations
 
@@ -119,6 +121,44 @@ class GaugeFieldBinary(_KeyedFile, GaugeField):
         if self.file != name:
             mm = np.memmap(name, dtype=self.elem.dtype, mode="r", shape=tuple(self.elem.shape))
             self.file, self.data = name, ArrayData(mm, name)
+        return self.data
+
+
+class GaugeFieldIldg(_KeyedFile, GaugeField):
+    """ILDG / LIME configuration (lattice/preset.py:140-148).  `load(key)[:]` is the binary payload as
+    stored, big-endian [Lt, Lz, Ly, Lx, Nd, Nc, Nc] (or `shape` with the same element count, e.g.
+    the reference's flattened default): one memory map per file, no host-side byte swap."""
+
+    def __init__(self, prefix: str, suffix: str, shape: List[int] = None) -> None:
+        _KeyedFile.__init__(self, prefix, ".lime" if suffix is None else suffix)
+        GaugeField.__init__(self, FileMetaData(shape or [], ">c16", 0))
+
+    def load(self, key: str):
+        from .fileio import ildg_layout, ildg_memmap
+
+        name = self._name(key)
+        if self.file != name:
+            data = ArrayData(ildg_memmap(name, self.elem.shape or None), name)
+            data.latt_size = ildg_layout(name)[2]
+            self.file, self.data = name, data
+        return self.data
+
+
+class EigenvectorTimeSlice(_KeyedFile, Eigenvector):
+    """QDP LazyDiskMapObj file with one big-endian complex64 record per (t, e)
+    (lattice/preset.py:55-63).  `shape` = [Lt, Ne, ..., Nc]; `load(key)[t]` returns all Ne records of a
+    timeslice from one memory map (the reference re-opens the file for every eigenvector)."""
+
+    def __init__(self, prefix: str, suffix: str, shape: List[int] = [128, 70, 16**3, 3], totNe: int = 70) -> None:
+        _KeyedFile.__init__(self, prefix, ".stout.n20.f0.12.laplace_eigs.3d.mod" if suffix is None else suffix)
+        Eigenvector.__init__(self, FileMetaData(shape, ">c8", 2), totNe)
+
+    def load(self, key: str):
+        from .fileio import TimesliceRecords
+
+        name = self._name(key)
+        if self.file != name:
+            self.file, self.data = name, TimesliceRecords(name, self.elem.shape, self.elem.dtype, self.elem.extra)
         return self.data
 
 

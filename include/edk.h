@@ -40,6 +40,13 @@ extern "C" {
 /* link layouts accepted by edk_set_links / edk_calc_host */
 #define EDK_LINKS_DIR_MAJOR 0 /* [3][Lz][Ly][Lx][3][3]   = the reference's U[:, t] made contiguous            */
 #define EDK_LINKS_FILE_T 1    /* [Lz][Ly][Lx][4][3][3]   = one timeslice of the file order, time links skipped */
+/* OR-ed into `layout`: the doubles are big-endian, as in the payload of an ILDG file; they are
+ * byte-swapped on the device instead of the host-side `.astype("<c16")` of filedata/ildg.py:70 */
+#define EDK_LINKS_BIG_ENDIAN 0x100
+
+/* eigenvector input flags of edk_set_eigvecs / edk_calc_host (the `is_c8` argument) */
+#define EDK_EIGVECS_C8 1         /* complex64 input (else complex128)                                         */
+#define EDK_EIGVECS_BIG_ENDIAN 2 /* big-endian words, as in a QDP timeslice file (filedata/timeslice.py:96)   */
 
 typedef struct edk_handle edk_handle;
 
@@ -89,6 +96,8 @@ size_t edk_workspace_bytes(const edk_handle* h);
  * displacement_elemental.py:88-89).  Eigenvectors are [Ne][Lz][Ly][Lx][3]; is_c8 = 1 for
  * complex64 input, 0 for complex128 input, which is value-rounded through complex64 on
  * the device exactly as the reference's complex64 `_V` buffer does (elemental.py:55).
+ * `is_c8` is a flag word: EDK_EIGVECS_C8 | EDK_EIGVECS_BIG_ENDIAN; `layout` may carry
+ * EDK_LINKS_BIG_ENDIAN.  Big-endian input is the raw file payload, swapped on the device.
  */
 int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream);
 int edk_set_eigvecs(edk_handle* h, const void* V_dev, int is_c8, void* stream);

@@ -391,6 +391,50 @@ def test_file_handles_and_elemental_npy_roundtrip(edb, tmp_path):
     _blocks_close(full[0].cpu().numpy(), g["E"][0], what="calc_all")
 
 
+def test_big_endian_files_are_converted_on_the_device(edb, tmp_path):
+    """ILDG gauge file + QDP timeslice eigenvector file (big-endian payloads, tests/golden made by
+    oracle/make_golden_files.py: the reference read the same two files through its own readers) go to
+    the GPU as raw bytes and are byte-swapped by the kernels; every calc flavour must match the
+    reference's elementals."""
+    import torch
+
+    g, latt, moms = _golden_case("files_ildg_qdp")
+    Lx, Ly, Lz, Lt = latt
+    Ne = int(g["Ne"])
+    g["lime_bytes"].tofile(tmp_path / "cfg.lime")
+    g["mod_bytes"].tofile(tmp_path / "cfg.mod")
+    prefix = str(tmp_path) + "/"
+    gauge = edb.GaugeFieldIldg(prefix, ".lime")
+    evec = edb.EigenvectorTimeSlice(prefix, ".mod", [Lt, Ne, Lz, Ly, Lx, 3], Ne)
+    gen = edb.ElementalGenerator(latt, gauge, evec, int(g["num_nabla"]), moms)
+    gen.load("cfg")
+    assert gen._U.dtype == np.dtype(">c16") and gen._eigvecs_of(0).dtype == np.dtype(">c8")  # no host-side swap
+    for t in range(Lt):
+        _blocks_close(gen.calc(t), g["E"][t], what=f"calc({t}) from ILDG/QDP files")
+        _blocks_close(gen.calc_device(t).cpu().numpy(), g["E"][t], what=f"calc_device({t}) from ILDG/QDP files")
+    block = gen.calc_range(0, Lt)  # streamed pipeline
+    for t in range(Lt):
+        _blocks_close(block[t], g["E"][t], what=f"calc_range[{t}] from ILDG/QDP files")
+    # in-memory big-endian arrays (page-locked in place by the pipeline), complex128 eigenvectors included
+    U_be = np.ascontiguousarray(g["U_ref"], dtype=">c16")
+    for vdt in (">c8", ">c16"):
+        V_be = np.ascontiguousarray(g["V_ref"], dtype=vdt)
+        gen2 = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_be), edb.EigenvectorHostmem(V_be), int(g["num_nabla"]), moms)
+        gen2.load("cfg")
+        _blocks_close(gen2.calc(1), g["E"][1], what=f"big-endian host arrays {vdt}")
+        block = gen2.calc_range(0, Lt)
+        for t in range(Lt):
+            _blocks_close(block[t], g["E"][t], what=f"big-endian host arrays {vdt}, streamed t={t}")
+    # the same through the displacement generator against the little-endian route
+    args = (latt, 2, moms)
+    d_be = edb.DisplacementElementalGenerator(latt, gauge, evec, 2, moms)
+    d_le = edb.DisplacementElementalGenerator(latt, edb.GaugeFieldHostmem(g["U_ref"]), edb.EigenvectorHostmem(g["V_ref"]), 2, moms)
+    d_be.load("cfg")
+    d_le.load("cfg")
+    assert np.array_equal(d_be.calc(0), d_le.calc(0)), args
+    torch.cuda.synchronize()
+
+
 def test_device_resident_inputs(edb):
     """the generators also take torch CUDA tensors (a handle whose load() returns a tensor)."""
     import torch

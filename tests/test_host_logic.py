@@ -206,3 +206,94 @@ def test_contraction_plan_host_logic():
     assert _capi.plan(_capi.MODE_DERIVATIVE, 3, m33)["operators"] == 40
     with pytest.raises(ValueError):
         _capi.plan(_capi.MODE_DERIVATIVE, 4, m9)
+
+
+# ---------------------------------------------------------------------------------------------
+# big-endian file formats (ILDG gauge field, QDP timeslice eigenvectors): reader parity against what
+# the reference's own readers returned for the same files (oracle/make_golden_files.py)
+# ---------------------------------------------------------------------------------------------
+def _ildg_qdp_files(tmp_path):
+    g = load_golden("files_ildg_qdp")
+    g["lime_bytes"].tofile(tmp_path / "cfg.lime")
+    g["mod_bytes"].tofile(tmp_path / "cfg.mod")
+    return g, str(tmp_path) + "/"
+
+
+def test_ildg_reader_matches_reference_reader(tmp_path):
+    from easydistillation_b200 import preset
+    from easydistillation_b200.fileio import ildg_layout, lime_records, write_ildg
+
+    g, prefix = _ildg_qdp_files(tmp_path)
+    Lx, Ly, Lz, Lt = (int(v) for v in g["latt_size"])
+    assert [r[0] for r in lime_records(prefix + "cfg.lime")] == ["ildg-format", "ildg-binary-data", "ildg-data-lfn"]
+    assert ildg_layout(prefix + "cfg.lime")[2:] == ([Lx, Ly, Lz, Lt], 64)
+    data = preset.GaugeFieldIldg(prefix, ".lime").load("cfg")
+    U = data[:]
+    assert U.dtype == np.dtype(">c16") and U.shape == (Lt, Lz, Ly, Lx, 4, 3, 3) and data.latt_size == [Lx, Ly, Lz, Lt]
+    assert np.array_equal(U, g["U_ref"])  # value comparison across byte orders
+    assert np.array_equal(data[1], g["U_ref"][1])
+    # the reference's flattened default shape [Lt, V, 4, 3, 3] and a wrong element count
+    flat = preset.GaugeFieldIldg(prefix, ".lime", [Lt, Lz * Ly * Lx, 4, 3, 3]).load("cfg")[:]
+    assert np.array_equal(flat.reshape(U.shape), g["U_ref"])
+    with pytest.raises(ValueError):
+        preset.GaugeFieldIldg(prefix, ".lime", [Lt + 1, Lz, Ly, Lx, 4, 3, 3]).load("cfg")
+    # single precision payload, byte-identical rewrite of the double precision file
+    write_ildg(prefix + "again.lime", g["U_ref"])
+    assert np.array_equal(np.fromfile(prefix + "again.lime", np.uint8), g["lime_bytes"])
+    write_ildg(prefix + "single.lime", g["U_ref"], precision=32)
+    single = preset.GaugeFieldIldg(prefix, ".lime").load("single")[:]
+    assert single.dtype == np.dtype(">c8") and np.array_equal(single, g["U_ref"].astype("<c8"))
+    (tmp_path / "bad.lime").write_bytes(b"\0" * 200)
+    with pytest.raises(ValueError):
+        preset.GaugeFieldIldg(prefix, ".lime").load("bad")
+
+
+def test_qdp_timeslice_reader_matches_reference_reader(tmp_path):
+    import struct
+
+    from easydistillation_b200 import preset
+    from easydistillation_b200.fileio import QDP_MAGIC, TimesliceRecords
+
+    g, prefix = _ildg_qdp_files(tmp_path)
+    Lx, Ly, Lz, Lt = (int(v) for v in g["latt_size"])
+    Ne = int(g["Ne"])
+    handle = preset.EigenvectorTimeSlice(prefix, ".mod", [Lt, Ne, Lz, Ly, Lx, 3], Ne)
+    data = handle.load("cfg")
+    assert handle.Ne == Ne and data.latt_size == [Lx, Ly, Lz, Lt] and handle.load("cfg") is data
+    for t in range(Lt):
+        block = data[t]
+        assert block.dtype == np.dtype(">c8") and block.shape == (Ne, Lz, Ly, Lx, 3)
+        assert np.array_equal(block, g["V_ref"][t])
+        assert np.array_equal(data[t, Ne - 1], g["V_ref"][t, Ne - 1])
+        assert np.array_equal(data[t, 2, 1], g["V_ref"][t, 2, 1])
+    with pytest.raises(IndexError):
+        data[Lt, 0]
+    with pytest.raises(IndexError):
+        data[Lt]
+    # records stored out of order (no back-to-back run): the gather path must give the same timeslice
+    V = g["V_ref"]
+    rec = V[0, 0].size * 8
+    magic, xml = QDP_MAGIC.encode(), b"<m><lattSize>%d %d %d %d</lattSize><decay_dir>3</decay_dir></m>" % (Lx, Ly, Lz, Lt)
+    head = struct.pack(">i", len(magic)) + magic + struct.pack(">ii", 1, len(xml)) + xml
+    order = [(t, e) for e in reversed(range(Ne)) for t in range(Lt)]
+    data_pos = len(head) + 16
+    with open(prefix + "shuffled.mod", "wb") as f:
+        f.write(head + struct.pack(">qq", 0, data_pos + len(order) * rec))
+        for t, e in order:
+            f.write(V[t, e].astype(">c8").tobytes())
+        f.write(struct.pack(">I", len(order)))
+        for i, (t, e) in enumerate(order):
+            f.write(struct.pack(">iii", 8, t, e) + struct.pack(">qq", 0, data_pos + i * rec))
+    shuffled = TimesliceRecords(prefix + "shuffled.mod", [Lt, Ne, Lz, Ly, Lx, 3], ">c8")
+    assert np.array_equal(shuffled[1], V[1]) and np.array_equal(shuffled[0, 3], V[0, 3])
+
+
+def test_raw_view_keeps_bytes_and_flags_big_endian():
+    from easydistillation_b200 import _capi
+
+    a = np.arange(6, dtype=">c8")
+    v, be = _capi.raw_view(a)
+    assert be and v.dtype == np.dtype("<c8") and v.tobytes() == a.tobytes() and np.shares_memory(v, a)
+    b = np.arange(6, dtype="<c16")
+    v, be = _capi.raw_view(b)
+    assert not be and v is b
