@@ -4,7 +4,8 @@ TEST INFRASTRUCTURE ONLY.  Run once from the repo root in the build container
 (where /root/reference exists); the resulting small fixtures are committed so
 that the GPU box, which has no /root/reference, can check against them.
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py                 # everything
+    python oracle/make_golden.py NAME [NAME ...] # only the named elemental cases
 
 How the reference is made importable without editing it:
   * oracle/shims/opt_einsum  -> numpy.einsum(optimize=True)
@@ -86,8 +87,14 @@ def main():
         "deriv_blend_4x4x4x1": ([4, 4, 4, 1], 6, "random", dict(num_nabla=1, momentum_list=[(0, 0, 0), (1, 0, -1)], dilution=([10, 7], [4, 2]))),
         "disp_weak_4x4x4x2": ([4, 4, 4, 2], 8, "weak", dict(distance=8, momentum_list=[(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 1, 2), (1, 1, 2)])),
         "disp_random_4x6x8x1": ([4, 6, 8, 1], 6, "random", dict(distance=3, momentum_list=[(0, 0, 0), (1, 0, 0), (0, -1, 2)])),
+        # the two ends of num_nabla: no derivative on odd y, z extents (the reference needs an even Lx: phase.py:25), and all 40 third-order operators
+        "deriv_n0_random_6x3x5x1": ([6, 3, 5, 1], 4, "random", dict(num_nabla=0, momentum_list=[(0, 0, 0), (1, -2, 0), (0, 0, 3)])),
+        "deriv_n3_random_4x4x6x1": ([4, 4, 6, 1], 4, "random", dict(num_nabla=3, momentum_list=[(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, -2)])),
     }
+    only = set(sys.argv[1:])
     for name, (latt, Ne, kind, kw) in cases.items():
+        if only and name not in only:
+            continue
         Lx, Ly, Lz, Lt = latt
         U_file = np.stack([orc.synthetic_links(latt, t, kind) for t in range(Lt)])
         V_file = np.stack([orc.synthetic_eigvecs(latt, Ne, t) for t in range(Lt)])
@@ -110,6 +117,9 @@ def main():
             **meta,
         )
         print(f"{name}: U{U_file.shape} V{V_file.shape} -> E{ref.shape}  |E|={np.linalg.norm(ref):.6e}")
+
+    if only:
+        return
 
     # gauge preprocessing: stout smearing and the unitarity projection, on a weak
     # field and on a slightly non-unitary one; the processed links are stored next to the elementals

@@ -56,7 +56,8 @@ def _golden_case(name):
 # ---------------------------------------------------------------------------------------------
 # (1) reference golden vectors
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["deriv_weak_4x4x4x2", "deriv_random_4x6x8x1", "deriv_n1_random_6x4x2x1"])
+@pytest.mark.parametrize("name", ["deriv_weak_4x4x4x2", "deriv_random_4x6x8x1", "deriv_n1_random_6x4x2x1",
+                                  "deriv_n0_random_6x3x5x1", "deriv_n3_random_4x4x6x1"])
 def test_derivative_elementals_match_reference_golden(edb, name):
     g, latt, moms = _golden_case(name)
     gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]),

@@ -8,7 +8,8 @@ from oracle import elemental_oracle as orc
 
 TOL = 1e-12  # oracle and reference share numpy/BLAS; only summation order differs
 
-DERIV_CASES = ["deriv_weak_4x4x4x2", "deriv_random_4x6x8x1", "deriv_n1_random_6x4x2x1"]
+DERIV_CASES = ["deriv_weak_4x4x4x2", "deriv_random_4x6x8x1", "deriv_n1_random_6x4x2x1", "deriv_n0_random_6x3x5x1",
+               "deriv_n3_random_4x4x6x1"]
 DISP_CASES = ["disp_weak_4x4x4x2", "disp_random_4x6x8x1"]
 
 
@@ -39,7 +40,8 @@ def test_elemental_faithful_and_closed_form(name):
         U_t = orc.links_file_to_spatial(g["U"][t])
         ref = g["E"][t]
         a = orc.elemental_timeslice(g["V"][t], U_t, latt, int(g["num_nabla"]), moms)
-        b = orc.elemental_timeslice_closed_form(g["V"][t], U_t, latt, int(g["num_nabla"]), moms)
+        # the closed form is written out for num_nabla <= 2; beyond that only the faithful form exists
+        b = orc.elemental_timeslice_closed_form(g["V"][t], U_t, latt, int(g["num_nabla"]), moms) if int(g["num_nabla"]) <= 2 else a
         for d in range(ref.shape[0]):
             for p in range(ref.shape[1]):
                 assert rel_err(a[d, p], ref[d, p]) < TOL, (name, t, d, p)
