@@ -2,6 +2,7 @@
 the generator-owned result buffer, batch/sharded iteration."""
 from __future__ import annotations
 
+from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -168,19 +169,30 @@ class _TimesliceGenerator:
         [Nop, Nmom, Lt, Ne, Ne] (tests/test_elemental.py:47, read back by ElementalNpy / lattice/data.py:26).
 
         `elemental` is an ElementalNpy-like handle with `create(key, shape, dtype)`; the file is
-        pre-sized once and every timeslice drops its slab in place as soon as its download has
-        finished, while the next timeslices are still being computed.  `t_range=(t0, t1)` writes
+        pre-sized once and every batch of timeslices drops its slab in place on a writer thread
+        while the next batch is being computed.  `t_range=(t0, t1)` writes
         only that slab (one rank of a sharded run; ranks share the file), `dtype="<c8"` down-casts
         to the complex64 the reference declares for stored elementals (preset.py:176)."""
         Lt = int(self.latt_size[3])
         t0, t1 = (0, Lt) if t_range is None else t_range
         shape = (self._engine.out_shape[0], self._engine.out_shape[1], Lt, self.Ne, self.Ne)
         mm = elemental.create(key, shape, dtype) if (t_range is None or t0 == 0) else elemental.open_rw(key, shape, dtype)
-        chunk = 4  # timeslices per streamed batch: bounds the host buffer
-        for a in range(t0, t1, chunk):
-            b = min(a + chunk, t1)
-            block = self.calc_range(a, b)  # [b-a, Nop, Nmom, Ne, Ne]
+        chunk = 4  # timeslices per streamed batch: bounds the host buffers (two batches alive at a time)
+
+        def drop(a, b, block):  # transposing (and down-casting) copy into the file mapping; numpy releases the GIL
             mm[:, :, a:b] = block.transpose(1, 2, 0, 3, 4)
+
+        # one writer thread: batch k goes to the file while batch k+1 is being computed
+        with ThreadPoolExecutor(max_workers=1) as writer:
+            pending = None
+            for a in range(t0, t1, chunk):
+                b = min(a + chunk, t1)
+                block = self.calc_range(a, b)  # [b-a, Nop, Nmom, Ne, Ne], a fresh array per batch
+                if pending is not None:
+                    pending.result()
+                pending = writer.submit(drop, a, b, block)
+            if pending is not None:
+                pending.result()
         mm.flush()
         return mm
 

@@ -297,3 +297,51 @@ def test_raw_view_keeps_bytes_and_flags_big_endian():
     b = np.arange(6, dtype="<c16")
     v, be = _capi.raw_view(b)
     assert not be and v is b
+
+
+def test_calc_to_file_layout_slabs_and_downcast(tmp_path):
+    """Host logic of the elemental file writer (reference layout [Nop, Nmom, Lt, Ne, Ne],
+    tests/test_elemental.py:47) with the device part replaced by a stand-in `calc_range`."""
+    import types
+
+    from easydistillation_b200.generator._base import _TimesliceGenerator
+
+    Nop, Nmom, Lt, Ne = 3, 2, 10, 4
+    rng = np.random.default_rng(5)
+    full = rng.standard_normal((Lt, Nop, Nmom, Ne, Ne)) + 1j * rng.standard_normal((Lt, Nop, Nmom, Ne, Ne))
+    calls = []
+
+    class Fake(_TimesliceGenerator):
+        def calc_range(self, t0, t1):
+            calls.append((t0, t1))
+            return full[t0:t1].copy()
+
+    gen = object.__new__(Fake)
+    gen.latt_size, gen.Ne = [4, 4, 4, Lt], Ne
+    gen._engine = types.SimpleNamespace(out_shape=(Nop, Nmom, Ne, Ne))
+    handle = edb.ElementalNpy(str(tmp_path) + "/", ".elemental.npy")
+    gen.calc_to_file(handle, "cfg")
+    assert calls == [(0, 4), (4, 8), (8, 10)]
+    stored = np.load(tmp_path / "cfg.elemental.npy")
+    assert stored.dtype == np.dtype("<c16") and np.array_equal(stored, full.transpose(1, 2, 0, 3, 4))
+    assert np.array_equal(handle.load("cfg")[1, 0, 7], full[7, 1, 0])
+    # two ranks writing their slabs into one file, down-cast to the complex64 the reference declares
+    calls.clear()
+    gen.calc_to_file(handle, "two", t_range=(0, 5), dtype="<c8")
+    gen.calc_to_file(handle, "two", t_range=(5, 10), dtype="<c8")
+    assert calls == [(0, 4), (4, 5), (5, 9), (9, 10)]
+    stored = np.load(tmp_path / "two.elemental.npy")
+    assert stored.dtype == np.dtype("<c8") and np.array_equal(stored, full.transpose(1, 2, 0, 3, 4).astype("<c8"))
+    with pytest.raises(ValueError):
+        gen.calc_to_file(handle, "two", t_range=(5, 10), dtype="<c16")  # existing file has another dtype
+
+    class Broken(Fake):
+        def calc_range(self, t0, t1):
+            if t0 >= 4:
+                raise RuntimeError("device failure")
+            return full[t0:t1].copy()
+
+    bad = object.__new__(Broken)
+    bad.__dict__.update(gen.__dict__)
+    with pytest.raises(RuntimeError, match="device failure"):
+        bad.calc_to_file(handle, "broken")
