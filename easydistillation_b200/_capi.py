@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libedk_sm100a.so")
+# EDK_LIBRARY points at another build of the same C ABI (A/B runs of an experimental kernel build)
+LIB_PATH = os.environ.get("EDK_LIBRARY") or os.path.join(PKG, "libedk_sm100a.so")
 
 EDK_OK = 0
 EDK_ERR_ARG = -1
