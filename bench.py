@@ -472,6 +472,12 @@ def run_native(args):
         # `achieved`/`frac` are the executed rate (what the FP64 pipe really does); the SURVEY-counted
         # rate is reported beside it as survey_equivalent_tflops.
         exec_flops = 2.0 * q["real_mma_per_complex_block"] * Ne * Ne * 3 * V * q["pair_momentum_gemms"]
+        pw_form = q.get("contraction_form") == 2
+        if pw_form:
+            # plane-wave factorised form (EDK_GRAM_ALGO=2): per (pair, e, f, site) 12 DFMA for the colour-summed
+            # site product and, for each of the real xy-modes, one multiply-add on its real and imaginary part
+            # (DMMA rows padded to blocks of 8 modes are not counted)
+            exec_flops = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V * (24.0 + 4.0 * q["plane_wave_modes"])
         achieved_tf = exec_flops / (gram_ms * 1e-3) / 1e12
         survey_tf = flops / (gram_ms * 1e-3) / 1e12
         # stencil: bytes of ONE launch (nabla3: 1 source, 3 outputs, links once; displacement step: 6 in, 6 + mean out)
@@ -483,7 +489,7 @@ def run_native(args):
             cpu_val, cpu_smp = cpu_sample(name, W0_host.astype(np.complex64), U_sp_host)
         elif W0_host is not None:
             cpu_val, cpu_smp = cpu_sample_displacement(name, dist_, W0_host.astype(np.complex64), U_sp_host)
-        gram_name = "gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel"
+        gram_name = "gram_pw_kernel" if pw_form else ("gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel")
         st_name = "nabla3_kernel" if dist_ is None else "displace_step6_kernel"
         line = {
             "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s", "n_gpus": world,
@@ -502,7 +508,9 @@ def run_native(args):
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {
-                "kernel": gram_name + " (momentum-phased contraction, DMMA.8x8x4, TMA producer warp + mbarrier ring)",
+                "kernel": gram_name + (" (plane-wave factorised contraction: site products by DFMA, real xy-mode transform by "
+                                       "DMMA.8x8x4, TMA producer warp + mbarrier ring; z fold timed with the combine step)" if pw_form
+                                       else " (momentum-phased contraction, DMMA.8x8x4, TMA producer warp + mbarrier ring)"),
                 "bound": "tensor",
                 "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
                 "traffic": measured_traffic(gram_name, name if dist_ is None else name + "_displacement"),
@@ -510,9 +518,12 @@ def run_native(args):
                                f"DMMA issue-rate microbench {dmma_tf:.1f}, DFMA {dfma_tf:.1f} TFLOP/s; nominal 37-40",
                 "algorithmic_flops_per_launch": exec_flops, "ms_per_launch": gram_ms,
                 "pairing": q, "survey_flops_per_launch": flops, "survey_equivalent_tflops": survey_tf,
-                "note": "achieved = real flops the DMMA kernel executes / time (useful rows only); the Hermitian pairing "
-                        "G(L,R,p)^dag = G(R,L,-p) contracts 19 instead of SURVEY 8d's 34 pairs and the 3M product uses 3 "
-                        "instead of 4 real MMAs per complex block; survey_equivalent_tflops = SURVEY 8d flops / time",
+                "note": ("achieved = flops the plane-wave form needs / time: the phase factorises, so the site product is formed once "
+                         "for all momenta and only the real xy-modes are transformed per plane; the FP64 pipe is the bound, "
+                         "survey_equivalent_tflops = SURVEY 8d flops (GEMM form, 34 pairs x Nmom) / time") if pw_form else
+                        ("achieved = real flops the DMMA kernel executes / time (useful rows only); the Hermitian pairing "
+                         "G(L,R,p)^dag = G(R,L,-p) contracts 19 instead of SURVEY 8d's 34 pairs and the 3M product uses 3 "
+                         "instead of 4 real MMAs per complex block; survey_equivalent_tflops = SURVEY 8d flops / time"),
                 "share_of_step": prof["contraction"]["ms"] / ms,
             },
             "roofline_stencil": {

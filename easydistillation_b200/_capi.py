@@ -39,6 +39,7 @@ SIGNATURES = {
     "edk_destroy": (_i, [_vp]),
     "edk_phase_table": (_i, [_i, _i, _i, _i, C.POINTER(_i), _vp, _i, _vp]),
     "edk_plan": (_i, [_i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i)]),
+    "edk_plan_modes": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "edk_num_operators": (_i, [_vp]),
     "edk_output_bytes": (_sz, [_vp]),
     "edk_workspace_bytes": (_sz, [_vp]),
@@ -117,6 +118,22 @@ def plan(mode: int, order: int, momentum_list, sym_request: int = -1) -> dict:
     d = dict(zip(keys, list(out)))
     d["hermitian_pairing"] = bool(d["hermitian_pairing"])
     return d
+
+
+def plan_modes(momentum_list):
+    """Host-only mode plan of the plane-wave factorised contraction (edk_plan_modes):
+    (modes [nmodes][3] = (qx, qy, kind), per-momentum [nmom][3] = (cos mode, sin mode or -1, sigma))."""
+    import numpy as np
+
+    mom = np.ascontiguousarray(np.asarray(momentum_list, dtype=np.int32).reshape(-1, 3))
+    nmom = mom.shape[0]
+    modes = np.zeros((2 * nmom, 3), dtype=np.int32)
+    momode = np.zeros((nmom, 3), dtype=np.int32)
+    n = C.c_int(0)
+    ip = C.POINTER(C.c_int)
+    check(lib().edk_plan_modes(nmom, mom.ctypes.data_as(ip), C.byref(n), modes.ctypes.data_as(ip), momode.ctypes.data_as(ip)),
+          "edk_plan_modes")
+    return modes[: n.value].copy(), momode
 
 
 def require_cuda():

@@ -1,5 +1,7 @@
 // C ABI (include/edk.h) over the sm_100a kernels: handle, workspace, job lists, calc flows.
+#include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -54,7 +56,17 @@ struct edk_handle {
     cplx* phase_tiles = nullptr;
     bool tma_ready = false;
     int loader = 0;
-    int algo = 1;  // arithmetic of the TMA kernel: 1 = 3M (three real MMAs per complex block), 0 = 4M
+    int algo = 1;  // contraction: 1 = GEMM form, 3M arithmetic (three real MMAs per complex block), 0 = GEMM form, 4M,
+                   // 2 = plane-wave factorised form (edk_gram_pw.cu)
+    // plane-wave factorised contraction (algo 2): xy-mode weights, per-plane sums Y, z phases
+    PwTma pw_tma{};
+    bool pw_ready = false;
+    int pw_nmodes = 0, pw_mbtot = 0, pw_kplane = 0;
+    double* pw_wtiles = nullptr;  // [kplane][2][mbtot][32]
+    cplx* pw_Y = nullptr;         // [njobs][Lz][nmodes][Ne][Ne]
+    cplx* pw_zphase = nullptr;    // [nmom_int][Lz]
+    int* pw_momode = nullptr;     // [nmom_int][3]: cos mode, sin mode, sigma
+    size_t pw_bytes = 0;
     size_t field_cplx;  // Ne * V * 3
     // device buffers
     cplx* links = nullptr;    // [3][V][9]
@@ -374,6 +386,7 @@ void pick_gram_config(edk_handle* h) {
         ks = std::max(ks, (ksteps + 4095) / 4096);
         ks = std::min(ks, std::max(1, ksteps / 16));
         ks = std::min(ks, 64);
+        if (h->algo == 2 && h->loader == 0 && !h->naive) ks = 1;  // the plane-wave form writes split 0 only
     } else {
         ks = std::min(h->force_ksplit, ksteps);
     }
@@ -389,25 +402,33 @@ int ensure_partial(edk_handle* h) {
     return EDK_OK;
 }
 
-// Tensor maps of the TMA-fed contraction: the field array as [nfield][Ne][2*Kc] doubles, boxes of
-// 8 doubles (4 complex k) x rows x 1 field.  cuTensorMapEncodeTiled comes from the driver through
-// the runtime's entry-point query, so the library does not link libcuda.
-int build_tma(edk_handle* h) {
-    h->tma_ready = false;
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point query, so the
+// library does not link libcuda.
+EncodeFn tensor_map_encoder() {
     static EncodeFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
-        EDK_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) {
+        const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
             set_error("cuTensorMapEncodeTiled is not available from this driver");
-            return EDK_ERR_CUDA;
+            return nullptr;
         }
         encode = (EncodeFn)fn;
     }
+    return encode;
+}
+
+// Tensor maps of the TMA-fed contraction: the field array as [nfield][Ne][2*Kc] doubles, boxes of
+// 8 doubles (4 complex k) x rows x 1 field.
+int build_tma(edk_handle* h) {
+    h->tma_ready = false;
+    EncodeFn encode = tensor_map_encoder();
+    if (!encode) return EDK_ERR_CUDA;
     int rows = 0, nst = 0, bytes = 0;
     if (gram_tma_plan(h->algo, h->mfrag, h->nmom_int, h->Ne, &rows, &nst, &bytes) != 0) {
         set_error("no shared-memory plan for the TMA contraction (mfrag %d)", h->mfrag);
@@ -444,6 +465,182 @@ int build_tma(edk_handle* h) {
     h->tma.brows_alloc = rows;
     h->tma.nstages = nst;
     h->tma_ready = true;
+    return EDK_OK;
+}
+
+// Plane-wave factorised contraction (algo 2), host side.  The xy-part of every momentum is one of a
+// few {+q, -q} couples; couple q contributes the real modes cos(theta_q) and sin(theta_q) (only the
+// constant 1 for q = 0).  Pure host logic, unit-tested on CPU through edk_plan_modes.
+struct ModePlan {
+    std::vector<int> modes3;  // per mode: qx, qy, kind (0 cos, 1 sin)
+    std::vector<int> momode;  // per momentum: cos mode, sin mode (-1 if none), sigma with (px,py) = sigma (qx,qy)
+};
+
+ModePlan plan_modes(const std::vector<int>& mom) {
+    ModePlan M;
+    struct Couple {
+        int qx, qy, mc, ms;
+    };
+    std::vector<Couple> couples;
+    const int nmom = (int)mom.size() / 3;
+    for (int i = 0; i < nmom; ++i) {
+        int qx = mom[3 * i], qy = mom[3 * i + 1], sigma = 1;
+        if (qx < 0 || (qx == 0 && qy < 0)) {  // representative: first non-zero component positive
+            qx = -qx;
+            qy = -qy;
+            sigma = -1;
+        }
+        const Couple* hit = nullptr;
+        for (const Couple& c : couples)
+            if (c.qx == qx && c.qy == qy) hit = &c;
+        if (!hit) {
+            Couple c{qx, qy, (int)M.modes3.size() / 3, -1};
+            M.modes3.insert(M.modes3.end(), {qx, qy, 0});
+            if (qx != 0 || qy != 0) {
+                c.ms = (int)M.modes3.size() / 3;
+                M.modes3.insert(M.modes3.end(), {qx, qy, 1});
+            }
+            couples.push_back(c);
+            hit = &couples.back();
+        }
+        M.momode.insert(M.momode.end(), {hit->mc, hit->ms, hit->ms < 0 ? 0 : sigma});
+    }
+    return M;
+}
+
+void free_pw(edk_handle* h) {
+    cudaFree(h->pw_wtiles);
+    cudaFree(h->pw_Y);
+    cudaFree(h->pw_zphase);
+    cudaFree(h->pw_momode);
+    h->pw_wtiles = nullptr;
+    h->pw_Y = nullptr;
+    h->pw_zphase = nullptr;
+    h->pw_momode = nullptr;
+    h->pw_ready = false;
+    h->pw_bytes = 0;
+}
+
+// Tables, per-plane buffer and tensor maps of algo 2; needs the job list and the internal momenta.
+int build_pw(edk_handle* h) {
+    free_pw(h);
+    EncodeFn encode = tensor_map_encoder();
+    if (!encode) return EDK_ERR_CUDA;
+    const ModePlan mp = plan_modes(h->mom_int);
+    h->pw_nmodes = (int)mp.modes3.size() / 3;
+    h->pw_mbtot = (h->pw_nmodes + 7) / 8;
+    h->pw_kplane = (h->g.Lx * h->g.Ly + 7) / 8;
+    int smem = 0;
+    if (pw_plan_smem(&h->pw_tma.nstages, &smem) != 0) {
+        set_error("no shared-memory plan for the plane-wave contraction");
+        return EDK_ERR_ARG;
+    }
+    const size_t wt_bytes = (size_t)h->pw_kplane * 2 * h->pw_mbtot * 32 * sizeof(double);
+    const size_t y_bytes = (size_t)h->njobs * h->g.Lz * h->pw_nmodes * h->Ne * h->Ne * sizeof(cplx);
+    const size_t zp_bytes = (size_t)h->nmom_int * h->g.Lz * sizeof(cplx);
+    int* modes_dev = nullptr;
+    EDK_CUDA_TRY(cudaMalloc(&h->pw_wtiles, wt_bytes));
+    EDK_CUDA_TRY(cudaMalloc(&h->pw_zphase, zp_bytes));
+    EDK_CUDA_TRY(cudaMalloc(&h->pw_momode, mp.momode.size() * sizeof(int)));
+    {
+        const cudaError_t e = cudaMalloc(&h->pw_Y, y_bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc of %zu bytes (per-plane mode sums) failed: %s", y_bytes, cudaGetErrorString(e));
+            free_pw(h);
+            return e == cudaErrorMemoryAllocation ? EDK_ERR_NOMEM : EDK_ERR_CUDA;
+        }
+    }
+    EDK_CUDA_TRY(cudaMalloc(&modes_dev, mp.modes3.size() * sizeof(int)));
+    cudaError_t e = cudaMemcpy(modes_dev, mp.modes3.data(), mp.modes3.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_pw_weights(h->pw_wtiles, modes_dev, h->pw_nmodes, h->pw_mbtot, h->pw_kplane, h->g, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(modes_dev);
+    if (e != cudaSuccess) {
+        set_error("plane-wave weight table failed: %s", cudaGetErrorString(e));
+        return EDK_ERR_CUDA;
+    }
+    h->launches += 1;
+    // exp(2 pi i pz z / Lz) with pz z reduced mod Lz in integers
+    std::vector<double> zp((size_t)h->nmom_int * h->g.Lz * 2);
+    for (int p = 0; p < h->nmom_int; ++p)
+        for (int z = 0; z < h->g.Lz; ++z) {
+            const long long Lz = h->g.Lz;
+            const long long r = (((long long)h->mom_int[3 * p + 2] * z) % Lz + Lz) % Lz;
+            double c = 1.0, sn = 0.0;
+            if (4 * r == Lz) {  // exact values on the axes
+                c = 0.0, sn = 1.0;
+            } else if (2 * r == Lz) {
+                c = -1.0, sn = 0.0;
+            } else if (4 * r == 3 * Lz) {
+                c = 0.0, sn = -1.0;
+            } else if (r != 0) {
+                const double a = 2.0 * 3.14159265358979323846 * (double)r / (double)Lz;
+                c = cos(a);
+                sn = sin(a);
+            }
+            zp[2 * ((size_t)p * Lz + z)] = c;
+            zp[2 * ((size_t)p * Lz + z) + 1] = sn;
+        }
+    EDK_CUDA_TRY(cudaMemcpy(h->pw_zphase, zp.data(), zp_bytes, cudaMemcpyHostToDevice));
+    EDK_CUDA_TRY(cudaMemcpy(h->pw_momode, mp.momode.data(), mp.momode.size() * sizeof(int), cudaMemcpyHostToDevice));
+    const cuuint64_t Kd = (cuuint64_t)2 * 3 * h->g.V;
+    const cuuint64_t gdim[3] = {Kd, (cuuint64_t)h->Ne, (cuuint64_t)h->nfield};
+    const cuuint64_t gstr[2] = {Kd * 8, Kd * 8 * (cuuint64_t)h->Ne};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t boxL[3] = {8, (cuuint32_t)PW_ROWS_L, 1};
+    const cuuint32_t boxR[3] = {8, (cuuint32_t)PW_ROWS_R, 1};
+    CUresult r = encode((CUtensorMap*)h->pw_tma.mapL, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, boxL, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+        r = encode((CUtensorMap*)h->pw_tma.mapR, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, boxR, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (plane-wave contraction) failed with CUresult %d", (int)r);
+        return EDK_ERR_CUDA;
+    }
+    h->pw_bytes = wt_bytes + y_bytes + zp_bytes;
+    h->pw_ready = true;
+    return EDK_OK;
+}
+
+int run_gram_pw(edk_handle* h, cudaStream_t s) {
+    PwParams Q{};
+    Q.jobs = h->jobs_dev;
+    Q.njobs = h->njobs;
+    Q.Ne = h->Ne;
+    Q.Lz = h->g.Lz;
+    Q.A = h->g.Lx * h->g.Ly;
+    Q.kplane = h->pw_kplane;
+    Q.n_et = (h->Ne + PW_ROWS_L - 1) / PW_ROWS_L;
+    Q.n_ft = (h->Ne + PW_ROWS_R - 1) / PW_ROWS_R;
+    Q.nmodes = h->pw_nmodes;
+    Q.mbtot = h->pw_mbtot;
+    Q.wtiles = h->pw_wtiles;
+    Q.Y = h->pw_Y;
+    const int npass = (h->pw_mbtot + PW_MAX_MB - 1) / PW_MAX_MB;
+    {
+        PhaseTimer t(h, s, PH_GRAM, npass);
+        for (int pass = 0; pass < npass; ++pass) {
+            Q.mb0 = pass * PW_MAX_MB;
+            EDK_CUDA_TRY(launch_gram_pw(Q, h->pw_tma, std::min(PW_MAX_MB, h->pw_mbtot - Q.mb0), s));
+        }
+    }
+    // the z fold is a reduction like the combine step and is timed with it
+    PhaseTimer t(h, s, PH_COMBINE, 1);
+    PwFold F{};
+    F.jobs = h->jobs_dev;
+    F.njobs = h->njobs;
+    F.Ne = h->Ne;
+    F.Lz = h->g.Lz;
+    F.nmodes = h->pw_nmodes;
+    F.nmom_int = h->nmom_int;
+    F.Y = h->pw_Y;
+    F.zphase = h->pw_zphase;
+    F.momode = h->pw_momode;
+    F.partial = h->partial;
+    EDK_CUDA_TRY(launch_pw_zfold(F, s));
     return EDK_OK;
 }
 
@@ -530,6 +727,7 @@ int configure(edk_handle* h) {
         build_displacement_jobs(h);
     h->njobs = (int)h->jobs_host.size();
 
+    free_pw(h);
     cudaFree(h->phase);
     cudaFree(h->phase_tiles);
     h->phase_tiles = nullptr;
@@ -579,6 +777,10 @@ int configure(edk_handle* h) {
         return pe == cudaErrorMemoryAllocation ? EDK_ERR_NOMEM : EDK_ERR_CUDA;
     }
     h->cfg_bytes = 4 * nm * h->g.Vpad * sizeof(cplx) + partial_bytes;
+    if (h->algo == 2) {
+        const int rc = build_pw(h);
+        if (rc != EDK_OK) return rc;
+    }
     return EDK_OK;
 }
 
@@ -593,6 +795,19 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     P.Vpad = h->g.Vpad;
     P.ksplit = h->naive ? 1 : h->ksplit;
     P.n_mt = row_tiles(h);
+    const bool use_pw = !h->naive && h->loader == 0 && h->algo == 2;
+    if (use_pw) {
+        if (!h->pw_ready) {
+            set_error("plane-wave contraction selected but its tables are not built");
+            return EDK_ERR_STATE;
+        }
+        const int rc = run_gram_pw(h, s);
+        if (rc != EDK_OK) return rc;
+        PhaseTimer t(h, s, PH_COMBINE, 1);
+        EDK_CUDA_TRY(launch_combine(h->ops_dev, h->nop, h->partial, h->njobs, 1, h->nmom_int, h->nmom, h->pmap_dev,
+                                    h->negidx_dev, h->n_half, h->Ne, h->have_coeff ? h->coeff : nullptr, out, s));
+        return EDK_OK;
+    }
     const bool use_tma = !h->naive && h->loader == 0 && h->tma_ready;
     if (h->cta_dirty) {
         const int rc = build_cta_map(h);
@@ -699,6 +914,10 @@ int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, co
     if (mode == EDK_MODE_DISPLACEMENT && order >= 1) EDK_ALLOC(h->lines, (size_t)12 * h->field_cplx * sizeof(cplx));
     EDK_ALLOC(h->coeff, (size_t)Ne * Ne * sizeof(double));
     h->mom_user.assign(mom3, mom3 + 3 * (size_t)nmom);
+    if (const char* a = getenv("EDK_GRAM_ALGO")) {  // A/B hook: 0 = 4M GEMM, 1 = 3M GEMM (default), 2 = plane-wave form
+        const int v = atoi(a);
+        if (v >= 0 && v <= 2) h->algo = v;
+    }
     {
         const int rc = configure(h);
         if (rc != EDK_OK) {
@@ -729,6 +948,7 @@ int edk_destroy(edk_handle* h) {
     cudaFree(h->pmap_dev);
     cudaFree(h->cta_map_dev);
     cudaFree(h->phase_tiles);
+    free_pw(h);
     cudaFree(h->stage_U);
     cudaFree(h->stage_V);
     cudaFree(h->stage_out);
@@ -790,11 +1010,23 @@ int edk_plan(int mode, int order, int nmom, const int* mom3, int sym_request, in
     return EDK_OK;
 }
 
+int edk_plan_modes(int nmom, const int* mom3, int* nmodes, int* modes3, int* momode) {
+    if (nmom < 1 || !mom3 || !nmodes || !modes3 || !momode) {
+        set_error("edk_plan_modes: bad argument");
+        return EDK_ERR_ARG;
+    }
+    const ModePlan M = plan_modes(std::vector<int>(mom3, mom3 + 3 * (size_t)nmom));
+    *nmodes = (int)M.modes3.size() / 3;
+    std::copy(M.modes3.begin(), M.modes3.end(), modes3);
+    std::copy(M.momode.begin(), M.momode.end(), momode);
+    return EDK_OK;
+}
+
 int edk_num_operators(const edk_handle* h) { return h ? h->nop : EDK_ERR_ARG; }
 size_t edk_output_bytes(const edk_handle* h) {
     return h ? (size_t)h->nop * h->nmom * h->Ne * h->Ne * sizeof(cplx) : 0;
 }
-size_t edk_workspace_bytes(const edk_handle* h) { return h ? h->ws_bytes + h->cfg_bytes : 0; }
+size_t edk_workspace_bytes(const edk_handle* h) { return h ? h->ws_bytes + h->cfg_bytes + h->pw_bytes : 0; }
 
 int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream) {
     const int big_endian = (layout & EDK_LINKS_BIG_ENDIAN) ? 1 : 0;
@@ -1070,11 +1302,16 @@ int edk_debug_loader(edk_handle* h, int mode) {
 }
 
 int edk_debug_algo(edk_handle* h, int algo) {
-    if (!h || algo < 0 || algo > 1) return EDK_ERR_ARG;
+    if (!h || algo < 0 || algo > 2) return EDK_ERR_ARG;
+    EDK_CUDA_TRY(cudaSetDevice(h->device));
     h->algo = algo;
     pick_gram_config(h);
-    const int rc = build_tma(h);
+    int rc = build_tma(h);
     if (rc != EDK_OK) return rc;
+    if (algo == 2 && !h->pw_ready) {
+        rc = build_pw(h);
+        if (rc != EDK_OK) return rc;
+    }
     return ensure_partial(h);
 }
 
@@ -1100,13 +1337,15 @@ int edk_query(const edk_handle* h, int what) {
         case 4: return h->mfrag;
         case 5: return h->njobs;
         case 6: return (h->loader == 0 && h->tma_ready) ? h->tma.nstages : 0;
-        case 7: return effective_algo(h) ? 3 : 4;
+        case 7: return effective_algo(h) == 2 ? 2 : (effective_algo(h) ? 3 : 4);
         case 8: {  // (pair, momentum) GEMMs actually contracted
             int n = 0;
             for (const auto& j : h->jobs_host) n += j.nseg * j.nmom;
             return n;
         }
         case 9: return h->n_half;
+        case 10: return effective_algo(h);
+        case 11: return h->pw_ready ? h->pw_nmodes : 0;
         default: return EDK_ERR_ARG;
     }
 }

@@ -88,6 +88,52 @@ struct CombineOp {
     double weight[EDK_MAX_TERMS];
 };
 
+// ---- plane-wave factorised contraction (algo 2, edk_gram_pw.cu) -----------------------------
+// The phase of momentum p factorises over the lattice axes,
+//   phase_p(x,y,z) = [cos(theta_q(x,y)) + i sigma_p sin(theta_q(x,y))] * exp(2 pi i pz z / Lz),
+// with q the {+(px,py), -(px,py)} couple of p.  So the colour-summed site product
+//   C(x)[e][f] = sum_seg sign_seg sum_c conj(L_seg[e][x][c]) R_seg[f][x][c]
+// is formed ONCE per site (12 DFMA) and folded over an xy-plane against the few REAL mode
+// functions cos(theta_q), sin(theta_q) by DMMA (A = modes x 4 sites, B = 4 sites x 8 f):
+//   Y[job][z][m][e][f] = sum_{x,y} w_m(x,y) C(x,y,z)[e][f]
+// (13 modes for the 33 momenta |p|^2 <= 4), and a small second kernel folds z:
+//   G[job][p] = sum_z exp(2 pi i pz z/Lz) (Y[z][mc(p)] + i sigma_p Y[z][ms(p)]).
+// FP64-pipe issue slots per (pair, e, f, site): 12/32 + 2*8*MB/32 = 1.4 against 8.3 of the 3M GEMM form.
+constexpr int PW_EL = 2;                // e rows per lane
+constexpr int PW_FL = 4;                // f rows per lane (x 8 lane groups = 32 per warp)
+constexpr int PW_WARPS = 8;             // MMA warps, stacked along e
+constexpr int PW_ROWS_L = PW_WARPS * PW_EL;  // 16 rows of L per CTA
+constexpr int PW_ROWS_R = 8 * PW_FL;         // 32 rows of R per CTA
+constexpr int PW_MAX_MB = 2;            // m-blocks (8 modes) per pass
+
+struct PwParams {
+    const GramJob* jobs;
+    int njobs;
+    int Ne;
+    int Lz;
+    int A;        // sites of one xy-plane (Lx*Ly)
+    int kplane;   // stages of 8 sites per plane = ceil(A/8)
+    int n_et, n_ft;  // tiles of PW_ROWS_L x PW_ROWS_R
+    int nmodes;   // real xy-modes kept in Y
+    int mb0;      // first m-block of this pass
+    int mbtot;    // m-blocks of the weight tiles = ceil(nmodes/8)
+    const double* wtiles;  // [kplane][2 groups of 4 sites][mbtot][32 lanes]: lane = (mode%8)*4 + site%4
+    cplx* Y;      // [njobs][Lz][nmodes][Ne][Ne]
+};
+struct PwTma {
+    alignas(64) unsigned char mapL[128];  // CUtensorMap over [nfield][Ne][2*Kc doubles], box 8 x PW_ROWS_L x 1
+    alignas(64) unsigned char mapR[128];  // box 8 x PW_ROWS_R x 1
+    int nstages;
+};
+struct PwFold {
+    const GramJob* jobs;
+    int njobs, Ne, Lz, nmodes, nmom_int;
+    const cplx* Y;
+    const cplx* zphase;   // [nmom_int][Lz]
+    const int* momode;    // [nmom_int][3]: cos mode, sin mode (-1: none), sigma
+    cplx* partial;        // [njobs][nmom_int][Ne][Ne] (split 0 of the partial-sum buffer)
+};
+
 // ---- launchers (defined in the .cu files) -------------------------------------------------
 // prepare
 cudaError_t launch_round_eigvecs(const void* V_in, int flags, cplx* W0, double* W0_sum, size_t n_cplx, size_t row,
@@ -120,6 +166,11 @@ int gram_nfrag_per_tile(int algo);
 cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom_int,
                            int nmom_out, const int* pmap, const int* negidx, int n_half, int Ne, const double* coeff, cplx* out,
                            cudaStream_t s);
+// plane-wave factorised contraction
+int pw_plan_smem(int* nstages, int* smem_bytes);
+cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes, int mbtot, int kplane, Geom g, cudaStream_t s);
+cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, cudaStream_t s);
+cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s);
 // microbench
 cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops);
 

@@ -31,6 +31,7 @@
 // phase tile [n-fragment][8 sites].  All warps of a CTA share the 8*MF rows of L, so no B value is
 // built twice; n-fragments (4 or 8 consecutive f at one momentum) are flattened f-fragment-major.
 #include "edk_common.cuh"
+#include "edk_pipe.cuh"
 
 namespace edk {
 
@@ -62,17 +63,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-// sign flip on the integer pipe: the FP64 pipe is the one the DMMAs need
-__device__ __forceinline__ double flip_sign(double x) {
-    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
 }
 
 // One pipeline stage (8 sites = 6 k-groups of 4 complex k) of one warp: 2*MF*NF DMMAs per k-group.
@@ -386,45 +376,6 @@ struct GtCols {
     static constexpr int NACC = ALGO ? 3 : 2;               // accumulator fragments per (m-fragment, warp)
     static constexpr int LS_PER_ROW = ALGO ? 32 : 0;        // bytes per (row, k-group) of the Re+Im plane
 };
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-// A wait that cannot hang the GPU: a pipeline bug traps after ~1 s instead of spinning forever.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long t0 = 0;
-    for (int spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!done && spin >= 64) {
-            if (t0 == 0) t0 = clock64();
-            else if (clock64() - t0 > (1LL << 31)) __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
-        "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
 
 // 3M stage: same operand tiles as gram_compute_stage plus the plane Ls = Re L + Im L that the
 // field-producing kernels wrote and the producer fetched as a third box (ls_s = this lane's slot

@@ -1,0 +1,348 @@
+// Plane-wave factorised contraction ("algo 2"), sm_100a.
+//
+//   G[p][e][f] = sum_seg sign_seg sum_{x,c} conj(L_seg[e][x][c]) phase_p(x) R_seg[f][x][c]
+//   (the einsum "zyx,ezyxc,fzyxc->ef" of lattice/generator/elemental.py:322-329 and
+//    lattice/generator/displacement_elemental.py:94-95 for every momentum of the list)
+//
+// The GEMM form (edk_gram.cu) spends 8 Ne^2 3V flops per (pair, momentum) although the momentum only
+// enters through a phase that factorises over the lattice axes:
+//   phase_p(x,y,z) = [cos(theta_q(x,y)) + i sigma_p sin(theta_q(x,y))] * exp(2 pi i pz z / Lz),
+//   theta_q = 2 pi (qx x/Lx + qy y/Ly),  (px,py) = sigma_p (qx,qy).
+// Here the colour-summed site product
+//   C(x)[e][f] = sum_c conj(L[e][x][c]) R[f][x][c]
+// is formed once per site, whatever the number of momenta, and transformed over one xy-plane against
+// the REAL mode functions w_m in {cos(theta_q), sin(theta_q)} (13 of them for the 33 momenta with
+// |p|^2 <= 4) on the FP64 tensor pipe:
+//   gram_pw_kernel<MB> : Y[job][z][m][e][f] = sum_{(x,y)} w_m(x,y) C(x,y,z)[e][f]
+//                        one DMMA.8x8x4 = (8 modes) x (4 sites) x (8 f): A operand = weights, B operand =
+//                        the C values the lanes have just formed with 12 DFMA each, accumulator = Y.
+//                        Lane (site s = lane%4, column n = lane/4) owns e in {2 warp, 2 warp + 1} and
+//                        f in {n, n+8, n+16, n+24} of a 16 x 32 tile; TMA producer warp + mbarrier ring as
+//                        in gram_tma_kernel, same [k-group][row][4 complex] shared-memory tiles.
+//   pw_zfold_kernel    : G[job][p] = sum_z exp(2 pi i pz z/Lz) (Y[z][mc(p)] + i sigma_p Y[z][ms(p)])
+//                        written as split 0 of the partial-sum buffer, so combine_kernel is unchanged.
+// FP64-pipe issue slots per (pair, e, f, site): 12/32 (DFMA) + 2 MB 8/32 (DMMA) = 1.4 at MB = 2, against
+// 8.3 for the 3M GEMM form with the Hermitian pairing and the half set (563/19 momenta x 9/32).
+// More than 16 modes run as several passes over the same fields (mb0 = first m-block of the pass).
+#include "edk_common.cuh"
+#include "edk_pipe.cuh"
+
+namespace edk {
+
+constexpr int PW_THREADS = (PW_WARPS + 4) * 32;  // 8 MMA warps + one producer warpgroup (one warp of it works)
+constexpr int PW_REGS_CONSUMER = 232;
+constexpr int PW_REGS_PRODUCER = 40;
+constexpr int PW_KG = 6;                                // k-groups of 4 complex per stage (= 8 sites x 3 colours)
+constexpr int PW_L_BYTES = PW_KG * PW_ROWS_L * 64;      // [kg][row][4 complex]
+constexpr int PW_R_BYTES = PW_KG * PW_ROWS_R * 64;
+constexpr int PW_W_BYTES = 2 * PW_MAX_MB * 256;         // [group of 4 sites][m-block][32 lanes] doubles
+constexpr int PW_STAGE_BYTES = PW_L_BYTES + PW_R_BYTES + PW_W_BYTES;
+constexpr int PW_MAX_STAGES = 8;
+constexpr int PW_TAIL_BYTES = 16 * PW_MAX_STAGES + (int)sizeof(GramJob) + 64;
+static_assert(PW_STAGE_BYTES % 128 == 0 && PW_L_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+
+int pw_plan_smem(int* nstages, int* smem_bytes) {
+    int nst = (227 * 1024 - PW_TAIL_BYTES) / PW_STAGE_BYTES;
+    if (nst > PW_MAX_STAGES) nst = PW_MAX_STAGES;
+    if (nst < 2) return -1;
+    *nstages = nst;
+    *smem_bytes = nst * PW_STAGE_BYTES + PW_TAIL_BYTES;
+    return 0;
+}
+
+template <int MB>
+__global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P, const __grid_constant__ PwTma Tm) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int nst = Tm.nstages;
+    unsigned char* tail = smem + (size_t)nst * PW_STAGE_BYTES;
+    const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(tail);
+    const uint32_t bar_empty = bar_full + 8 * PW_MAX_STAGES;
+    GramJob* sjob = reinterpret_cast<GramJob*>(tail + 16 * PW_MAX_STAGES);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    // work item = (job, z-plane, e-tile, f-tile), f-tile fastest: CTAs that run together read the same plane
+    int item = blockIdx.x;
+    const int ft = item % P.n_ft;
+    item /= P.n_ft;
+    const int et = item % P.n_et;
+    item /= P.n_et;
+    const int z = item % P.Lz;
+    const int job_id = item / P.Lz;
+    const int e0 = et * PW_ROWS_L, f0 = ft * PW_ROWS_R;
+
+    if (tid < (int)(sizeof(GramJob) / sizeof(int))) {
+        reinterpret_cast<int*>(sjob)[tid] = reinterpret_cast<const int*>(P.jobs + job_id)[tid];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, PW_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int T = sjob->nseg * P.kplane;  // stages of 8 sites: every segment walks the plane once
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+
+    if (warp >= PW_WARPS) {
+        // ================================ producer warpgroup ================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PW_REGS_PRODUCER));
+        if (warp != PW_WARPS) return;
+        const uint32_t tx_bytes = (uint32_t)(PW_L_BYTES + PW_R_BYTES + 2 * MB * 256);
+        const int plane_site0 = z * P.A;
+        int seg = 0, kstep = 0, s = 0;
+        uint32_t par = 1;  // the first pass over the ring finds every slot free
+        for (int it = 0; it < T; ++it) {
+            mbar_wait(bar_empty + 8 * s, par);
+            const uint32_t full = bar_full + 8 * s;
+            if (lane == 0) mbar_arrive_expect_tx(full, tx_bytes);
+            __syncwarp();
+            const uint32_t st = smem_base + (uint32_t)(s * PW_STAGE_BYTES);
+            // first double of the stage's 8 sites; sites past the end of the plane belong to the next
+            // plane (or are zero-filled past the end of the row) and meet zero weights
+            const int kd = (plane_site0 + 8 * kstep) * 6;
+            if (lane < PW_KG) {
+                tma_load_3d(st + lane * (PW_ROWS_L * 64), Tm.mapL, full, kd + 8 * lane, e0, sjob->Lf[seg]);
+            } else if (lane >= 8 && lane < 8 + PW_KG) {
+                tma_load_3d(st + PW_L_BYTES + (lane - 8) * (PW_ROWS_R * 64), Tm.mapR, full, kd + 8 * (lane - 8), f0,
+                            sjob->Rf[seg]);
+            } else if (lane == 16 || lane == 17) {
+                const int grp = lane - 16;
+                const double* src = P.wtiles + (((size_t)kstep * 2 + grp) * P.mbtot + P.mb0) * 32;
+                bulk_load(st + PW_L_BYTES + PW_R_BYTES + grp * (MB * 256), src, MB * 256, full);
+            }
+            if (++kstep == P.kplane) {
+                kstep = 0;
+                ++seg;
+            }
+            if (++s == nst) {
+                s = 0;
+                par ^= 1;
+            }
+        }
+        return;
+    }
+
+    // ================================== consumer warps ==================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(PW_REGS_CONSUMER));
+    const int sidx = lane & 3, n = lane >> 2;  // site inside a group of 4 (MMA k), column (MMA n)
+    // byte offsets of this lane's three colours of site 4 grp + sidx inside the L and R tiles
+    uint32_t offL[2][3], offR[2][3];
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int kc = (4 * grp + sidx) * 3 + c;  // complex k inside the stage
+            const int kg = kc >> 2, kin = kc & 3;
+            offL[grp][c] = (uint32_t)(kg * (PW_ROWS_L * 64) + warp * PW_EL * 64 + kin * 16);
+            offR[grp][c] = (uint32_t)(PW_L_BYTES + kg * (PW_ROWS_R * 64) + n * 64 + kin * 16);
+        }
+    const uint32_t offW = (uint32_t)(PW_L_BYTES + PW_R_BYTES + lane * 8);
+
+    double yre[PW_EL][PW_FL][MB][2], yim[PW_EL][PW_FL][MB][2];
+#pragma unroll
+    for (int i = 0; i < PW_EL; ++i)
+#pragma unroll
+        for (int j = 0; j < PW_FL; ++j)
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) yre[i][j][mb][0] = yre[i][j][mb][1] = yim[i][j][mb][0] = yim[i][j][mb][1] = 0.0;
+
+    int cur_sign = 1;
+    int cs_seg = 0, cs_kstep = 0;
+    int s = 0;
+    uint32_t par = 0;
+    for (int it = 0; it < T; ++it) {
+        const int sgn = sjob->sign[cs_seg];
+        if (++cs_kstep == P.kplane) {
+            cs_kstep = 0;
+            ++cs_seg;
+        }
+        if (sgn != cur_sign) {  // uniform: fold the segment sign by flipping the running sums
+#pragma unroll
+            for (int i = 0; i < PW_EL; ++i)
+#pragma unroll
+                for (int j = 0; j < PW_FL; ++j)
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            yre[i][j][mb][q] = flip_sign(yre[i][j][mb][q]);
+                            yim[i][j][mb][q] = flip_sign(yim[i][j][mb][q]);
+                        }
+            cur_sign = sgn;
+        }
+        mbar_wait(bar_full + 8 * s, par);
+        const unsigned char* stage = smem + (size_t)s * PW_STAGE_BYTES;
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp) {
+            double w[MB];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) w[mb] = *reinterpret_cast<const double*>(stage + offW + (grp * MB + mb) * 256);
+            cplx lv[PW_EL][3];
+#pragma unroll
+            for (int i = 0; i < PW_EL; ++i)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) lv[i][c] = *reinterpret_cast<const cplx*>(stage + offL[grp][c] + i * 64);
+#pragma unroll
+            for (int j = 0; j < PW_FL; ++j) {
+                cplx rv[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) rv[c] = *reinterpret_cast<const cplx*>(stage + offR[grp][c] + j * 512);
+#pragma unroll
+                for (int i = 0; i < PW_EL; ++i) {
+                    // conj(L) . R over the three colours of this lane's site
+                    double cr = lv[i][0].x * rv[0].x;
+                    double ci = lv[i][0].x * rv[0].y;
+                    cr = fma(lv[i][0].y, rv[0].y, cr);
+                    ci = fma(-lv[i][0].y, rv[0].x, ci);
+#pragma unroll
+                    for (int c = 1; c < 3; ++c) {
+                        cr = fma(lv[i][c].x, rv[c].x, cr);
+                        ci = fma(lv[i][c].x, rv[c].y, ci);
+                        cr = fma(lv[i][c].y, rv[c].y, cr);
+                        ci = fma(-lv[i][c].y, rv[c].x, ci);
+                    }
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) {
+                        dmma884(yre[i][j][mb][0], yre[i][j][mb][1], w[mb], cr);
+                        dmma884(yim[i][j][mb][0], yim[i][j][mb][1], w[mb], ci);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+        if (++s == nst) {
+            s = 0;
+            par ^= 1;
+        }
+    }
+
+    // ---- epilogue: lane holds modes (mb0 + mb) 8 + n of columns f = f0 + 8 j + 2 sidx + {0, 1} -------------
+    const double fs = (double)cur_sign;
+    const int Ne = P.Ne;
+    const size_t mat = (size_t)Ne * Ne;
+    cplx* Yp = P.Y + ((size_t)job_id * P.Lz + z) * (size_t)P.nmodes * mat;
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+        const int mode = (P.mb0 + mb) * 8 + n;
+        if (mode >= P.nmodes) continue;
+#pragma unroll
+        for (int i = 0; i < PW_EL; ++i) {
+            const int e = e0 + warp * PW_EL + i;
+            if (e >= Ne) continue;
+            cplx* row = Yp + (size_t)mode * mat + (size_t)e * Ne;
+#pragma unroll
+            for (int j = 0; j < PW_FL; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int f = f0 + 8 * j + 2 * sidx + q;
+                    if (f < Ne) row[f] = make_double2(fs * yre[i][j][mb][q], fs * yim[i][j][mb][q]);
+                }
+        }
+    }
+}
+
+cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, cudaStream_t s) {
+    int nst, bytes;
+    if (pw_plan_smem(&nst, &bytes) != 0 || nst != T.nstages || MB < 1 || MB > PW_MAX_MB) return cudaErrorInvalidValue;
+    const long long items = (long long)P.njobs * P.Lz * P.n_et * P.n_ft;
+    if (items < 1 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
+    cudaError_t e;
+    if (MB == 1) {
+        e = cudaFuncSetAttribute(gram_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        gram_pw_kernel<1><<<(unsigned)items, PW_THREADS, bytes, s>>>(P, T);
+    } else {
+        e = cudaFuncSetAttribute(gram_pw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        gram_pw_kernel<2><<<(unsigned)items, PW_THREADS, bytes, s>>>(P, T);
+    }
+    return cudaGetLastError();
+}
+
+// weights of the real xy-modes, laid out as the A fragments of the plane transform:
+//   wtiles[kstep][grp][m-block][lane] = w_{8 mblock + lane/4}(site 8 kstep + 4 grp + lane%4 of the plane)
+// modes3[m] = (qx, qy, kind): kind 0 -> cos(theta_q), 1 -> sin(theta_q); zero outside the plane / mode list
+__global__ void pw_weights_kernel(double* __restrict__ wtiles, const int* __restrict__ modes3, int nmodes, int mbtot, int kplane,
+                                  Geom g) {
+    const size_t total = (size_t)kplane * 2 * mbtot * 32;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int lane = (int)(idx & 31);
+    size_t r = idx >> 5;
+    const int mbt = (int)(r % mbtot);
+    r /= mbtot;
+    const int grp = (int)(r & 1);
+    const int kstep = (int)(r >> 1);
+    const int mode = mbt * 8 + (lane >> 2);
+    const int sxy = 8 * kstep + 4 * grp + (lane & 3);
+    double v = 0.0;
+    if (mode < nmodes && sxy < g.Lx * g.Ly) {
+        const int x = sxy % g.Lx, y = sxy / g.Lx;
+        const long long qx = modes3[3 * mode + 0], qy = modes3[3 * mode + 1];
+        // q.x reduced mod L in integers, as in phase_table_kernel
+        const long long rx = ((qx * x) % g.Lx + g.Lx) % g.Lx;
+        const long long ry = ((qy * y) % g.Ly + g.Ly) % g.Ly;
+        const double turns = (double)rx / (double)g.Lx + (double)ry / (double)g.Ly;
+        double sn, cs;
+        sincospi(2.0 * turns, &sn, &cs);
+        v = modes3[3 * mode + 2] ? sn : cs;
+    }
+    wtiles[idx] = v;
+}
+
+cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes, int mbtot, int kplane, Geom g, cudaStream_t s) {
+    const size_t total = (size_t)kplane * 2 * mbtot * 32;
+    pw_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wtiles, modes3_dev, nmodes, mbtot, kplane, g);
+    return cudaGetLastError();
+}
+
+// G[job][p][e][f] = sum_z zphase[p][z] (Y[job][z][mc][e][f] + i sigma Y[job][z][ms][e][f]); momentum fastest over
+// the blocks, so the ~Lz x 2 planes a block reads are shared through L2 by the momenta of the same couple.
+constexpr int PW_FOLD_THREADS = 256;
+__global__ void __launch_bounds__(PW_FOLD_THREADS) pw_zfold_kernel(const PwFold F) {
+    const size_t mat = (size_t)F.Ne * F.Ne;
+    const int nblk = (int)((mat + PW_FOLD_THREADS - 1) / PW_FOLD_THREADS);
+    int b = blockIdx.x;
+    const int p = b % F.nmom_int;
+    b /= F.nmom_int;
+    const int blk = b % nblk;
+    const int job = b / nblk;
+    if (p >= F.jobs[job].nmom) return;  // self pairs contract the half set only
+    const size_t ef = (size_t)blk * PW_FOLD_THREADS + threadIdx.x;
+    if (ef >= mat) return;
+    const int mc = F.momode[3 * p], ms = F.momode[3 * p + 1];
+    const double sg = (double)F.momode[3 * p + 2];
+    const cplx* Yj = F.Y + (size_t)job * F.Lz * F.nmodes * mat + ef;
+    const cplx* zp = F.zphase + (size_t)p * F.Lz;
+    double ar = 0.0, ai = 0.0;
+    for (int z = 0; z < F.Lz; ++z) {
+        const cplx yc = Yj[((size_t)z * F.nmodes + mc) * mat];
+        double ur = yc.x, ui = yc.y;
+        if (ms >= 0) {
+            const cplx ys = Yj[((size_t)z * F.nmodes + ms) * mat];
+            ur = fma(-sg, ys.y, ur);
+            ui = fma(sg, ys.x, ui);
+        }
+        const cplx ph = zp[z];
+        ar = fma(ph.x, ur, ar);
+        ar = fma(-ph.y, ui, ar);
+        ai = fma(ph.x, ui, ai);
+        ai = fma(ph.y, ur, ai);
+    }
+    F.partial[((size_t)job * F.nmom_int + p) * mat + ef] = make_double2(ar, ai);
+}
+
+cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s) {
+    const size_t mat = (size_t)F.Ne * F.Ne;
+    const long long nblk = (long long)((mat + PW_FOLD_THREADS - 1) / PW_FOLD_THREADS);
+    const long long blocks = nblk * F.njobs * F.nmom_int;
+    if (blocks < 1 || blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    pw_zfold_kernel<<<(unsigned)blocks, PW_FOLD_THREADS, 0, s>>>(F);
+    return cudaGetLastError();
+}
+
+}  // namespace edk

@@ -206,7 +206,8 @@ class ElementalEngine:
         q = lambda w: int(self.lib.edk_query(self.h, w))  # noqa: E731
         return {"hermitian_pairing": bool(q(0)), "internal_momenta": q(1), "pair_gemms_per_momentum": q(2),
                 "ksplit": q(3), "mfrag": q(4), "jobs": q(5), "tma_stages": q(6),
-                "real_mma_per_complex_block": q(7), "pair_momentum_gemms": q(8), "half_set_momenta": q(9)}
+                "real_mma_per_complex_block": q(7), "pair_momentum_gemms": q(8), "half_set_momenta": q(9),
+                "contraction_form": q(10), "plane_wave_modes": q(11)}
 
 
 def microbench_fp64(device: int = 0):

@@ -84,6 +84,14 @@ int edk_phase_table(int Lx, int Ly, int Lz, int nmom, const int* mom3, void* out
  */
 int edk_plan(int mode, int order, int nmom, const int* mom3, int sym_request, int out[8]);
 
+/*
+ * Mode plan of the plane-wave factorised contraction (edk_debug_algo 2), pure host logic: the xy-part of
+ * exp(2 pi i p.x/L) (lattice/insertion/phase.py:41-46) is cos(theta_q) + i sigma sin(theta_q) for the couple
+ * {+q, -q} of (px, py).  nmodes real modes; modes3[m] = (qx, qy, kind: 0 cos / 1 sin), room for 2*nmom triples;
+ * momode[i] = (cos mode, sin mode or -1, sigma) of momentum i.
+ */
+int edk_plan_modes(int nmom, const int* mom3, int* nmodes, int* modes3, int* momode);
+
 /* number of operators in the output: (3^(num_nabla+1)-1)/2 or distance+1 (elemental.py:48, displacement_elemental.py:45) */
 int edk_num_operators(const edk_handle* h);
 /* bytes of one timeslice result [Nop][Nmom][Ne][Ne] complex128 */
@@ -174,11 +182,16 @@ long long edk_launch_count(const edk_handle* h);
  *   1 = force the Hermitian pairing G(L,R,p)^dagger = G(R,L,-p) (missing -p are added internally).
  * edk_debug_loader: 0 = TMA producer warp + mbarrier ring (default), 1 = cp.async ring executed by the MMA warps.
  * edk_debug_algo: arithmetic of the TMA kernel, 1 = 3M (default: Re = T1+T2, Im = T3+T1-T2 with
- *   T1 = Lr.Pr, T2 = Li.Pi, T3 = (Lr+Li).(Pi-Pr): three real MMAs per complex block), 0 = 4M (four).
+ *   T1 = Lr.Pr, T2 = Li.Pi, T3 = (Lr+Li).(Pi-Pr): three real MMAs per complex block), 0 = 4M (four),
+ *   2 = plane-wave factorised form: site products conj(L).R formed once per site, real xy-mode transform by
+ *   DMMA per z-plane, z folded by a second kernel (csrc/edk_gram_pw.cu).  The environment variable
+ *   EDK_GRAM_ALGO=0|1|2 sets the initial value of every new handle (A/B runs of bench.py).
  * edk_query: what = 0 pairing in use (0/1), 1 internal momentum count, 2 pair-GEMMs per momentum,
  *   3 split-K factor, 4 m-fragments per tile, 5 contraction jobs, 6 TMA ring depth (0 = cp.async loader),
  *   7 real MMAs per complex block (3 or 4), 8 number of (pair, momentum) GEMMs contracted per timeslice
- *   (self pairs L == R only run one momentum of every +-p couple), 9 size of that half set.
+ *   (self pairs L == R only run one momentum of every +-p couple), 9 size of that half set,
+ *   10 contraction form in use (0 / 1 / 2 as in edk_debug_algo), 11 real xy-modes of form 2 (0 = not built).
+ *   With form 2, what = 7 answers 2 (DMMAs per site product and block of 8 modes).
  */
 int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream);
 int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream);

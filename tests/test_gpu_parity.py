@@ -612,3 +612,29 @@ def test_linearity_and_scaling_property(edb):
     expect[:, :, :, 5] *= 4j
     expect[:, :, 5, :] *= -4j
     _blocks_close(outs[1], expect, what="sesquilinearity")
+
+
+# ---------------------------------------------------------------------------------------------
+# (6) experimental: plane-wave factorised contraction (edk_debug_algo 2), checked in its own process
+# ---------------------------------------------------------------------------------------------
+def test_zz_plane_wave_form_in_subprocess(edb):
+    """csrc/edk_gram_pw.cu was written after the round's GPU budget was spent: its index arithmetic is pinned
+    on CPU by tests/test_pw_model.py, but the kernel has not run on hardware yet and is NOT the default
+    contraction.  The check (tools/check_plane_wave.py: oracle + GEMM-form parity on ragged / multi-tile /
+    multi-segment shapes) runs in a subprocess so that a fault cannot poison this process's CUDA context;
+    a failure is reported as xfail with the tail of its output, a pass is a real pass."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import REPO
+
+    try:
+        r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "check_plane_wave.py")], capture_output=True,
+                           text=True, timeout=600)
+    except subprocess.TimeoutExpired:
+        pytest.xfail("plane-wave form (experimental, not the default path): check timed out")
+    tail = (r.stdout + r.stderr)[-1500:]
+    print(tail)
+    if r.returncode != 0:
+        pytest.xfail("plane-wave form (experimental, not the default path) failed its first hardware run:\n" + tail)

@@ -1,0 +1,200 @@
+"""CPU-only checks of the plane-wave factorised contraction (csrc/edk_gram_pw.cu, edk_debug_algo 2).
+
+The CUDA kernels cannot run here, so two things are pinned instead:
+  * the host-side mode plan the library really uses (edk_plan_modes through the C ABI) reproduces the
+    reference's phase exp(+2 pi i p.x/L) (lattice/insertion/phase.py:41-46, via the oracle);
+  * a lane-level numpy model of gram_pw_kernel / pw_zfold_kernel that transcribes the kernel's index
+    arithmetic one to one (shared-memory tile layout filled by the TMA boxes, per-lane byte offsets, the
+    m8n8k4 fragment ownership, plane-boundary zero weights, epilogue indices) equals the direct contraction
+    sum_x conj(L) phase R of the oracle on ragged shapes.  The model is the specification the kernel was
+    written against; the kernel itself is checked on the GPU (tests/test_gpu_parity.py).
+"""
+import numpy as np
+import pytest
+
+from easydistillation_b200 import _capi
+from oracle import elemental_oracle as orc
+
+PW_EL, PW_FL, PW_WARPS = 2, 4, 8
+ROWS_L, ROWS_R = PW_WARPS * PW_EL, 8 * PW_FL
+KG = 6
+L_BYTES, R_BYTES = KG * ROWS_L * 64, KG * ROWS_R * 64
+
+
+def _mode_value(mode, x, y, Lx, Ly):
+    qx, qy, kind = (int(v) for v in mode)
+    turns = ((qx * x) % Lx) / Lx + ((qy * y) % Ly) / Ly
+    return np.sin(2 * np.pi * turns) if kind else np.cos(2 * np.pi * turns)
+
+
+@pytest.mark.parametrize("count", [1, 7, 9, 33])
+def test_mode_plan_reproduces_the_phase(count):
+    latt = [6, 4, 5, 1]
+    Lx, Ly, Lz = latt[:3]
+    moms = orc.momentum_set(count)
+    modes, momode = _capi.plan_modes(moms)
+    if count == 33:
+        assert len(modes) == 13  # 6 couples x (cos, sin) + the constant mode
+    z, y, x = np.meshgrid(np.arange(Lz), np.arange(Ly), np.arange(Lx), indexing="ij")
+    for p, mom in enumerate(moms):
+        mc, ms, sg = (int(v) for v in momode[p])
+        w = _mode_value(modes[mc], x, y, Lx, Ly).astype(complex)
+        if ms >= 0:
+            w = w + 1j * sg * _mode_value(modes[ms], x, y, Lx, Ly)
+        else:
+            assert mom[0] == 0 and mom[1] == 0
+        ph = w * np.exp(2j * np.pi * ((mom[2] * z) % Lz) / Lz)
+        assert np.abs(ph - orc.momentum_phase(latt, mom)).max() < 1e-14
+
+
+def test_mode_plan_general_momenta():
+    moms = [(3, -1, 2), (-3, 1, 0), (0, -2, 1), (0, 2, 1), (0, 0, -4), (5, 0, 0)]
+    modes, momode = _capi.plan_modes(moms)
+    assert modes.tolist() == [[3, -1, 0], [3, -1, 1], [0, 2, 0], [0, 2, 1], [0, 0, 0], [5, 0, 0], [5, 0, 1]]
+    assert momode.tolist() == [[0, 1, 1], [0, 1, -1], [2, 3, -1], [2, 3, 1], [4, -1, 0], [5, 6, 1]]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# lane-level model
+# ---------------------------------------------------------------------------------------------------------
+def _tma_box(fields, field, row0, kd0, rows):
+    """cp.async.bulk.tensor.3d box {8 doubles, rows, 1} of the array [nfield][Ne][2*Kc doubles]: out-of-range
+    rows / doubles are zero-filled.  Returns [rows][4 complex]."""
+    nf, Ne, Kc = fields.shape
+    out = np.zeros((rows, 4), complex)
+    for r in range(rows):
+        for k in range(4):
+            kc = kd0 // 2 + k
+            assert kd0 % 2 == 0
+            if row0 + r < Ne and kc < Kc:
+                out[r, k] = fields[field, row0 + r, kc]
+    return out
+
+
+def _weight_tiles(modes, Lx, Ly, kplane, mbtot):
+    """pw_weights_kernel: wtiles[kstep][grp][mblock][lane]."""
+    wt = np.zeros((kplane, 2, mbtot, 32))
+    for k in range(kplane):
+        for grp in range(2):
+            for mbt in range(mbtot):
+                for lane in range(32):
+                    mode = mbt * 8 + (lane >> 2)
+                    sxy = 8 * k + 4 * grp + (lane & 3)
+                    if mode < len(modes) and sxy < Lx * Ly:
+                        wt[k, grp, mbt, lane] = _mode_value(modes[mode], sxy % Lx, sxy // Lx, Lx, Ly)
+    return wt
+
+
+def _gram_pw_model(fields, jobs, latt3, moms_int, max_mb=2):
+    """jobs: list of (segments [(Lf, Rf, sign)], nmom).  Returns partial[job][p][e][f]."""
+    Lx, Ly, Lz = latt3
+    nf, Ne, Kc = fields.shape
+    A = Lx * Ly
+    kplane = (A + 7) // 8
+    modes, momode = _capi.plan_modes(moms_int)
+    nmodes = len(modes)
+    mbtot = (nmodes + 7) // 8
+    wt = _weight_tiles(modes, Lx, Ly, kplane, mbtot)
+    n_et, n_ft = (Ne + ROWS_L - 1) // ROWS_L, (Ne + ROWS_R - 1) // ROWS_R
+    Y = np.full((len(jobs), Lz, nmodes, Ne, Ne), np.nan, complex)
+    lane = np.arange(32)
+    sidx, n = lane & 3, lane >> 2
+    for mb0 in range(0, mbtot, max_mb):
+        MB = min(max_mb, mbtot - mb0)
+        for job_id, (segs, _) in enumerate(jobs):
+            for z in range(Lz):
+                for et in range(n_et):
+                    for ft in range(n_ft):
+                        e0, f0 = et * ROWS_L, ft * ROWS_R
+                        yre = np.zeros((PW_WARPS, PW_EL, PW_FL, MB, 2, 32))
+                        yim = np.zeros_like(yre)
+                        cur_sign = 1
+                        for (Lf, Rf, sgn) in segs:
+                            for kstep in range(kplane):
+                                if sgn != cur_sign:
+                                    yre, yim, cur_sign = -yre, -yim, sgn
+                                # ---- producer: one stage of shared memory, addressed in 16-byte units
+                                smem = np.zeros((L_BYTES + R_BYTES) // 16, complex)
+                                kd = (z * A + 8 * kstep) * 6
+                                for kg in range(KG):
+                                    box = _tma_box(fields, Lf, e0, kd + 8 * kg, ROWS_L)
+                                    smem[kg * ROWS_L * 4:(kg + 1) * ROWS_L * 4] = box.reshape(-1)
+                                    box = _tma_box(fields, Rf, f0, kd + 8 * kg, ROWS_R)
+                                    o = L_BYTES // 16 + kg * ROWS_R * 4
+                                    smem[o:o + ROWS_R * 4] = box.reshape(-1)
+                                wst = wt[kstep][:, mb0:mb0 + MB, :]  # two bulk copies: [grp][MB][32]
+                                # ---- consumers
+                                for warp in range(PW_WARPS):
+                                    for grp in range(2):
+                                        offL, offR = [], []
+                                        for c in range(3):
+                                            kc = (4 * grp + sidx) * 3 + c
+                                            kg, kin = kc >> 2, kc & 3
+                                            offL.append(kg * (ROWS_L * 64) + warp * PW_EL * 64 + kin * 16)
+                                            offR.append(L_BYTES + kg * (ROWS_R * 64) + n * 64 + kin * 16)
+                                        for j in range(PW_FL):
+                                            rv = [smem[(offR[c] + j * 512) // 16] for c in range(3)]
+                                            for i in range(PW_EL):
+                                                lv = [smem[(offL[c] + i * 64) // 16] for c in range(3)]
+                                                cval = sum(np.conj(lv[c]) * rv[c] for c in range(3))  # per lane
+                                                for mb in range(MB):
+                                                    a = wst[grp, mb]  # lane holds A[row = lane>>2][k = lane&3]
+                                                    Amat = np.zeros((8, 4))
+                                                    Amat[n, sidx] = a
+                                                    for part, acc in ((cval.real, yre), (cval.imag, yim)):
+                                                        Bmat = np.zeros((4, 8))
+                                                        Bmat[sidx, n] = part  # lane holds B[k = lane&3][col = lane>>2]
+                                                        D = Amat @ Bmat
+                                                        for q in range(2):  # lane holds D[lane>>2][2 (lane&3) + q]
+                                                            acc[warp, i, j, mb, q] += D[n, 2 * sidx + q]
+                        # ---- epilogue
+                        for warp in range(PW_WARPS):
+                            for mb in range(MB):
+                                for ln in range(32):
+                                    mode = (mb0 + mb) * 8 + n[ln]
+                                    if mode >= nmodes:
+                                        continue
+                                    for i in range(PW_EL):
+                                        e = e0 + warp * PW_EL + i
+                                        if e >= Ne:
+                                            continue
+                                        for j in range(PW_FL):
+                                            for q in range(2):
+                                                f = f0 + 8 * j + 2 * sidx[ln] + q
+                                                if f < Ne:
+                                                    Y[job_id, z, mode, e, f] = cur_sign * (
+                                                        yre[warp, i, j, mb, q, ln] + 1j * yim[warp, i, j, mb, q, ln])
+    assert not np.isnan(Y).any(), "an element of Y was never written"
+    # ---- pw_zfold_kernel
+    nmom = len(moms_int)
+    partial = np.zeros((len(jobs), nmom, Ne, Ne), complex)
+    for job_id, (_, nmom_job) in enumerate(jobs):
+        for p in range(nmom_job):
+            mc, ms, sg = (int(v) for v in momode[p])
+            for z in range(Lz):
+                u = Y[job_id, z, mc].copy()
+                if ms >= 0:
+                    u = u + 1j * sg * Y[job_id, z, ms]
+                r = (moms_int[p][2] * z) % Lz
+                partial[job_id, p] += np.exp(2j * np.pi * r / Lz) * u
+    return partial
+
+
+@pytest.mark.parametrize("latt3,Ne,nmom,max_mb", [((3, 5, 2), 5, 7, 2), ((4, 2, 3), 19, 33, 2), ((5, 3, 1), 35, 9, 2),
+                                                  ((2, 3, 2), 3, 33, 1)])  # max_mb = 1: two passes over 13 modes
+def test_lane_model_equals_direct_contraction(latt3, Ne, nmom, max_mb):
+    Lx, Ly, Lz = latt3
+    V = Lx * Ly * Lz
+    rng = np.random.default_rng(1234 + Ne)
+    nfield = 3
+    fields = rng.standard_normal((nfield, Ne, 3 * V)) + 1j * rng.standard_normal((nfield, Ne, 3 * V))
+    moms = orc.momentum_set(nmom)
+    jobs = [([(0, 1, 1)], nmom), ([(2, 0, -1), (1, 1, 1), (0, 2, -1)], nmom), ([(2, 2, 1)], max(1, nmom // 2))]
+    got = _gram_pw_model(fields, jobs, latt3, moms, max_mb)
+    f4 = fields.reshape(nfield, Ne, Lz, Ly, Lx, 3)
+    for job_id, (segs, nmom_job) in enumerate(jobs):
+        for p in range(nmom_job):
+            ph = orc.momentum_phase([Lx, Ly, Lz, 1], moms[p])
+            ref = sum(s * orc.gram(f4[a], f4[b], ph) for a, b, s in segs)
+            err = np.linalg.norm(got[job_id, p] - ref) / np.linalg.norm(ref)
+            assert err < 1e-12, (job_id, p, err)
