@@ -24,6 +24,9 @@
 // FP64-pipe issue slots per (pair, e, f, site): 12/32 (DFMA) + 2 MB 8/32 (DMMA) = 1.4 at MB = 2, against
 // 8.3 for the 3M GEMM form with the Hermitian pairing and the half set (563/19 momenta x 9/32).
 // More than 16 modes run as several passes over the same fields (mb0 = first m-block of the pass).
+// Self pairs (L == R) have a Hermitian site product: their tiles below the diagonal are skipped and the fold
+// kernel reads the mirror element conjugated.  tests/test_pw_model.py is a lane-level numpy transcription of
+// the index arithmetic below (tile layout, fragment ownership, plane-boundary weights, mirror reads).
 #include "edk_common.cuh"
 #include "edk_pipe.cuh"
 
@@ -83,6 +86,9 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
+    // self pair (L == R): the site product is Hermitian in (e, f) and the weights are real, so
+    // Y[m][e][f] = conj(Y[m][f][e]); tiles entirely below the diagonal are left to the fold kernel's mirror read
+    if (sjob->nseg == 1 && sjob->Lf[0] == sjob->Rf[0] && e0 > f0 + PW_ROWS_R - 1) return;
     const int T = sjob->nseg * P.kplane;  // stages of 8 sites: every segment walks the plane once
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 
@@ -311,20 +317,25 @@ __global__ void __launch_bounds__(PW_FOLD_THREADS) pw_zfold_kernel(const PwFold 
     b /= F.nmom_int;
     const int blk = b % nblk;
     const int job = b / nblk;
-    if (p >= F.jobs[job].nmom) return;  // self pairs contract the half set only
+    const GramJob& J = F.jobs[job];
+    if (p >= J.nmom) return;  // self pairs contract the half set only
     const size_t ef = (size_t)blk * PW_FOLD_THREADS + threadIdx.x;
     if (ef >= mat) return;
+    // tiles of a self pair below the diagonal were not computed: read the mirror element, conjugated
+    const int e = (int)(ef / F.Ne), f = (int)(ef - (size_t)e * F.Ne);
+    const bool mirror = J.nseg == 1 && J.Lf[0] == J.Rf[0] && (e / PW_ROWS_L) * PW_ROWS_L > (f / PW_ROWS_R) * PW_ROWS_R + PW_ROWS_R - 1;
+    const double cj = mirror ? -1.0 : 1.0;
     const int mc = F.momode[3 * p], ms = F.momode[3 * p + 1];
     const double sg = (double)F.momode[3 * p + 2];
-    const cplx* Yj = F.Y + (size_t)job * F.Lz * F.nmodes * mat + ef;
+    const cplx* Yj = F.Y + (size_t)job * F.Lz * F.nmodes * mat + (mirror ? (size_t)f * F.Ne + e : ef);
     const cplx* zp = F.zphase + (size_t)p * F.Lz;
     double ar = 0.0, ai = 0.0;
     for (int z = 0; z < F.Lz; ++z) {
         const cplx yc = Yj[((size_t)z * F.nmodes + mc) * mat];
-        double ur = yc.x, ui = yc.y;
+        double ur = yc.x, ui = cj * yc.y;
         if (ms >= 0) {
             const cplx ys = Yj[((size_t)z * F.nmodes + ms) * mat];
-            ur = fma(-sg, ys.y, ur);
+            ur = fma(-sg, cj * ys.y, ur);
             ui = fma(sg, ys.x, ui);
         }
         const cplx ph = zp[z];

@@ -106,6 +106,8 @@ def _gram_pw_model(fields, jobs, latt3, moms_int, max_mb=2):
                 for et in range(n_et):
                     for ft in range(n_ft):
                         e0, f0 = et * ROWS_L, ft * ROWS_R
+                        if len(segs) == 1 and segs[0][0] == segs[0][1] and e0 > f0 + ROWS_R - 1:
+                            continue  # self pair: tile below the diagonal, the fold reads the mirror
                         yre = np.zeros((PW_WARPS, PW_EL, PW_FL, MB, 2, 32))
                         yim = np.zeros_like(yre)
                         cur_sign = 1
@@ -164,17 +166,31 @@ def _gram_pw_model(fields, jobs, latt3, moms_int, max_mb=2):
                                                 if f < Ne:
                                                     Y[job_id, z, mode, e, f] = cur_sign * (
                                                         yre[warp, i, j, mb, q, ln] + 1j * yim[warp, i, j, mb, q, ln])
-    assert not np.isnan(Y).any(), "an element of Y was never written"
+    for job_id, (segs, _) in enumerate(jobs):  # what pw_zfold_kernel reads must have been written
+        self_pair = len(segs) == 1 and segs[0][0] == segs[0][1]
+        for e in range(Ne):
+            for f in range(Ne):
+                mirror = self_pair and (e // ROWS_L) * ROWS_L > (f // ROWS_R) * ROWS_R + ROWS_R - 1
+                src = Y[job_id, :, :, f, e] if mirror else Y[job_id, :, :, e, f]
+                assert not np.isnan(src).any(), "the fold would read an element of Y that was never written"
     # ---- pw_zfold_kernel
     nmom = len(moms_int)
     partial = np.zeros((len(jobs), nmom, Ne, Ne), complex)
     for job_id, (_, nmom_job) in enumerate(jobs):
         for p in range(nmom_job):
             mc, ms, sg = (int(v) for v in momode[p])
+            segs = jobs[job_id][0]
+            self_pair = len(segs) == 1 and segs[0][0] == segs[0][1]
+            e_idx, f_idx = np.meshgrid(np.arange(Ne), np.arange(Ne), indexing="ij")
+            mirror = self_pair & ((e_idx // ROWS_L) * ROWS_L > (f_idx // ROWS_R) * ROWS_R + ROWS_R - 1)
+
+            def read(m, z):
+                return np.where(mirror, np.conj(Y[job_id, z, m].T), Y[job_id, z, m])
+
             for z in range(Lz):
-                u = Y[job_id, z, mc].copy()
+                u = read(mc, z)
                 if ms >= 0:
-                    u = u + 1j * sg * Y[job_id, z, ms]
+                    u = u + 1j * sg * read(ms, z)
                 r = (moms_int[p][2] * z) % Lz
                 partial[job_id, p] += np.exp(2j * np.pi * r / Lz) * u
     return partial
