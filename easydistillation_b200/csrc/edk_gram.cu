@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, GT_CONSUMERS);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
     const int nseg = sjob->nseg;
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     if (warp >= GT_CONSUMERS) {
         // ================================ producer warpgroup ================================
         // hands its registers to the MMA warpgroups; only its first warp issues copies
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(GT_REGS_PRODUCER));
+        warpgroup_reg_dealloc<GT_REGS_PRODUCER>();
         if (warp != GT_CONSUMERS) return;
         const int nvalid = nflat_last - nflat0 + 1;  // n-fragments of this tile that exist
         const int p0 = nflat0 - ff0 * nmom;
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gram_tma_kernel(const GramParam
     }
 
     // ================================== consumer warps ==================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(GT_REGS_CONSUMER));
+    warpgroup_reg_alloc<GT_REGS_CONSUMER>();
     int my_ffrag[C::NF], my_p[C::NF];
     bool my_valid[C::NF];
     uint32_t my_boff[C::NF];

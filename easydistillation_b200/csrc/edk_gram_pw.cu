@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, PW_WARPS);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
     // self pair (L == R): the site product is Hermitian in (e, f) and the weights are real, so
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
 
     if (warp >= PW_WARPS) {
         // ================================ producer warpgroup ================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(PW_REGS_PRODUCER));
+        warpgroup_reg_dealloc<PW_REGS_PRODUCER>();
         if (warp != PW_WARPS) return;
         const uint32_t tx_bytes = (uint32_t)(PW_L_BYTES + PW_R_BYTES + 2 * MB * 256);
         const int plane_site0 = z * P.A;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
     }
 
     // ================================== consumer warps ==================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(PW_REGS_CONSUMER));
+    warpgroup_reg_alloc<PW_REGS_CONSUMER>();
     const int sidx = lane & 3, n = lane >> 2;  // site inside a group of 4 (MMA k), column (MMA n)
     // byte offsets of this lane's three colours of site 4 grp + sidx inside the L and R tiles
     uint32_t offL[2][3], offR[2][3];
@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
     }
 }
 
+#ifndef EDK_HOST_EMU
 cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, cudaStream_t s) {
     int nst, bytes;
     if (pw_plan_smem(&nst, &bytes) != 0 || nst != T.nstages || MB < 1 || MB > PW_MAX_MB) return cudaErrorInvalidValue;
@@ -268,6 +269,8 @@ cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, cudaStream
     }
     return cudaGetLastError();
 }
+
+#endif  // EDK_HOST_EMU
 
 // weights of the real xy-modes, laid out as the A fragments of the plane transform:
 //   wtiles[kstep][grp][m-block][lane] = w_{8 mblock + lane/4}(site 8 kstep + 4 grp + lane%4 of the plane)
@@ -300,11 +303,14 @@ __global__ void pw_weights_kernel(double* __restrict__ wtiles, const int* __rest
     wtiles[idx] = v;
 }
 
+#ifndef EDK_HOST_EMU
 cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes, int mbtot, int kplane, Geom g, cudaStream_t s) {
     const size_t total = (size_t)kplane * 2 * mbtot * 32;
     pw_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wtiles, modes3_dev, nmodes, mbtot, kplane, g);
     return cudaGetLastError();
 }
+
+#endif  // EDK_HOST_EMU
 
 // G[job][p][e][f] = sum_z zphase[p][z] (Y[job][z][mc][e][f] + i sigma Y[job][z][ms][e][f]); momentum fastest over
 // the blocks, so the ~Lz x 2 planes a block reads are shared through L2 by the momenta of the same couple.
@@ -347,6 +353,7 @@ __global__ void __launch_bounds__(PW_FOLD_THREADS) pw_zfold_kernel(const PwFold 
     F.partial[((size_t)job * F.nmom_int + p) * mat + ef] = make_double2(ar, ai);
 }
 
+#ifndef EDK_HOST_EMU
 cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s) {
     const size_t mat = (size_t)F.Ne * F.Ne;
     const long long nblk = (long long)((mat + PW_FOLD_THREADS - 1) / PW_FOLD_THREADS);
@@ -355,5 +362,7 @@ cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s) {
     pw_zfold_kernel<<<(unsigned)blocks, PW_FOLD_THREADS, 0, s>>>(F);
     return cudaGetLastError();
 }
+
+#endif  // EDK_HOST_EMU
 
 }  // namespace edk

@@ -2,6 +2,11 @@
 #pragma once
 #include "edk_common.cuh"
 
+#ifdef EDK_HOST_EMU
+// tests/emu: the same helpers executed by host threads (one per CUDA thread), so that the kernel sources
+// themselves can be run on a machine without a GPU.  Test infrastructure only, never part of the library.
+#include "edk_emu.h"
+#else
 namespace edk {
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
@@ -15,6 +20,17 @@ __device__ __forceinline__ double flip_sign(double x) {
     return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
 }
 
+// make the initialised barriers visible to the async (TMA) proxy
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+// setmaxnreg: a producer warpgroup hands registers to the MMA warpgroups (all warps of a warpgroup call it)
+template <int N>
+__device__ __forceinline__ void warpgroup_reg_dealloc() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void warpgroup_reg_alloc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N));
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
 }
@@ -55,3 +71,4 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 }
 
 }  // namespace edk
+#endif  // EDK_HOST_EMU

@@ -1,0 +1,213 @@
+// Host emulation of the device helpers in csrc/edk_pipe.cuh (TEST INFRASTRUCTURE ONLY).
+//
+// The contraction kernels are compiled by g++ with -DEDK_HOST_EMU and executed with one host thread per
+// CUDA thread of a CTA, CTAs one after another:
+//   * shared memory  = one global buffer, "shared addresses" are byte offsets into it
+//   * mbarrier       = arrival count + transaction bytes + phase counter (try_wait.parity semantics of PTX:
+//                      waiting on parity P succeeds once the phase with that parity has completed; a fresh
+//                      barrier is in phase 0, so waiting on parity 1 succeeds at once)
+//   * TMA            = cp.async.bulk.tensor.3d over a tiled descriptor {base, dims, byte strides, box}: box
+//                      written dimension-0 fastest, out-of-range elements zero-filled, the full box size is
+//                      signalled to the barrier (complete_tx) whether or not parts were out of range
+//   * DMMA           = mma.sync.m8n8k4 row.col f64 by exchanging the operands of the 32 lanes of the calling
+//                      warp: A[row = lane/4][k = lane%4], B[k = lane%4][col = lane/4],
+//                      C/D[row = lane/4][col = 2 (lane%4) + {0,1}]
+// These are the semantics the GPU-validated gram_tma_kernel already relies on.
+#pragma once
+#include <math.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+
+#include "edk_common.cuh"
+
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+
+struct EmuIdx {
+    unsigned x = 0, y = 0, z = 0;
+};
+extern thread_local EmuIdx threadIdx, blockIdx, blockDim;
+
+namespace edk {
+
+constexpr int EMU_SMEM_BYTES = 232448;
+extern unsigned char smem[EMU_SMEM_BYTES];  // `extern __shared__ unsigned char smem[]` of the kernels binds to this
+
+// ---- CTA-wide state (reset by the driver before every CTA) --------------------------------------------
+struct EmuBarrier {  // reusable counting barrier
+    std::mutex m;
+    std::condition_variable cv;
+    int waiting = 0, generation = 0;
+    void wait(int n) {
+        std::unique_lock<std::mutex> lk(m);
+        const int gen = generation;
+        if (++waiting == n) {
+            waiting = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != gen; });
+        }
+    }
+};
+struct EmuMbar {
+    bool live = false;
+    int init = 0, pending = 0;
+    long long tx = 0;
+    unsigned phase = 0;
+};
+struct EmuCta {
+    int nthreads = 0;
+    EmuBarrier cta_barrier;
+    EmuBarrier warp_barrier[32];
+    double xa[32][32], xb[32][32];
+    std::mutex mb_mutex;
+    std::condition_variable mb_cv;
+    EmuMbar mbar[EMU_SMEM_BYTES / 8];
+    bool failed = false;
+};
+extern EmuCta g_cta;
+
+struct EmuTensorMap {  // what the driver stores in the 128 bytes of a CUtensorMap
+    const double* base;
+    long long dim[3];
+    long long stride_bytes[2];  // of dimensions 1 and 2
+    int box[3];
+};
+
+inline uint32_t __cvta_generic_to_shared(const void* p) {
+    const long long off = (const unsigned char*)p - smem;
+    if (off < 0 || off >= EMU_SMEM_BYTES) throw std::runtime_error("pointer outside shared memory");
+    return (uint32_t)off;
+}
+inline void __syncthreads() { g_cta.cta_barrier.wait(g_cta.nthreads); }
+inline void __syncwarp() { g_cta.warp_barrier[threadIdx.x >> 5].wait(32); }
+
+inline void dmma884(double& c0, double& c1, const double a, const double b) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    g_cta.xa[warp][lane] = a;
+    g_cta.xb[warp][lane] = b;
+    g_cta.warp_barrier[warp].wait(32);
+    const int row = lane >> 2;
+    for (int q = 0; q < 2; ++q) {
+        const int col = 2 * (lane & 3) + q;
+        double acc = q ? c1 : c0;
+        for (int k = 0; k < 4; ++k) acc = fma(g_cta.xa[warp][row * 4 + k], g_cta.xb[warp][col * 4 + k], acc);
+        (q ? c1 : c0) = acc;
+    }
+    g_cta.warp_barrier[warp].wait(32);
+}
+
+inline double flip_sign(double x) { return -x; }
+
+inline void mbar_init_fence() {}
+template <int N>
+inline void warpgroup_reg_dealloc() {
+    static_assert(N % 8 == 0 && N >= 24 && N <= 256, "setmaxnreg operand");
+}
+template <int N>
+inline void warpgroup_reg_alloc() {
+    static_assert(N % 8 == 0 && N >= 24 && N <= 256, "setmaxnreg operand");
+}
+
+inline EmuMbar& emu_bar(uint32_t bar) {
+    if (bar % 8 != 0 || bar >= (uint32_t)EMU_SMEM_BYTES) throw std::runtime_error("bad mbarrier address");
+    return g_cta.mbar[bar / 8];
+}
+inline void emu_bar_check_complete(EmuMbar& b) {  // caller holds mb_mutex
+    if (b.pending == 0 && b.tx == 0) {
+        ++b.phase;
+        b.pending = b.init;
+        g_cta.mb_cv.notify_all();
+    }
+}
+inline void mbar_init(uint32_t bar, uint32_t count) {
+    std::lock_guard<std::mutex> lk(g_cta.mb_mutex);
+    EmuMbar& b = emu_bar(bar);
+    b.live = true;
+    b.init = b.pending = (int)count;
+    b.tx = 0;
+    b.phase = 0;
+}
+inline void mbar_arrive(uint32_t bar) {
+    std::lock_guard<std::mutex> lk(g_cta.mb_mutex);
+    EmuMbar& b = emu_bar(bar);
+    if (!b.live || b.pending <= 0) {
+        g_cta.failed = true;
+        throw std::runtime_error("arrive on an uninitialised or over-arrived mbarrier");
+    }
+    --b.pending;
+    emu_bar_check_complete(b);
+}
+inline void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    std::lock_guard<std::mutex> lk(g_cta.mb_mutex);
+    EmuMbar& b = emu_bar(bar);
+    if (!b.live || b.pending <= 0) {
+        g_cta.failed = true;
+        throw std::runtime_error("arrive.expect_tx on an uninitialised or over-arrived mbarrier");
+    }
+    b.tx += bytes;
+    --b.pending;
+    emu_bar_check_complete(b);
+}
+inline void emu_complete_tx(uint32_t bar, long long bytes) {
+    std::lock_guard<std::mutex> lk(g_cta.mb_mutex);
+    EmuMbar& b = emu_bar(bar);
+    if (!b.live) throw std::runtime_error("complete_tx on an uninitialised mbarrier");
+    b.tx -= bytes;
+    emu_bar_check_complete(b);
+}
+inline void mbar_wait(uint32_t bar, uint32_t parity) {
+    std::unique_lock<std::mutex> lk(g_cta.mb_mutex);
+    EmuMbar& b = emu_bar(bar);
+    if (!b.live) throw std::runtime_error("wait on an uninitialised mbarrier");
+    // a hang in the kernel's protocol becomes a test failure instead of a stuck test
+    if (!g_cta.mb_cv.wait_for(lk, std::chrono::seconds(20), [&] { return (b.phase & 1u) != parity; })) {
+        g_cta.failed = true;
+        throw std::runtime_error("mbarrier wait timed out (pipeline protocol bug)");
+    }
+}
+
+inline void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    EmuTensorMap T;
+    std::memcpy(&T, tmap, sizeof(T));
+    if (dst % 128 != 0) throw std::runtime_error("TMA destination not 128-byte aligned");
+    const long long bytes = 8LL * T.box[0] * T.box[1] * T.box[2];
+    if ((long long)dst + bytes > EMU_SMEM_BYTES) throw std::runtime_error("TMA box past the end of shared memory");
+    double* out = reinterpret_cast<double*>(smem + dst);
+    for (int k = 0; k < T.box[2]; ++k)
+        for (int j = 0; j < T.box[1]; ++j)
+            for (int i = 0; i < T.box[0]; ++i) {
+                const long long x0 = (long long)c0 + i, x1 = (long long)c1 + j, x2 = (long long)c2 + k;
+                double v = 0.0;
+                if (x0 >= 0 && x0 < T.dim[0] && x1 >= 0 && x1 < T.dim[1] && x2 >= 0 && x2 < T.dim[2])
+                    v = *reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(T.base) + x0 * 8 +
+                                                         x1 * T.stride_bytes[0] + x2 * T.stride_bytes[1]);
+                *out++ = v;
+            }
+    emu_complete_tx(bar, bytes);
+}
+inline void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    if (dst % 16 != 0 || bytes % 16 != 0 || bytes == 0 || reinterpret_cast<uintptr_t>(src) % 16 != 0)
+        throw std::runtime_error("cp.async.bulk needs 16-byte aligned addresses and size");
+    if ((long long)dst + bytes > EMU_SMEM_BYTES) throw std::runtime_error("bulk copy past the end of shared memory");
+    std::memcpy(smem + dst, src, bytes);
+    emu_complete_tx(bar, bytes);
+}
+
+inline void sincospi(double x, double* s, double* c) {
+    // exact on multiples of 1/2, like the device function
+    const double r = x - 2.0 * floor(x / 2.0);  // [0, 2)
+    if (r == 0.0) { *s = 0.0; *c = 1.0; }
+    else if (r == 0.5) { *s = 1.0; *c = 0.0; }
+    else if (r == 1.0) { *s = 0.0; *c = -1.0; }
+    else if (r == 1.5) { *s = -1.0; *c = 0.0; }
+    else { *s = sin(3.14159265358979323846 * r); *c = cos(3.14159265358979323846 * r); }
+}
+
+}  // namespace edk

@@ -214,3 +214,71 @@ def test_lane_model_equals_direct_contraction(latt3, Ne, nmom, max_mb):
             ref = sum(s * orc.gram(f4[a], f4[b], ph) for a, b, s in segs)
             err = np.linalg.norm(got[job_id, p] - ref) / np.linalg.norm(ref)
             assert err < 1e-12, (job_id, p, err)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the kernel SOURCES on a host emulator (tests/emu): TMA producer warp, mbarrier ring, DMMA fragments, fold
+# ---------------------------------------------------------------------------------------------------------
+def _build_emulator(tmp_path):
+    import os
+    import subprocess
+
+    from conftest import REPO
+
+    exe = str(tmp_path / "pw_emu")
+    cmd = ["g++", "-std=c++17", "-O1", "-DEDK_HOST_EMU", "-I", os.path.join(REPO, "tests", "emu"),
+           "-I", os.path.join(REPO, "easydistillation_b200", "csrc"), "-I", os.path.join(REPO, "include"),
+           "-I", "/usr/local/cuda/include", "-x", "c++", os.path.join(REPO, "tests", "emu", "pw_emu.cpp"), "-o", exe, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+def _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages):
+    import subprocess
+
+    Lx, Ly, Lz = latt3
+    nfield, Ne, Kc = fields.shape
+    modes, momode = _capi.plan_modes(moms)
+    jraw = np.zeros((len(jobs), 26), np.int32)
+    for j, (segs, nmom_job) in enumerate(jobs):
+        jraw[j, 0], jraw[j, 1] = len(segs), nmom_job
+        for s, (a, b, sg) in enumerate(segs):
+            jraw[j, 2 + s], jraw[j, 10 + s], jraw[j, 18 + s] = a, b, sg
+    zphase = np.array([[np.exp(2j * np.pi * ((m[2] * z) % Lz) / Lz) for z in range(Lz)] for m in moms])
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        np.array([Lx, Ly, Lz, Ne, nfield, len(jobs), len(moms), len(modes), max_mb, nstages], np.int32).tofile(f)
+        jraw.tofile(f)
+        modes.astype(np.int32).tofile(f)
+        momode.astype(np.int32).tofile(f)
+        np.ascontiguousarray(zphase).view(np.float64).tofile(f)
+        np.ascontiguousarray(fields).view(np.float64).tofile(f)
+    r = subprocess.run([exe, str(inp), str(out)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, f"emulated kernels failed ({r.returncode}): {r.stderr[-2000:]}"
+    return np.fromfile(out, np.complex128).reshape(len(jobs), len(moms), Ne, Ne)
+
+
+@pytest.mark.parametrize("latt3,Ne,nmom,max_mb,nstages", [
+    ((5, 8, 2), 35, 33, 2, 0),   # 3 x 2 tiles, 13 modes in one pass, 15 stages through the 8-deep ring, mirror tiles
+    ((3, 5, 2), 5, 33, 1, 3),    # ragged plane (15 sites), two passes of one m-block, 3-deep ring
+])
+def test_kernel_sources_on_host_emulator(tmp_path, latt3, Ne, nmom, max_mb, nstages):
+    """edk_gram_pw.cu itself (not a transcription), compiled by g++ against tests/emu/edk_emu.h and run with one
+    host thread per CUDA thread, equals the direct contraction."""
+    Lx, Ly, Lz = latt3
+    V = Lx * Ly * Lz
+    rng = np.random.default_rng(99 + Ne)
+    nfield = 3
+    fields = rng.standard_normal((nfield, Ne, 3 * V)) + 1j * rng.standard_normal((nfield, Ne, 3 * V))
+    moms = orc.momentum_set(nmom)
+    jobs = [([(0, 1, 1)], nmom), ([(2, 0, -1), (1, 1, 1), (0, 2, -1)], nmom), ([(2, 2, 1)], max(1, nmom // 2))]
+    exe = _build_emulator(tmp_path)
+    got = _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages)
+    f4 = fields.reshape(nfield, Ne, Lz, Ly, Lx, 3)
+    for job_id, (segs, nmom_job) in enumerate(jobs):
+        for p in range(nmom_job):
+            ph = orc.momentum_phase([Lx, Ly, Lz, 1], moms[p])
+            ref = sum(s * orc.gram(f4[a], f4[b], ph) for a, b, s in segs)
+            err = np.linalg.norm(got[job_id, p] - ref) / np.linalg.norm(ref)
+            assert err < 1e-12, (job_id, p, err)
