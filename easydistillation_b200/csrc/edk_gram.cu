@@ -55,16 +55,6 @@ struct GramSmem {
     static constexpr int TOTAL = JOB_OFF + (int)sizeof(GramJob);
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-    const int sz = valid ? 16 : 0;  // src-size 0 -> 16 zero bytes
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-
 // One pipeline stage (8 sites = 6 k-groups of 4 complex k) of one warp: 2*MF*NF DMMAs per k-group.
 //   a_s : this lane's slot in A[kg][row][4]  (+ (kg*ROWS_A + 8 i)*64 selects fragment i)
 //   b_s : B[kg][row][4], b_kg_stride bytes per k-group; my_boff = this lane's (row, k) offset
@@ -687,6 +677,7 @@ int gram_tma_plan(int algo, int mfrag, int nmom, int Ne, int* brows_alloc, int* 
 int gram_nfrag_per_tile(int algo) { return algo ? 8 : 16; }
 int gram_fwidth(int algo) { return algo ? 8 : 4; }
 
+#ifndef EDK_HOST_EMU
 template <int MF, int ALGO>
 static cudaError_t launch_gram_tma_mf(const GramParams& P, const GramTma& T, cudaStream_t s) {
     int rows, nst, bytes;
@@ -709,6 +700,7 @@ cudaError_t launch_gram_tma(const GramParams& P, const GramTma& T, int mfrag, in
     }
 #undef EDK_TMA_CASE
 }
+#endif  // EDK_HOST_EMU
 
 // phase[2][nmom][Vpad] -> tiles[kstep][2][nmom][8]
 __global__ void phase_tiles_kernel(const cplx* __restrict__ phase2, cplx* __restrict__ tiles, int nmom, int Vpad) {
@@ -721,11 +713,13 @@ __global__ void phase_tiles_kernel(const cplx* __restrict__ phase2, cplx* __rest
     tiles[((((size_t)(site >> 3)) * 2 + tab) * nmom + p) * 8 + (site & 7)] = phase2[i];
 }
 
+#ifndef EDK_HOST_EMU
 cudaError_t launch_phase_tiles(const cplx* phase2, cplx* tiles, int nmom, int Vpad, cudaStream_t s) {
     const size_t n = (size_t)2 * nmom * Vpad;
     phase_tiles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(phase2, tiles, nmom, Vpad);
     return cudaGetLastError();
 }
+#endif  // EDK_HOST_EMU
 
 // available tile heights (m-fragments of 8 rows per CTA)
 static const int kMfragAvail[] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13};
@@ -740,6 +734,7 @@ int gram_pick_mfrag(int Ne) {
 }
 int gram_rows_per_tile(int mfrag) { return 8 * mfrag; }
 
+#ifndef EDK_HOST_EMU
 template <int MF>
 static cudaError_t launch_gram_mf(const GramParams& P, cudaStream_t s) {
     using S = GramSmem<MF>;
@@ -763,6 +758,7 @@ cudaError_t launch_gram_dmma(const GramParams& P, int mfrag, cudaStream_t s) {
     }
 #undef EDK_DMMA_CASE
 }
+#endif  // EDK_HOST_EMU
 
 bool gram_mfrag_available(int mfrag) {
     for (int v : kMfragAvail)
@@ -807,11 +803,13 @@ __global__ void gram_naive_kernel(const GramParams P) {
     P.partial[idx] = make_double2(sr, si);
 }
 
+#ifndef EDK_HOST_EMU
 cudaError_t launch_gram_naive(const GramParams& P, cudaStream_t s) {
     const size_t n = (size_t)P.njobs * P.nmom * P.Ne * P.Ne;
     gram_naive_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P);
     return cudaGetLastError();
 }
+#endif  // EDK_HOST_EMU
 
 // ---------------------------------------------------------------------------------------
 // combine: out[op][p] = coeff * sum_terms w * sum_split (partial[job][p]  or  partial[job][-p]^dagger)
@@ -859,6 +857,7 @@ __global__ void combine_kernel(const CombineOp* __restrict__ ops, int nop, const
     out[idx] = make_double2(sr, si);
 }
 
+#ifndef EDK_HOST_EMU
 cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom_int,
                            int nmom_out, const int* pmap, const int* negidx, int n_half, int Ne, const double* coeff, cplx* out,
                            cudaStream_t s) {
@@ -867,6 +866,7 @@ cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partia
                                                                negidx, n_half, Ne, coeff, out);
     return cudaGetLastError();
 }
+#endif  // EDK_HOST_EMU
 
 // ---------------------------------------------------------------------------------------
 // FP64 pipe micro-benchmarks (roofline denominators measured on the box)
@@ -901,6 +901,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters)
     if (s == 123.456) sink[0] = s;
 }
 
+#ifndef EDK_HOST_EMU
 cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops) {
     double* sink = nullptr;
     cudaError_t e = cudaMalloc(&sink, 8);
@@ -943,5 +944,6 @@ cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops) {
     cudaFree(sink);
     return e;
 }
+#endif  // EDK_HOST_EMU
 
 }  // namespace edk

@@ -15,6 +15,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, 
                  : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;  // src-size 0 -> 16 zero bytes
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
 // sign flip on the integer pipe: the FP64 pipe is the one the DMMAs need
 __device__ __forceinline__ double flip_sign(double x) {
     return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));

@@ -16,6 +16,8 @@
 #pragma once
 #include <math.h>
 
+#include <algorithm>
+
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
@@ -104,6 +106,21 @@ inline void dmma884(double& c0, double& c1, const double a, const double b) {
 }
 
 inline double flip_sign(double x) { return -x; }
+
+using std::max;
+using std::min;
+
+// cp.async (16 bytes, zero-fill when !valid), executed synchronously: the kernels wait and barrier before use
+inline void cp_async16(uint32_t dst, const void* src, bool valid) {
+    if (dst % 16 != 0 || (long long)dst + 16 > EMU_SMEM_BYTES) throw std::runtime_error("bad cp.async destination");
+    if (valid)
+        std::memcpy(smem + dst, src, 16);
+    else
+        std::memset(smem + dst, 0, 16);
+}
+inline void cp_async_commit() {}
+template <int N>
+inline void cp_async_wait() {}
 
 inline void mbar_init_fence() {}
 template <int N>

@@ -220,18 +220,7 @@ def test_lane_model_equals_direct_contraction(latt3, Ne, nmom, max_mb):
 # the kernel SOURCES on a host emulator (tests/emu): TMA producer warp, mbarrier ring, DMMA fragments, fold
 # ---------------------------------------------------------------------------------------------------------
 def _build_emulator(tmp_path):
-    import os
-    import subprocess
-
-    from conftest import REPO
-
-    exe = str(tmp_path / "pw_emu")
-    cmd = ["g++", "-std=c++17", "-O1", "-DEDK_HOST_EMU", "-I", os.path.join(REPO, "tests", "emu"),
-           "-I", os.path.join(REPO, "easydistillation_b200", "csrc"), "-I", os.path.join(REPO, "include"),
-           "-I", "/usr/local/cuda/include", "-x", "c++", os.path.join(REPO, "tests", "emu", "pw_emu.cpp"), "-o", exe, "-lpthread"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    return exe
+    return _build(tmp_path, "pw_emu.cpp", "pw_emu")
 
 
 def _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages):
@@ -282,3 +271,60 @@ def test_kernel_sources_on_host_emulator(tmp_path, latt3, Ne, nmom, max_mb, nsta
             ref = sum(s * orc.gram(f4[a], f4[b], ph) for a, b, s in segs)
             err = np.linalg.norm(got[job_id, p] - ref) / np.linalg.norm(ref)
             assert err < 1e-12, (job_id, p, err)
+
+
+def _build(tmp_path, src, name):
+    import os
+    import subprocess
+
+    from conftest import REPO
+
+    exe = str(tmp_path / name)
+    cmd = ["g++", "-std=c++17", "-O1", "-DEDK_HOST_EMU", "-I", os.path.join(REPO, "tests", "emu"),
+           "-I", os.path.join(REPO, "easydistillation_b200", "csrc"), "-I", os.path.join(REPO, "include"),
+           "-I", "/usr/local/cuda/include", "-x", "c++", os.path.join(REPO, "tests", "emu", src), "-o", exe, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+@pytest.mark.parametrize("kernel", [1, 0, 2])  # TMA 3M (the product path), TMA 4M, cp.async 4M
+def test_emulator_calibration_on_gpu_validated_kernels(tmp_path, kernel):
+    """The emulator must also reproduce the contraction through the kernels that ARE validated on the B200
+    (gram_tma_kernel / gram_dmma_kernel of edk_gram.cu): this pins its TMA-box, mbarrier-parity and m8n8k4 fragment
+    semantics to the hardware's, which is what gives the emulated run of edk_gram_pw.cu above its weight."""
+    import subprocess
+
+    Lx, Ly, Lz = 3, 5, 2  # V = 30: the last 8-site stage is ragged
+    V, Ne, nfield, ksplit = Lx * Ly * Lz, 21, 3, 2
+    Vpad = (V + 7) // 8 * 8
+    rng = np.random.default_rng(7 + kernel)
+    fields = rng.standard_normal((nfield, Ne, 3 * V)) + 1j * rng.standard_normal((nfield, Ne, 3 * V))
+    moms = orc.momentum_set(7)
+    jobs = [([(0, 1, 1)], 7), ([(2, 0, -1), (1, 1, 1), (0, 2, -1)], 7), ([(2, 2, 1)], 4)]
+    jraw = np.zeros((len(jobs), 26), np.int32)
+    for j, (segs, nmom_job) in enumerate(jobs):
+        jraw[j, 0], jraw[j, 1] = len(segs), nmom_job
+        for s, (a, b, sg) in enumerate(segs):
+            jraw[j, 2 + s], jraw[j, 10 + s], jraw[j, 18 + s] = a, b, sg
+    phase = np.zeros((2, len(moms), Vpad), complex)
+    for p, m in enumerate(moms):
+        phase[0, p, :V] = orc.momentum_phase([Lx, Ly, Lz, 1], m).reshape(-1)
+    phase[1] = -1j * phase[0]
+    exe = _build(tmp_path, "gram_emu.cpp", "gram_emu")
+    inp, out = tmp_path / "gin.bin", tmp_path / "gout.bin"
+    with open(inp, "wb") as f:
+        np.array([Lx, Ly, Lz, Ne, nfield, len(jobs), len(moms), kernel, ksplit], np.int32).tofile(f)
+        jraw.tofile(f)
+        phase.view(np.float64).tofile(f)
+        np.ascontiguousarray(fields).view(np.float64).tofile(f)
+    r = subprocess.run([exe, str(inp), str(out)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, f"emulated kernels failed ({r.returncode}): {r.stderr[-2000:]}"
+    got = np.fromfile(out, np.complex128).reshape(ksplit, len(jobs), len(moms), Ne, Ne).sum(axis=0)
+    f4 = fields.reshape(nfield, Ne, Lz, Ly, Lx, 3)
+    for job_id, (segs, nmom_job) in enumerate(jobs):
+        for p in range(nmom_job):
+            ph = orc.momentum_phase([Lx, Ly, Lz, 1], moms[p])
+            ref = sum(s * orc.gram(f4[a], f4[b], ph) for a, b, s in segs)
+            err = np.linalg.norm(got[job_id, p] - ref) / np.linalg.norm(ref)
+            assert err < 1e-12, (kernel, job_id, p, err)
