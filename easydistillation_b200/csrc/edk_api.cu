@@ -62,6 +62,7 @@ struct edk_handle {
     PwTma pw_tma{};
     bool pw_ready = false;
     int pw_nmodes = 0, pw_mbtot = 0, pw_kplane = 0;
+    int pw_el = 2, pw_fl = 4;     // tile shape: (8 el) rows of L x (8 fl) rows of R per CTA
     double* pw_wtiles = nullptr;  // [kplane][2][mbtot][32]
     cplx* pw_Y = nullptr;         // [njobs][Lz][nmodes][Ne][Ne]
     cplx* pw_zphase = nullptr;    // [nmom_int][Lz]
@@ -530,8 +531,14 @@ int build_pw(edk_handle* h) {
     h->pw_nmodes = (int)mp.modes3.size() / 3;
     h->pw_mbtot = (h->pw_nmodes + 7) / 8;
     h->pw_kplane = (h->g.Lx * h->g.Ly + 7) / 8;
+    pw_pick_tile(h->Ne, &h->pw_el, &h->pw_fl);
+    if (const char* t = getenv("EDK_PW_TILE")) {  // A/B hook: "24" = 16 x 32 tiles, "25" = 16 x 40
+        if (!strcmp(t, "24")) h->pw_el = 2, h->pw_fl = 4;
+        if (!strcmp(t, "25")) h->pw_el = 2, h->pw_fl = 5;
+    }
+    const int rows_l = PW_WARPS * h->pw_el, rows_r = 8 * h->pw_fl;
     int smem = 0;
-    if (pw_plan_smem(&h->pw_tma.nstages, &smem) != 0) {
+    if (pw_plan_smem(h->pw_el, h->pw_fl, &h->pw_tma.nstages, &smem) != 0) {
         set_error("no shared-memory plan for the plane-wave contraction");
         return EDK_ERR_ARG;
     }
@@ -587,8 +594,8 @@ int build_pw(edk_handle* h) {
     const cuuint64_t gdim[3] = {Kd, (cuuint64_t)h->Ne, (cuuint64_t)h->nfield};
     const cuuint64_t gstr[2] = {Kd * 8, Kd * 8 * (cuuint64_t)h->Ne};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const cuuint32_t boxL[3] = {8, (cuuint32_t)PW_ROWS_L, 1};
-    const cuuint32_t boxR[3] = {8, (cuuint32_t)PW_ROWS_R, 1};
+    const cuuint32_t boxL[3] = {8, (cuuint32_t)rows_l, 1};
+    const cuuint32_t boxR[3] = {8, (cuuint32_t)rows_r, 1};
     CUresult r = encode((CUtensorMap*)h->pw_tma.mapL, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, boxL, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -613,8 +620,9 @@ int run_gram_pw(edk_handle* h, cudaStream_t s) {
     Q.Lz = h->g.Lz;
     Q.A = h->g.Lx * h->g.Ly;
     Q.kplane = h->pw_kplane;
-    Q.n_et = (h->Ne + PW_ROWS_L - 1) / PW_ROWS_L;
-    Q.n_ft = (h->Ne + PW_ROWS_R - 1) / PW_ROWS_R;
+    const int rows_l = PW_WARPS * h->pw_el, rows_r = 8 * h->pw_fl;
+    Q.n_et = (h->Ne + rows_l - 1) / rows_l;
+    Q.n_ft = (h->Ne + rows_r - 1) / rows_r;
     Q.nmodes = h->pw_nmodes;
     Q.mbtot = h->pw_mbtot;
     Q.wtiles = h->pw_wtiles;
@@ -624,7 +632,7 @@ int run_gram_pw(edk_handle* h, cudaStream_t s) {
         PhaseTimer t(h, s, PH_GRAM, npass);
         for (int pass = 0; pass < npass; ++pass) {
             Q.mb0 = pass * PW_MAX_MB;
-            EDK_CUDA_TRY(launch_gram_pw(Q, h->pw_tma, std::min(PW_MAX_MB, h->pw_mbtot - Q.mb0), s));
+            EDK_CUDA_TRY(launch_gram_pw(Q, h->pw_tma, std::min(PW_MAX_MB, h->pw_mbtot - Q.mb0), h->pw_el, h->pw_fl, s));
         }
     }
     // the z fold is a reduction like the combine step and is timed with it
@@ -636,6 +644,8 @@ int run_gram_pw(edk_handle* h, cudaStream_t s) {
     F.Lz = h->g.Lz;
     F.nmodes = h->pw_nmodes;
     F.nmom_int = h->nmom_int;
+    F.rows_l = rows_l;
+    F.rows_r = rows_r;
     F.Y = h->pw_Y;
     F.zphase = h->pw_zphase;
     F.momode = h->pw_momode;
@@ -1346,6 +1356,7 @@ int edk_query(const edk_handle* h, int what) {
         case 9: return h->n_half;
         case 10: return effective_algo(h);
         case 11: return h->pw_ready ? h->pw_nmodes : 0;
+        case 12: return h->pw_ready ? 10 * h->pw_el + h->pw_fl : 0;
         default: return EDK_ERR_ARG;
     }
 }

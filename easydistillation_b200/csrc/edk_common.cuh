@@ -99,11 +99,9 @@ struct CombineOp {
 // (13 modes for the 33 momenta |p|^2 <= 4), and a small second kernel folds z:
 //   G[job][p] = sum_z exp(2 pi i pz z/Lz) (Y[z][mc(p)] + i sigma_p Y[z][ms(p)]).
 // FP64-pipe issue slots per (pair, e, f, site): 12/32 + 2*8*MB/32 = 1.4 against 8.3 of the 3M GEMM form.
-constexpr int PW_EL = 2;                // e rows per lane
-constexpr int PW_FL = 4;                // f rows per lane (x 8 lane groups = 32 per warp)
+// A lane owns EL e-rows x FL f-columns of its warp's (EL) x (8 FL) tile; the 8 MMA warps are stacked along e, so a
+// CTA tile is 8 EL rows of L by 8 FL rows of R.  Instantiated shapes: (2,4) = 16 x 32 and (2,5) = 16 x 40.
 constexpr int PW_WARPS = 8;             // MMA warps, stacked along e
-constexpr int PW_ROWS_L = PW_WARPS * PW_EL;  // 16 rows of L per CTA
-constexpr int PW_ROWS_R = 8 * PW_FL;         // 32 rows of R per CTA
 constexpr int PW_MAX_MB = 2;            // m-blocks (8 modes) per pass
 
 struct PwParams {
@@ -113,7 +111,7 @@ struct PwParams {
     int Lz;
     int A;        // sites of one xy-plane (Lx*Ly)
     int kplane;   // stages of 8 sites per plane = ceil(A/8)
-    int n_et, n_ft;  // tiles of PW_ROWS_L x PW_ROWS_R
+    int n_et, n_ft;  // tiles of (8 EL) x (8 FL) rows
     int nmodes;   // real xy-modes kept in Y
     int mb0;      // first m-block of this pass
     int mbtot;    // m-blocks of the weight tiles = ceil(nmodes/8)
@@ -121,13 +119,14 @@ struct PwParams {
     cplx* Y;      // [njobs][Lz][nmodes][Ne][Ne]
 };
 struct PwTma {
-    alignas(64) unsigned char mapL[128];  // CUtensorMap over [nfield][Ne][2*Kc doubles], box 8 x PW_ROWS_L x 1
-    alignas(64) unsigned char mapR[128];  // box 8 x PW_ROWS_R x 1
+    alignas(64) unsigned char mapL[128];  // CUtensorMap over [nfield][Ne][2*Kc doubles], box 8 x (8 EL) x 1
+    alignas(64) unsigned char mapR[128];  // box 8 x (8 FL) x 1
     int nstages;
 };
 struct PwFold {
     const GramJob* jobs;
     int njobs, Ne, Lz, nmodes, nmom_int;
+    int rows_l, rows_r;   // tile shape of the plane kernel (self pairs: tiles below the diagonal are mirror reads)
     const cplx* Y;
     const cplx* zphase;   // [nmom_int][Lz]
     const int* momode;    // [nmom_int][3]: cos mode, sin mode (-1: none), sigma
@@ -167,9 +166,10 @@ cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partia
                            int nmom_out, const int* pmap, const int* negidx, int n_half, int Ne, const double* coeff, cplx* out,
                            cudaStream_t s);
 // plane-wave factorised contraction
-int pw_plan_smem(int* nstages, int* smem_bytes);
+int pw_plan_smem(int el, int fl, int* nstages, int* smem_bytes);
+void pw_pick_tile(int Ne, int* el, int* fl);
 cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes, int mbtot, int kplane, Geom g, cudaStream_t s);
-cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, cudaStream_t s);
+cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, int el, int fl, cudaStream_t s);
 cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s);
 // microbench
 cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops);

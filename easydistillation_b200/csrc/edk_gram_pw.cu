@@ -16,9 +16,9 @@
 //   gram_pw_kernel<MB> : Y[job][z][m][e][f] = sum_{(x,y)} w_m(x,y) C(x,y,z)[e][f]
 //                        one DMMA.8x8x4 = (8 modes) x (4 sites) x (8 f): A operand = weights, B operand =
 //                        the C values the lanes have just formed with 12 DFMA each, accumulator = Y.
-//                        Lane (site s = lane%4, column n = lane/4) owns e in {2 warp, 2 warp + 1} and
-//                        f in {n, n+8, n+16, n+24} of a 16 x 32 tile; TMA producer warp + mbarrier ring as
-//                        in gram_tma_kernel, same [k-group][row][4 complex] shared-memory tiles.
+//                        Lane (site s = lane%4, column n = lane/4) owns EL e-rows {EL warp + i} and FL f-columns
+//                        {n + 8 j} of an (8 EL) x (8 FL) tile (16 x 32 or 16 x 40); TMA producer warp + mbarrier
+//                        ring as in gram_tma_kernel, same [k-group][row][4 complex] shared-memory tiles.
 //   pw_zfold_kernel    : G[job][p] = sum_z exp(2 pi i pz z/Lz) (Y[z][mc(p)] + i sigma_p Y[z][ms(p)])
 //                        written as split 0 of the partial-sum buffer, so combine_kernel is unchanged.
 // FP64-pipe issue slots per (pair, e, f, site): 12/32 (DFMA) + 2 MB 8/32 (DMMA) = 1.4 at MB = 2, against
@@ -36,25 +36,44 @@ constexpr int PW_THREADS = (PW_WARPS + 4) * 32;  // 8 MMA warps + one producer w
 constexpr int PW_REGS_CONSUMER = 232;
 constexpr int PW_REGS_PRODUCER = 40;
 constexpr int PW_KG = 6;                                // k-groups of 4 complex per stage (= 8 sites x 3 colours)
-constexpr int PW_L_BYTES = PW_KG * PW_ROWS_L * 64;      // [kg][row][4 complex]
-constexpr int PW_R_BYTES = PW_KG * PW_ROWS_R * 64;
 constexpr int PW_W_BYTES = 2 * PW_MAX_MB * 256;         // [group of 4 sites][m-block][32 lanes] doubles
-constexpr int PW_STAGE_BYTES = PW_L_BYTES + PW_R_BYTES + PW_W_BYTES;
 constexpr int PW_MAX_STAGES = 8;
 constexpr int PW_TAIL_BYTES = 16 * PW_MAX_STAGES + (int)sizeof(GramJob) + 64;
-static_assert(PW_STAGE_BYTES % 128 == 0 && PW_L_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+__host__ __device__ constexpr int pw_stage_bytes(int el, int fl) { return PW_KG * (PW_WARPS * el + 8 * fl) * 64 + PW_W_BYTES; }
 
-int pw_plan_smem(int* nstages, int* smem_bytes) {
-    int nst = (227 * 1024 - PW_TAIL_BYTES) / PW_STAGE_BYTES;
+int pw_plan_smem(int el, int fl, int* nstages, int* smem_bytes) {
+    const int stage = pw_stage_bytes(el, fl);
+    int nst = (227 * 1024 - PW_TAIL_BYTES) / stage;
     if (nst > PW_MAX_STAGES) nst = PW_MAX_STAGES;
     if (nst < 2) return -1;
     *nstages = nst;
-    *smem_bytes = nst * PW_STAGE_BYTES + PW_TAIL_BYTES;
+    *smem_bytes = nst * stage + PW_TAIL_BYTES;
     return 0;
 }
 
-template <int MB>
+// tile shape with the least padded work for this Ne (ties: the wider tile, fewer CTAs and less operand traffic)
+static const int kPwTiles[][2] = {{2, 5}, {2, 4}};
+void pw_pick_tile(int Ne, int* el, int* fl) {
+    long long best = -1;
+    for (const auto& t : kPwTiles) {
+        const int rl = PW_WARPS * t[0], rr = 8 * t[1];
+        const long long work = (long long)((Ne + rl - 1) / rl) * ((Ne + rr - 1) / rr) * t[0] * t[1];
+        if (best < 0 || work < best) {
+            best = work;
+            *el = t[0];
+            *fl = t[1];
+        }
+    }
+}
+
+template <int MB, int PW_EL, int PW_FL>
 __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P, const __grid_constant__ PwTma Tm) {
+    constexpr int PW_ROWS_L = PW_WARPS * PW_EL, PW_ROWS_R = 8 * PW_FL;
+    constexpr int PW_L_BYTES = PW_KG * PW_ROWS_L * 64;  // [kg][row][4 complex]
+    constexpr int PW_R_BYTES = PW_KG * PW_ROWS_R * 64;
+    constexpr int PW_STAGE_BYTES = pw_stage_bytes(PW_EL, PW_FL);
+    static_assert(PW_STAGE_BYTES % 128 == 0 && PW_L_BYTES % 128 == 0 && (PW_ROWS_L * 64) % 128 == 0 && (PW_ROWS_R * 64) % 128 == 0,
+                  "TMA destinations are 128-byte aligned");
     extern __shared__ __align__(1024) unsigned char smem[];
     const int nst = Tm.nstages;
     unsigned char* tail = smem + (size_t)nst * PW_STAGE_BYTES;
@@ -87,9 +106,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
     }
     __syncthreads();
     // self pair (L == R): the site product is Hermitian in (e, f) and the weights are real, so
-    // Y[m][e][f] = conj(Y[m][f][e]); tiles entirely below the diagonal are left to the fold kernel's mirror read
-    if (sjob->nseg == 1 && sjob->Lf[0] == sjob->Rf[0] && e0 > f0 + PW_ROWS_R - 1) return;
-    const int T = sjob->nseg * P.kplane;  // stages of 8 sites: every segment walks the plane once
+    // Y[m][e][f] = conj(Y[m][f][e]); tiles entirely below the diagonal are left to the fold kernel's mirror read.
+    // (No early return here: an exit ahead of setmaxnreg makes ptxas spill the accumulators in the stage loop.)
+    const bool skip_tile = sjob->nseg == 1 && sjob->Lf[0] == sjob->Rf[0] && e0 > f0 + PW_ROWS_R - 1;
+    const int T = skip_tile ? 0 : sjob->nseg * P.kplane;  // stages of 8 sites: every segment walks the plane once
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 
     if (warp >= PW_WARPS) {
@@ -227,6 +247,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
     }
 
     // ---- epilogue: lane holds modes (mb0 + mb) 8 + n of columns f = f0 + 8 j + 2 sidx + {0, 1} -------------
+    if (skip_tile) return;
     const double fs = (double)cur_sign;
     const int Ne = P.Ne;
     const size_t mat = (size_t)Ne * Ne;
@@ -252,24 +273,24 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
 }
 
 #ifndef EDK_HOST_EMU
-cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, cudaStream_t s) {
-    int nst, bytes;
-    if (pw_plan_smem(&nst, &bytes) != 0 || nst != T.nstages || MB < 1 || MB > PW_MAX_MB) return cudaErrorInvalidValue;
-    const long long items = (long long)P.njobs * P.Lz * P.n_et * P.n_ft;
-    if (items < 1 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
-    cudaError_t e;
-    if (MB == 1) {
-        e = cudaFuncSetAttribute(gram_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return e;
-        gram_pw_kernel<1><<<(unsigned)items, PW_THREADS, bytes, s>>>(P, T);
-    } else {
-        e = cudaFuncSetAttribute(gram_pw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return e;
-        gram_pw_kernel<2><<<(unsigned)items, PW_THREADS, bytes, s>>>(P, T);
-    }
+template <int MB, int EL, int FL>
+static cudaError_t launch_gram_pw_t(const PwParams& P, const PwTma& T, int bytes, unsigned items, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(gram_pw_kernel<MB, EL, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    gram_pw_kernel<MB, EL, FL><<<items, PW_THREADS, bytes, s>>>(P, T);
     return cudaGetLastError();
 }
 
+cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, int el, int fl, cudaStream_t s) {
+    int nst, bytes;
+    if (pw_plan_smem(el, fl, &nst, &bytes) != 0 || nst != T.nstages || MB < 1 || MB > PW_MAX_MB) return cudaErrorInvalidValue;
+    const long long items = (long long)P.njobs * P.Lz * P.n_et * P.n_ft;
+    if (items < 1 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const unsigned n = (unsigned)items;
+    if (el == 2 && fl == 4) return MB == 1 ? launch_gram_pw_t<1, 2, 4>(P, T, bytes, n, s) : launch_gram_pw_t<2, 2, 4>(P, T, bytes, n, s);
+    if (el == 2 && fl == 5) return MB == 1 ? launch_gram_pw_t<1, 2, 5>(P, T, bytes, n, s) : launch_gram_pw_t<2, 2, 5>(P, T, bytes, n, s);
+    return cudaErrorInvalidValue;
+}
 #endif  // EDK_HOST_EMU
 
 // weights of the real xy-modes, laid out as the A fragments of the plane transform:
@@ -329,7 +350,7 @@ __global__ void __launch_bounds__(PW_FOLD_THREADS) pw_zfold_kernel(const PwFold 
     if (ef >= mat) return;
     // tiles of a self pair below the diagonal were not computed: read the mirror element, conjugated
     const int e = (int)(ef / F.Ne), f = (int)(ef - (size_t)e * F.Ne);
-    const bool mirror = J.nseg == 1 && J.Lf[0] == J.Rf[0] && (e / PW_ROWS_L) * PW_ROWS_L > (f / PW_ROWS_R) * PW_ROWS_R + PW_ROWS_R - 1;
+    const bool mirror = J.nseg == 1 && J.Lf[0] == J.Rf[0] && (e / F.rows_l) * F.rows_l > (f / F.rows_r) * F.rows_r + F.rows_r - 1;
     const double cj = mirror ? -1.0 : 1.0;
     const int mc = F.momode[3 * p], ms = F.momode[3 * p + 1];
     const double sg = (double)F.momode[3 * p + 2];

@@ -207,7 +207,7 @@ class ElementalEngine:
         return {"hermitian_pairing": bool(q(0)), "internal_momenta": q(1), "pair_gemms_per_momentum": q(2),
                 "ksplit": q(3), "mfrag": q(4), "jobs": q(5), "tma_stages": q(6),
                 "real_mma_per_complex_block": q(7), "pair_momentum_gemms": q(8), "half_set_momenta": q(9),
-                "contraction_form": q(10), "plane_wave_modes": q(11)}
+                "contraction_form": q(10), "plane_wave_modes": q(11), "plane_wave_tile": q(12)}
 
 
 def microbench_fp64(device: int = 0):

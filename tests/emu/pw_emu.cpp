@@ -3,7 +3,7 @@
 // and pw_zfold_kernel.  TEST INFRASTRUCTURE ONLY - driven by tests/test_pw_model.py.
 //
 //   pw_emu <input.bin> <output.bin>
-// input : int32 header {Lx, Ly, Lz, Ne, nfield, njobs, nmom_int, nmodes, max_mb, nstages}
+// input : int32 header {Lx, Ly, Lz, Ne, nfield, njobs, nmom_int, nmodes, max_mb, nstages, el, fl}
 //         int32 jobs[njobs][2 + 3*8]  = nseg, nmom, Lf[8], Rf[8], sign[8]
 //         int32 modes3[nmodes][3], int32 momode[nmom_int][3]
 //         f64   zphase[nmom_int][Lz][2], f64 fields[nfield][Ne][3V][2]
@@ -73,9 +73,9 @@ int main(int argc, char** argv) {
     if (argc != 3) return 1;
     FILE* f = std::fopen(argv[1], "rb");
     if (!f) return 1;
-    const auto hd = read_vec<int>(f, 10);
+    const auto hd = read_vec<int>(f, 12);
     const int Lx = hd[0], Ly = hd[1], Lz = hd[2], Ne = hd[3], nfield = hd[4], njobs = hd[5], nmom = hd[6], nmodes = hd[7],
-              max_mb = hd[8], nstages = hd[9];
+              max_mb = hd[8], nstages = hd[9], el = hd[10], fl = hd[11];
     const int V = Lx * Ly * Lz, Kc = 3 * V;
     const auto jraw = read_vec<int>(f, (size_t)njobs * 26);
     const auto modes3 = read_vec<int>(f, (size_t)nmodes * 3);
@@ -119,15 +119,16 @@ int main(int argc, char** argv) {
     P.Lz = Lz;
     P.A = Lx * Ly;
     P.kplane = kplane;
-    P.n_et = (Ne + PW_ROWS_L - 1) / PW_ROWS_L;
-    P.n_ft = (Ne + PW_ROWS_R - 1) / PW_ROWS_R;
+    const int rows_l = PW_WARPS * el, rows_r = 8 * fl;
+    P.n_et = (Ne + rows_l - 1) / rows_l;
+    P.n_ft = (Ne + rows_r - 1) / rows_r;
     P.nmodes = nmodes;
     P.mbtot = mbtot;
     P.wtiles = wtiles;
     P.Y = Y.data();
     PwTma T{};
     int plan_nst = 0, smem_bytes = 0;
-    if (pw_plan_smem(&plan_nst, &smem_bytes) != 0 || smem_bytes > EMU_SMEM_BYTES) return 1;
+    if (pw_plan_smem(el, fl, &plan_nst, &smem_bytes) != 0 || smem_bytes > EMU_SMEM_BYTES) return 1;
     T.nstages = nstages > 0 ? nstages : plan_nst;
     EmuTensorMap M{};
     M.base = fields.data();
@@ -138,9 +139,9 @@ int main(int argc, char** argv) {
     M.stride_bytes[1] = 2LL * Kc * 8 * Ne;
     M.box[0] = 8;
     M.box[2] = 1;
-    M.box[1] = PW_ROWS_L;
+    M.box[1] = rows_l;
     std::memcpy(T.mapL, &M, sizeof(M));
-    M.box[1] = PW_ROWS_R;
+    M.box[1] = rows_r;
     std::memcpy(T.mapR, &M, sizeof(M));
     static_assert(sizeof(EmuTensorMap) <= 128, "descriptor fits the CUtensorMap slot");
     const unsigned items = (unsigned)(njobs * Lz * P.n_et * P.n_ft);
@@ -148,10 +149,16 @@ int main(int argc, char** argv) {
         P.mb0 = mb0;
         const int MB = std::min(max_mb, mbtot - mb0);
         for (unsigned b = 0; b < items; ++b) {
-            if (MB == 1)
-                run_cta(PW_THREADS, b, [&] { gram_pw_kernel<1>(P, T); });
+            if (el == 2 && fl == 4 && MB == 1)
+                run_cta(PW_THREADS, b, [&] { gram_pw_kernel<1, 2, 4>(P, T); });
+            else if (el == 2 && fl == 4)
+                run_cta(PW_THREADS, b, [&] { gram_pw_kernel<2, 2, 4>(P, T); });
+            else if (el == 2 && fl == 5 && MB == 1)
+                run_cta(PW_THREADS, b, [&] { gram_pw_kernel<1, 2, 5>(P, T); });
+            else if (el == 2 && fl == 5)
+                run_cta(PW_THREADS, b, [&] { gram_pw_kernel<2, 2, 5>(P, T); });
             else
-                run_cta(PW_THREADS, b, [&] { gram_pw_kernel<2>(P, T); });
+                return 1;
         }
     }
 
@@ -164,6 +171,8 @@ int main(int argc, char** argv) {
     F.Lz = Lz;
     F.nmodes = nmodes;
     F.nmom_int = nmom;
+    F.rows_l = rows_l;
+    F.rows_r = rows_r;
     F.Y = Y.data();
     F.zphase = reinterpret_cast<const cplx*>(zphase.data());
     F.momode = momode.data();

@@ -15,10 +15,7 @@ import pytest
 from easydistillation_b200 import _capi
 from oracle import elemental_oracle as orc
 
-PW_EL, PW_FL, PW_WARPS = 2, 4, 8
-ROWS_L, ROWS_R = PW_WARPS * PW_EL, 8 * PW_FL
-KG = 6
-L_BYTES, R_BYTES = KG * ROWS_L * 64, KG * ROWS_R * 64
+PW_WARPS, KG = 8, 6
 
 
 def _mode_value(mode, x, y, Lx, Ly):
@@ -85,8 +82,10 @@ def _weight_tiles(modes, Lx, Ly, kplane, mbtot):
     return wt
 
 
-def _gram_pw_model(fields, jobs, latt3, moms_int, max_mb=2):
+def _gram_pw_model(fields, jobs, latt3, moms_int, max_mb=2, PW_EL=2, PW_FL=4):
     """jobs: list of (segments [(Lf, Rf, sign)], nmom).  Returns partial[job][p][e][f]."""
+    ROWS_L, ROWS_R = PW_WARPS * PW_EL, 8 * PW_FL
+    L_BYTES, R_BYTES = KG * ROWS_L * 64, KG * ROWS_R * 64
     Lx, Ly, Lz = latt3
     nf, Ne, Kc = fields.shape
     A = Lx * Ly
@@ -196,9 +195,10 @@ def _gram_pw_model(fields, jobs, latt3, moms_int, max_mb=2):
     return partial
 
 
-@pytest.mark.parametrize("latt3,Ne,nmom,max_mb", [((3, 5, 2), 5, 7, 2), ((4, 2, 3), 19, 33, 2), ((5, 3, 1), 35, 9, 2),
-                                                  ((2, 3, 2), 3, 33, 1)])  # max_mb = 1: two passes over 13 modes
-def test_lane_model_equals_direct_contraction(latt3, Ne, nmom, max_mb):
+@pytest.mark.parametrize("latt3,Ne,nmom,max_mb,fl", [((3, 5, 2), 5, 7, 2, 4), ((4, 2, 3), 19, 33, 2, 4), ((5, 3, 1), 35, 9, 2, 4),
+                                                     ((2, 3, 2), 3, 33, 1, 4),   # max_mb = 1: two passes over 13 modes
+                                                     ((3, 2, 2), 43, 9, 2, 5)])  # 16 x 40 tiles
+def test_lane_model_equals_direct_contraction(latt3, Ne, nmom, max_mb, fl):
     Lx, Ly, Lz = latt3
     V = Lx * Ly * Lz
     rng = np.random.default_rng(1234 + Ne)
@@ -206,7 +206,7 @@ def test_lane_model_equals_direct_contraction(latt3, Ne, nmom, max_mb):
     fields = rng.standard_normal((nfield, Ne, 3 * V)) + 1j * rng.standard_normal((nfield, Ne, 3 * V))
     moms = orc.momentum_set(nmom)
     jobs = [([(0, 1, 1)], nmom), ([(2, 0, -1), (1, 1, 1), (0, 2, -1)], nmom), ([(2, 2, 1)], max(1, nmom // 2))]
-    got = _gram_pw_model(fields, jobs, latt3, moms, max_mb)
+    got = _gram_pw_model(fields, jobs, latt3, moms, max_mb, 2, fl)
     f4 = fields.reshape(nfield, Ne, Lz, Ly, Lx, 3)
     for job_id, (segs, nmom_job) in enumerate(jobs):
         for p in range(nmom_job):
@@ -223,7 +223,7 @@ def _build_emulator(tmp_path):
     return _build(tmp_path, "pw_emu.cpp", "pw_emu")
 
 
-def _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages):
+def _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages, el=2, fl=4):
     import subprocess
 
     Lx, Ly, Lz = latt3
@@ -237,7 +237,7 @@ def _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages):
     zphase = np.array([[np.exp(2j * np.pi * ((m[2] * z) % Lz) / Lz) for z in range(Lz)] for m in moms])
     inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
     with open(inp, "wb") as f:
-        np.array([Lx, Ly, Lz, Ne, nfield, len(jobs), len(moms), len(modes), max_mb, nstages], np.int32).tofile(f)
+        np.array([Lx, Ly, Lz, Ne, nfield, len(jobs), len(moms), len(modes), max_mb, nstages, el, fl], np.int32).tofile(f)
         jraw.tofile(f)
         modes.astype(np.int32).tofile(f)
         momode.astype(np.int32).tofile(f)
@@ -248,11 +248,13 @@ def _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages):
     return np.fromfile(out, np.complex128).reshape(len(jobs), len(moms), Ne, Ne)
 
 
-@pytest.mark.parametrize("latt3,Ne,nmom,max_mb,nstages", [
-    ((5, 8, 2), 35, 33, 2, 0),   # 3 x 2 tiles, 13 modes in one pass, 15 stages through the 8-deep ring, mirror tiles
-    ((3, 5, 2), 5, 33, 1, 3),    # ragged plane (15 sites), two passes of one m-block, 3-deep ring
+@pytest.mark.parametrize("latt3,Ne,nmom,max_mb,nstages,fl", [
+    ((5, 8, 2), 35, 33, 2, 0, 4),   # 3 x 2 tiles, 13 modes in one pass, 15 stages through the 8-deep ring, mirror tiles
+    ((3, 5, 2), 5, 33, 1, 3, 4),    # ragged plane (15 sites), two passes of one m-block, 3-deep ring
+    ((5, 8, 1), 43, 33, 2, 0, 5),   # 16 x 40 tiles: 3 x 2 tiles, mirror tile (e0 = 32 > f0 + 39 is never true: none skipped)
+    ((3, 3, 2), 90, 7, 2, 2, 5),    # 16 x 40 tiles with skipped mirror tiles (e0 >= 48), 2-deep ring
 ])
-def test_kernel_sources_on_host_emulator(tmp_path, latt3, Ne, nmom, max_mb, nstages):
+def test_kernel_sources_on_host_emulator(tmp_path, latt3, Ne, nmom, max_mb, nstages, fl):
     """edk_gram_pw.cu itself (not a transcription), compiled by g++ against tests/emu/edk_emu.h and run with one
     host thread per CUDA thread, equals the direct contraction."""
     Lx, Ly, Lz = latt3
@@ -263,7 +265,7 @@ def test_kernel_sources_on_host_emulator(tmp_path, latt3, Ne, nmom, max_mb, nsta
     moms = orc.momentum_set(nmom)
     jobs = [([(0, 1, 1)], nmom), ([(2, 0, -1), (1, 1, 1), (0, 2, -1)], nmom), ([(2, 2, 1)], max(1, nmom // 2))]
     exe = _build_emulator(tmp_path)
-    got = _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages)
+    got = _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages, 2, fl)
     f4 = fields.reshape(nfield, Ne, Lz, Ly, Lx, 3)
     for job_id, (segs, nmom_job) in enumerate(jobs):
         for p in range(nmom_job):
