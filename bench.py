@@ -8,6 +8,9 @@ Native arm: `value` is measured with the step's inputs already resident in HBM, 
 the host-buffer C-ABI call (edk_calc_host) with H2D/D2H inside the timed region.  For N > 1 each
 rank owns its own timeslices (weak scaling), and the timed region ends with the NCCL gather of
 all results onto rank 0 - the only exchange step this path has.
+Contraction form: by default (`--contraction auto`) an untimed set-up step validates the newer plane-wave
+factorised form against the GEMM form at the workload's shape in a child process and uses it only if it agrees to
+1e-10 and is faster (easydistillation_b200/tuning.py); the line reports the decision under "contraction".
 Reference arm (`--impl reference`): the numpy restatement of the reference algorithm
 (oracle/elemental_oracle.py, kind "port": the reference itself is a Python package that does
 not exist on the GPU box) timed on the host cores on a bounded sample of the same workload.
@@ -335,10 +338,33 @@ def run_native(args):
     K, W = args.steps, args.warmup
     moms = momentum_set(nmom)
     dist_ = args.distance if args.generator == "displacement" else None
-    if dist_ is None:
-        eng = ElementalEngine((Lx, Ly, Lz), Ne, _capi.MODE_DERIVATIVE, nabla, moms, device=local)
+    mode_, order_ = (_capi.MODE_DERIVATIVE, nabla) if dist_ is None else (_capi.MODE_DISPLACEMENT, dist_)
+
+    # ---- contraction form (untimed set-up, like a user's one-off `python -m easydistillation_b200.tuning`) ----
+    # "auto": a child process validates the plane-wave form against the GEMM form at this workload's shape and
+    # through the public class API, times both, and the faster validated one becomes the default of this process.
+    contraction = {"requested": args.contraction}
+    if os.environ.get("EDK_GRAM_ALGO"):
+        contraction.update(form=int(os.environ["EDK_GRAM_ALGO"]), reason="EDK_GRAM_ALGO set by the caller")
+    elif args.contraction == "auto":
+        from easydistillation_b200 import tuning
+
+        decision = tuning.select_contraction((Lx, Ly, Lz), Ne, mode_, order_, moms, device=local, reps=2, timeout=420.0)
+        form = int(decision["form"])
+        if world > 1:  # every rank uses the same form: the slowest decision wins
+            tf = torch.tensor([form], dtype=torch.int32, device=dev)
+            dist.all_reduce(tf, op=dist.ReduceOp.MIN)
+            form = int(tf.item())
+        decision["form"] = form
+        tuning.apply(decision)
+        contraction.update(decision)
+        if rank == 0:
+            print(f"bench.py: contraction form {form} ({decision['reason']})", file=sys.stderr, flush=True)
     else:
-        eng = ElementalEngine((Lx, Ly, Lz), Ne, _capi.MODE_DISPLACEMENT, dist_, moms, device=local)
+        form = 2 if args.contraction == "planewave" else 1
+        os.environ["EDK_GRAM_ALGO"] = str(form)
+        contraction.update(form=form, reason="forced by --contraction")
+    eng = ElementalEngine((Lx, Ly, Lz), Ne, mode_, order_, moms, device=local)
 
     if os.environ.get("EDK_BENCH_GRAM"):  # tuning hook: "mfrag,ksplit" (0 = auto)
         mf, ks = (int(v) for v in os.environ["EDK_BENCH_GRAM"].split(","))
@@ -506,6 +532,7 @@ def run_native(args):
                     "api": "ElementalGenerator.calc_range over host arrays (streamed: pinned staging, H2D/D2H overlapped with the kernels)",
                     "checksum": checksum},
             "gpu_launches": int(launches),
+            "contraction": contraction,
             "clocks": clocks.summary(),
             "roofline": {
                 "kernel": gram_name + (" (plane-wave factorised contraction: site products by DFMA, real xy-mode transform by "
@@ -555,6 +582,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=os.environ.get("EDK_BENCH_WORKLOAD", "config5"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contraction", default=os.environ.get("EDK_BENCH_CONTRACTION", "auto"), choices=["auto", "gemm", "planewave"],
+                    help="contraction form: auto = validate and time the plane-wave form against the GEMM form in a child "
+                         "process first and use the faster validated one; gemm / planewave force one")
     ap.add_argument("--generator", default="derivative", choices=["derivative", "displacement"],
                     help="ElementalGenerator (default, the graded workload) or DisplacementElementalGenerator")
     ap.add_argument("--distance", type=int, default=2, help="displacement generator: number of link steps")

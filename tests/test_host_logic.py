@@ -345,3 +345,23 @@ def test_calc_to_file_layout_slabs_and_downcast(tmp_path):
     bad.__dict__.update(gen.__dict__)
     with pytest.raises(RuntimeError, match="device failure"):
         bad.calc_to_file(handle, "broken")
+
+
+def test_contraction_tuning_falls_back_to_the_gemm_form_without_a_gpu():
+    """tuning.select_contraction runs its trial in a child process; anything but a clean, faster, validated
+    plane-wave run - here: no CUDA device - must leave the validated GEMM form (1) in place."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from easydistillation_b200 import tuning
+
+    d = tuning.select_contraction((4, 4, 4), 8, _capi.MODE_DERIVATIVE, 2, tuning.momentum_set(7), device=0, timeout=300)
+    assert d["form"] == 1 and not d["validated"] and "child failed" in d["reason"]
+    saved = os.environ.pop("EDK_GRAM_ALGO", None)
+    try:
+        assert tuning.apply(d) == 1 and os.environ["EDK_GRAM_ALGO"] == "1"
+    finally:
+        os.environ.pop("EDK_GRAM_ALGO", None)
+        if saved is not None:
+            os.environ["EDK_GRAM_ALGO"] = saved
