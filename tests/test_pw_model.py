@@ -330,3 +330,54 @@ def test_emulator_calibration_on_gpu_validated_kernels(tmp_path, kernel):
             ref = sum(s * orc.gram(f4[a], f4[b], ph) for a, b, s in segs)
             err = np.linalg.norm(got[job_id, p] - ref) / np.linalg.norm(ref)
             assert err < 1e-12, (kernel, job_id, p, err)
+
+
+def test_shared_memory_pipeline_is_race_free_under_thread_sanitizer(tmp_path):
+    """racecheck without a GPU: the emulated CTA (one host thread per CUDA thread, TMA writes as plain stores of the
+    producer thread, mbarriers as mutex-protected counters) runs under ThreadSanitizer.  The real full/empty protocol
+    of gram_pw_kernel must be silent; the same build with waits that do not wait must be reported (self-test)."""
+    import os
+    import subprocess
+
+    from conftest import REPO
+
+    def build(name, extra):
+        exe = str(tmp_path / name)
+        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-DEDK_HOST_EMU", *extra, "-I", os.path.join(REPO, "tests", "emu"),
+               "-I", os.path.join(REPO, "easydistillation_b200", "csrc"), "-I", os.path.join(REPO, "include"),
+               "-I", "/usr/local/cuda/include", "-x", "c++", os.path.join(REPO, "tests", "emu", "pw_emu.cpp"), "-o", exe, "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("no ThreadSanitizer runtime for this g++: " + r.stderr[-300:])
+        return exe
+
+    Lx, Ly, Lz, Ne, nfield = 3, 5, 1, 20, 3
+    rng = np.random.default_rng(5)
+    fields = rng.standard_normal((nfield, Ne, 3 * Lx * Ly * Lz)) + 1j * rng.standard_normal((nfield, Ne, 3 * Lx * Ly * Lz))
+    moms = orc.momentum_set(7)
+    jobs = [([(0, 1, 1)], 7), ([(2, 0, -1), (1, 1, 1)], 7), ([(2, 2, 1)], 4)]
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0")
+    counts = {}
+    for name, extra in (("good", []), ("broken", ["-DEDK_EMU_BREAK_PROTOCOL"])):
+        exe = build("pw_emu_tsan_" + name, extra)
+        sub = tmp_path / name
+        sub.mkdir()
+        # same input writer as the plain emulator run; 2-deep ring so that slots are reused many times
+        modes, momode = _capi.plan_modes(moms)
+        jraw = np.zeros((len(jobs), 26), np.int32)
+        for j, (segs, nmom_job) in enumerate(jobs):
+            jraw[j, 0], jraw[j, 1] = len(segs), nmom_job
+            for s, (a, b, sg) in enumerate(segs):
+                jraw[j, 2 + s], jraw[j, 10 + s], jraw[j, 18 + s] = a, b, sg
+        zphase = np.array([[np.exp(2j * np.pi * ((m[2] * z) % Lz) / Lz) for z in range(Lz)] for m in moms])
+        with open(sub / "in.bin", "wb") as f:
+            np.array([Lx, Ly, Lz, Ne, nfield, len(jobs), len(moms), len(modes), 2, 2, 2, 4], np.int32).tofile(f)
+            jraw.tofile(f)
+            modes.astype(np.int32).tofile(f)
+            momode.astype(np.int32).tofile(f)
+            np.ascontiguousarray(zphase).view(np.float64).tofile(f)
+            np.ascontiguousarray(fields).view(np.float64).tofile(f)
+        r = subprocess.run([exe, str(sub / "in.bin"), str(sub / "out.bin")], capture_output=True, text=True, timeout=900, env=env)
+        counts[name] = (r.stdout + r.stderr).count("WARNING: ThreadSanitizer")
+    assert counts["good"] == 0, "data race in the kernel's shared-memory pipeline"
+    assert counts["broken"] > 0, "the race detection did not see a deliberately broken protocol"
