@@ -253,6 +253,8 @@ def _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages, el=
     ((3, 5, 2), 5, 33, 1, 3, 4),    # ragged plane (15 sites), two passes of one m-block, 3-deep ring
     ((5, 8, 1), 43, 33, 2, 0, 5),   # 16 x 40 tiles: 3 x 2 tiles, mirror tile (e0 = 32 > f0 + 39 is never true: none skipped)
     ((3, 3, 2), 90, 7, 2, 2, 5),    # 16 x 40 tiles with skipped mirror tiles (e0 >= 48), 2-deep ring
+    ((2, 2, 2), 1, 1, 2, 0, 4),     # one eigenvector, p = 0 only (a single constant mode), planes of 4 sites
+    ((4, 3, 2), 7, [(0, 0, 1), (1, 2, 0), (3, -1, 2), (0, -2, 1), (-5, 0, 7)], 2, 0, 5),  # non-closed list, |p| > L
 ])
 def test_kernel_sources_on_host_emulator(tmp_path, latt3, Ne, nmom, max_mb, nstages, fl):
     """edk_gram_pw.cu itself (not a transcription), compiled by g++ against tests/emu/edk_emu.h and run with one
@@ -262,7 +264,8 @@ def test_kernel_sources_on_host_emulator(tmp_path, latt3, Ne, nmom, max_mb, nsta
     rng = np.random.default_rng(99 + Ne)
     nfield = 3
     fields = rng.standard_normal((nfield, Ne, 3 * V)) + 1j * rng.standard_normal((nfield, Ne, 3 * V))
-    moms = orc.momentum_set(nmom)
+    moms = orc.momentum_set(nmom) if isinstance(nmom, int) else nmom
+    nmom = len(moms)
     jobs = [([(0, 1, 1)], nmom), ([(2, 0, -1), (1, 1, 1), (0, 2, -1)], nmom), ([(2, 2, 1)], max(1, nmom // 2))]
     exe = _build_emulator(tmp_path)
     got = _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages, 2, fl)
