@@ -504,6 +504,7 @@ def run_native(args):
             # site product and, for each of the real xy-modes, one multiply-add on its real and imaginary part
             # (DMMA rows padded to blocks of 8 modes are not counted)
             exec_flops = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V * (24.0 + 4.0 * q["plane_wave_modes"])
+            pw_padded_flops = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V * (24.0 + 4.0 * 8 * ((q["plane_wave_modes"] + 7) // 8))
         achieved_tf = exec_flops / (gram_ms * 1e-3) / 1e12
         survey_tf = flops / (gram_ms * 1e-3) / 1e12
         # stencil: bytes of ONE launch (nabla3: 1 source, 3 outputs, links once; displacement step: 6 in, 6 + mean out)
@@ -545,6 +546,7 @@ def run_native(args):
                                f"DMMA issue-rate microbench {dmma_tf:.1f}, DFMA {dfma_tf:.1f} TFLOP/s; nominal 37-40",
                 "algorithmic_flops_per_launch": exec_flops, "ms_per_launch": gram_ms,
                 "pairing": q, "survey_flops_per_launch": flops, "survey_equivalent_tflops": survey_tf,
+                **({"executed_tflops_incl_padded_mode_rows": pw_padded_flops / (gram_ms * 1e-3) / 1e12} if pw_form else {}),
                 "note": ("achieved = flops the plane-wave form needs / time: the phase factorises, so the site product is formed once "
                          "for all momenta and only the real xy-modes are transformed per plane; the FP64 pipe is the bound, "
                          "survey_equivalent_tflops = SURVEY 8d flops (GEMM form, 34 pairs x Nmom) / time") if pw_form else
