@@ -10,6 +10,18 @@
 #error "edk kernels are written for sm_100a (B200) only"
 #endif
 
+// Kernel launches go through one macro so that tests/emu can run the whole library (host glue, launchers and
+// kernel sources) on a machine without a GPU: under EDK_HOST_EMU (test builds by g++ only, never the shipped
+// library) a launch runs the kernel body on host threads, one per CUDA thread.
+#ifdef EDK_HOST_EMU
+#define EDK_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) \
+    ::edk::emu_launch(dim3(grid), dim3(block), (size_t)(smem_bytes), [&] { kernel(__VA_ARGS__); })
+#define EDK_SHARED static
+#else
+#define EDK_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) kernel<<<(grid), (block), (smem_bytes), (stream)>>>(__VA_ARGS__)
+#define EDK_SHARED __shared__
+#endif
+
 namespace edk {
 
 typedef double2 cplx;  // (re, im)
@@ -175,3 +187,7 @@ cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s);
 cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops);
 
 }  // namespace edk
+
+#ifdef EDK_HOST_EMU
+#include "edk_emu.h"  // tests/emu: host implementations of threadIdx, barriers, launches (test builds only)
+#endif

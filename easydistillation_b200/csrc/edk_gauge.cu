@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(128) stout_step_kernel(const cplx* __restrict_
 
 cudaError_t launch_stout_step(const cplx* Uin, cplx* Uout, double rho, Geom g, cudaStream_t s) {
     dim3 block(128), grid((g.V + 127) / 128, 3);
-    stout_step_kernel<<<grid, block, 0, s>>>(Uin, Uout, rho, g);
+    EDK_LAUNCH(stout_step_kernel, grid, block, 0, s, Uin, Uout, rho, g);
     return cudaGetLastError();
 }
 
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(128) project_su3_kernel(cplx* __restrict__ U, 
 
 cudaError_t launch_project_su3(cplx* U, Geom g, cudaStream_t s) {
     const size_t n = (size_t)3 * g.V;
-    project_su3_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(U, n);
+    EDK_LAUNCH(project_su3_kernel, (unsigned)((n + 127) / 128), 128, 0, s, U, n);
     return cudaGetLastError();
 }
 

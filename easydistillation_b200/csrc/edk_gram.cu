@@ -677,16 +677,17 @@ int gram_tma_plan(int algo, int mfrag, int nmom, int Ne, int* brows_alloc, int* 
 int gram_nfrag_per_tile(int algo) { return algo ? 8 : 16; }
 int gram_fwidth(int algo) { return algo ? 8 : 4; }
 
-#ifndef EDK_HOST_EMU
+#ifndef EDK_EMU_NO_LAUNCHERS
 template <int MF, int ALGO>
 static cudaError_t launch_gram_tma_mf(const GramParams& P, const GramTma& T, cudaStream_t s) {
     int rows, nst, bytes;
     if (gram_tma_plan(ALGO, MF, P.nmom, P.Ne, &rows, &nst, &bytes) != 0 || rows != T.brows_alloc || nst != T.nstages)
         return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<MF, ALGO>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    auto kern = gram_tma_kernel<MF, ALGO>;
+    cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)P.ncta, (unsigned)P.ksplit);
-    gram_tma_kernel<MF, ALGO><<<grid, GT_THREADS, bytes, s>>>(P, T);
+    EDK_LAUNCH(kern, grid, GT_THREADS, bytes, s, P, T);
     return cudaGetLastError();
 }
 
@@ -700,7 +701,7 @@ cudaError_t launch_gram_tma(const GramParams& P, const GramTma& T, int mfrag, in
     }
 #undef EDK_TMA_CASE
 }
-#endif  // EDK_HOST_EMU
+#endif  // EDK_EMU_NO_LAUNCHERS
 
 // phase[2][nmom][Vpad] -> tiles[kstep][2][nmom][8]
 __global__ void phase_tiles_kernel(const cplx* __restrict__ phase2, cplx* __restrict__ tiles, int nmom, int Vpad) {
@@ -713,13 +714,13 @@ __global__ void phase_tiles_kernel(const cplx* __restrict__ phase2, cplx* __rest
     tiles[((((size_t)(site >> 3)) * 2 + tab) * nmom + p) * 8 + (site & 7)] = phase2[i];
 }
 
-#ifndef EDK_HOST_EMU
+#ifndef EDK_EMU_NO_LAUNCHERS
 cudaError_t launch_phase_tiles(const cplx* phase2, cplx* tiles, int nmom, int Vpad, cudaStream_t s) {
     const size_t n = (size_t)2 * nmom * Vpad;
-    phase_tiles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(phase2, tiles, nmom, Vpad);
+    EDK_LAUNCH(phase_tiles_kernel, (unsigned)((n + 255) / 256), 256, 0, s, phase2, tiles, nmom, Vpad);
     return cudaGetLastError();
 }
-#endif  // EDK_HOST_EMU
+#endif  // EDK_EMU_NO_LAUNCHERS
 
 // available tile heights (m-fragments of 8 rows per CTA)
 static const int kMfragAvail[] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13};
@@ -734,17 +735,15 @@ int gram_pick_mfrag(int Ne) {
 }
 int gram_rows_per_tile(int mfrag) { return 8 * mfrag; }
 
-#ifndef EDK_HOST_EMU
+#ifndef EDK_EMU_NO_LAUNCHERS
 template <int MF>
 static cudaError_t launch_gram_mf(const GramParams& P, cudaStream_t s) {
     using S = GramSmem<MF>;
-    static bool configured = false;  // per template instance; attribute is per device function
-    cudaError_t e = cudaFuncSetAttribute(gram_dmma_kernel<MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    auto kern = gram_dmma_kernel<MF>;
+    cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return e;
-    configured = true;
-    (void)configured;
     dim3 grid((unsigned)P.ncta, (unsigned)P.ksplit);
-    gram_dmma_kernel<MF><<<grid, GRAM_NTHREADS, S::TOTAL, s>>>(P);
+    EDK_LAUNCH(kern, grid, GRAM_NTHREADS, S::TOTAL, s, P);
     return cudaGetLastError();
 }
 
@@ -758,7 +757,7 @@ cudaError_t launch_gram_dmma(const GramParams& P, int mfrag, cudaStream_t s) {
     }
 #undef EDK_DMMA_CASE
 }
-#endif  // EDK_HOST_EMU
+#endif  // EDK_EMU_NO_LAUNCHERS
 
 bool gram_mfrag_available(int mfrag) {
     for (int v : kMfragAvail)
@@ -803,13 +802,13 @@ __global__ void gram_naive_kernel(const GramParams P) {
     P.partial[idx] = make_double2(sr, si);
 }
 
-#ifndef EDK_HOST_EMU
+#ifndef EDK_EMU_NO_LAUNCHERS
 cudaError_t launch_gram_naive(const GramParams& P, cudaStream_t s) {
     const size_t n = (size_t)P.njobs * P.nmom * P.Ne * P.Ne;
-    gram_naive_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P);
+    EDK_LAUNCH(gram_naive_kernel, (unsigned)((n + 127) / 128), 128, 0, s, P);
     return cudaGetLastError();
 }
-#endif  // EDK_HOST_EMU
+#endif  // EDK_EMU_NO_LAUNCHERS
 
 // ---------------------------------------------------------------------------------------
 // combine: out[op][p] = coeff * sum_terms w * sum_split (partial[job][p]  or  partial[job][-p]^dagger)
@@ -857,16 +856,16 @@ __global__ void combine_kernel(const CombineOp* __restrict__ ops, int nop, const
     out[idx] = make_double2(sr, si);
 }
 
-#ifndef EDK_HOST_EMU
+#ifndef EDK_EMU_NO_LAUNCHERS
 cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partial, int njobs, int ksplit, int nmom_int,
                            int nmom_out, const int* pmap, const int* negidx, int n_half, int Ne, const double* coeff, cplx* out,
                            cudaStream_t s) {
     const size_t n = (size_t)nop * nmom_out * Ne * Ne;
-    combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ops_dev, nop, partial, njobs, ksplit, nmom_int, nmom_out, pmap,
-                                                               negidx, n_half, Ne, coeff, out);
+    EDK_LAUNCH(combine_kernel, (unsigned)((n + 255) / 256), 256, 0, s, ops_dev, nop, partial, njobs, ksplit, nmom_int, nmom_out, pmap,
+               negidx, n_half, Ne, coeff, out);
     return cudaGetLastError();
 }
-#endif  // EDK_HOST_EMU
+#endif  // EDK_EMU_NO_LAUNCHERS
 
 // ---------------------------------------------------------------------------------------
 // FP64 pipe micro-benchmarks (roofline denominators measured on the box)
@@ -944,6 +943,8 @@ cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops) {
     cudaFree(sink);
     return e;
 }
+#elif !defined(EDK_EMU_NO_LAUNCHERS)
+cudaError_t microbench_fp64(double*, double*) { return cudaErrorNotSupported; }  // timing loops make no sense on the emulator
 #endif  // EDK_HOST_EMU
 
 }  // namespace edk

@@ -272,12 +272,13 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
     }
 }
 
-#ifndef EDK_HOST_EMU
+#ifndef EDK_EMU_NO_LAUNCHERS
 template <int MB, int EL, int FL>
 static cudaError_t launch_gram_pw_t(const PwParams& P, const PwTma& T, int bytes, unsigned items, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(gram_pw_kernel<MB, EL, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    auto kern = gram_pw_kernel<MB, EL, FL>;
+    cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    gram_pw_kernel<MB, EL, FL><<<items, PW_THREADS, bytes, s>>>(P, T);
+    EDK_LAUNCH(kern, items, PW_THREADS, bytes, s, P, T);
     return cudaGetLastError();
 }
 
@@ -291,7 +292,7 @@ cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, int el, in
     if (el == 2 && fl == 5) return MB == 1 ? launch_gram_pw_t<1, 2, 5>(P, T, bytes, n, s) : launch_gram_pw_t<2, 2, 5>(P, T, bytes, n, s);
     return cudaErrorInvalidValue;
 }
-#endif  // EDK_HOST_EMU
+#endif  // EDK_EMU_NO_LAUNCHERS
 
 // weights of the real xy-modes, laid out as the A fragments of the plane transform:
 //   wtiles[kstep][grp][m-block][lane] = w_{8 mblock + lane/4}(site 8 kstep + 4 grp + lane%4 of the plane)
@@ -324,14 +325,14 @@ __global__ void pw_weights_kernel(double* __restrict__ wtiles, const int* __rest
     wtiles[idx] = v;
 }
 
-#ifndef EDK_HOST_EMU
+#ifndef EDK_EMU_NO_LAUNCHERS
 cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes, int mbtot, int kplane, Geom g, cudaStream_t s) {
     const size_t total = (size_t)kplane * 2 * mbtot * 32;
-    pw_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wtiles, modes3_dev, nmodes, mbtot, kplane, g);
+    EDK_LAUNCH(pw_weights_kernel, (unsigned)((total + 255) / 256), 256, 0, s, wtiles, modes3_dev, nmodes, mbtot, kplane, g);
     return cudaGetLastError();
 }
 
-#endif  // EDK_HOST_EMU
+#endif  // EDK_EMU_NO_LAUNCHERS
 
 // G[job][p][e][f] = sum_z zphase[p][z] (Y[job][z][mc][e][f] + i sigma Y[job][z][ms][e][f]); momentum fastest over
 // the blocks, so the ~Lz x 2 planes a block reads are shared through L2 by the momenta of the same couple.
@@ -374,16 +375,16 @@ __global__ void __launch_bounds__(PW_FOLD_THREADS) pw_zfold_kernel(const PwFold 
     F.partial[((size_t)job * F.nmom_int + p) * mat + ef] = make_double2(ar, ai);
 }
 
-#ifndef EDK_HOST_EMU
+#ifndef EDK_EMU_NO_LAUNCHERS
 cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s) {
     const size_t mat = (size_t)F.Ne * F.Ne;
     const long long nblk = (long long)((mat + PW_FOLD_THREADS - 1) / PW_FOLD_THREADS);
     const long long blocks = nblk * F.njobs * F.nmom_int;
     if (blocks < 1 || blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    pw_zfold_kernel<<<(unsigned)blocks, PW_FOLD_THREADS, 0, s>>>(F);
+    EDK_LAUNCH(pw_zfold_kernel, (unsigned)blocks, PW_FOLD_THREADS, 0, s, F);
     return cudaGetLastError();
 }
 
-#endif  // EDK_HOST_EMU
+#endif  // EDK_EMU_NO_LAUNCHERS
 
 }  // namespace edk

@@ -105,10 +105,11 @@ cudaError_t launch_round_eigvecs(const void* V_in, int flags, cplx* W0, double* 
     size_t want = (n_cplx + block - 1) / block;
     int grid = (int)(want < (size_t)148 * 16 ? (want ? want : 1) : (size_t)148 * 16);
     const bool c8 = flags & EDK_EIGVECS_C8, be = flags & EDK_EIGVECS_BIG_ENDIAN;
-    if (c8 && be) round_eigvecs_kernel<true, true><<<grid, block, 0, s>>>(V_in, W0, W0_sum, n_cplx, row, sum_row);
-    else if (c8) round_eigvecs_kernel<true, false><<<grid, block, 0, s>>>(V_in, W0, W0_sum, n_cplx, row, sum_row);
-    else if (be) round_eigvecs_kernel<false, true><<<grid, block, 0, s>>>(V_in, W0, W0_sum, n_cplx, row, sum_row);
-    else round_eigvecs_kernel<false, false><<<grid, block, 0, s>>>(V_in, W0, W0_sum, n_cplx, row, sum_row);
+    auto kern = round_eigvecs_kernel<false, false>;
+    if (c8 && be) kern = round_eigvecs_kernel<true, true>;
+    else if (c8) kern = round_eigvecs_kernel<true, false>;
+    else if (be) kern = round_eigvecs_kernel<false, true>;
+    EDK_LAUNCH(kern, grid, block, 0, s, V_in, W0, W0_sum, n_cplx, row, sum_row);
     return cudaGetLastError();
 }
 
@@ -133,7 +134,7 @@ __global__ void reorder_links_kernel(const cplx* __restrict__ in, int layout, in
 cudaError_t launch_reorder_links(const cplx* U_in, int layout, int big_endian, cplx* U_out, Geom g, cudaStream_t s) {
     size_t n = (size_t)3 * g.V * 9;
     int block = 256;
-    reorder_links_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(U_in, layout, big_endian, U_out, g.V);
+    EDK_LAUNCH(reorder_links_kernel, (unsigned)((n + block - 1) / block), block, 0, s, U_in, layout, big_endian, U_out, g.V);
     return cudaGetLastError();
 }
 
@@ -163,7 +164,7 @@ __global__ void phase_table_kernel(cplx* __restrict__ phase, cplx* __restrict__ 
 
 cudaError_t launch_phase_table(cplx* phase, cplx* rot, const int* mom3_dev, int nmom, Geom g, cudaStream_t s) {
     dim3 block(256), grid((g.Vpad + 255) / 256, nmom);
-    phase_table_kernel<<<grid, block, 0, s>>>(phase, rot, mom3_dev, nmom, g);
+    EDK_LAUNCH(phase_table_kernel, grid, block, 0, s, phase, rot, mom3_dev, nmom, g);
     return cudaGetLastError();
 }
 
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(NABLA_THREADS, 2)
 nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restrict__ o1, cplx* __restrict__ o2,
               double* __restrict__ s0, double* __restrict__ s1, double* __restrict__ s2, size_t sum_row,
               const cplx* __restrict__ links, Geom g, int Ne, int chunk) {
-    __shared__ cplx stage[NABLA_THREADS / 32][96];
+    EDK_SHARED cplx stage[NABLA_THREADS / 32][96];
     const int site = blockIdx.x * NABLA_SITES + threadIdx.x;
     const int d = threadIdx.y;
     const int lane = threadIdx.x & 31;
@@ -298,7 +299,7 @@ cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_
     const int chunk = stencil_chunk(g.V, NABLA_SITES, Ne);
     dim3 block(NABLA_SITES, 3);
     dim3 grid((g.V + NABLA_SITES - 1) / NABLA_SITES, (Ne + chunk - 1) / chunk);
-    nabla3_kernel<<<grid, block, 0, s>>>(W_in, out_x, out_y, out_z, sum_x, sum_y, sum_z, sum_row, links, g, Ne, chunk);
+    EDK_LAUNCH(nabla3_kernel, grid, block, 0, s, W_in, out_x, out_y, out_z, sum_x, sum_y, sum_z, sum_row, links, g, Ne, chunk);
     return cudaGetLastError();
 }
 
@@ -311,7 +312,7 @@ constexpr int DISP_SITES = 64;
 
 __global__ void __launch_bounds__(DISP_SITES * 6)
 displace_step6_kernel(Ptr6 p, cplx* __restrict__ mean_out, const cplx* __restrict__ links, Geom g, int Ne, int chunk) {
-    __shared__ cplx red[6][DISP_SITES][3];
+    EDK_SHARED cplx red[6][DISP_SITES][3];
     const int site = blockIdx.x * DISP_SITES + threadIdx.x;
     const int line = threadIdx.y;
     const bool fwd = line < 3;
@@ -378,7 +379,7 @@ cudaError_t launch_displace_step6(Ptr6 p, cplx* mean_out, const cplx* links, Geo
     const int chunk = stencil_chunk(g.V, DISP_SITES, Ne);
     dim3 block(DISP_SITES, 6);
     dim3 grid((g.V + DISP_SITES - 1) / DISP_SITES, (Ne + chunk - 1) / chunk);
-    displace_step6_kernel<<<grid, block, 0, s>>>(p, mean_out, links, g, Ne, chunk);
+    EDK_LAUNCH(displace_step6_kernel, grid, block, 0, s, p, mean_out, links, g, Ne, chunk);
     return cudaGetLastError();
 }
 
@@ -394,7 +395,7 @@ constexpr int LAP_EB = 16;
 
 __global__ void __launch_bounds__(LAP_SITES * 3)
 laplacian_kernel(const cplx* __restrict__ F, cplx* __restrict__ out, const cplx* __restrict__ links, Geom g, int nvec) {
-    __shared__ cplx red[3][LAP_SITES][3];
+    EDK_SHARED cplx red[3][LAP_SITES][3];
     const int site = blockIdx.x * LAP_SITES + threadIdx.x;
     const int d = threadIdx.y;
     const bool active = site < g.V;
@@ -458,7 +459,7 @@ laplacian_kernel(const cplx* __restrict__ F, cplx* __restrict__ out, const cplx*
 cudaError_t launch_laplacian(const cplx* F, cplx* out, const cplx* links, Geom g, int nvec, cudaStream_t s) {
     dim3 block(LAP_SITES, 3);
     dim3 grid((g.V + LAP_SITES - 1) / LAP_SITES, (nvec + LAP_EB - 1) / LAP_EB);
-    laplacian_kernel<<<grid, block, 0, s>>>(F, out, links, g, nvec);
+    EDK_LAUNCH(laplacian_kernel, grid, block, 0, s, F, out, links, g, nvec);
     return cudaGetLastError();
 }
 

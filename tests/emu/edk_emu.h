@@ -21,6 +21,8 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <string>
 #include <mutex>
 #include <stdexcept>
 
@@ -34,6 +36,12 @@ struct EmuIdx {
     unsigned x = 0, y = 0, z = 0;
 };
 extern thread_local EmuIdx threadIdx, blockIdx, blockDim;
+#ifndef EDK_EMU_NO_LAUNCHERS
+extern thread_local EmuIdx gridDim;  // only the whole-library build (emu_runtime.cpp) defines it
+#endif
+// linear thread index inside the CTA (x fastest), which is what warps are made of; harnesses that only set
+// threadIdx.x and blockDim.x get threadIdx.x
+inline int emu_tid() { return (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)); }
 
 namespace edk {
 
@@ -41,20 +49,33 @@ constexpr int EMU_SMEM_BYTES = 232448;
 extern unsigned char smem[EMU_SMEM_BYTES];  // `extern __shared__ unsigned char smem[]` of the kernels binds to this
 
 // ---- CTA-wide state (reset by the driver before every CTA) --------------------------------------------
-struct EmuBarrier {  // reusable counting barrier
+struct EmuBarrier {  // reusable counting barrier; threads that have left the kernel no longer count
     std::mutex m;
     std::condition_variable cv;
-    int waiting = 0, generation = 0;
+    int waiting = 0, generation = 0, gone = 0;
+    void release_locked() {
+        waiting = 0;
+        ++generation;
+        cv.notify_all();
+    }
     void wait(int n) {
         std::unique_lock<std::mutex> lk(m);
         const int gen = generation;
-        if (++waiting == n) {
-            waiting = 0;
-            ++generation;
-            cv.notify_all();
-        } else {
-            cv.wait(lk, [&] { return generation != gen; });
+        if (++waiting >= n - gone) {
+            release_locked();
+        } else if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return generation != gen; })) {
+            throw std::runtime_error("barrier timed out (divergent __syncthreads / __syncwarp?)");
         }
+    }
+    void leave(int n) {  // the calling thread returned from the kernel
+        std::lock_guard<std::mutex> lk(m);
+        ++gone;
+        if (waiting > 0 && waiting >= n - gone) release_locked();
+    }
+    void reset() {
+        std::lock_guard<std::mutex> lk(m);
+        waiting = 0;
+        gone = 0;
     }
 };
 struct EmuMbar {
@@ -88,10 +109,14 @@ inline uint32_t __cvta_generic_to_shared(const void* p) {
     return (uint32_t)off;
 }
 inline void __syncthreads() { g_cta.cta_barrier.wait(g_cta.nthreads); }
-inline void __syncwarp() { g_cta.warp_barrier[threadIdx.x >> 5].wait(32); }
+inline int emu_warp_size(int warp) { return std::min(32, g_cta.nthreads - 32 * warp); }  // the last warp may be partial
+inline void __syncwarp() {
+    const int warp = emu_tid() >> 5;
+    g_cta.warp_barrier[warp].wait(emu_warp_size(warp));
+}
 
 inline void dmma884(double& c0, double& c1, const double a, const double b) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = emu_tid() >> 5, lane = emu_tid() & 31;
     g_cta.xa[warp][lane] = a;
     g_cta.xb[warp][lane] = b;
     g_cta.warp_barrier[warp].wait(32);
@@ -231,5 +256,86 @@ inline void sincospi(double x, double* s, double* c) {
     else if (r == 1.5) { *s = -1.0; *c = 0.0; }
     else { *s = sin(3.14159265358979323846 * r); *c = cos(3.14159265358979323846 * r); }
 }
+
+
+// ---- device intrinsics of the stencil / gauge / preparation kernels ---------------------------------------
+template <class T>
+inline T __ldg(const T* p) { return *p; }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+    const unsigned long long src = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned n = (sel >> (4 * i)) & 0x7;  // selectors 8..15 (sign replication) are not used by the kernels
+        r |= (unsigned)((src >> (8 * n)) & 0xff) << (8 * i);
+    }
+    return r;
+}
+inline int __double2hiint(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+inline int __double2loint(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL); }
+inline double __hiloint2double(int hi, int lo) {
+    const unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+    double x;
+    std::memcpy(&x, &b, 8);
+    return x;
+}
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float __double2float_rn(double x) { return (float)x; }  // round-to-nearest-even is the host default
+
+#ifndef EDK_EMU_NO_LAUNCHERS
+// ---- kernel launch: one host thread per CUDA thread, CTAs one after another ----------------------------------
+// Used by EDK_LAUNCH (csrc/edk_common.cuh) when the whole library is built for the host (tests/emu/emu_runtime.cpp).
+// The threads are created once per launch and walk the grid together; between two CTAs they meet at a barrier and
+// thread 0 resets the per-CTA state (mbarriers, participation counts, shared memory poisoned with a NaN pattern).
+cudaError_t emu_launch_error(cudaError_t e, const char* what);  // records cudaGetLastError + message (emu_runtime.cpp)
+void emu_run_threads(int nthreads, const std::function<void(int)>& fn);
+
+template <class Body>
+cudaError_t emu_launch(dim3 grid, dim3 block, size_t smem_bytes, Body body) {
+    const long long nthreads = (long long)block.x * block.y * block.z;
+    const long long nctas = (long long)grid.x * grid.y * grid.z;
+    if (nthreads < 1 || nthreads > 1024 || nctas < 1 || grid.y > 65535 || grid.z > 65535)
+        return emu_launch_error(cudaErrorInvalidConfiguration, "launch configuration");
+    if (smem_bytes > (size_t)EMU_SMEM_BYTES) return emu_launch_error(cudaErrorInvalidValue, "dynamic shared memory above 227 KB");
+    g_cta.nthreads = (int)nthreads;
+    g_cta.failed = false;
+    EmuBarrier between;  // all threads of the launch, between two CTAs
+    std::mutex err_m;
+    std::string err;
+    emu_run_threads((int)nthreads, [&](int t) {
+        for (long long c = 0; c < nctas; ++c) {
+            if (t == 0) {
+                for (auto& b : g_cta.mbar) b.live = false;
+                g_cta.cta_barrier.reset();
+                for (auto& w : g_cta.warp_barrier) w.reset();
+                std::memset(smem, 0xff, smem_bytes ? smem_bytes : 0);
+            }
+            between.wait((int)nthreads);
+            threadIdx.x = (unsigned)(t % block.x);
+            threadIdx.y = (unsigned)((t / block.x) % block.y);
+            threadIdx.z = (unsigned)(t / (block.x * block.y));
+            blockIdx.x = (unsigned)(c % grid.x);
+            blockIdx.y = (unsigned)((c / grid.x) % grid.y);
+            blockIdx.z = (unsigned)(c / ((long long)grid.x * grid.y));
+            blockDim.x = block.x, blockDim.y = block.y, blockDim.z = block.z;
+            gridDim.x = grid.x, gridDim.y = grid.y, gridDim.z = grid.z;
+            try {
+                body();
+            } catch (const std::exception& e) {
+                std::lock_guard<std::mutex> lk(err_m);
+                if (err.empty()) err = e.what();
+                g_cta.failed = true;
+            }
+            // a thread that has returned no longer takes part in the CTA's barriers
+            g_cta.cta_barrier.leave((int)nthreads);
+            g_cta.warp_barrier[t >> 5].leave(emu_warp_size(t >> 5));
+            between.wait((int)nthreads);
+            if (g_cta.failed) return;
+        }
+    });
+    if (!err.empty()) return emu_launch_error(cudaErrorLaunchFailure, err.c_str());
+    return cudaSuccess;
+}
+#endif  // EDK_EMU_NO_LAUNCHERS
 
 }  // namespace edk

@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#define EDK_EMU_NO_LAUNCHERS  // this harness drives the kernels itself
 #include "edk_emu.h"
 
 thread_local EmuIdx threadIdx, blockIdx, blockDim;

@@ -1,0 +1,228 @@
+"""The WHOLE library on a machine without a GPU: csrc/*.cu (host glue of edk_api.cu, every launcher, every kernel
+source) compiled by g++ with -DEDK_HOST_EMU against tests/emu (kernel launches = one host thread per CUDA thread,
+device memory = host memory, cuTensorMapEncodeTiled = the emulator's box descriptor) and driven through the C ABI
+of include/edk.h exactly as easydistillation_b200/engine.py drives libedk_sm100a.so, against the numpy oracle.
+
+What this covers that the kernel-level emulator tests (test_pw_model.py) do not: job lists, momentum bookkeeping,
+buffer sizes, tensor-map encoding, launch configurations, the switching between the contraction forms
+(edk_debug_algo / EDK_GRAM_ALGO / edk_debug_symmetry / loader / scalar kernel), link preprocessing, blending and
+the host-buffer entry point - i.e. everything between the ctypes call and the kernel.  TEST INFRASTRUCTURE ONLY:
+the emulator library is built into a temporary directory and is never loaded by the package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+from easydistillation_b200 import _capi
+from oracle import elemental_oracle as orc
+
+SOURCES = ["edk_stencil.cu", "edk_gauge.cu", "edk_gram.cu", "edk_gram_pw.cu", "edk_api.cu"]
+D, X = _capi.MODE_DERIVATIVE, _capi.MODE_DISPLACEMENT
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("edk_emu")
+    flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-DEDK_HOST_EMU", "-I", os.path.join(REPO, "tests", "emu"),
+             "-I", os.path.join(REPO, "easydistillation_b200", "csrc"), "-I", os.path.join(REPO, "include"),
+             "-I", "/usr/local/cuda/include"]
+    jobs = []
+    for src in SOURCES:
+        obj = str(out / (src + ".o"))
+        jobs.append((obj, subprocess.Popen(["g++", *flags, "-x", "c++", "-c", os.path.join(REPO, "easydistillation_b200", "csrc", src),
+                                            "-o", obj], stderr=subprocess.PIPE, text=True)))
+    obj = str(out / "emu_runtime.o")
+    jobs.append((obj, subprocess.Popen(["g++", *flags, "-c", os.path.join(REPO, "tests", "emu", "emu_runtime.cpp"), "-o", obj],
+                                       stderr=subprocess.PIPE, text=True)))
+    for obj, p in jobs:
+        _, err = p.communicate()
+        assert p.returncode == 0, f"{obj}: {err[-3000:]}"
+    so = str(out / "libedk_emu.so")
+    r = subprocess.run(["g++", "-shared", "-o", so, *[o for o, _ in jobs], "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = C.CDLL(so)
+    for name, (res, args) in _capi.SIGNATURES.items():  # the emulator build exports the same C ABI
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+class Handle:
+    """The calls engine.py makes, on host arrays."""
+
+    def __init__(self, lib, latt3, Ne, mode, order, moms):
+        self.lib, self.latt3, self.Ne = lib, list(latt3), Ne
+        mom = np.ascontiguousarray(np.asarray(moms, np.int32).reshape(-1, 3))
+        self.h = C.c_void_p()
+        self.check(lib.edk_create(*self.latt3, Ne, mode, order, len(mom), mom.ctypes.data_as(C.POINTER(C.c_int)), 0,
+                                  C.byref(self.h)), "edk_create")
+        self.nop, self.nmom = lib.edk_num_operators(self.h), len(mom)
+
+    def check(self, rc, what):
+        assert rc == _capi.EDK_OK, f"{what}: status {rc}: {self.lib.edk_last_error().decode()}"
+
+    def set_inputs(self, U_file, V):
+        self.U, self.V = np.ascontiguousarray(U_file), np.ascontiguousarray(V)  # kept alive
+        self.check(self.lib.edk_set_links(self.h, self.U.ctypes.data, _capi.LINKS_FILE_T, None), "edk_set_links")
+        flags = _capi.EIGVECS_C8 if self.V.dtype == np.complex64 else 0
+        self.check(self.lib.edk_set_eigvecs(self.h, self.V.ctypes.data, flags, None), "edk_set_eigvecs")
+
+    def calc(self):
+        out = np.full((self.nop, self.nmom, self.Ne, self.Ne), np.nan + 0j, np.complex128)
+        self.check(self.lib.edk_calc(self.h, out.ctypes.data, None), "edk_calc")
+        return out
+
+    def query(self, what):
+        return self.lib.edk_query(self.h, what)
+
+    def close(self):
+        self.lib.edk_destroy(self.h)
+
+
+def worst_block_error(got, ref):
+    norms = np.sqrt((np.abs(ref) ** 2).sum(axis=(-1, -2)))
+    floor = 1e-4 * norms.max()
+    return max(float(np.linalg.norm(got[a, p] - ref[a, p]) / max(norms[a, p], floor))
+               for a in range(ref.shape[0]) for p in range(ref.shape[1]))
+
+
+def inputs_and_reference(latt3, Ne, mode, order, moms, seed=3):
+    latt = list(latt3) + [1]
+    U_file = orc.synthetic_links(latt, seed)
+    V = orc.synthetic_eigvecs(latt, Ne, seed)
+    U = orc.links_file_to_spatial(U_file)
+    if mode == D:
+        ref = (orc.elemental_timeslice_closed_form if order <= 2 else orc.elemental_timeslice)(V, U, latt, order, moms)
+    else:
+        ref = orc.displacement_timeslice(V, U, latt, order, moms)
+    return U_file, V, ref
+
+
+def test_every_contraction_path_through_the_c_abi(emu):
+    """num_nabla = 1, 7 momenta: TMA 3M (default), TMA 4M, plane-wave form, cp.async loader, scalar kernel - each
+    selected the way engine.py selects it, each against the oracle."""
+    latt3, Ne, moms = (4, 4, 2), 5, orc.momentum_set(7)
+    U_file, V, ref = inputs_and_reference(latt3, Ne, D, 1, moms)
+    h = Handle(emu, latt3, Ne, D, 1, moms)
+    h.set_inputs(U_file, V)
+    assert h.query(10) == 1 and h.query(7) == 3  # the library default: GEMM form, 3M
+    seen = {}
+    for algo, form, mmas in ((1, 1, 3), (0, 0, 4), (2, 2, 2)):
+        h.check(emu.edk_debug_algo(h.h, algo), "edk_debug_algo")
+        assert h.query(10) == form and h.query(7) == mmas
+        seen[f"algo {algo}"] = h.calc()
+    assert h.query(11) == 5 and h.query(3) == 1  # xy-couples (0,0), (0,1), (1,0): modes 1, cos/sin x 2; no split-K in form 2
+    h.check(emu.edk_debug_loader(h.h, 1), "edk_debug_loader")
+    assert h.query(10) == 0 and h.query(6) == 0
+    seen["cp.async loader"] = h.calc()
+    h.check(emu.edk_debug_loader(h.h, 0), "edk_debug_loader")
+    h.check(emu.edk_debug_use_naive_gram(h.h, 1), "edk_debug_use_naive_gram")
+    seen["scalar kernel"] = h.calc()
+    h.check(emu.edk_debug_use_naive_gram(h.h, 0), "edk_debug_use_naive_gram")
+    assert h.query(10) == 2  # back on the plane-wave form that was selected last
+    seen["plane-wave again"] = h.calc()
+    h.close()
+    for tag, got in seen.items():
+        assert worst_block_error(got, ref) < 1e-10, tag
+    assert np.array_equal(seen["algo 2"], seen["plane-wave again"])
+
+
+def test_plane_wave_form_selected_by_environment_and_pairing_switches(emu, monkeypatch):
+    """EDK_GRAM_ALGO=2 at edk_create (the path bench.py / tuning.apply use): configure() builds the plane-wave tables
+    itself; then both pairing modes (edk_debug_symmetry re-configures: tables are rebuilt for the new job list and
+    internal momentum list) and a switch back to the GEMM form.  num_nabla = 2, non-closed momentum list, ragged
+    planes of 15 sites."""
+    latt3, Ne = (3, 5, 2), 6
+    moms = [(0, 0, 0), (0, 0, 1), (1, 0, 0), (1, -1, 0), (0, 2, 1)]
+    U_file, V, ref = inputs_and_reference(latt3, Ne, D, 2, moms)
+    monkeypatch.setenv("EDK_GRAM_ALGO", "2")
+    h = Handle(emu, latt3, Ne, D, 2, moms)
+    monkeypatch.delenv("EDK_GRAM_ALGO")
+    assert h.query(10) == 2 and h.query(11) >= 1
+    h.set_inputs(U_file, V)
+    results = {"created with form 2": h.calc()}
+    for sym in (1, 0):
+        h.check(emu.edk_debug_symmetry(h.h, sym), "edk_debug_symmetry")
+        assert h.query(0) == sym and h.query(10) == 2 and h.query(11) >= 1
+        assert h.query(2) == (19 if sym else 34)  # pair-GEMMs: Hermitian pairing / distinct direct pairs
+        results[f"form 2, pairing {sym}"] = h.calc()
+    h.check(emu.edk_debug_algo(h.h, 1), "edk_debug_algo")
+    results["GEMM form, direct pairs"] = h.calc()
+    h.close()
+    for tag, got in results.items():
+        assert worst_block_error(got, ref) < 1e-10, tag
+
+
+def test_plane_wave_multi_tile_and_mirror_tiles(emu):
+    """Ne = 45 -> 16 x 32 tiles, 3 x 2 of them; the self pair (W0, W0) of num_nabla = 1 skips the tile below the
+    diagonal and the fold kernel reads its mirror."""
+    latt3, Ne, moms = (4, 2, 2), 45, orc.momentum_set(7)
+    U_file, V, ref = inputs_and_reference(latt3, Ne, D, 1, moms)
+    h = Handle(emu, latt3, Ne, D, 1, moms)
+    h.check(emu.edk_debug_algo(h.h, 2), "edk_debug_algo")
+    assert h.query(12) == 24 and h.query(0) == 1
+    h.set_inputs(U_file, V)
+    got = h.calc()
+    h.close()
+    assert worst_block_error(got, ref) < 1e-10
+
+
+def test_displacement_mode_both_forms(emu):
+    latt3, Ne, moms = (3, 5, 2), 7, orc.momentum_set(9)
+    U_file, V, ref = inputs_and_reference(latt3, Ne, X, 3, moms)
+    h = Handle(emu, latt3, Ne, X, 3, moms)
+    h.set_inputs(U_file, V)
+    for algo in (1, 2):
+        h.check(emu.edk_debug_algo(h.h, algo), "edk_debug_algo")
+        assert worst_block_error(h.calc(), ref) < 1e-10, algo
+    h.close()
+
+
+def test_link_preprocessing_blending_and_host_entry_point(emu):
+    """stout smearing + SU(3) projection recorded with edk_set_link_ops, the blending matrix, and edk_calc_host
+    (host buffers in, result out, staging inside) with big-endian complex64 eigenvectors and big-endian links, on the
+    plane-wave form."""
+    latt3, Ne, moms = (4, 4, 2), 4, orc.momentum_set(7)
+    latt = list(latt3) + [1]
+    U_file = orc.synthetic_links(latt, 5, kind="weak")
+    V = orc.synthetic_eigvecs(latt, Ne, 5)
+    U = orc.project_su3_timeslice(orc.stout_smear_timeslice(orc.links_file_to_spatial(U_file), 2, 0.1))
+    coeff = orc.blending_matrix(Ne, ([6, 5], [2, 2]))
+    ref = orc.elemental_timeslice_closed_form(V, U, latt, 1, moms, stocastic_coeff=coeff)
+    h = Handle(emu, latt3, Ne, D, 1, moms)
+    h.check(emu.edk_debug_algo(h.h, 2), "edk_debug_algo")
+    kinds, nsteps, rhos = (C.c_int * 2)(1, 2), (C.c_int * 2)(2, 0), (C.c_double * 2)(0.1, 0.0)
+    h.check(emu.edk_set_link_ops(h.h, 2, kinds, nsteps, rhos), "edk_set_link_ops")
+    cf = np.ascontiguousarray(coeff, np.float64)
+    h.check(emu.edk_set_blending(h.h, cf.ctypes.data, None), "edk_set_blending")
+    U_be = np.ascontiguousarray(U_file.astype(">c16"))
+    V_be = np.ascontiguousarray(orc.round_through_c8(V).astype(">c8"))
+    out = np.full(ref.shape, np.nan + 0j, np.complex128)
+    h.check(emu.edk_calc_host(h.h, U_be.ctypes.data, _capi.LINKS_FILE_T | _capi.LINKS_BIG_ENDIAN, V_be.ctypes.data,
+                              _capi.EIGVECS_C8 | _capi.EIGVECS_BIG_ENDIAN, out.ctypes.data, None), "edk_calc_host")
+    links = np.empty((3, latt3[2], latt3[1], latt3[0], 3, 3), np.complex128)
+    h.check(emu.edk_debug_links(h.h, links.ctypes.data, None), "edk_debug_links")
+    h.close()
+    assert np.abs(links - U).max() < 1e-12
+    assert worst_block_error(out, ref) < 1e-10
+
+
+def test_laplacian_and_state_errors(emu):
+    latt3, Ne, moms = (4, 3, 2), 3, [(0, 0, 0)]
+    latt = list(latt3) + [1]
+    U_file, V, _ = inputs_and_reference(latt3, Ne, D, 0, moms)
+    h = Handle(emu, latt3, Ne, D, 0, moms)
+    out = np.empty((1, 1, Ne, Ne), np.complex128)
+    assert emu.edk_calc(h.h, out.ctypes.data, None) == _capi.EDK_ERR_STATE  # nothing set yet
+    assert b"must be set first" in emu.edk_last_error()
+    assert emu.edk_debug_algo(h.h, 3) == _capi.EDK_ERR_ARG
+    h.set_inputs(U_file, V)
+    F = np.ascontiguousarray(orc.round_through_c8(V).astype(np.complex128))
+    LF = np.empty_like(F)
+    h.check(emu.edk_laplacian(h.h, F.ctypes.data, LF.ctypes.data, Ne, None), "edk_laplacian")
+    h.close()
+    ref = orc.laplacian(F, orc.links_file_to_spatial(U_file))
+    assert np.linalg.norm(LF - ref) / np.linalg.norm(ref) < 1e-13
