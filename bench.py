@@ -63,13 +63,14 @@ def algorithmic(name, distance=None):
     return flops, 4 * Ne * V * 48.0 + 3 * V * 144.0
 
 
-def stencil_bytes_moved(name, distance=None):
-    """... plus what this build's nabla3 additionally has to write: the Re+Im plane of each output
-    field (8 B per element), which the 3M contraction reads as its third A operand."""
+def stencil_bytes_moved(name, distance=None, planes=True):
+    """... plus what this build's nabla3 additionally has to write when the GEMM form of the contraction is in
+    use: the Re+Im plane of each output field (8 B per element), which the 3M arithmetic reads as its third A
+    operand.  With the plane-wave form (`planes=False`) the pass moves SURVEY's bytes and nothing else."""
     Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
     V = Lx * Ly * Lz
     base = algorithmic(name, distance)[1]
-    return base if distance is not None else base + 3 * Ne * V * 24.0
+    return base if (distance is not None or not planes) else base + 3 * Ne * V * 24.0
 
 
 def measured_traffic(kernel, name):
@@ -508,7 +509,7 @@ def run_native(args):
         achieved_tf = exec_flops / (gram_ms * 1e-3) / 1e12
         survey_tf = flops / (gram_ms * 1e-3) / 1e12
         # stencil: bytes of ONE launch (nabla3: 1 source, 3 outputs, links once; displacement step: 6 in, 6 + mean out)
-        st_moved = stencil_bytes_moved(name, dist_)
+        st_moved = stencil_bytes_moved(name, dist_, planes=not pw_form)
         st_gbs = st_moved / (st_ms * 1e-3) / 1e9 if prof["stencil"]["launches"] else None
         st_survey_gbs = st_bytes_launch / (st_ms * 1e-3) / 1e9 if prof["stencil"]["launches"] else None
         cpu_val, cpu_smp = (None, "skipped (--no-cpu-baseline)")
@@ -561,8 +562,10 @@ def run_native(args):
                 "achieved": st_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (st_gbs / hbm_peak) if st_gbs else None,
                 "traffic": measured_traffic(st_name, name if dist_ is None else name + "_displacement"), "peak_source": hbm_src, "algorithmic_bytes_per_launch": st_moved,
                 "survey_bytes_per_launch": st_bytes_launch, "survey_equivalent_gbs": st_survey_gbs,
-                "note": "algorithmic bytes = 1 field in + 3 fields out + links (SURVEY 8d) + the 3 Re+Im planes (8 B per element) "
-                        "this build's stencil writes for the 3M contraction; survey_equivalent_gbs counts SURVEY's bytes only",
+                "note": ("algorithmic bytes = 1 field in + 3 fields out + links (SURVEY 8d); the Re+Im planes are not written "
+                         "when the plane-wave form of the contraction is in use") if (pw_form or dist_ is not None) else
+                        ("algorithmic bytes = 1 field in + 3 fields out + links (SURVEY 8d) + the 3 Re+Im planes (8 B per element) "
+                         "this build's stencil writes for the 3M contraction; survey_equivalent_gbs counts SURVEY's bytes only"),
                 "ms_per_launch": st_ms, "launches_per_step": st_launch / K,
                 "share_of_step": prof["stencil"]["ms"] / ms,
             },

@@ -1132,11 +1132,15 @@ int edk_calc(edk_handle* h, void* out_dev, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     EDK_CUDA_TRY(cudaSetDevice(h->device));
     if (h->mode == EDK_MODE_DERIVATIVE) {
+        // only the GEMM form's 3M arithmetic reads the Re + Im planes of the derived fields; the fields are rebuilt by
+        // every call, so the choice follows the contraction form in use right now (W0's plane is always written)
+        const bool planes = effective_algo(h) != 2;
         for (const auto& hop : h->hops) {
             PhaseTimer t(h, s, PH_STENCIL, 1);
             EDK_CUDA_TRY(launch_nabla3(h->field(hop.first), h->field(hop.second), h->field(hop.second + 1),
-                                       h->field(hop.second + 2), h->field_sum(hop.second), h->field_sum(hop.second + 1),
-                                       h->field_sum(hop.second + 2), h->sum_row, h->links, h->g, h->Ne, s));
+                                       h->field(hop.second + 2), planes ? h->field_sum(hop.second) : nullptr,
+                                       planes ? h->field_sum(hop.second + 1) : nullptr,
+                                       planes ? h->field_sum(hop.second + 2) : nullptr, h->sum_row, h->links, h->g, h->Ne, s));
         }
     } else {
         for (int k = 1; k <= h->order; ++k) {

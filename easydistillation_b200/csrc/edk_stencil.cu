@@ -188,6 +188,9 @@ cudaError_t launch_phase_table(cplx* phase, cplx* rot, const int* mom3_dev, int 
 constexpr int NABLA_SITES = 64;  // sites per CTA (threadIdx.x), threadIdx.y = direction
 constexpr int NABLA_THREADS = NABLA_SITES * 3;
 
+// PLANE: also write the real Re + Im plane of every output element (the third A operand of the 3M contraction);
+// the plane-wave form of the contraction does not read it, and without it the pass moves 27 % fewer bytes.
+template <bool PLANE>
 __global__ void __launch_bounds__(NABLA_THREADS, 2)
 nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restrict__ o1, cplx* __restrict__ o2,
               double* __restrict__ s0, double* __restrict__ s1, double* __restrict__ s2, size_t sum_row,
@@ -234,7 +237,7 @@ nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restric
         Ub[m] = ldg(pl + m);
     }
     cplx* out = (d == 0 ? o0 : (d == 1 ? o1 : o2)) + (size_t)warp_site0 * 3;  // the warp's block
-    double* outs = (d == 0 ? s0 : (d == 1 ? s1 : s2)) + (size_t)warp_site0 * 3;  // its Re + Im plane
+    double* outs = PLANE ? (d == 0 ? s0 : (d == 1 ? s1 : s2)) + (size_t)warp_site0 * 3 : nullptr;  // its Re + Im plane
     const int warp_cplx = warp_sites * 3;
     auto apply = [&](int e, const cplx (&f)[3], const cplx (&b)[3]) {
         cplx r[3];
@@ -258,7 +261,7 @@ nabla3_kernel(const cplx* __restrict__ W, cplx* __restrict__ o0, cplx* __restric
             if (j * 32 + lane < warp_cplx) {
                 const cplx v = my_stage[j * 32 + lane];
                 po[j * 32 + lane] = v;
-                ps[j * 32 + lane] = v.x + v.y;
+                if (PLANE) ps[j * 32 + lane] = v.x + v.y;
             }
     };
     for (int e = e0; e < e1; e += 2) {
@@ -299,7 +302,9 @@ cudaError_t launch_nabla3(const cplx* W_in, cplx* out_x, cplx* out_y, cplx* out_
     const int chunk = stencil_chunk(g.V, NABLA_SITES, Ne);
     dim3 block(NABLA_SITES, 3);
     dim3 grid((g.V + NABLA_SITES - 1) / NABLA_SITES, (Ne + chunk - 1) / chunk);
-    EDK_LAUNCH(nabla3_kernel, grid, block, 0, s, W_in, out_x, out_y, out_z, sum_x, sum_y, sum_z, sum_row, links, g, Ne, chunk);
+    if ((sum_x != nullptr) != (sum_y != nullptr) || (sum_x != nullptr) != (sum_z != nullptr)) return cudaErrorInvalidValue;
+    auto kern = sum_x ? nabla3_kernel<true> : nabla3_kernel<false>;  // planes are written for all three outputs or none
+    EDK_LAUNCH(kern, grid, block, 0, s, W_in, out_x, out_y, out_z, sum_x, sum_y, sum_z, sum_row, links, g, Ne, chunk);
     return cudaGetLastError();
 }
 
