@@ -9,6 +9,7 @@ from .preset import (
     EigenvectorHostmem,
     EigenvectorNpy,
     EigenvectorTimeSlice,
+    ElementalBinary,
     ElementalNpy,
     GaugeFieldBinary,
     GaugeFieldHostmem,
@@ -20,5 +21,5 @@ __all__ = [
     "ElementalGenerator", "DisplacementElementalGenerator", "Laplacian", "MomentumPhase", "derivative",
     "GaugeFieldBinary", "GaugeFieldNpy", "GaugeFieldHostmem", "GaugeFieldIldg", "EigenvectorNpy", "EigenvectorHostmem",
     "EigenvectorTimeSlice",
-    "ElementalNpy", "Nc", "Ns", "Nd",
+    "ElementalNpy", "ElementalBinary", "Nc", "Ns", "Nd",
 ]

@@ -214,3 +214,40 @@ class ElementalNpy(_KeyedFile, Elemental):
             raise ValueError(f"{self._name(key)} has shape {mm.shape} / dtype {mm.dtype}, expected {tuple(shape)} / {dtype}")
         self.file = self.data = None
         return mm
+
+
+class ElementalBinary(_KeyedFile, Elemental):
+    """Raw little-endian binary [Nop, Nmom, Lt, Ne, Ne] without a header (lattice/preset.py:129-137,
+    lattice/filedata/binary.py:16-62): shape and dtype come from the constructor, as in the reference."""
+
+    def __init__(self, prefix: str, suffix: str, shape: List[int] = [40, 27, 128, 70, 70], totNe: int = 70, dtype: str = "<c16") -> None:
+        _KeyedFile.__init__(self, prefix, ".stout.n20.f0.12.nev70.meson" if suffix is None else suffix)
+        Elemental.__init__(self, FileMetaData(shape, dtype, 0), totNe)
+
+    def load(self, key: str):
+        name = self._name(key)
+        if self.file != name:
+            mm = np.memmap(name, dtype=self.elem.dtype, mode="r", shape=tuple(self.elem.shape))
+            self.file, self.data = name, ArrayData(mm, name)
+        return self.data
+
+    def _check(self, shape, dtype):
+        if [int(v) for v in shape] != [int(v) for v in self.elem.shape] or np.dtype(dtype) != np.dtype(self.elem.dtype):
+            raise ValueError(f"ElementalBinary declared {self.elem.shape} / {self.elem.dtype}, asked to hold {list(shape)} / {dtype}: "
+                             "a headerless file can only be read back with the shape and dtype it was written with")
+
+    def create(self, key: str, shape: Sequence[int], dtype: str = "<c16") -> np.memmap:
+        self._check(shape, dtype)
+        self.file = self.data = None
+        return np.memmap(self._name(key), dtype=dtype, mode="w+", shape=tuple(int(v) for v in shape))
+
+    def open_rw(self, key: str, shape: Sequence[int], dtype: str = "<c16") -> np.memmap:
+        import os
+
+        self._check(shape, dtype)
+        name = self._name(key)
+        want = int(np.prod([int(v) for v in shape])) * np.dtype(dtype).itemsize
+        if os.path.getsize(name) != want:
+            raise ValueError(f"{name} holds {os.path.getsize(name)} bytes, expected {want}")
+        self.file = self.data = None
+        return np.memmap(name, dtype=dtype, mode="r+", shape=tuple(int(v) for v in shape))

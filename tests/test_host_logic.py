@@ -335,6 +335,17 @@ def test_calc_to_file_layout_slabs_and_downcast(tmp_path):
     with pytest.raises(ValueError):
         gen.calc_to_file(handle, "two", t_range=(5, 10), dtype="<c16")  # existing file has another dtype
 
+    # the reference's other elemental preset: headerless raw binary, shape and dtype declared by the handle
+    # (lattice/preset.py:129-137); written here, read back by the REFERENCE's byte layout (numpy.fromfile)
+    raw = edb.ElementalBinary(str(tmp_path) + "/", ".meson", [Nop, Nmom, Lt, Ne, Ne], Ne)
+    gen.calc_to_file(raw, "bin", t_range=(0, 5))
+    gen.calc_to_file(raw, "bin", t_range=(5, 10))
+    flat = np.fromfile(tmp_path / "bin.meson", dtype="<c16").reshape(Nop, Nmom, Lt, Ne, Ne)
+    assert np.array_equal(flat, full.transpose(1, 2, 0, 3, 4))
+    assert np.array_equal(raw.load("bin")[2, 1, 9], full[9, 2, 1])
+    with pytest.raises(ValueError):
+        gen.calc_to_file(raw, "bin", dtype="<c8")  # a headerless file cannot change dtype silently
+
     class Broken(Fake):
         def calc_range(self, t0, t1):
             if t0 >= 4:
