@@ -23,10 +23,8 @@ SOURCES = ["edk_stencil.cu", "edk_gauge.cu", "edk_gram.cu", "edk_gram_pw.cu", "e
 D, X = _capi.MODE_DERIVATIVE, _capi.MODE_DISPLACEMENT
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    out = tmp_path_factory.mktemp("edk_emu")
-    flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-DEDK_HOST_EMU", "-I", os.path.join(REPO, "tests", "emu"),
+def build_emulator_library(out, extra_flags=()):
+    flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-DEDK_HOST_EMU", *extra_flags, "-I", os.path.join(REPO, "tests", "emu"),
              "-I", os.path.join(REPO, "easydistillation_b200", "csrc"), "-I", os.path.join(REPO, "include"),
              "-I", "/usr/local/cuda/include"]
     jobs = []
@@ -41,13 +39,22 @@ def emu(tmp_path_factory):
         _, err = p.communicate()
         assert p.returncode == 0, f"{obj}: {err[-3000:]}"
     so = str(out / "libedk_emu.so")
-    r = subprocess.run(["g++", "-shared", "-o", so, *[o for o, _ in jobs], "-lpthread"], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", *extra_flags, "-o", so, *[o for o, _ in jobs], "-lpthread"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+    return so
+
+
+def load_emulator_library(so):
     lib = C.CDLL(so)
     for name, (res, args) in _capi.SIGNATURES.items():  # the emulator build exports the same C ABI
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
     return lib
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    return load_emulator_library(build_emulator_library(tmp_path_factory.mktemp("edk_emu")))
 
 
 class Handle:
@@ -135,8 +142,8 @@ def test_plane_wave_form_selected_by_environment_and_pairing_switches(emu, monke
     itself; then both pairing modes (edk_debug_symmetry re-configures: tables are rebuilt for the new job list and
     internal momentum list) and a switch back to the GEMM form.  num_nabla = 2, non-closed momentum list, ragged
     planes of 15 sites."""
-    latt3, Ne = (3, 5, 2), 6
-    moms = [(0, 0, 0), (0, 0, 1), (1, 0, 0), (1, -1, 0), (0, 2, 1)]
+    latt3, Ne = (3, 5, 2), 4
+    moms = [(0, 0, 1), (1, 0, 0), (1, -1, 0), (0, 2, 1)]
     U_file, V, ref = inputs_and_reference(latt3, Ne, D, 2, moms)
     monkeypatch.setenv("EDK_GRAM_ALGO", "2")
     h = Handle(emu, latt3, Ne, D, 2, moms)
@@ -226,3 +233,41 @@ def test_laplacian_and_state_errors(emu):
     h.close()
     ref = orc.laplacian(F, orc.links_file_to_spatial(U_file))
     assert np.linalg.norm(LF - ref) / np.linalg.norm(ref) < 1e-13
+
+
+def memcheck_cases(lib):
+    """Small runs that touch every kernel family; executed by the AddressSanitizer test below in a child process."""
+    cases = [((4, 4, 2), 5, D, 1, orc.momentum_set(7), (1, 0, 2)),            # stencil + GEMM forms + plane-wave form
+             ((3, 5, 2), 3, D, 2, [(1, -1, 0), (0, 2, 1)], (2, 1)),            # ragged planes, second-order fields
+             ((3, 5, 2), 7, X, 2, orc.momentum_set(9), (1, 2)),                 # displacement lines
+             ((4, 2, 2), 45, D, 1, orc.momentum_set(7), (2,))]                  # multi-tile plane-wave run with mirror tiles
+    worst = 0.0
+    for latt3, Ne, mode, order, moms, algos in cases:
+        U_file, V, ref = inputs_and_reference(latt3, Ne, mode, order, moms)
+        h = Handle(lib, latt3, Ne, mode, order, moms)
+        h.set_inputs(U_file, V)
+        for algo in algos:
+            h.check(lib.edk_debug_algo(h.h, algo), "edk_debug_algo")
+            worst = max(worst, worst_block_error(h.calc(), ref))
+        h.close()
+    return worst
+
+
+def test_emulated_library_is_clean_under_address_sanitizer(tmp_path):
+    """compute-sanitizer memcheck without a GPU: the emulator build with -fsanitize=address (every cudaMalloc is a
+    separate redzoned heap block, kernels touch it through plain pointers) runs the stencil, both GEMM arithmetics,
+    the plane-wave form and the displacement lines; any out-of-bounds global access of a kernel or of the host glue
+    aborts the child."""
+    import sys
+
+    libasan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(libasan) or not os.path.exists(libasan):
+        pytest.skip("no AddressSanitizer runtime for this g++")
+    so = build_emulator_library(tmp_path, ("-g", "-fsanitize=address", "-fno-omit-frame-pointer"))
+    code = ("import sys; sys.path[:0] = [%r, %r]; import test_emu_library as T; "
+            "w = T.memcheck_cases(T.load_emulator_library(%r)); print('EDK_ASAN_OK', w); assert w < 1e-10"
+            % (REPO, os.path.join(REPO, "tests"), so))
+    env = dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1:abort_on_error=0")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=1500)
+    assert r.returncode == 0 and "EDK_ASAN_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-4000:])
+
