@@ -132,8 +132,13 @@ def elemental_timeslice(V_t, U_t, latt_size, num_nabla, momentum_list, stocastic
     For every derivative tuple and every left/right split S of its positions:
     right = nabla over the picked directions in order, left = nabla over the
     remaining ones in reversed order, weight (-1)^|S| (elemental.py:309-329).
-    Returns (num_derivative, Nmom, Ne, Ne) complex128."""
-    V = round_through_c8(np.asarray(V_t))
+    Returns (num_derivative, Nmom, Ne, Ne) complex128.
+
+    The rounded eigenvectors are held in complex128: the reference keeps them in its complex64 buffer and relies on
+    the einsum path (phase x left first, then a complex128 tensordot) for FP64 accumulation, which is the path at
+    every size its tests and the goldens use; for toy shapes (Ne = 2, V = 8) numpy's path optimiser may instead
+    multiply the two complex64 operands first, which would make the zero-derivative block a float32 sum."""
+    V = round_through_c8(np.asarray(V_t)).astype(np.complex128)
     Ne = V.shape[0]
     nder = num_derivative(num_nabla)
     out = np.zeros((nder, len(momentum_list), Ne, Ne), np.complex128)

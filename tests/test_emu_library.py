@@ -235,6 +235,21 @@ def test_laplacian_and_state_errors(emu):
     assert np.linalg.norm(LF - ref) / np.linalg.norm(ref) < 1e-13
 
 
+@pytest.mark.parametrize("latt3,Ne,order,moms", [
+    ((2, 2, 2), 2, 3, [(0, 0, 0), (1, 0, 1)]),                      # num_nabla = 3: 40 operators, jobs of up to 8 segments
+    ((4, 2, 2), 3, 1, [(0, 1, 0), (0, 1, 0), (0, -1, 0), (5, 0, -3)]),  # repeated momenta, |p| > L
+    ((3, 2, 1), 1, 2, [(0, 0, 0)]),                                 # one eigenvector, one momentum, Lz = 1
+])
+def test_plane_wave_form_edge_cases(emu, latt3, Ne, order, moms):
+    U_file, V, ref = inputs_and_reference(latt3, Ne, D, order, moms)
+    h = Handle(emu, latt3, Ne, D, order, moms)
+    h.check(emu.edk_debug_algo(h.h, 2), "edk_debug_algo")
+    h.set_inputs(U_file, V)
+    got = h.calc()
+    h.close()
+    assert worst_block_error(got, ref) < 1e-10
+
+
 def memcheck_cases(lib):
     """Small runs that touch every kernel family; executed by the AddressSanitizer test below in a child process."""
     cases = [((4, 4, 2), 5, D, 1, orc.momentum_set(7), (1, 0, 2)),            # stencil + GEMM forms + plane-wave form
