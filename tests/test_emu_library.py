@@ -250,6 +250,42 @@ def test_plane_wave_form_edge_cases(emu, latt3, Ne, order, moms):
     assert worst_block_error(got, ref) < 1e-10
 
 
+def test_integration_md_ctypes_stub_runs_as_written(emu):
+    """INTEGRATION.md section B shows the ctypes stub a reference maintainer would add (lattice/generator/_edk.py).
+    The code block is executed here verbatim, bound to the emulator build of the same C ABI, and its
+    EdkHandle.calc(U_t, V_t, out) must reproduce the reference algorithm for one timeslice."""
+    import re
+
+    text = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# lattice/generator/_edk\.py.*?)```", text, re.S).group(1)
+    assert 'C.CDLL("libedk_sm100a.so")' in block
+    ns = {}
+    exec(compile(block.replace('C.CDLL("libedk_sm100a.so")', f"C.CDLL({emu._name!r})"), "INTEGRATION.md", "exec"), ns)
+    latt, Ne, moms = [4, 2, 2, 1], 3, [(0, 0, 0), (0, 1, 1)]
+    U_file, V, ref = inputs_and_reference(latt[:3], Ne, D, 1, moms)
+    V8 = np.ascontiguousarray(V.astype(np.complex64))  # the reference's staging buffer is complex64 (elemental.py:55)
+    out = np.zeros(ref.shape, np.complex128)
+    handle = ns["EdkHandle"](latt, Ne, ns["EDK_MODE_DERIVATIVE"], 1, moms)
+    handle.calc(np.ascontiguousarray(U_file), V8, out)
+    assert worst_block_error(out, ref) < 1e-10
+    with pytest.raises(ValueError):  # EDK_ERR_ARG maps to the reference's ValueError
+        ns["EdkHandle"](latt, 0, ns["EDK_MODE_DERIVATIVE"], 1, moms)
+
+
+def test_reference_class_bound_to_the_c_abi_matches_its_own_numpy_path(emu):
+    """Where the reference checkout exists (the build container): the UNMODIFIED lattice.ElementalGenerator with the
+    three touch points of INTEGRATION.md B and the stub of that section, fed by the reference's own loaders, against
+    the reference's own numpy calc(t) (tests/emu/reference_binding_check.py, in a child process because importing
+    the reference needs the oracle's shims on sys.path)."""
+    import sys
+
+    if not os.path.isdir(os.environ.get("EDK_REFERENCE_ROOT", "/root/reference")):
+        pytest.skip("no reference checkout on this machine")
+    r = subprocess.run([sys.executable, os.path.join(REPO, "tests", "emu", "reference_binding_check.py"), emu._name],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "EDK_BINDING_OK" in r.stdout, (r.stdout[-1000:], r.stderr[-3000:])
+
+
 def memcheck_cases(lib):
     """Small runs that touch every kernel family; executed by the AddressSanitizer test below in a child process."""
     cases = [((4, 4, 2), 5, D, 1, orc.momentum_set(7), (1, 0, 2)),            # stencil + GEMM forms + plane-wave form
