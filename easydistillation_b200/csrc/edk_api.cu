@@ -57,10 +57,13 @@ struct edk_handle {
     bool tma_ready = false;
     int loader = 0;
     int algo = 1;  // contraction: 1 = GEMM form, 3M arithmetic (three real MMAs per complex block), 0 = GEMM form, 4M,
-                   // 2 = plane-wave factorised form (edk_gram_pw.cu)
+                   // 2 = plane-wave factorised form (edk_gram_pw.cu), 3 = the same with centre-symmetric site pairs folded
     // plane-wave factorised contraction (algo 2): xy-mode weights, per-plane sums Y, z phases
     PwTma pw_tma{};
     bool pw_ready = false;
+    int pw_algo = 0;              // the form (2 or 3) the tables below were built for
+    int pw_npass = 0;             // launches of the plane kernel per timeslice
+    int* pw_slotmode = nullptr;   // form 3: [mbtot][8] compact mode index of every weight-tile row (-1 = unused)
     int pw_nmodes = 0, pw_mbtot = 0, pw_kplane = 0;
     int pw_el = 2, pw_fl = 4;     // tile shape: (8 el) rows of L x (8 fl) rows of R per CTA
     double* pw_wtiles = nullptr;  // [kplane][2][mbtot][32]
@@ -387,7 +390,7 @@ void pick_gram_config(edk_handle* h) {
         ks = std::max(ks, (ksteps + 4095) / 4096);
         ks = std::min(ks, std::max(1, ksteps / 16));
         ks = std::min(ks, 64);
-        if (h->algo == 2 && h->loader == 0 && !h->naive) ks = 1;  // the plane-wave form writes split 0 only
+        if (h->algo >= 2 && h->loader == 0 && !h->naive) ks = 1;  // the plane-wave forms write split 0 only
     } else {
         ks = std::min(h->force_ksplit, ksteps);
     }
@@ -514,6 +517,8 @@ void free_pw(edk_handle* h) {
     cudaFree(h->pw_Y);
     cudaFree(h->pw_zphase);
     cudaFree(h->pw_momode);
+    cudaFree(h->pw_slotmode);
+    h->pw_slotmode = nullptr;
     h->pw_wtiles = nullptr;
     h->pw_Y = nullptr;
     h->pw_zphase = nullptr;
@@ -528,17 +533,41 @@ int build_pw(edk_handle* h) {
     EncodeFn encode = tensor_map_encoder();
     if (!encode) return EDK_ERR_CUDA;
     const ModePlan mp = plan_modes(h->mom_int);
+    const bool fold = h->algo == 3;
+    const int A = h->g.Lx * h->g.Ly;
     h->pw_nmodes = (int)mp.modes3.size() / 3;
-    h->pw_mbtot = (h->pw_nmodes + 7) / 8;
-    h->pw_kplane = (h->g.Lx * h->g.Ly + 7) / 8;
-    pw_pick_tile(h->Ne, &h->pw_el, &h->pw_fl);
+    // form 3: the {+q, -q} couples, eight per pass; a pass has a block of cos rows and a block of sin rows
+    std::vector<int> slotmode;
+    if (fold) {
+        std::vector<std::pair<int, int>> couples;  // (cos mode, sin mode or -1), in mode order
+        for (int m = 0; m < h->pw_nmodes; ++m) {
+            if (mp.modes3[3 * m + 2] != 0) continue;
+            const bool has_sin = m + 1 < h->pw_nmodes && mp.modes3[3 * (m + 1) + 2] == 1 &&
+                                 mp.modes3[3 * (m + 1)] == mp.modes3[3 * m] && mp.modes3[3 * (m + 1) + 1] == mp.modes3[3 * m + 1];
+            couples.push_back({m, has_sin ? m + 1 : -1});
+        }
+        h->pw_npass = ((int)couples.size() + 7) / 8;
+        h->pw_mbtot = 2 * h->pw_npass;
+        slotmode.assign((size_t)h->pw_mbtot * 8, -1);
+        for (size_t c = 0; c < couples.size(); ++c) {
+            slotmode[(2 * (c / 8)) * 8 + c % 8] = couples[c].first;
+            slotmode[(2 * (c / 8) + 1) * 8 + c % 8] = couples[c].second;
+        }
+        h->pw_kplane = ((A + 1) / 2 + 7) / 8;  // stages of 8 site pairs
+        h->pw_el = 2, h->pw_fl = 4;           // both sites' operands are live: only 16 x 32 tiles stay spill-free
+    } else {
+        h->pw_mbtot = (h->pw_nmodes + 7) / 8;
+        h->pw_npass = (h->pw_mbtot + PW_MAX_MB - 1) / PW_MAX_MB;
+        h->pw_kplane = (A + 7) / 8;
+        pw_pick_tile(h->Ne, &h->pw_el, &h->pw_fl);
+    }
     if (const char* t = getenv("EDK_PW_TILE")) {  // A/B hook: "24" = 16 x 32 tiles, "25" = 16 x 40
         if (!strcmp(t, "24")) h->pw_el = 2, h->pw_fl = 4;
         if (!strcmp(t, "25")) h->pw_el = 2, h->pw_fl = 5;
     }
     const int rows_l = PW_WARPS * h->pw_el, rows_r = 8 * h->pw_fl;
     int smem = 0;
-    if (pw_plan_smem(h->pw_el, h->pw_fl, &h->pw_tma.nstages, &smem) != 0) {
+    if ((fold ? pwf_plan_smem(h->pw_el, h->pw_fl, &h->pw_tma.nstages, &smem) : pw_plan_smem(h->pw_el, h->pw_fl, &h->pw_tma.nstages, &smem)) != 0) {
         set_error("no shared-memory plan for the plane-wave contraction");
         return EDK_ERR_ARG;
     }
@@ -549,6 +578,10 @@ int build_pw(edk_handle* h) {
     EDK_CUDA_TRY(cudaMalloc(&h->pw_wtiles, wt_bytes));
     EDK_CUDA_TRY(cudaMalloc(&h->pw_zphase, zp_bytes));
     EDK_CUDA_TRY(cudaMalloc(&h->pw_momode, mp.momode.size() * sizeof(int)));
+    if (fold) {
+        EDK_CUDA_TRY(cudaMalloc(&h->pw_slotmode, slotmode.size() * sizeof(int)));
+        EDK_CUDA_TRY(cudaMemcpy(h->pw_slotmode, slotmode.data(), slotmode.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     {
         const cudaError_t e = cudaMalloc(&h->pw_Y, y_bytes);
         if (e != cudaSuccess) {
@@ -559,7 +592,9 @@ int build_pw(edk_handle* h) {
     }
     EDK_CUDA_TRY(cudaMalloc(&modes_dev, mp.modes3.size() * sizeof(int)));
     cudaError_t e = cudaMemcpy(modes_dev, mp.modes3.data(), mp.modes3.size() * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_pw_weights(h->pw_wtiles, modes_dev, h->pw_nmodes, h->pw_mbtot, h->pw_kplane, h->g, 0);
+    if (e == cudaSuccess)
+        e = fold ? launch_pwf_weights(h->pw_wtiles, modes_dev, h->pw_slotmode, h->pw_mbtot, h->pw_kplane, h->g, 0)
+                 : launch_pw_weights(h->pw_wtiles, modes_dev, h->pw_nmodes, h->pw_mbtot, h->pw_kplane, h->g, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(modes_dev);
     if (e != cudaSuccess) {
@@ -567,27 +602,42 @@ int build_pw(edk_handle* h) {
         return EDK_ERR_CUDA;
     }
     h->launches += 1;
-    // exp(2 pi i pz z / Lz) with pz z reduced mod Lz in integers
-    std::vector<double> zp((size_t)h->nmom_int * h->g.Lz * 2);
-    for (int p = 0; p < h->nmom_int; ++p)
-        for (int z = 0; z < h->g.Lz; ++z) {
-            const long long Lz = h->g.Lz;
-            const long long r = (((long long)h->mom_int[3 * p + 2] * z) % Lz + Lz) % Lz;
-            double c = 1.0, sn = 0.0;
-            if (4 * r == Lz) {  // exact values on the axes
-                c = 0.0, sn = 1.0;
-            } else if (2 * r == Lz) {
-                c = -1.0, sn = 0.0;
-            } else if (4 * r == 3 * Lz) {
-                c = 0.0, sn = -1.0;
-            } else if (r != 0) {
-                const double a = 2.0 * 3.14159265358979323846 * (double)r / (double)Lz;
-                c = cos(a);
-                sn = sin(a);
-            }
-            zp[2 * ((size_t)p * Lz + z)] = c;
-            zp[2 * ((size_t)p * Lz + z) + 1] = sn;
+    // exp(2 pi i pz z / Lz) with pz z reduced mod Lz in integers; form 3 takes its xy-modes about the centre of the
+    // plane, which leaves the constant exp(i sigma delta_q), delta_q = pi (qx (Lx-1)/Lx + qy (Ly-1)/Ly), per momentum
+    auto unit = [](long long num, long long den, double& c, double& sn) {  // exp(2 pi i num / den), exact on the axes
+        const long long r = (num % den + den) % den;
+        c = 1.0, sn = 0.0;
+        if (4 * r == den) {
+            c = 0.0, sn = 1.0;
+        } else if (2 * r == den) {
+            c = -1.0, sn = 0.0;
+        } else if (4 * r == 3 * den) {
+            c = 0.0, sn = -1.0;
+        } else if (r != 0) {
+            const double a = 2.0 * 3.14159265358979323846 * (double)r / (double)den;
+            c = cos(a);
+            sn = sin(a);
         }
+    };
+    std::vector<double> zp((size_t)h->nmom_int * h->g.Lz * 2);
+    for (int p = 0; p < h->nmom_int; ++p) {
+        double kc = 1.0, ks = 0.0;  // the constant of form 3
+        if (fold) {
+            const int mc = mp.momode[3 * p], sigma = mp.momode[3 * p + 2];
+            const long long qx = mp.modes3[3 * mc], qy = mp.modes3[3 * mc + 1];
+            double cx, sx, cy, sy;
+            unit(sigma * qx * (h->g.Lx - 1), 2LL * h->g.Lx, cx, sx);
+            unit(sigma * qy * (h->g.Ly - 1), 2LL * h->g.Ly, cy, sy);
+            kc = cx * cy - sx * sy;
+            ks = cx * sy + sx * cy;
+        }
+        for (int z = 0; z < h->g.Lz; ++z) {
+            double c, sn;
+            unit((long long)h->mom_int[3 * p + 2] * z, h->g.Lz, c, sn);
+            zp[2 * ((size_t)p * h->g.Lz + z)] = c * kc - sn * ks;
+            zp[2 * ((size_t)p * h->g.Lz + z) + 1] = c * ks + sn * kc;
+        }
+    }
     EDK_CUDA_TRY(cudaMemcpy(h->pw_zphase, zp.data(), zp_bytes, cudaMemcpyHostToDevice));
     EDK_CUDA_TRY(cudaMemcpy(h->pw_momode, mp.momode.data(), mp.momode.size() * sizeof(int), cudaMemcpyHostToDevice));
     const cuuint64_t Kd = (cuuint64_t)2 * 3 * h->g.V;
@@ -608,6 +658,7 @@ int build_pw(edk_handle* h) {
         return EDK_ERR_CUDA;
     }
     h->pw_bytes = wt_bytes + y_bytes + zp_bytes;
+    h->pw_algo = h->algo;
     h->pw_ready = true;
     return EDK_OK;
 }
@@ -627,12 +678,18 @@ int run_gram_pw(edk_handle* h, cudaStream_t s) {
     Q.mbtot = h->pw_mbtot;
     Q.wtiles = h->pw_wtiles;
     Q.Y = h->pw_Y;
-    const int npass = (h->pw_mbtot + PW_MAX_MB - 1) / PW_MAX_MB;
+    Q.slotmode = h->pw_slotmode;
+    const int npass = h->pw_npass;
     {
         PhaseTimer t(h, s, PH_GRAM, npass);
         for (int pass = 0; pass < npass; ++pass) {
-            Q.mb0 = pass * PW_MAX_MB;
-            EDK_CUDA_TRY(launch_gram_pw(Q, h->pw_tma, std::min(PW_MAX_MB, h->pw_mbtot - Q.mb0), h->pw_el, h->pw_fl, s));
+            if (h->pw_algo == 3) {
+                Q.mb0 = 2 * pass;  // the pass's cos block, its sin block follows
+                EDK_CUDA_TRY(launch_gram_pwf(Q, h->pw_tma, h->pw_el, h->pw_fl, s));
+            } else {
+                Q.mb0 = pass * PW_MAX_MB;
+                EDK_CUDA_TRY(launch_gram_pw(Q, h->pw_tma, std::min(PW_MAX_MB, h->pw_mbtot - Q.mb0), h->pw_el, h->pw_fl, s));
+            }
         }
     }
     // the z fold is a reduction like the combine step and is timed with it
@@ -787,7 +844,7 @@ int configure(edk_handle* h) {
         return pe == cudaErrorMemoryAllocation ? EDK_ERR_NOMEM : EDK_ERR_CUDA;
     }
     h->cfg_bytes = 4 * nm * h->g.Vpad * sizeof(cplx) + partial_bytes;
-    if (h->algo == 2) {
+    if (h->algo >= 2) {
         const int rc = build_pw(h);
         if (rc != EDK_OK) return rc;
     }
@@ -805,9 +862,9 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     P.Vpad = h->g.Vpad;
     P.ksplit = h->naive ? 1 : h->ksplit;
     P.n_mt = row_tiles(h);
-    const bool use_pw = !h->naive && h->loader == 0 && h->algo == 2;
+    const bool use_pw = !h->naive && h->loader == 0 && h->algo >= 2;
     if (use_pw) {
-        if (!h->pw_ready) {
+        if (!h->pw_ready || h->pw_algo != h->algo) {
             set_error("plane-wave contraction selected but its tables are not built");
             return EDK_ERR_STATE;
         }
@@ -924,9 +981,9 @@ int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, co
     if (mode == EDK_MODE_DISPLACEMENT && order >= 1) EDK_ALLOC(h->lines, (size_t)12 * h->field_cplx * sizeof(cplx));
     EDK_ALLOC(h->coeff, (size_t)Ne * Ne * sizeof(double));
     h->mom_user.assign(mom3, mom3 + 3 * (size_t)nmom);
-    if (const char* a = getenv("EDK_GRAM_ALGO")) {  // A/B hook: 0 = 4M GEMM, 1 = 3M GEMM (default), 2 = plane-wave form
+    if (const char* a = getenv("EDK_GRAM_ALGO")) {  // A/B hook: 0 = 4M GEMM, 1 = 3M GEMM (default), 2 / 3 = plane-wave forms
         const int v = atoi(a);
-        if (v >= 0 && v <= 2) h->algo = v;
+        if (v >= 0 && v <= 3) h->algo = v;
     }
     {
         const int rc = configure(h);
@@ -1134,7 +1191,7 @@ int edk_calc(edk_handle* h, void* out_dev, void* stream) {
     if (h->mode == EDK_MODE_DERIVATIVE) {
         // only the GEMM form's 3M arithmetic reads the Re + Im planes of the derived fields; the fields are rebuilt by
         // every call, so the choice follows the contraction form in use right now (W0's plane is always written)
-        const bool planes = effective_algo(h) != 2;
+        const bool planes = effective_algo(h) < 2;
         for (const auto& hop : h->hops) {
             PhaseTimer t(h, s, PH_STENCIL, 1);
             EDK_CUDA_TRY(launch_nabla3(h->field(hop.first), h->field(hop.second), h->field(hop.second + 1),
@@ -1316,13 +1373,13 @@ int edk_debug_loader(edk_handle* h, int mode) {
 }
 
 int edk_debug_algo(edk_handle* h, int algo) {
-    if (!h || algo < 0 || algo > 2) return EDK_ERR_ARG;
+    if (!h || algo < 0 || algo > 3) return EDK_ERR_ARG;
     EDK_CUDA_TRY(cudaSetDevice(h->device));
     h->algo = algo;
     pick_gram_config(h);
     int rc = build_tma(h);
     if (rc != EDK_OK) return rc;
-    if (algo == 2 && !h->pw_ready) {
+    if (algo >= 2 && (!h->pw_ready || h->pw_algo != algo)) {  // the two plane-wave forms have different tables
         rc = build_pw(h);
         if (rc != EDK_OK) return rc;
     }
@@ -1351,7 +1408,7 @@ int edk_query(const edk_handle* h, int what) {
         case 4: return h->mfrag;
         case 5: return h->njobs;
         case 6: return (h->loader == 0 && h->tma_ready) ? h->tma.nstages : 0;
-        case 7: return effective_algo(h) == 2 ? 2 : (effective_algo(h) ? 3 : 4);
+        case 7: return effective_algo(h) >= 2 ? 4 - effective_algo(h) : (effective_algo(h) ? 3 : 4);
         case 8: {  // (pair, momentum) GEMMs actually contracted
             int n = 0;
             for (const auto& j : h->jobs_host) n += j.nseg * j.nmom;

@@ -129,6 +129,7 @@ struct PwParams {
     int mbtot;    // m-blocks of the weight tiles = ceil(nmodes/8)
     const double* wtiles;  // [kplane][2 groups of 4 sites][mbtot][32 lanes]: lane = (mode%8)*4 + site%4
     cplx* Y;      // [njobs][Lz][nmodes][Ne][Ne]
+    const int* slotmode;  // folded variant only: [mbtot][8] compact mode index held by a weight-tile row, -1 = unused
 };
 struct PwTma {
     alignas(64) unsigned char mapL[128];  // CUtensorMap over [nfield][Ne][2*Kc doubles], box 8 x (8 EL) x 1
@@ -182,6 +183,11 @@ int pw_plan_smem(int el, int fl, int* nstages, int* smem_bytes);
 void pw_pick_tile(int Ne, int* el, int* fl);
 cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes, int mbtot, int kplane, Geom g, cudaStream_t s);
 cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, int el, int fl, cudaStream_t s);
+// folded variant (centre-symmetric site pairs): m-blocks come in (cos, sin) pairs, one pair per pass
+int pwf_plan_smem(int el, int fl, int* nstages, int* smem_bytes);
+cudaError_t launch_gram_pwf(const PwParams& P, const PwTma& T, int el, int fl, cudaStream_t s);
+cudaError_t launch_pwf_weights(double* wtiles, const int* modes3_dev, const int* slotmode_dev, int mbtot, int kplane, Geom g,
+                               cudaStream_t s);
 cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s);
 // microbench
 cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops);

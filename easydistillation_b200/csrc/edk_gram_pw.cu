@@ -272,6 +272,245 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Folded variant ("algo 3"): centre-symmetric site pairs.
+// With the modes taken about the centre of the plane, w^c_q(s) = cos(theta_q(s) - delta_q) is even and
+// w^s_q(s) = sin(theta_q(s) - delta_q) is odd under s -> A-1-s (the site (Lx-1-x, Ly-1-y)); the constant phase
+// exp(i sigma delta_q) of a momentum goes into the z-phase table.  So for the pair (s, sbar = A-1-s)
+//   sum over both sites of w^c C = w^c(s) (C(s) + C(sbar)),   of w^s C = w^s(s) (C(s) - C(sbar)):
+// a lane forms the site products of BOTH sites of its pair (24 DFMA), their sum and difference (4 DADD) and feeds the
+// sum to one block of <= 8 cos-modes and the difference to one block of <= 8 sin-modes - half the DMMAs per site.
+// A stage = 8 pairs: the 8 front sites 8k..8k+7 and the 8 back sites A-8-8k..A-1-8k of the plane (two sets of TMA
+// boxes; the back run may start before the plane or the row and then meets zero weights / zero fill).  For an odd
+// plane the middle site is its own partner and carries half the cos weight.  More than 8 {+q,-q} couples run as
+// passes.  The operands of two sites are live at once, which fits the register budget with 16 x 32 tiles only.
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int pwf_stage_bytes(int el, int fl) { return 2 * PW_KG * (PW_WARPS * el + 8 * fl) * 64 + 2 * 2 * 256; }
+
+int pwf_plan_smem(int el, int fl, int* nstages, int* smem_bytes) {
+    const int stage = pwf_stage_bytes(el, fl);
+    int nst = (227 * 1024 - PW_TAIL_BYTES) / stage;
+    if (nst > PW_MAX_STAGES) nst = PW_MAX_STAGES;
+    if (nst < 2) return -1;
+    *nstages = nst;
+    *smem_bytes = nst * stage + PW_TAIL_BYTES;
+    return 0;
+}
+
+template <int PW_EL, int PW_FL>
+__global__ void __launch_bounds__(PW_THREADS, 1) gram_pwf_kernel(const PwParams P, const __grid_constant__ PwTma Tm) {
+    constexpr int PW_ROWS_L = PW_WARPS * PW_EL, PW_ROWS_R = 8 * PW_FL;
+    constexpr int PW_L_BYTES = PW_KG * PW_ROWS_L * 64;  // [kg][row][4 complex], one set of 8 sites
+    constexpr int PW_R_BYTES = PW_KG * PW_ROWS_R * 64;
+    constexpr int PW_HALF_BYTES = PW_L_BYTES + PW_R_BYTES;  // front set, then back set, then the weights
+    constexpr int PW_STAGE_BYTES = pwf_stage_bytes(PW_EL, PW_FL);
+    static_assert(PW_STAGE_BYTES % 128 == 0 && PW_HALF_BYTES % 128 == 0 && PW_L_BYTES % 128 == 0 && (PW_ROWS_L * 64) % 128 == 0 &&
+                      (PW_ROWS_R * 64) % 128 == 0,
+                  "TMA destinations are 128-byte aligned");
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int nst = Tm.nstages;
+    unsigned char* tail = smem + (size_t)nst * PW_STAGE_BYTES;
+    const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(tail);
+    const uint32_t bar_empty = bar_full + 8 * PW_MAX_STAGES;
+    GramJob* sjob = reinterpret_cast<GramJob*>(tail + 16 * PW_MAX_STAGES);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    int item = blockIdx.x;
+    const int ft = item % P.n_ft;
+    item /= P.n_ft;
+    const int et = item % P.n_et;
+    item /= P.n_et;
+    const int z = item % P.Lz;
+    const int job_id = item / P.Lz;
+    const int e0 = et * PW_ROWS_L, f0 = ft * PW_ROWS_R;
+
+    if (tid < (int)(sizeof(GramJob) / sizeof(int))) {
+        reinterpret_cast<int*>(sjob)[tid] = reinterpret_cast<const int*>(P.jobs + job_id)[tid];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, PW_WARPS);
+        }
+        mbar_init_fence();
+    }
+    __syncthreads();
+    const bool skip_tile = sjob->nseg == 1 && sjob->Lf[0] == sjob->Rf[0] && e0 > f0 + PW_ROWS_R - 1;
+    const int T = skip_tile ? 0 : sjob->nseg * P.kplane;  // stages of 8 pairs
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+
+    if (warp >= PW_WARPS) {
+        // ================================ producer warpgroup ================================
+        warpgroup_reg_dealloc<PW_REGS_PRODUCER>();
+        if (warp != PW_WARPS) return;
+        const uint32_t tx_bytes = (uint32_t)(2 * PW_HALF_BYTES + 2 * 2 * 256);
+        const int plane_site0 = z * P.A;
+        int seg = 0, kstep = 0, s = 0;
+        uint32_t par = 1;
+        for (int it = 0; it < T; ++it) {
+            mbar_wait(bar_empty + 8 * s, par);
+            const uint32_t full = bar_full + 8 * s;
+            if (lane == 0) mbar_arrive_expect_tx(full, tx_bytes);
+            __syncwarp();
+            const uint32_t st = smem_base + (uint32_t)(s * PW_STAGE_BYTES);
+            // lanes 0-5 / 8-13: L and R boxes of the front sites, lanes 16-21 / 24-29: of the back sites
+            const int half = lane >> 4, sub = lane & 15;
+            const int site0 = half ? plane_site0 + P.A - 8 - 8 * kstep : plane_site0 + 8 * kstep;
+            const int kd = site0 * 6;
+            const uint32_t hb = st + (uint32_t)(half * PW_HALF_BYTES);
+            if (sub < PW_KG) {
+                tma_load_3d(hb + sub * (PW_ROWS_L * 64), Tm.mapL, full, kd + 8 * sub, e0, sjob->Lf[seg]);
+            } else if (sub >= 8 && sub < 8 + PW_KG) {
+                tma_load_3d(hb + PW_L_BYTES + (sub - 8) * (PW_ROWS_R * 64), Tm.mapR, full, kd + 8 * (sub - 8), f0, sjob->Rf[seg]);
+            } else if (sub == 6) {  // lanes 6 and 22: the weights of one group of 4 pairs (cos block, sin block)
+                const double* src = P.wtiles + (((size_t)kstep * 2 + half) * P.mbtot + P.mb0) * 32;
+                bulk_load(st + 2 * PW_HALF_BYTES + half * 512, src, 512, full);
+            }
+            if (++kstep == P.kplane) {
+                kstep = 0;
+                ++seg;
+            }
+            if (++s == nst) {
+                s = 0;
+                par ^= 1;
+            }
+        }
+        return;
+    }
+
+    // ================================== consumer warps ==================================
+    warpgroup_reg_alloc<PW_REGS_CONSUMER>();
+    const int sidx = lane & 3, n = lane >> 2;  // pair inside a group of 4 (MMA k), column (MMA n)
+    const uint32_t offW = (uint32_t)(2 * PW_HALF_BYTES + lane * 8);
+
+    double yc_re[PW_EL][PW_FL][2], yc_im[PW_EL][PW_FL][2], ys_re[PW_EL][PW_FL][2], ys_im[PW_EL][PW_FL][2];
+#pragma unroll
+    for (int i = 0; i < PW_EL; ++i)
+#pragma unroll
+        for (int j = 0; j < PW_FL; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) yc_re[i][j][q] = yc_im[i][j][q] = ys_re[i][j][q] = ys_im[i][j][q] = 0.0;
+
+    int cur_sign = 1;
+    int cs_seg = 0, cs_kstep = 0;
+    int s = 0;
+    uint32_t par = 0;
+    for (int it = 0; it < T; ++it) {
+        const int sgn = sjob->sign[cs_seg];
+        if (++cs_kstep == P.kplane) {
+            cs_kstep = 0;
+            ++cs_seg;
+        }
+        if (sgn != cur_sign) {
+#pragma unroll
+            for (int i = 0; i < PW_EL; ++i)
+#pragma unroll
+                for (int j = 0; j < PW_FL; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        yc_re[i][j][q] = flip_sign(yc_re[i][j][q]);
+                        yc_im[i][j][q] = flip_sign(yc_im[i][j][q]);
+                        ys_re[i][j][q] = flip_sign(ys_re[i][j][q]);
+                        ys_im[i][j][q] = flip_sign(ys_im[i][j][q]);
+                    }
+            cur_sign = sgn;
+        }
+        mbar_wait(bar_full + 8 * s, par);
+        const unsigned char* stage = smem + (size_t)s * PW_STAGE_BYTES;
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp) {
+            const double wc = *reinterpret_cast<const double*>(stage + offW + grp * 512);
+            const double ws = *reinterpret_cast<const double*>(stage + offW + grp * 512 + 256);
+            // local site of this lane's pair in the front set, and of its partner in the back set (stored ascending)
+            const int tf = 4 * grp + sidx, tb = 7 - tf;
+            uint32_t oLf[3], oLb[3], oRf[3], oRb[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int kf = tf * 3 + c, kb = tb * 3 + c;
+                oLf[c] = (uint32_t)((kf >> 2) * (PW_ROWS_L * 64) + warp * PW_EL * 64 + (kf & 3) * 16);
+                oLb[c] = (uint32_t)(PW_HALF_BYTES + (kb >> 2) * (PW_ROWS_L * 64) + warp * PW_EL * 64 + (kb & 3) * 16);
+                oRf[c] = (uint32_t)(PW_L_BYTES + (kf >> 2) * (PW_ROWS_R * 64) + n * 64 + (kf & 3) * 16);
+                oRb[c] = (uint32_t)(PW_HALF_BYTES + PW_L_BYTES + (kb >> 2) * (PW_ROWS_R * 64) + n * 64 + (kb & 3) * 16);
+            }
+#pragma unroll
+            for (int j = 0; j < PW_FL; ++j) {
+                cplx rf[3], rb[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    rf[c] = *reinterpret_cast<const cplx*>(stage + oRf[c] + j * 512);
+                    rb[c] = *reinterpret_cast<const cplx*>(stage + oRb[c] + j * 512);
+                }
+#pragma unroll
+                for (int i = 0; i < PW_EL; ++i) {
+                    cplx lf[3], lb[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        lf[c] = *reinterpret_cast<const cplx*>(stage + oLf[c] + i * 64);
+                        lb[c] = *reinterpret_cast<const cplx*>(stage + oLb[c] + i * 64);
+                    }
+                    double fr = lf[0].x * rf[0].x, fi = lf[0].x * rf[0].y;
+                    double br = lb[0].x * rb[0].x, bi = lb[0].x * rb[0].y;
+                    fr = fma(lf[0].y, rf[0].y, fr);
+                    fi = fma(-lf[0].y, rf[0].x, fi);
+                    br = fma(lb[0].y, rb[0].y, br);
+                    bi = fma(-lb[0].y, rb[0].x, bi);
+#pragma unroll
+                    for (int c = 1; c < 3; ++c) {
+                        fr = fma(lf[c].x, rf[c].x, fr);
+                        fi = fma(lf[c].x, rf[c].y, fi);
+                        br = fma(lb[c].x, rb[c].x, br);
+                        bi = fma(lb[c].x, rb[c].y, bi);
+                        fr = fma(lf[c].y, rf[c].y, fr);
+                        fi = fma(-lf[c].y, rf[c].x, fi);
+                        br = fma(lb[c].y, rb[c].y, br);
+                        bi = fma(-lb[c].y, rb[c].x, bi);
+                    }
+                    dmma884(yc_re[i][j][0], yc_re[i][j][1], wc, fr + br);
+                    dmma884(yc_im[i][j][0], yc_im[i][j][1], wc, fi + bi);
+                    dmma884(ys_re[i][j][0], ys_re[i][j][1], ws, fr - br);
+                    dmma884(ys_im[i][j][0], ys_im[i][j][1], ws, fi - bi);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+        if (++s == nst) {
+            s = 0;
+            par ^= 1;
+        }
+    }
+
+    // ---- epilogue: lane holds rows n of the cos block and of the sin block, columns f0 + 8 j + 2 sidx + {0, 1} ----
+    if (skip_tile) return;
+    const double fs = (double)cur_sign;
+    const int Ne = P.Ne;
+    const size_t mat = (size_t)Ne * Ne;
+    cplx* Yp = P.Y + ((size_t)job_id * P.Lz + z) * (size_t)P.nmodes * mat;
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+        const int mode = P.slotmode[(P.mb0 + blk) * 8 + n];  // compact mode index of this row, -1: unused
+        if (mode < 0) continue;
+#pragma unroll
+        for (int i = 0; i < PW_EL; ++i) {
+            const int e = e0 + warp * PW_EL + i;
+            if (e >= Ne) continue;
+            cplx* row = Yp + (size_t)mode * mat + (size_t)e * Ne;
+#pragma unroll
+            for (int j = 0; j < PW_FL; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int f = f0 + 8 * j + 2 * sidx + q;
+                    if (f < Ne)
+                        row[f] = blk ? make_double2(fs * ys_re[i][j][q], fs * ys_im[i][j][q])
+                                     : make_double2(fs * yc_re[i][j][q], fs * yc_im[i][j][q]);
+                }
+        }
+    }
+}
+
 #ifndef EDK_EMU_NO_LAUNCHERS
 template <int MB, int EL, int FL>
 static cudaError_t launch_gram_pw_t(const PwParams& P, const PwTma& T, int bytes, unsigned items, cudaStream_t s) {
@@ -279,6 +518,18 @@ static cudaError_t launch_gram_pw_t(const PwParams& P, const PwTma& T, int bytes
     cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     EDK_LAUNCH(kern, items, PW_THREADS, bytes, s, P, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gram_pwf(const PwParams& P, const PwTma& T, int el, int fl, cudaStream_t s) {
+    int nst, bytes;
+    if (pwf_plan_smem(el, fl, &nst, &bytes) != 0 || nst != T.nstages || !P.slotmode || el != 2 || (fl != 4 && fl != 5)) return cudaErrorInvalidValue;
+    const long long items = (long long)P.njobs * P.Lz * P.n_et * P.n_ft;
+    if (items < 1 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
+    auto kern = fl == 4 ? gram_pwf_kernel<2, 4> : gram_pwf_kernel<2, 5>;
+    cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    EDK_LAUNCH(kern, (unsigned)items, PW_THREADS, bytes, s, P, T);
     return cudaGetLastError();
 }
 
@@ -325,7 +576,47 @@ __global__ void pw_weights_kernel(double* __restrict__ wtiles, const int* __rest
     wtiles[idx] = v;
 }
 
+// weights of the folded variant, about the centre of the plane:
+//   wtiles[kstep][grp][block][lane] = w_{slotmode[block][lane/4]}(front site of pair 8 kstep + 4 grp + lane%4)
+// with w = cos(theta_q - delta_q) or sin(theta_q - delta_q), theta_q - delta_q = pi (qx (2x - Lx + 1)/Lx + qy (2y - Ly + 1)/Ly);
+// zero for unused rows and past the last pair; the middle site of an odd plane is its own partner: half the cos weight.
+__global__ void pwf_weights_kernel(double* __restrict__ wtiles, const int* __restrict__ modes3, const int* __restrict__ slotmode,
+                                   int mbtot, int kplane, Geom g) {
+    const size_t total = (size_t)kplane * 2 * mbtot * 32;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int lane = (int)(idx & 31);
+    size_t r = idx >> 5;
+    const int mbt = (int)(r % mbtot);
+    r /= mbtot;
+    const int grp = (int)(r & 1);
+    const int kstep = (int)(r >> 1);
+    const int mode = slotmode[mbt * 8 + (lane >> 2)];
+    const int A = g.Lx * g.Ly;
+    const int pair = 8 * kstep + 4 * grp + (lane & 3);
+    double v = 0.0;
+    if (mode >= 0 && 2 * pair < A) {  // pairs 0 .. ceil(A/2) - 1
+        const int x = pair % g.Lx, y = pair / g.Lx;
+        const long long qx = modes3[3 * mode + 0], qy = modes3[3 * mode + 1];
+        const long long mx = 2LL * g.Lx, my = 2LL * g.Ly;
+        const long long rx = ((qx * (2 * x - g.Lx + 1)) % mx + mx) % mx;  // in units of pi / Lx
+        const long long ry = ((qy * (2 * y - g.Ly + 1)) % my + my) % my;
+        double sn, cs;
+        sincospi((double)rx / (double)g.Lx + (double)ry / (double)g.Ly, &sn, &cs);
+        v = modes3[3 * mode + 2] ? sn : cs;
+        if (2 * pair == A - 1) v *= 0.5;
+    }
+    wtiles[idx] = v;
+}
+
 #ifndef EDK_EMU_NO_LAUNCHERS
+cudaError_t launch_pwf_weights(double* wtiles, const int* modes3_dev, const int* slotmode_dev, int mbtot, int kplane, Geom g,
+                               cudaStream_t s) {
+    const size_t total = (size_t)kplane * 2 * mbtot * 32;
+    EDK_LAUNCH(pwf_weights_kernel, (unsigned)((total + 255) / 256), 256, 0, s, wtiles, modes3_dev, slotmode_dev, mbtot, kplane, g);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes, int mbtot, int kplane, Geom g, cudaStream_t s) {
     const size_t total = (size_t)kplane * 2 * mbtot * 32;
     EDK_LAUNCH(pw_weights_kernel, (unsigned)((total + 255) / 256), 256, 0, s, wtiles, modes3_dev, nmodes, mbtot, kplane, g);

@@ -199,7 +199,8 @@ class ElementalEngine:
         _capi.check(self.lib.edk_debug_loader(self.h, int(mode)), "edk_debug_loader")
 
     def debug_algo(self, algo: int):
-        """1 = 3M arithmetic (default), 0 = 4M, for the TMA kernel."""
+        """Contraction form: 1 = GEMM form, 3M arithmetic (default), 0 = GEMM form, 4M, 2 = plane-wave factorised form,
+        3 = plane-wave form with centre-symmetric site pairs folded (include/edk.h, edk_debug_algo)."""
         _capi.check(self.lib.edk_debug_algo(self.h, int(algo)), "edk_debug_algo")
 
     def query(self):

@@ -184,15 +184,17 @@ long long edk_launch_count(const edk_handle* h);
  * edk_debug_algo: arithmetic of the TMA kernel, 1 = 3M (default: Re = T1+T2, Im = T3+T1-T2 with
  *   T1 = Lr.Pr, T2 = Li.Pi, T3 = (Lr+Li).(Pi-Pr): three real MMAs per complex block), 0 = 4M (four),
  *   2 = plane-wave factorised form: site products conj(L).R formed once per site, real xy-mode transform by
- *   DMMA per z-plane, z folded by a second kernel (csrc/edk_gram_pw.cu).  The environment variable
- *   EDK_GRAM_ALGO=0|1|2 sets the initial value of every new handle (A/B runs of bench.py).
+ *   DMMA per z-plane, z folded by a second kernel (csrc/edk_gram_pw.cu), 3 = form 2 with centre-symmetric site pairs
+ *   folded (modes about the centre of the plane are even / odd under s -> A-1-s: the sum of the two site products
+ *   feeds the cos modes, their difference the sin modes - half the DMMAs per site).  The environment variable
+ *   EDK_GRAM_ALGO=0|1|2|3 sets the initial value of every new handle (A/B runs of bench.py).
  * edk_query: what = 0 pairing in use (0/1), 1 internal momentum count, 2 pair-GEMMs per momentum,
  *   3 split-K factor, 4 m-fragments per tile, 5 contraction jobs, 6 TMA ring depth (0 = cp.async loader),
  *   7 real MMAs per complex block (3 or 4), 8 number of (pair, momentum) GEMMs contracted per timeslice
  *   (self pairs L == R only run one momentum of every +-p couple), 9 size of that half set,
- *   10 contraction form in use (0 / 1 / 2 as in edk_debug_algo), 11 real xy-modes of form 2 (0 = not built),
- *   12 tile shape of form 2 as 10 el + fl (24 = 16 x 32 rows, 25 = 16 x 40; environment EDK_PW_TILE overrides the pick).
- *   With form 2, what = 7 answers 2 (DMMAs per site product and block of 8 modes).
+ *   10 contraction form in use (0 / 1 / 2 / 3 as in edk_debug_algo), 11 real xy-modes of forms 2 / 3 (0 = not built),
+ *   12 tile shape of forms 2 / 3 as 10 el + fl (24 = 16 x 32 rows, 25 = 16 x 40; environment EDK_PW_TILE overrides the pick).
+ *   With forms 2 / 3, what = 7 answers 2 / 1 (DMMAs per site, real or imaginary part and block of 8 modes).
  */
 int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream);
 int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream);

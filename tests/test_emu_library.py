@@ -225,7 +225,7 @@ def test_laplacian_and_state_errors(emu):
     out = np.empty((1, 1, Ne, Ne), np.complex128)
     assert emu.edk_calc(h.h, out.ctypes.data, None) == _capi.EDK_ERR_STATE  # nothing set yet
     assert b"must be set first" in emu.edk_last_error()
-    assert emu.edk_debug_algo(h.h, 3) == _capi.EDK_ERR_ARG
+    assert emu.edk_debug_algo(h.h, 4) == _capi.EDK_ERR_ARG
     h.set_inputs(U_file, V)
     F = np.ascontiguousarray(orc.round_through_c8(V).astype(np.complex128))
     LF = np.empty_like(F)
@@ -248,6 +248,40 @@ def test_plane_wave_form_edge_cases(emu, latt3, Ne, order, moms):
     got = h.calc()
     h.close()
     assert worst_block_error(got, ref) < 1e-10
+
+
+MANY_COUPLES = [(0, 0, 0), (1, 0, 0), (0, 1, 1), (1, 1, 0), (1, -1, 0), (2, 0, 1), (0, 2, 0), (2, 1, 0), (1, 2, 0), (-2, 1, 0),
+                (3, 0, 0), (-1, -1, 1)]  # 10 {+q, -q} couples of (px, py): two passes of the folded form, three m-blocks of form 2
+
+
+@pytest.mark.parametrize("latt3,Ne,mode,order,moms,sym,switch", [
+    ((4, 4, 2), 5, D, 1, orc.momentum_set(7), None, True),      # even planes of 16 sites
+    ((3, 5, 2), 3, D, 2, [(0, 0, 1), (1, -1, 0), (0, 2, 1)], 1, True),   # odd planes: the middle site is its own partner
+    ((3, 5, 1), 3, D, 2, [(1, -1, 0), (0, 2, 1)], 0, False),    # direct pairs: multi-segment jobs with signs
+    ((2, 2, 2), 3, D, 1, orc.momentum_set(7), None, False),     # planes of 4 sites: the back run starts before the plane
+    ((3, 3, 1), 2, D, 2, orc.momentum_set(33), None, False),    # 33 momenta: 7 couples, 13 modes, plane of 9 sites
+    ((5, 4, 1), 2, D, 1, MANY_COUPLES, None, False),            # more than 8 couples: two passes
+    ((3, 5, 2), 7, X, 3, orc.momentum_set(9), None, False),     # displacement lines
+    ((4, 2, 2), 35, D, 1, orc.momentum_set(7), None, False),    # 3 x 2 tiles of 16 x 32, mirror tile of the self pair
+])
+def test_folded_plane_wave_form(emu, latt3, Ne, mode, order, moms, sym, switch):
+    """Form 3 (centre-symmetric site pairs folded, gram_pwf_kernel) through the C ABI against the oracle, and (`switch`)
+    switching between the two plane-wave forms on one handle: their weight tables and z-phase constants differ."""
+    U_file, V, ref = inputs_and_reference(latt3, Ne, mode, order, moms)
+    h = Handle(emu, latt3, Ne, mode, order, moms)
+    if sym is not None:
+        h.check(emu.edk_debug_symmetry(h.h, sym), "edk_debug_symmetry")
+    h.set_inputs(U_file, V)
+    h.check(emu.edk_debug_algo(h.h, 3), "edk_debug_algo")
+    assert h.query(10) == 3 and h.query(12) == 24 and h.query(3) == 1
+    folded = h.calc()
+    assert worst_block_error(folded, ref) < 1e-10
+    if switch:
+        h.check(emu.edk_debug_algo(h.h, 2), "edk_debug_algo")
+        assert worst_block_error(h.calc(), ref) < 1e-10
+        h.check(emu.edk_debug_algo(h.h, 3), "edk_debug_algo")
+        assert np.array_equal(folded, h.calc())
+    h.close()
 
 
 def test_integration_md_ctypes_stub_runs_as_written(emu):
@@ -288,10 +322,11 @@ def test_reference_class_bound_to_the_c_abi_matches_its_own_numpy_path(emu):
 
 def memcheck_cases(lib):
     """Small runs that touch every kernel family; executed by the AddressSanitizer test below in a child process."""
-    cases = [((4, 4, 2), 5, D, 1, orc.momentum_set(7), (1, 0, 2)),            # stencil + GEMM forms + plane-wave form
-             ((3, 5, 2), 3, D, 2, [(1, -1, 0), (0, 2, 1)], (2, 1)),            # ragged planes, second-order fields
+    cases = [((4, 4, 2), 5, D, 1, orc.momentum_set(7), (1, 0, 2, 3)),         # stencil + GEMM forms + plane-wave forms
+             ((2, 2, 2), 3, D, 1, orc.momentum_set(7), (3,)),                   # folded form, back run before the plane
+             ((3, 5, 1), 3, D, 2, [(1, -1, 0), (0, 2, 1)], (2, 3, 1)),         # ragged / odd planes, second-order fields
              ((3, 5, 2), 7, X, 2, orc.momentum_set(9), (1, 2)),                 # displacement lines
-             ((4, 2, 2), 45, D, 1, orc.momentum_set(7), (2,))]                  # multi-tile plane-wave run with mirror tiles
+             ((4, 2, 2), 35, D, 1, orc.momentum_set(7), (2, 3))]                # multi-tile plane-wave runs with mirror tiles
     worst = 0.0
     for latt3, Ne, mode, order, moms, algos in cases:
         U_file, V, ref = inputs_and_reference(latt3, Ne, mode, order, moms)
