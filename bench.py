@@ -356,13 +356,14 @@ def run_native(args):
             tf = torch.tensor([form], dtype=torch.int32, device=dev)
             dist.all_reduce(tf, op=dist.ReduceOp.MIN)
             form = int(tf.item())
-        decision["form"] = form
+        if form != decision["form"]:
+            decision.update(form=form, tile=None)
         tuning.apply(decision)
         contraction.update(decision)
         if rank == 0:
             print(f"bench.py: contraction form {form} ({decision['reason']})", file=sys.stderr, flush=True)
     else:
-        form = 2 if args.contraction == "planewave" else 1
+        form = {"planewave": 2, "planewave-folded": 3}.get(args.contraction, 1)
         os.environ["EDK_GRAM_ALGO"] = str(form)
         contraction.update(form=form, reason="forced by --contraction")
     eng = ElementalEngine((Lx, Ly, Lz), Ne, mode_, order_, moms, device=local)
@@ -499,13 +500,19 @@ def run_native(args):
         # `achieved`/`frac` are the executed rate (what the FP64 pipe really does); the SURVEY-counted
         # rate is reported beside it as survey_equivalent_tflops.
         exec_flops = 2.0 * q["real_mma_per_complex_block"] * Ne * Ne * 3 * V * q["pair_momentum_gemms"]
-        pw_form = q.get("contraction_form") == 2
+        pw_form = q.get("contraction_form") in (2, 3)
+        folded = q.get("contraction_form") == 3
         if pw_form:
             # plane-wave factorised form (EDK_GRAM_ALGO=2): per (pair, e, f, site) 12 DFMA for the colour-summed
             # site product and, for each of the real xy-modes, one multiply-add on its real and imaginary part
             # (DMMA rows padded to blocks of 8 modes are not counted)
-            exec_flops = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V * (24.0 + 4.0 * q["plane_wave_modes"])
-            pw_padded_flops = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V * (24.0 + 4.0 * 8 * ((q["plane_wave_modes"] + 7) // 8))
+            # folded form (3): the two sites of a centre-symmetric pair share one multiply-add per mode after one add /
+            # subtract per real and imaginary part: 2 flops per site for the folding, 2 per mode and site
+            per_mode = 2.0 if folded else 4.0
+            fold_adds = 2.0 if folded else 0.0
+            exec_flops = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V * (24.0 + fold_adds + per_mode * q["plane_wave_modes"])
+            rows = 16 * ((q["plane_wave_modes"] // 2 + 8) // 8) if folded else 8 * ((q["plane_wave_modes"] + 7) // 8)
+            pw_padded_flops = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V * (24.0 + fold_adds + per_mode * rows)
         achieved_tf = exec_flops / (gram_ms * 1e-3) / 1e12
         survey_tf = flops / (gram_ms * 1e-3) / 1e12
         # stencil: bytes of ONE launch (nabla3: 1 source, 3 outputs, links once; displacement step: 6 in, 6 + mean out)
@@ -517,7 +524,7 @@ def run_native(args):
             cpu_val, cpu_smp = cpu_sample(name, W0_host.astype(np.complex64), U_sp_host)
         elif W0_host is not None:
             cpu_val, cpu_smp = cpu_sample_displacement(name, dist_, W0_host.astype(np.complex64), U_sp_host)
-        gram_name = "gram_pw_kernel" if pw_form else ("gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel")
+        gram_name = "gram_pwf_kernel" if folded else "gram_pw_kernel" if pw_form else ("gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel")
         st_name = "nabla3_kernel" if dist_ is None else "displace_step6_kernel"
         line = {
             "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s", "n_gpus": world,
@@ -538,7 +545,8 @@ def run_native(args):
             "clocks": clocks.summary(),
             "roofline": {
                 "kernel": gram_name + (" (plane-wave factorised contraction: site products by DFMA, real xy-mode transform by "
-                                       "DMMA.8x8x4, TMA producer warp + mbarrier ring; z fold timed with the combine step)" if pw_form
+                                       "DMMA.8x8x4" + (", centre-symmetric site pairs folded" if folded else "") +
+                                       ", TMA producer warp + mbarrier ring; z fold timed with the combine step)" if pw_form
                                        else " (momentum-phased contraction, DMMA.8x8x4, TMA producer warp + mbarrier ring)"),
                 "bound": "tensor",
                 "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
@@ -587,7 +595,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=os.environ.get("EDK_BENCH_WORKLOAD", "config5"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contraction", default=os.environ.get("EDK_BENCH_CONTRACTION", "auto"), choices=["auto", "gemm", "planewave"],
+    ap.add_argument("--contraction", default=os.environ.get("EDK_BENCH_CONTRACTION", "auto"), choices=["auto", "gemm", "planewave", "planewave-folded"],
                     help="contraction form: auto = validate and time the plane-wave form against the GEMM form in a child "
                          "process first and use the faster validated one; gemm / planewave force one")
     ap.add_argument("--generator", default="derivative", choices=["derivative", "displacement"],

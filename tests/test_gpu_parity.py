@@ -617,12 +617,14 @@ def test_linearity_and_scaling_property(edb):
 # ---------------------------------------------------------------------------------------------
 # (6) experimental: plane-wave factorised contraction (edk_debug_algo 2), checked in its own process
 # ---------------------------------------------------------------------------------------------
-def test_zz_plane_wave_form_in_subprocess(edb):
-    """csrc/edk_gram_pw.cu was written after the round's GPU budget was spent: its index arithmetic is pinned
-    on CPU by tests/test_pw_model.py, but the kernel has not run on hardware yet and is NOT the default
-    contraction.  The check (tools/check_plane_wave.py: oracle + GEMM-form parity on ragged / multi-tile /
-    multi-segment shapes) runs in a subprocess so that a fault cannot poison this process's CUDA context;
-    a failure is reported as xfail with the tail of its output, a pass is a real pass."""
+@pytest.mark.parametrize("form", [2, 3])
+def test_zz_plane_wave_form_in_subprocess(edb, form):
+    """csrc/edk_gram_pw.cu (form 2, and its folded variant, form 3) was written after the round's GPU budget was spent:
+    the kernel sources and the host glue are validated on the host emulator (tests/test_pw_model.py,
+    tests/test_emu_library.py), but they have not run on hardware yet and are NOT the default contraction.  The check
+    (tools/check_plane_wave.py: oracle + GEMM-form parity on ragged / multi-tile / multi-segment shapes) runs in a
+    subprocess so that a fault cannot poison this process's CUDA context; a failure is reported as xfail with the
+    tail of its output, a pass is a real pass."""
     import os
     import subprocess
     import sys
@@ -630,8 +632,8 @@ def test_zz_plane_wave_form_in_subprocess(edb):
     from conftest import REPO
 
     try:
-        r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "check_plane_wave.py")], capture_output=True,
-                           text=True, timeout=600)
+        r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "check_plane_wave.py"), *(["--form3"] if form == 3 else [])],
+                           capture_output=True, text=True, timeout=600)
     except subprocess.TimeoutExpired:
         pytest.xfail("plane-wave form (experimental, not the default path): check timed out")
     except Exception as exc:  # the experimental check must never turn the default path's suite red

@@ -24,6 +24,7 @@ from easydistillation_b200.engine import ElementalEngine  # noqa: E402
 from oracle import elemental_oracle as orc  # noqa: E402
 
 TOL = 1e-10
+FORM = 3 if "--form3" in sys.argv else 2  # the candidate: plane-wave form (2) or its folded variant (3)
 
 
 def worst_block_error(got, ref):
@@ -51,12 +52,13 @@ def run_case(latt, Ne, mode, order, moms, sym):
     eng.set_eigvecs(torch.from_numpy(V).cuda())
     eng.debug_algo(1)
     gemm = eng.calc().cpu().numpy()
-    eng.debug_algo(2)
+    eng.debug_algo(FORM)
     q = eng.query()
-    assert q["contraction_form"] == 2 and q["plane_wave_modes"] >= 1, q
+    assert q["contraction_form"] == FORM and q["plane_wave_modes"] >= 1, q
     pw = eng.calc().cpu().numpy()
     pw_again = eng.calc().cpu().numpy()
-    res = {"latt": latt, "Ne": Ne, "mode": mode, "order": order, "nmom": len(moms), "sym": sym, "modes": q["plane_wave_modes"],
+    res = {"form": FORM, "latt": latt, "Ne": Ne, "mode": mode, "order": order, "nmom": len(moms), "sym": sym,
+           "modes": q["plane_wave_modes"], "tile": q["plane_wave_tile"],
            "err_vs_oracle": worst_block_error(pw, ref), "err_vs_gemm_form": worst_block_error(pw, gemm),
            "gemm_vs_oracle": worst_block_error(gemm, ref), "deterministic": bool(np.array_equal(pw, pw_again))}
     res["ok"] = bool(res["err_vs_oracle"] < TOL and res["err_vs_gemm_form"] < TOL and res["deterministic"])
@@ -76,7 +78,7 @@ def time_forms(latt, Ne, nabla, nmom, reps=3):
     eng.set_eigvecs(v)
     out = {}
     results = {}
-    for algo in (1, 2):
+    for algo in (1, FORM):
         eng.debug_algo(algo)
         res = eng.calc()
         torch.cuda.synchronize()
@@ -88,7 +90,7 @@ def time_forms(latt, Ne, nabla, nmom, reps=3):
         torch.cuda.synchronize()
         out[f"form{algo}_ms_per_timeslice"] = e0.elapsed_time(e1) / reps
         results[algo] = res.cpu().numpy()
-    out["err_form2_vs_form1"] = worst_block_error(results[2], results[1])
+    out[f"err_form{FORM}_vs_form1"] = worst_block_error(results[FORM], results[1])
     out["shape"] = {"latt": latt, "Ne": Ne, "num_nabla": nabla, "nmom": nmom}
     eng.close()
     return out
@@ -104,7 +106,8 @@ def main():
         ([4, 6, 8], 35, D, 2, orc.momentum_set(33), 1),        # 3 x 2 tiles, 13 modes, Hermitian pairing + half set
         ([4, 6, 8], 19, D, 2, orc.momentum_set(33), 0),        # direct pairs: multi-segment jobs with signs
         ([6, 4, 2], 21, D, 2, [(0, 0, 1), (1, 2, 0), (3, -1, 2), (0, -2, 1)], None),  # non-closed, larger momenta
-        ([2, 2, 2], 1, D, 2, orc.momentum_set(7), None),
+        ([2, 2, 2], 1, D, 2, orc.momentum_set(7), None),      # planes of 4 sites (form 3: back run before the plane)
+        ([3, 3, 2], 9, D, 2, orc.momentum_set(33), None),     # odd planes of 9 sites (form 3: self-paired middle site)
         ([4, 4, 6], 13, D, 3, orc.momentum_set(7), None),
         ([4, 6, 8], 12, X, 3, orc.momentum_set(9), None),
         ([5, 3, 7], 110, D, 1, orc.momentum_set(9), None),     # 7 x 4 tiles
@@ -121,9 +124,9 @@ def main():
         report["timing"] = [time_forms([24, 24, 24], 100, 2, 33), time_forms([32, 32, 32], 200, 2, 33, reps=2)]
         print(json.dumps(report["timing"]), flush=True)
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(REPO, "gpurun_out", "plane_wave_check.json"), "w") as f:
+    with open(os.path.join(REPO, "gpurun_out", f"plane_wave_check_form{FORM}.json"), "w") as f:
         json.dump(report, f, indent=1)
-    print("plane-wave form:", "OK" if report["ok"] else "MISMATCH")
+    print(f"plane-wave form {FORM}:", "OK" if report["ok"] else "MISMATCH")
     return 0 if report["ok"] else 1
 
 

@@ -11,11 +11,14 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 # 2. plane-wave form against the oracle and the GEMM form, with timing at config 3 / config 4
 timeout 600 python tools/check_plane_wave.py --bench > gpurun_out/plane_wave_check.log 2>&1; tail -4 gpurun_out/plane_wave_check.log
+timeout 600 python tools/check_plane_wave.py --form3 --bench > gpurun_out/plane_wave_check_form3.log 2>&1; tail -4 gpurun_out/plane_wave_check_form3.log
 # 3. both forms, both tile shapes, at the graded workloads
 for wl in config4 config5; do
   timeout 400 python bench.py --workload $wl --contraction gemm --no-cpu-baseline > gpurun_out/bench_${wl}_gemm.json 2> gpurun_out/bench_${wl}_gemm.err
   EDK_PW_TILE=25 timeout 400 python bench.py --workload $wl --contraction planewave --no-cpu-baseline > gpurun_out/bench_${wl}_pw25.json 2> gpurun_out/bench_${wl}_pw25.err
   EDK_PW_TILE=24 timeout 400 python bench.py --workload $wl --contraction planewave --no-cpu-baseline > gpurun_out/bench_${wl}_pw24.json 2> gpurun_out/bench_${wl}_pw24.err
+  timeout 400 python bench.py --workload $wl --contraction planewave-folded --no-cpu-baseline > gpurun_out/bench_${wl}_pwf24.json 2> gpurun_out/bench_${wl}_pwf24.err
+  EDK_PW_TILE=25 timeout 400 python bench.py --workload $wl --contraction planewave-folded --no-cpu-baseline > gpurun_out/bench_${wl}_pwf25.json 2> gpurun_out/bench_${wl}_pwf25.err
 done
 # 4. the default line (auto selection, CPU baseline included)
 timeout 600 python bench.py > gpurun_out/bench_config5_auto.json 2> gpurun_out/bench_config5_auto.err; tail -2 gpurun_out/bench_config5_auto.err
