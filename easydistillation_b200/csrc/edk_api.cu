@@ -554,13 +554,12 @@ int build_pw(edk_handle* h) {
             slotmode[(2 * (c / 8) + 1) * 8 + c % 8] = couples[c].second;
         }
         h->pw_kplane = ((A + 1) / 2 + 7) / 8;  // stages of 8 site pairs
-        h->pw_el = 2, h->pw_fl = 4;           // both sites' operands are live: only 16 x 32 tiles stay spill-free
     } else {
         h->pw_mbtot = (h->pw_nmodes + 7) / 8;
         h->pw_npass = (h->pw_mbtot + PW_MAX_MB - 1) / PW_MAX_MB;
         h->pw_kplane = (A + 7) / 8;
-        pw_pick_tile(h->Ne, &h->pw_el, &h->pw_fl);
     }
+    pw_pick_tile(h->Ne, &h->pw_el, &h->pw_fl);
     if (const char* t = getenv("EDK_PW_TILE")) {  // A/B hook: "24" = 16 x 32 tiles, "25" = 16 x 40
         if (!strcmp(t, "24")) h->pw_el = 2, h->pw_fl = 4;
         if (!strcmp(t, "25")) h->pw_el = 2, h->pw_fl = 5;

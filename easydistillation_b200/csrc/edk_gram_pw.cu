@@ -445,11 +445,18 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pwf_kernel(const PwParams 
                 }
 #pragma unroll
                 for (int i = 0; i < PW_EL; ++i) {
+                    // 16 x 40 tiles: the L fragments are re-read for every f-block (broadcast loads, one wavefront each)
+                    // instead of being kept across the j loop, which is what keeps this instance inside 232 registers
                     cplx lf[3], lb[3];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        lf[c] = *reinterpret_cast<const cplx*>(stage + oLf[c] + i * 64);
-                        lb[c] = *reinterpret_cast<const cplx*>(stage + oLb[c] + i * 64);
+                        if (PW_FL > 4) {
+                            lf[c] = lds128_again(stage + oLf[c] + i * 64);
+                            lb[c] = lds128_again(stage + oLb[c] + i * 64);
+                        } else {
+                            lf[c] = *reinterpret_cast<const cplx*>(stage + oLf[c] + i * 64);
+                            lb[c] = *reinterpret_cast<const cplx*>(stage + oLb[c] + i * 64);
+                        }
                     }
                     double fr = lf[0].x * rf[0].x, fi = lf[0].x * rf[0].y;
                     double br = lb[0].x * rb[0].x, bi = lb[0].x * rb[0].y;

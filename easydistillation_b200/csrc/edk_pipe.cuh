@@ -25,6 +25,14 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// A 16-byte shared-memory load the compiler neither merges with an identical earlier one nor hoists out of an
+// unrolled loop: re-reading a broadcast operand costs one wavefront, keeping it costs four registers.
+__device__ __forceinline__ double2 lds128_again(const void* p) {
+    double2 v;
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 // sign flip on the integer pipe: the FP64 pipe is the one the DMMAs need
 __device__ __forceinline__ double flip_sign(double x) {
     return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));

@@ -172,7 +172,7 @@ def _run_candidate(form, tile, latt3, Ne, mode, order, momentum_list, device, re
 
 
 # candidates in the order they are tried: (form, EDK_PW_TILE or None = the library's own pick)
-CANDIDATES = ((2, None), (3, None), (3, "25"))
+CANDIDATES = ((2, None), (3, "25"), (3, "24"))
 
 
 def select_contraction(latt3, Ne, mode, order, momentum_list, device: int = 0, reps: int = 2, timeout: float = 900.0,

@@ -131,6 +131,7 @@ inline void dmma884(double& c0, double& c1, const double a, const double b) {
 }
 
 inline double flip_sign(double x) { return -x; }
+inline double2 lds128_again(const void* p) { return *reinterpret_cast<const double2*>(p); }
 
 using std::max;
 using std::min;
