@@ -340,9 +340,9 @@ def memcheck_cases(lib):
     """Small runs that touch every kernel family; executed by the AddressSanitizer test below in a child process."""
     cases = [((4, 4, 2), 5, D, 1, orc.momentum_set(7), (1, 0, 2, 3)),         # stencil + GEMM forms + plane-wave forms
              ((2, 2, 2), 3, D, 1, orc.momentum_set(7), (3,)),                   # folded form, back run before the plane
-             ((3, 5, 1), 3, D, 2, [(1, -1, 0), (0, 2, 1)], (2, 3, 1)),         # ragged / odd planes, second-order fields
+             ((3, 5, 1), 3, D, 2, [(1, -1, 0), (0, 2, 1)], (3, 1)),            # ragged / odd planes, second-order fields
              ((3, 5, 2), 7, X, 2, orc.momentum_set(9), (1, 2)),                 # displacement lines
-             ((4, 2, 2), 35, D, 1, orc.momentum_set(7), (2, 3))]                # multi-tile plane-wave runs with mirror tiles
+             ((4, 2, 1), 35, D, 1, orc.momentum_set(7), (2, 3))]                # multi-tile plane-wave runs with mirror tiles
     worst = 0.0
     for latt3, Ne, mode, order, moms, algos in cases:
         U_file, V, ref = inputs_and_reference(latt3, Ne, mode, order, moms)
