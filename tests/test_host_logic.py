@@ -376,3 +376,43 @@ def test_contraction_tuning_falls_back_to_the_gemm_form_without_a_gpu():
         os.environ.pop("EDK_GRAM_ALGO", None)
         if saved is not None:
             os.environ["EDK_GRAM_ALGO"] = saved
+
+
+def test_contraction_selection_picks_the_fastest_validated_candidate(monkeypatch):
+    """Decision logic of tuning.select_contraction with the child processes replaced by canned reports: a candidate
+    that failed validation or crashed is never chosen, the fastest validated one wins only if it beats the GEMM form,
+    and the chosen tile shape travels with the decision (tuning.apply exports EDK_GRAM_ALGO / EDK_PW_TILE)."""
+    from easydistillation_b200 import tuning
+
+    ok = lambda ms: {"ok": True, "cases": [{"case": "x", "err": 3e-14}], "form1_ms": 100.0, "form2_ms": ms}  # noqa: E731
+    canned = {(2, None): ok(40.0), (3, "25"): {"ok": False, "reason": "tuning child failed (exit -6): trap"}, (3, "24"): ok(25.0)}
+    calls = []
+
+    def fake(form, tile, *a):
+        calls.append((form, tile))
+        return dict(canned[(form, tile)])
+
+    monkeypatch.setattr(tuning, "_run_candidate", fake)
+    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900)
+    assert calls == [(2, None), (3, "25"), (3, "24")]
+    assert d["form"] == 3 and d["tile"] == "24" and d["validated"] and d["form2_ms"] == 25.0 and "4.00x faster" in d["reason"]
+    assert [c["ok"] for c in d["candidates"]] == [True, False, True]
+    for k in ("EDK_GRAM_ALGO", "EDK_PW_TILE"):
+        monkeypatch.delenv(k, raising=False)
+    assert tuning.apply(d) == 3 and os.environ["EDK_GRAM_ALGO"] == "3" and os.environ["EDK_PW_TILE"] == "24"
+    # validated but slower than the GEMM form: stay on form 1, no tile
+    canned[(2, None)], canned[(3, "24")] = ok(140.0), ok(120.0)
+    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900)
+    assert d["form"] == 1 and d["tile"] is None and d["validated"] and "not faster" in d["reason"]
+    assert tuning.apply(d) == 1 and os.environ["EDK_GRAM_ALGO"] == "1" and "EDK_PW_TILE" not in os.environ
+    # a differing result is never chosen, however fast
+    canned[(2, None)] = {"ok": False, "cases": [{"case": "x", "err": 2e-3}], "form1_ms": 100.0, "form2_ms": 1.0, "reason": "differs"}
+    canned[(3, "24")] = {"ok": False, "reason": "tuning child timed out after 10 s"}
+    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900)
+    assert d["form"] == 1 and not d["validated"] and "no plane-wave candidate validated" in d["reason"]
+    # no time left: candidates are skipped, not started
+    calls.clear()
+    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=5)
+    assert calls == [] and d["form"] == 1
+    os.environ.pop("EDK_GRAM_ALGO", None)
+
