@@ -393,7 +393,8 @@ def test_contraction_selection_picks_the_fastest_validated_candidate(monkeypatch
         return dict(canned[(form, tile)])
 
     monkeypatch.setattr(tuning, "_run_candidate", fake)
-    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900)
+    three = ((2, None), (3, "25"), (3, "24"))
+    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900, candidates=three)
     assert calls == [(2, None), (3, "25"), (3, "24")]
     assert d["form"] == 3 and d["tile"] == "24" and d["validated"] and d["form2_ms"] == 25.0 and "4.00x faster" in d["reason"]
     assert [c["ok"] for c in d["candidates"]] == [True, False, True]
@@ -402,13 +403,13 @@ def test_contraction_selection_picks_the_fastest_validated_candidate(monkeypatch
     assert tuning.apply(d) == 3 and os.environ["EDK_GRAM_ALGO"] == "3" and os.environ["EDK_PW_TILE"] == "24"
     # validated but slower than the GEMM form: stay on form 1, no tile
     canned[(2, None)], canned[(3, "24")] = ok(140.0), ok(120.0)
-    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900)
+    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900, candidates=three)
     assert d["form"] == 1 and d["tile"] is None and d["validated"] and "not faster" in d["reason"]
     assert tuning.apply(d) == 1 and os.environ["EDK_GRAM_ALGO"] == "1" and "EDK_PW_TILE" not in os.environ
     # a differing result is never chosen, however fast
     canned[(2, None)] = {"ok": False, "cases": [{"case": "x", "err": 2e-3}], "form1_ms": 100.0, "form2_ms": 1.0, "reason": "differs"}
     canned[(3, "24")] = {"ok": False, "reason": "tuning child timed out after 10 s"}
-    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900)
+    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900, candidates=three)
     assert d["form"] == 1 and not d["validated"] and "no plane-wave candidate validated" in d["reason"]
     # no time left: candidates are skipped, not started
     calls.clear()
