@@ -560,9 +560,9 @@ int build_pw(edk_handle* h) {
         h->pw_kplane = (A + 7) / 8;
     }
     pw_pick_tile(h->Ne, &h->pw_el, &h->pw_fl);
-    if (const char* t = getenv("EDK_PW_TILE")) {  // A/B hook: "24" = 16 x 32 tiles, "25" = 16 x 40
-        if (!strcmp(t, "24")) h->pw_el = 2, h->pw_fl = 4;
-        if (!strcmp(t, "25")) h->pw_el = 2, h->pw_fl = 5;
+    if (const char* t = getenv("EDK_PW_TILE")) {  // A/B hook: "24" = 16 x 32 tiles, "25" = 16 x 40, "17" = 8 x 56
+        const int v = atoi(t);
+        if (pw_tile_available(v / 10, v % 10)) h->pw_el = v / 10, h->pw_fl = v % 10;
     }
     const int rows_l = PW_WARPS * h->pw_el, rows_r = 8 * h->pw_fl;
     int smem = 0;

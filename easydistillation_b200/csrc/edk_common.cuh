@@ -112,7 +112,7 @@ struct CombineOp {
 //   G[job][p] = sum_z exp(2 pi i pz z/Lz) (Y[z][mc(p)] + i sigma_p Y[z][ms(p)]).
 // FP64-pipe issue slots per (pair, e, f, site): 12/32 + 2*8*MB/32 = 1.4 against 8.3 of the 3M GEMM form.
 // A lane owns EL e-rows x FL f-columns of its warp's (EL) x (8 FL) tile; the 8 MMA warps are stacked along e, so a
-// CTA tile is 8 EL rows of L by 8 FL rows of R.  Instantiated shapes: (2,4) = 16 x 32 and (2,5) = 16 x 40.
+// CTA tile is 8 EL rows of L by 8 FL rows of R.  Instantiated shapes: (2,4) = 16 x 32, (2,5) = 16 x 40, (1,7) = 8 x 56.
 constexpr int PW_WARPS = 8;             // MMA warps, stacked along e
 constexpr int PW_MAX_MB = 2;            // m-blocks (8 modes) per pass
 
@@ -181,6 +181,7 @@ cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partia
 // plane-wave factorised contraction
 int pw_plan_smem(int el, int fl, int* nstages, int* smem_bytes);
 void pw_pick_tile(int Ne, int* el, int* fl);
+bool pw_tile_available(int el, int fl);
 cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes, int mbtot, int kplane, Geom g, cudaStream_t s);
 cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, int el, int fl, cudaStream_t s);
 // folded variant (centre-symmetric site pairs): m-blocks come in (cos, sin) pairs, one pair per pass

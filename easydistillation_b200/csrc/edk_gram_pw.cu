@@ -51,19 +51,27 @@ int pw_plan_smem(int el, int fl, int* nstages, int* smem_bytes) {
     return 0;
 }
 
-// tile shape with the least padded work for this Ne (ties: the wider tile, fewer CTAs and less operand traffic)
-static const int kPwTiles[][2] = {{2, 5}, {2, 4}};
+// tile shape with the least padded work for this Ne (ties: the first = wider tile, fewer CTAs and less operand traffic).
+// (1, 7) = 8 x 56 is for Ne that leave the 16-row tiles half empty (Ne = 100: 16.5 % padded work instead of 34 %); it
+// reads 1.6x the operand bytes per site product, so it has to win by more than 5 %.
+static const int kPwTiles[][3] = {{2, 5, 100}, {2, 4, 100}, {1, 7, 105}};
 void pw_pick_tile(int Ne, int* el, int* fl) {
     long long best = -1;
     for (const auto& t : kPwTiles) {
         const int rl = PW_WARPS * t[0], rr = 8 * t[1];
-        const long long work = (long long)((Ne + rl - 1) / rl) * ((Ne + rr - 1) / rr) * t[0] * t[1];
+        const long long work = (long long)((Ne + rl - 1) / rl) * ((Ne + rr - 1) / rr) * t[0] * t[1] * t[2];
         if (best < 0 || work < best) {
             best = work;
             *el = t[0];
             *fl = t[1];
         }
     }
+}
+
+bool pw_tile_available(int el, int fl) {
+    for (const auto& t : kPwTiles)
+        if (t[0] == el && t[1] == fl) return true;
+    return false;
 }
 
 template <int MB, int PW_EL, int PW_FL>
@@ -530,10 +538,10 @@ static cudaError_t launch_gram_pw_t(const PwParams& P, const PwTma& T, int bytes
 
 cudaError_t launch_gram_pwf(const PwParams& P, const PwTma& T, int el, int fl, cudaStream_t s) {
     int nst, bytes;
-    if (pwf_plan_smem(el, fl, &nst, &bytes) != 0 || nst != T.nstages || !P.slotmode || el != 2 || (fl != 4 && fl != 5)) return cudaErrorInvalidValue;
+    if (pwf_plan_smem(el, fl, &nst, &bytes) != 0 || nst != T.nstages || !P.slotmode || !pw_tile_available(el, fl)) return cudaErrorInvalidValue;
     const long long items = (long long)P.njobs * P.Lz * P.n_et * P.n_ft;
     if (items < 1 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
-    auto kern = fl == 4 ? gram_pwf_kernel<2, 4> : gram_pwf_kernel<2, 5>;
+    auto kern = el == 1 ? gram_pwf_kernel<1, 7> : (fl == 4 ? gram_pwf_kernel<2, 4> : gram_pwf_kernel<2, 5>);
     cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     EDK_LAUNCH(kern, (unsigned)items, PW_THREADS, bytes, s, P, T);
@@ -548,6 +556,7 @@ cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, int el, in
     const unsigned n = (unsigned)items;
     if (el == 2 && fl == 4) return MB == 1 ? launch_gram_pw_t<1, 2, 4>(P, T, bytes, n, s) : launch_gram_pw_t<2, 2, 4>(P, T, bytes, n, s);
     if (el == 2 && fl == 5) return MB == 1 ? launch_gram_pw_t<1, 2, 5>(P, T, bytes, n, s) : launch_gram_pw_t<2, 2, 5>(P, T, bytes, n, s);
+    if (el == 1 && fl == 7) return MB == 1 ? launch_gram_pw_t<1, 1, 7>(P, T, bytes, n, s) : launch_gram_pw_t<2, 1, 7>(P, T, bytes, n, s);
     return cudaErrorInvalidValue;
 }
 #endif  // EDK_EMU_NO_LAUNCHERS
