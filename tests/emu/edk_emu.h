@@ -88,7 +88,7 @@ struct EmuCta {
     int nthreads = 0;
     EmuBarrier cta_barrier;
     EmuBarrier warp_barrier[32];
-    double xa[32][32], xb[32][32];
+    double xa[2][32][32], xb[2][32][32];
     std::mutex mb_mutex;
     std::condition_variable mb_cv;
     EmuMbar mbar[EMU_SMEM_BYTES / 8];
@@ -116,18 +116,24 @@ inline void __syncwarp() {
 }
 
 inline void dmma884(double& c0, double& c1, const double a, const double b) {
+    // operands are exchanged through one of two buffers, alternating per call, so that one warp barrier per DMMA is
+    // enough: a lane can only overwrite buffer k after every lane has passed the barrier of call k+1, i.e. finished
+    // reading buffer k.  The lanes of a warp execute the same sequence of DMMAs (mma.sync.aligned), so their private
+    // call counters stay in step.
+    static thread_local unsigned turn = 0;
     const int warp = emu_tid() >> 5, lane = emu_tid() & 31;
-    g_cta.xa[warp][lane] = a;
-    g_cta.xb[warp][lane] = b;
-    g_cta.warp_barrier[warp].wait(32);
+    double(*xa)[32] = g_cta.xa[turn & 1], (*xb)[32] = g_cta.xb[turn & 1];
+    ++turn;
+    xa[warp][lane] = a;
+    xb[warp][lane] = b;
+    g_cta.warp_barrier[warp].wait(emu_warp_size(warp));
     const int row = lane >> 2;
     for (int q = 0; q < 2; ++q) {
         const int col = 2 * (lane & 3) + q;
         double acc = q ? c1 : c0;
-        for (int k = 0; k < 4; ++k) acc = fma(g_cta.xa[warp][row * 4 + k], g_cta.xb[warp][col * 4 + k], acc);
+        for (int k = 0; k < 4; ++k) acc = fma(xa[warp][row * 4 + k], xb[warp][col * 4 + k], acc);
         (q ? c1 : c0) = acc;
     }
-    g_cta.warp_barrier[warp].wait(32);
 }
 
 inline double flip_sign(double x) { return -x; }
