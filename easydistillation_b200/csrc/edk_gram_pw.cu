@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pwf_kernel(const PwParams 
                     cplx lf[3], lb[3];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        if (PW_FL > 4) {
+                        if (PW_EL * PW_FL > 8) {
                             lf[c] = lds128_again(stage + oLf[c] + i * 64);
                             lb[c] = lds128_again(stage + oLb[c] + i * 64);
                         } else {
