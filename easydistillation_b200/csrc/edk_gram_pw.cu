@@ -445,48 +445,46 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pwf_kernel(const PwParams 
             }
 #pragma unroll
             for (int j = 0; j < PW_FL; ++j) {
-                cplx rf[3], rb[3];
+                // front site first, then its partner: only one site's R fragment is live at a time.
+                // 16 x 40 tiles: the L fragments are re-read for every f-block (broadcast loads, one wavefront each)
+                // instead of being kept across the j loop, which is what keeps that instance inside 232 registers.
+                auto site_products = [&](const uint32_t (&oL)[3], const uint32_t (&oR)[3], double (&pr)[PW_EL], double (&pi)[PW_EL]) {
+                    cplx r[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    rf[c] = *reinterpret_cast<const cplx*>(stage + oRf[c] + j * 512);
-                    rb[c] = *reinterpret_cast<const cplx*>(stage + oRb[c] + j * 512);
-                }
+                    for (int c = 0; c < 3; ++c)
+                        r[c] = (PW_EL * PW_FL > 8) ? lds128_again(stage + oR[c] + j * 512)
+                                                   : *reinterpret_cast<const cplx*>(stage + oR[c] + j * 512);
+#pragma unroll
+                    for (int i = 0; i < PW_EL; ++i) {
+                        cplx l[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            l[c] = (PW_EL * PW_FL > 8) ? lds128_again(stage + oL[c] + i * 64)
+                                                       : *reinterpret_cast<const cplx*>(stage + oL[c] + i * 64);
+                        // conj(L) . R over the three colours of the site
+                        double cr = l[0].x * r[0].x, ci = l[0].x * r[0].y;
+                        cr = fma(l[0].y, r[0].y, cr);
+                        ci = fma(-l[0].y, r[0].x, ci);
+#pragma unroll
+                        for (int c = 1; c < 3; ++c) {
+                            cr = fma(l[c].x, r[c].x, cr);
+                            ci = fma(l[c].x, r[c].y, ci);
+                            cr = fma(l[c].y, r[c].y, cr);
+                            ci = fma(-l[c].y, r[c].x, ci);
+                        }
+                        pr[i] = cr;
+                        pi[i] = ci;
+                    }
+                };
+                double fr[PW_EL], fi[PW_EL], br[PW_EL], bi[PW_EL];
+                site_products(oLf, oRf, fr, fi);
+                site_products(oLb, oRb, br, bi);
 #pragma unroll
                 for (int i = 0; i < PW_EL; ++i) {
-                    // 16 x 40 tiles: the L fragments are re-read for every f-block (broadcast loads, one wavefront each)
-                    // instead of being kept across the j loop, which is what keeps this instance inside 232 registers
-                    cplx lf[3], lb[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (PW_EL * PW_FL > 8) {
-                            lf[c] = lds128_again(stage + oLf[c] + i * 64);
-                            lb[c] = lds128_again(stage + oLb[c] + i * 64);
-                        } else {
-                            lf[c] = *reinterpret_cast<const cplx*>(stage + oLf[c] + i * 64);
-                            lb[c] = *reinterpret_cast<const cplx*>(stage + oLb[c] + i * 64);
-                        }
-                    }
-                    double fr = lf[0].x * rf[0].x, fi = lf[0].x * rf[0].y;
-                    double br = lb[0].x * rb[0].x, bi = lb[0].x * rb[0].y;
-                    fr = fma(lf[0].y, rf[0].y, fr);
-                    fi = fma(-lf[0].y, rf[0].x, fi);
-                    br = fma(lb[0].y, rb[0].y, br);
-                    bi = fma(-lb[0].y, rb[0].x, bi);
-#pragma unroll
-                    for (int c = 1; c < 3; ++c) {
-                        fr = fma(lf[c].x, rf[c].x, fr);
-                        fi = fma(lf[c].x, rf[c].y, fi);
-                        br = fma(lb[c].x, rb[c].x, br);
-                        bi = fma(lb[c].x, rb[c].y, bi);
-                        fr = fma(lf[c].y, rf[c].y, fr);
-                        fi = fma(-lf[c].y, rf[c].x, fi);
-                        br = fma(lb[c].y, rb[c].y, br);
-                        bi = fma(-lb[c].y, rb[c].x, bi);
-                    }
-                    dmma884(yc_re[i][j][0], yc_re[i][j][1], wc, fr + br);
-                    dmma884(yc_im[i][j][0], yc_im[i][j][1], wc, fi + bi);
-                    dmma884(ys_re[i][j][0], ys_re[i][j][1], ws, fr - br);
-                    dmma884(ys_im[i][j][0], ys_im[i][j][1], ws, fi - bi);
+                    dmma884(yc_re[i][j][0], yc_re[i][j][1], wc, fr[i] + br[i]);
+                    dmma884(yc_im[i][j][0], yc_im[i][j][1], wc, fi[i] + bi[i]);
+                    dmma884(ys_re[i][j][0], ys_re[i][j][1], ws, fr[i] - br[i]);
+                    dmma884(ys_im[i][j][0], ys_im[i][j][1], ws, fi[i] - bi[i]);
                 }
             }
         }
