@@ -62,6 +62,7 @@ struct edk_handle {
     PwTma pw_tma{};
     bool pw_ready = false;
     int pw_algo = 0;              // the form (2 or 3) the tables below were built for
+    bool pw_fold = false;         // the tables are those of the folded kernel (form 3 on planes of at least 8 sites)
     int pw_npass = 0;             // launches of the plane kernel per timeslice
     int* pw_slotmode = nullptr;   // form 3: [mbtot][8] compact mode index of every weight-tile row (-1 = unused)
     int pw_nmodes = 0, pw_mbtot = 0, pw_kplane = 0;
@@ -533,8 +534,10 @@ int build_pw(edk_handle* h) {
     EncodeFn encode = tensor_map_encoder();
     if (!encode) return EDK_ERR_CUDA;
     const ModePlan mp = plan_modes(h->mom_int);
-    const bool fold = h->algo == 3;
     const int A = h->g.Lx * h->g.Ly;
+    // Form 3 on a plane of fewer than 8 sites would start its back run of 8 sites before the plane (for z = 0: before
+    // the array); such toy planes simply run the unfolded kernel - same Y, same result.
+    const bool fold = h->algo == 3 && A >= 8;
     h->pw_nmodes = (int)mp.modes3.size() / 3;
     // form 3: the {+q, -q} couples, eight per pass; a pass has a block of cos rows and a block of sin rows
     std::vector<int> slotmode;
@@ -658,6 +661,7 @@ int build_pw(edk_handle* h) {
     }
     h->pw_bytes = wt_bytes + y_bytes + zp_bytes;
     h->pw_algo = h->algo;
+    h->pw_fold = fold;
     h->pw_ready = true;
     return EDK_OK;
 }
@@ -682,7 +686,7 @@ int run_gram_pw(edk_handle* h, cudaStream_t s) {
     {
         PhaseTimer t(h, s, PH_GRAM, npass);
         for (int pass = 0; pass < npass; ++pass) {
-            if (h->pw_algo == 3) {
+            if (h->pw_fold) {
                 Q.mb0 = 2 * pass;  // the pass's cos block, its sin block follows
                 EDK_CUDA_TRY(launch_gram_pwf(Q, h->pw_tma, h->pw_el, h->pw_fl, s));
             } else {

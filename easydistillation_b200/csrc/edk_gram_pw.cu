@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
 // a lane forms the site products of BOTH sites of its pair (24 DFMA), their sum and difference (4 DADD) and feeds the
 // sum to one block of <= 8 cos-modes and the difference to one block of <= 8 sin-modes - half the DMMAs per site.
 // A stage = 8 pairs: the 8 front sites 8k..8k+7 and the 8 back sites A-8-8k..A-1-8k of the plane (two sets of TMA
-// boxes; the back run may start before the plane or the row and then meets zero weights / zero fill).  For an odd
+// boxes; sites of the last stage that belong to no pair meet zero weights).  The host only selects this kernel for
+// planes of at least 8 sites, so a back run never starts before its plane.  For an odd
 // plane the middle site is its own partner and carries half the cos weight.  More than 8 {+q,-q} couples run as
 // passes.  The operands of two sites are live at once, which fits the register budget with 16 x 32 tiles only.
 // ---------------------------------------------------------------------------------------------------------

@@ -274,7 +274,8 @@ MANY_COUPLES = [(0, 0, 0), (1, 0, 0), (0, 1, 1), (1, 1, 0), (1, -1, 0), (2, 0, 1
     ((4, 4, 2), 5, D, 1, orc.momentum_set(7), None, True),      # even planes of 16 sites
     ((3, 5, 2), 3, D, 2, [(0, 0, 1), (1, -1, 0), (0, 2, 1)], 1, True),   # odd planes: the middle site is its own partner
     ((3, 5, 1), 3, D, 2, [(1, -1, 0), (0, 2, 1)], 0, False),    # direct pairs: multi-segment jobs with signs
-    ((2, 2, 2), 3, D, 1, orc.momentum_set(7), None, False),     # planes of 4 sites: the back run starts before the plane
+    ((2, 2, 2), 3, D, 1, orc.momentum_set(7), None, False),     # planes of 4 sites: too small to fold, run unfolded
+    ((4, 2, 2), 3, D, 1, orc.momentum_set(7), None, False),     # planes of 8 sites: one stage, back run = the whole plane
     ((3, 3, 1), 2, D, 2, orc.momentum_set(33), None, False),    # 33 momenta: 7 couples, 13 modes, plane of 9 sites
     ((5, 4, 1), 2, D, 1, MANY_COUPLES, None, False),            # more than 8 couples: two passes
     ((3, 5, 2), 7, X, 3, orc.momentum_set(9), None, False),     # displacement lines
@@ -339,7 +340,7 @@ def test_reference_class_bound_to_the_c_abi_matches_its_own_numpy_path(emu):
 def memcheck_cases(lib):
     """Small runs that touch every kernel family; executed by the AddressSanitizer test below in a child process."""
     cases = [((4, 4, 2), 5, D, 1, orc.momentum_set(7), (1, 0, 2, 3)),         # stencil + GEMM forms + plane-wave forms
-             ((2, 2, 2), 3, D, 1, orc.momentum_set(7), (3,)),                   # folded form, back run before the plane
+             ((4, 2, 2), 3, D, 1, orc.momentum_set(7), (3,)),                   # folded form, planes of exactly one stage
              ((3, 5, 1), 3, D, 2, [(1, -1, 0), (0, 2, 1)], (3, 1)),            # ragged / odd planes, second-order fields
              ((3, 5, 2), 7, X, 2, orc.momentum_set(9), (1, 2)),                 # displacement lines
              ((4, 2, 1), 35, D, 1, orc.momentum_set(7), (2, 3))]                # multi-tile plane-wave runs with mirror tiles
