@@ -417,3 +417,24 @@ def test_contraction_selection_picks_the_fastest_validated_candidate(monkeypatch
     assert calls == [] and d["form"] == 1
     os.environ.pop("EDK_GRAM_ALGO", None)
 
+
+def test_parallel_copy_matches_plain_copy():
+    """Host side of the streamed pipeline: the threaded copy of a result into the caller's array equals numpy's own
+    copy for contiguous and strided destinations, small and large, and refuses mismatched shapes."""
+    from easydistillation_b200.pipeline import parallel_copy
+
+    rng = np.random.default_rng(3)
+    for shape in [(13, 5, 40, 40), (1, 3, 8, 8), (3, 2, 200, 200), (7,)]:
+        src = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex128)
+        dst = np.full(shape, np.nan + 0j)
+        parallel_copy(dst, src, min_bytes=1)
+        assert np.array_equal(dst, src)
+        big = np.full((2,) + shape, np.nan + 0j)
+        parallel_copy(big[1], src, min_bytes=1)  # a slab of a larger array, as calc_range uses it
+        assert np.array_equal(big[1], src) and np.isnan(big[0]).all()
+    wide = np.zeros((4, 6), np.complex128)
+    parallel_copy(wide[:, ::2], np.ones((4, 3), np.complex128), min_bytes=1)  # non-contiguous destination
+    assert wide[:, ::2].sum() == 12 and wide[:, 1::2].sum() == 0
+    with pytest.raises(ValueError):
+        parallel_copy(np.zeros((4, 3)), np.zeros((3, 4)))
+
