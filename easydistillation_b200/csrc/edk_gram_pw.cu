@@ -27,6 +27,8 @@
 // Self pairs (L == R) have a Hermitian site product: their tiles below the diagonal are skipped and the fold
 // kernel reads the mirror element conjugated.  tests/test_pw_model.py is a lane-level numpy transcription of
 // the index arithmetic below (tile layout, fragment ownership, plane-boundary weights, mirror reads).
+#include <type_traits>
+
 #include "edk_common.cuh"
 #include "edk_pipe.cuh"
 
@@ -174,6 +176,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
             offR[grp][c] = (uint32_t)(PW_L_BYTES + kg * (PW_ROWS_R * 64) + n * 64 + kin * 16);
         }
     const uint32_t offW = (uint32_t)(PW_L_BYTES + PW_R_BYTES + lane * 8);
+    // padded work of edge tiles is skipped where whole warps / whole f-blocks are padding: a warp whose rows are all
+    // past Ne only keeps the ring moving, and f-blocks past Ne are not formed (both conditions are warp-uniform)
+    const bool warp_active = e0 + warp * PW_EL < P.Ne;
+    const int jmax = min(PW_FL, (P.Ne - f0 + 7) / 8);
 
     double yre[PW_EL][PW_FL][MB][2], yim[PW_EL][PW_FL][MB][2];
 #pragma unroll
@@ -209,6 +215,9 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
         }
         mbar_wait(bar_full + 8 * s, par);
         const unsigned char* stage = smem + (size_t)s * PW_STAGE_BYTES;
+        // full tiles run the unguarded body (one basic block per stage: DFMAs, DMMAs and loads of different f-blocks
+        // interleave freely); only edge tiles pay for the per-f-block guard
+        auto stage_body = [&](auto guarded) {
 #pragma unroll
         for (int grp = 0; grp < 2; ++grp) {
             double w[MB];
@@ -221,6 +230,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
                 for (int c = 0; c < 3; ++c) lv[i][c] = *reinterpret_cast<const cplx*>(stage + offL[grp][c] + i * 64);
 #pragma unroll
             for (int j = 0; j < PW_FL; ++j) {
+                if (decltype(guarded)::value && j >= jmax) break;
                 cplx rv[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) rv[c] = *reinterpret_cast<const cplx*>(stage + offR[grp][c] + j * 512);
@@ -245,6 +255,13 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pw_kernel(const PwParams P
                     }
                 }
             }
+        }
+        };
+        if (warp_active) {
+            if (jmax == PW_FL)
+                stage_body(std::false_type{});
+            else
+                stage_body(std::true_type{});
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
@@ -394,6 +411,8 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pwf_kernel(const PwParams 
     warpgroup_reg_alloc<PW_REGS_CONSUMER>();
     const int sidx = lane & 3, n = lane >> 2;  // pair inside a group of 4 (MMA k), column (MMA n)
     const uint32_t offW = (uint32_t)(2 * PW_HALF_BYTES + lane * 8);
+    const bool warp_active = e0 + warp * PW_EL < P.Ne;  // see gram_pw_kernel: padding-only warps and f-blocks are skipped
+    const int jmax = min(PW_FL, (P.Ne - f0 + 7) / 8);
 
     double yc_re[PW_EL][PW_FL][2], yc_im[PW_EL][PW_FL][2], ys_re[PW_EL][PW_FL][2], ys_im[PW_EL][PW_FL][2];
 #pragma unroll
@@ -429,6 +448,9 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pwf_kernel(const PwParams 
         }
         mbar_wait(bar_full + 8 * s, par);
         const unsigned char* stage = smem + (size_t)s * PW_STAGE_BYTES;
+        // full tiles run the unguarded body (one basic block per stage: DFMAs, DMMAs and loads of different f-blocks
+        // interleave freely); only edge tiles pay for the per-f-block guard
+        auto stage_body = [&](auto guarded) {
 #pragma unroll
         for (int grp = 0; grp < 2; ++grp) {
             const double wc = *reinterpret_cast<const double*>(stage + offW + grp * 512);
@@ -446,6 +468,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pwf_kernel(const PwParams 
             }
 #pragma unroll
             for (int j = 0; j < PW_FL; ++j) {
+                if (decltype(guarded)::value && j >= jmax) break;
                 // front site first, then its partner: only one site's R fragment is live at a time.
                 // 16 x 40 tiles: the L fragments are re-read for every f-block (broadcast loads, one wavefront each)
                 // instead of being kept across the j loop, which is what keeps that instance inside 232 registers.
@@ -488,6 +511,13 @@ __global__ void __launch_bounds__(PW_THREADS, 1) gram_pwf_kernel(const PwParams 
                     dmma884(ys_im[i][j][0], ys_im[i][j][1], ws, fi[i] - bi[i]);
                 }
             }
+        }
+        };
+        if (warp_active) {
+            if (jmax == PW_FL)
+                stage_body(std::false_type{});
+            else
+                stage_body(std::true_type{});
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);

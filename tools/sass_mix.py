@@ -29,6 +29,8 @@ def main():
             funcs[cur].append((int(m.group(1), 16), m.group(2)))
     print("# main (stage) loop of every contraction kernel: the innermost backward branch that contains DMMAs")
     print("# one stage = 8 sites (gram_tma / gram_pw) or 8 site pairs = 16 sites (gram_pwf); counts are per warp and stage")
+    print("# gram_pw / gram_pwf loops hold TWO copies of the stage body (full tiles: unguarded; edge tiles: f-blocks past Ne skipped),")
+    print("# so their counts are twice what one stage executes")
     for name in sorted(funcs):
         if not re.search(r"gram_(pw|pwf|tma)_kernel", name):
             continue
