@@ -53,17 +53,21 @@ int pw_plan_smem(int el, int fl, int* nstages, int* smem_bytes) {
     return 0;
 }
 
-// tile shape with the least padded work for this Ne (ties: the first = wider tile, fewer CTAs and less operand traffic).
-// (1, 7) = 8 x 56 is for Ne that leave the 16-row tiles half empty (Ne = 100: 16.5 % padded work instead of 34 %); it
-// reads 1.6x the operand bytes per site product, so it has to win by more than 5 %.
+// Tile shape with the least FP64-pipe time for this Ne (ties: the first = widest tile, fewest CTAs, least operand
+// traffic).  f-blocks past Ne are skipped by the kernels, so only the e side pads: an e-tile costs two warp slots per
+// SM sub-partition (8 MMA warps on 4 sub-partitions), the last one a single slot if at most 4 of its warps own real
+// rows.  (1, 7) = 8 x 56 halves the row granularity; it reads 1.6x the operand bytes per site product, so it has to
+// win by more than 5 %.
 static const int kPwTiles[][3] = {{2, 5, 100}, {2, 4, 100}, {1, 7, 105}};
 void pw_pick_tile(int Ne, int* el, int* fl) {
     long long best = -1;
     for (const auto& t : kPwTiles) {
-        const int rl = PW_WARPS * t[0], rr = 8 * t[1];
-        const long long work = (long long)((Ne + rl - 1) / rl) * ((Ne + rr - 1) / rr) * t[0] * t[1] * t[2];
-        if (best < 0 || work < best) {
-            best = work;
+        const int rl = PW_WARPS * t[0];
+        const int n_et = (Ne + rl - 1) / rl;
+        const int active_last = (Ne - (n_et - 1) * rl + t[0] - 1) / t[0];  // warps of the last e-tile with real rows
+        const long long cost = (long long)((n_et - 1) * 2 + (active_last > 4 ? 2 : 1)) * t[0] * t[2];
+        if (best < 0 || cost < best) {
+            best = cost;
             *el = t[0];
             *fl = t[1];
         }

@@ -164,13 +164,13 @@ def test_plane_wave_form_selected_by_environment_and_pairing_switches(emu, monke
 
 
 def test_plane_wave_multi_tile_and_mirror_tiles(emu):
-    """Ne = 45 -> 8 x 56 tiles, 6 x 1 of them; the self pair (W0, W0) of num_nabla = 1 skips the tiles below the
-    diagonal and the fold kernel reads their mirror."""
-    latt3, Ne, moms = (4, 2, 2), 45, orc.momentum_set(7)
+    """Ne = 64 -> 16 x 40 tiles, 4 x 2 of them; the self pair (W0, W0) of num_nabla = 1 skips the tile below the
+    diagonal (e0 = 48 > 39) and the fold kernel reads its mirror; the second f-tile has 3 of 5 f-blocks inside Ne."""
+    latt3, Ne, moms = (4, 2, 1), 64, orc.momentum_set(7)
     U_file, V, ref = inputs_and_reference(latt3, Ne, D, 1, moms)
     h = Handle(emu, latt3, Ne, D, 1, moms)
     h.check(emu.edk_debug_algo(h.h, 2), "edk_debug_algo")
-    assert h.query(12) == 17 and h.query(0) == 1  # 8 x 56 tiles: 6 x 1 of them leave the least padded work at Ne = 45
+    assert h.query(12) == 25 and h.query(0) == 1
     h.set_inputs(U_file, V)
     got = h.calc()
     h.close()
