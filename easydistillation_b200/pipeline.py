@@ -177,8 +177,11 @@ class TimeslicePipeline:
             self._compute(b, dev[b])
             done = torch.cuda.Event()
             done.record(cur)
-            if i >= 2:
-                flush(i - 2)  # pinned slot b is about to be reused
+            if i >= 1:
+                # Timeslice i is queued behind everything the device still has to do, so the host can now wait for
+                # the download of i-1 (complete about when the kernels of i start) and copy it out while i computes;
+                # this also frees the other pinned slot long before timeslice i+1 needs it.
+                flush(i - 1)
             with torch.cuda.stream(self.out_stream):
                 self.out_stream.wait_event(done)
                 pin[b].copy_(dev[b], non_blocking=True)
@@ -187,6 +190,5 @@ class TimeslicePipeline:
                 ev_out[b] = e1
                 ev_drained[b] = e1
             self.d2h_bytes += pin[b].numel() * 16
-        for j in range(max(0, len(ts) - 2), len(ts)):
-            flush(j)
+        flush(len(ts) - 1)
         return out
