@@ -301,6 +301,38 @@ def test_folded_plane_wave_form(emu, latt3, Ne, mode, order, moms, sym, switch):
     h.close()
 
 
+@pytest.mark.parametrize("name,forms,timeslices", [
+    ("deriv_n1_random_6x4x2x1", (1, 2, 3), (0,)),
+    ("deriv_n0_random_6x3x5x1", (2, 3), (0,)),
+    ("deriv_blend_4x4x4x1", (2, 3), (0,)),
+    ("deriv_weak_4x4x4x2", (2, 3), (1,)),       # the shape of the reference's own tests/test_elemental.py: num_nabla = 2, 7 momenta
+    ("disp_random_4x6x8x1", (2, 3), (0,)),
+    ("deriv_n3_random_4x4x6x1", (3,), (0,)),    # all 40 third-order operators
+    ("deriv_random_4x6x8x1", (3,), (0,)),
+    ("disp_weak_4x4x4x2", (2,), (0,)),          # distance 8, the shape of tests/test_displacement_elemental.py
+])
+def test_reference_goldens_through_every_contraction_form(emu, name, forms, timeslices):
+    """Outputs of the UNMODIFIED reference (tests/golden/*.npz, made by oracle/make_golden.py through the reference's
+    own loaders and generators) against the library on the host emulator, for the plane-wave forms that have not run
+    on hardware yet: parity with the reference itself, not only with the oracle."""
+    from conftest import load_golden
+
+    g = load_golden(name)
+    latt = [int(v) for v in g["latt_size"]]
+    Ne, moms = int(g["Ne"]), [tuple(int(c) for c in m) for m in g["momentum_list"]]
+    disp = "distance" in g.files
+    h = Handle(emu, latt[:3], Ne, X if disp else D, int(g["distance"] if disp else g["num_nabla"]), moms)
+    if "dilution_tot" in g.files:
+        coeff = np.ascontiguousarray(orc.blending_matrix(Ne, (list(g["dilution_tot"]), list(g["dilution_used"]))), np.float64)
+        h.check(emu.edk_set_blending(h.h, coeff.ctypes.data, None), "edk_set_blending")
+    for t in timeslices:
+        h.set_inputs(g["U"][t], g["V"][t])
+        for form in forms:
+            h.check(emu.edk_debug_algo(h.h, form), "edk_debug_algo")
+            assert worst_block_error(h.calc(), g["E"][t]) < 1e-10, (name, t, form)
+    h.close()
+
+
 def test_integration_md_ctypes_stub_runs_as_written(emu):
     """INTEGRATION.md section B shows the ctypes stub a reference maintainer would add (lattice/generator/_edk.py).
     The code block is executed here verbatim, bound to the emulator build of the same C ABI, and its
