@@ -674,52 +674,81 @@ cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes,
 
 #endif  // EDK_EMU_NO_LAUNCHERS
 
-// G[job][p][e][f] = sum_z zphase[p][z] (Y[job][z][mc][e][f] + i sigma Y[job][z][ms][e][f]); momentum fastest over
-// the blocks, so the ~Lz x 2 planes a block reads are shared through L2 by the momenta of the same couple.
+// G[job][p][e][f] = sum_z zphase[p][z] (Y[job][z][mc][e][f] + i sigma_p Y[job][z][ms][e][f]).
+// One block folds one {+q, -q} couple of one (job, 256 matrix elements): the couple's two planes of Y are read once
+// per z and feed all its momenta (up to 8 accumulators at a time; 5-6 momenta per couple for the |p|^2 <= 4 set), so Y
+// is read once instead of once per momentum.  Blocks are indexed by mode; those of a sin mode have nothing to do.
 constexpr int PW_FOLD_THREADS = 256;
+constexpr int PW_FOLD_MAXM = 8;
 __global__ void __launch_bounds__(PW_FOLD_THREADS) pw_zfold_kernel(const PwFold F) {
     const size_t mat = (size_t)F.Ne * F.Ne;
     const int nblk = (int)((mat + PW_FOLD_THREADS - 1) / PW_FOLD_THREADS);
     int b = blockIdx.x;
-    const int p = b % F.nmom_int;
-    b /= F.nmom_int;
+    const int mc = b % F.nmodes;
+    b /= F.nmodes;
     const int blk = b % nblk;
     const int job = b / nblk;
     const GramJob& J = F.jobs[job];
-    if (p >= J.nmom) return;  // self pairs contract the half set only
     const size_t ef = (size_t)blk * PW_FOLD_THREADS + threadIdx.x;
     if (ef >= mat) return;
     // tiles of a self pair below the diagonal were not computed: read the mirror element, conjugated
     const int e = (int)(ef / F.Ne), f = (int)(ef - (size_t)e * F.Ne);
     const bool mirror = J.nseg == 1 && J.Lf[0] == J.Rf[0] && (e / F.rows_l) * F.rows_l > (f / F.rows_r) * F.rows_r + F.rows_r - 1;
     const double cj = mirror ? -1.0 : 1.0;
-    const int mc = F.momode[3 * p], ms = F.momode[3 * p + 1];
-    const double sg = (double)F.momode[3 * p + 2];
     const cplx* Yj = F.Y + (size_t)job * F.Lz * F.nmodes * mat + (mirror ? (size_t)f * F.Ne + e : ef);
-    const cplx* zp = F.zphase + (size_t)p * F.Lz;
-    double ar = 0.0, ai = 0.0;
-    for (int z = 0; z < F.Lz; ++z) {
-        const cplx yc = Yj[((size_t)z * F.nmodes + mc) * mat];
-        double ur = yc.x, ui = cj * yc.y;
-        if (ms >= 0) {
-            const cplx ys = Yj[((size_t)z * F.nmodes + ms) * mat];
-            ur = fma(-sg, cj * ys.y, ur);
-            ui = fma(sg, ys.x, ui);
+    // momenta of this couple among the first J.nmom (self pairs contract the half set only), 8 at a time
+    for (int base = 0; base < J.nmom;) {
+        int pl[PW_FOLD_MAXM];
+        double sg[PW_FOLD_MAXM];
+        int cnt = 0, ms = -1, p = base;
+        for (; p < J.nmom && cnt < PW_FOLD_MAXM; ++p) {
+            if (F.momode[3 * p] != mc) continue;
+            ms = F.momode[3 * p + 1];
+#pragma unroll
+            for (int k = 0; k < PW_FOLD_MAXM; ++k)
+                if (k == cnt) {
+                    pl[k] = p;
+                    sg[k] = (double)F.momode[3 * p + 2];
+                }
+            ++cnt;
         }
-        const cplx ph = zp[z];
-        ar = fma(ph.x, ur, ar);
-        ar = fma(-ph.y, ui, ar);
-        ai = fma(ph.x, ui, ai);
-        ai = fma(ph.y, ur, ai);
+        base = p;
+        if (cnt == 0) continue;
+        double ar[PW_FOLD_MAXM], ai[PW_FOLD_MAXM];
+#pragma unroll
+        for (int k = 0; k < PW_FOLD_MAXM; ++k) ar[k] = ai[k] = 0.0;
+        for (int z = 0; z < F.Lz; ++z) {
+            const cplx yc = Yj[((size_t)z * F.nmodes + mc) * mat];
+            const double cr = yc.x, ci = cj * yc.y;
+            double sr = 0.0, si = 0.0;  // i * (sin plane), up to the sign sigma_p
+            if (ms >= 0) {
+                const cplx ys = Yj[((size_t)z * F.nmodes + ms) * mat];
+                sr = -cj * ys.y;
+                si = ys.x;
+            }
+#pragma unroll
+            for (int k = 0; k < PW_FOLD_MAXM; ++k) {
+                if (k < cnt) {
+                    const double ur = fma(sg[k], sr, cr), ui = fma(sg[k], si, ci);
+                    const cplx ph = F.zphase[(size_t)pl[k] * F.Lz + z];
+                    ar[k] = fma(ph.x, ur, ar[k]);
+                    ar[k] = fma(-ph.y, ui, ar[k]);
+                    ai[k] = fma(ph.x, ui, ai[k]);
+                    ai[k] = fma(ph.y, ur, ai[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PW_FOLD_MAXM; ++k)
+            if (k < cnt) F.partial[((size_t)job * F.nmom_int + pl[k]) * mat + ef] = make_double2(ar[k], ai[k]);
     }
-    F.partial[((size_t)job * F.nmom_int + p) * mat + ef] = make_double2(ar, ai);
 }
 
 #ifndef EDK_EMU_NO_LAUNCHERS
 cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s) {
     const size_t mat = (size_t)F.Ne * F.Ne;
     const long long nblk = (long long)((mat + PW_FOLD_THREADS - 1) / PW_FOLD_THREADS);
-    const long long blocks = nblk * F.njobs * F.nmom_int;
+    const long long blocks = nblk * F.njobs * F.nmodes;
     if (blocks < 1 || blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
     EDK_LAUNCH(pw_zfold_kernel, (unsigned)blocks, PW_FOLD_THREADS, 0, s, F);
     return cudaGetLastError();

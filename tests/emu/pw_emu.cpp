@@ -179,7 +179,7 @@ int main(int argc, char** argv) {
     F.momode = momode.data();
     F.partial = partial.data();
     const unsigned nblk = (unsigned)((mat + PW_FOLD_THREADS - 1) / PW_FOLD_THREADS);
-    run_simple(nblk * njobs * nmom, PW_FOLD_THREADS, [&] { pw_zfold_kernel(F); });
+    run_simple(nblk * njobs * nmodes, PW_FOLD_THREADS, [&] { pw_zfold_kernel(F); });  // one block per (job, 256 elements, mode)
 
     FILE* o = std::fopen(argv[2], "wb");
     if (!o) return 1;
