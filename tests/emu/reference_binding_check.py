@@ -72,7 +72,25 @@ def main(lib_path):
             for d in range(ref.shape[0]):
                 for p in range(ref.shape[1]):
                     worst = max(worst, float(np.linalg.norm(got[d, p] - ref[d, p]) / max(scale[d, p], floor)))
-    print(f"EDK_BINDING_OK worst block error {worst:.3e}")
+    # the elemental files this package writes, read back by the REFERENCE's own readers (lattice/preset.py:129-137,173-181)
+    import easydistillation_b200.preset as ours
+
+    rng = np.random.default_rng(1)
+    Nop, Nmom, Lt2 = 3, 2, 4
+    data = (rng.standard_normal((Nop, Nmom, Lt2, Ne, Ne)) + 1j * rng.standard_normal((Nop, Nmom, Lt2, Ne, Ne))).astype("<c16")
+    with tempfile.TemporaryDirectory() as tmp:
+        prefix = tmp + "/"
+        mm = ours.ElementalBinary(prefix, ".meson", [Nop, Nmom, Lt2, Ne, Ne], Ne).create("cfg", data.shape)
+        mm[...] = data
+        mm.flush()
+        ref_bin = lattice.preset.ElementalBinary(prefix, ".meson", [Nop, Nmom, Lt2, Ne, Ne], Ne).load("cfg")
+        assert np.array_equal(ref_bin[2, 1, 3], data[2, 1, 3]) and np.array_equal(ref_bin[0, 0], data[0, 0])
+        mm = ours.ElementalNpy(prefix, ".meson.npy").create("cfg", data.shape)
+        mm[...] = data
+        mm.flush()
+        ref_npy = lattice.ElementalNpy(prefix, ".meson.npy", [Nop, Nmom, Lt2, Ne, Ne], Ne).load("cfg")
+        assert np.array_equal(ref_npy[1, 0, 2], data[1, 0, 2])
+    print(f"EDK_BINDING_OK worst block error {worst:.3e}; elemental files readable by the reference's ElementalBinary / ElementalNpy")
     return 0 if worst < 1e-10 else 1
 
 
