@@ -196,8 +196,9 @@ def elemental_timeslice_closed_form(V_t, U_t, latt_size, num_nabla, momentum_lis
 # --------------------------------------------------------------------------
 def displacement_fields(V_t, U_t, distance):
     """Yield D_k for k = 0..distance: mean of the six straight Wilson lines of
-    length k ending at x (displacement_elemental.py:53-71)."""
-    W0 = round_through_c8(np.asarray(V_t))
+    length k ending at x (displacement_elemental.py:53-71).  Rounded eigenvectors are held in complex128, see
+    elemental_timeslice."""
+    W0 = round_through_c8(np.asarray(V_t)).astype(np.complex128)
     yield W0
     lines = None
     for k in range(1, distance + 1):
@@ -215,7 +216,7 @@ def displacement_fields(V_t, U_t, distance):
 
 def displacement_timeslice(V_t, U_t, latt_size, distance, momentum_list):
     """E[k, p] = G(W0, D_k, p), shape (distance+1, Nmom, Ne, Ne)."""
-    W0 = round_through_c8(np.asarray(V_t))
+    W0 = round_through_c8(np.asarray(V_t)).astype(np.complex128)
     Ne = W0.shape[0]
     out = np.zeros((distance + 1, len(momentum_list), Ne, Ne), np.complex128)
     phases = [momentum_phase(latt_size, p) for p in momentum_list]
