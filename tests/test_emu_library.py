@@ -239,6 +239,7 @@ def test_laplacian_and_state_errors(emu):
     ((2, 2, 2), 2, 3, [(0, 0, 0), (1, 0, 1)]),                      # num_nabla = 3: 40 operators, jobs of up to 8 segments
     ((4, 2, 2), 3, 1, [(0, 1, 0), (0, 1, 0), (0, -1, 0), (5, 0, -3)]),  # repeated momenta, |p| > L
     ((3, 2, 1), 1, 2, [(0, 0, 0)]),                                 # one eigenvector, one momentum, Lz = 1
+    ((2, 3, 4), 3, 1, [(0, 1, k) for k in range(-5, 6)] + [(0, -1, 2)]),  # 12 momenta in one couple: the z fold works in chunks of 8
 ])
 def test_plane_wave_form_edge_cases(emu, latt3, Ne, order, moms):
     U_file, V, ref = inputs_and_reference(latt3, Ne, D, order, moms)
