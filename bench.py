@@ -81,6 +81,31 @@ def measured_traffic(kernel, name):
         return None
 
 
+def contraction_accounting(q, Ne, V):
+    """Flops the contraction kernel of this handle EXECUTES per timeslice, from `ElementalEngine.query()`.
+
+    GEMM forms: 2 x (real MMAs per complex block) x Ne^2 x 3V per (pair, momentum) - the Hermitian pairing contracts
+    19 instead of SURVEY 8d's 34 pairs (self pairs only for one momentum of each +-p couple) and the 3M product needs
+    3 real MMAs instead of 4.  Plane-wave form (2): per (pair, e, f, site) 12 DFMA for the colour-summed site product
+    and, for each real xy-mode, one multiply-add on its real and imaginary part.  Folded form (3): the two sites of a
+    centre-symmetric pair share that multiply-add after one add / subtract per real and imaginary part - 2 flops per
+    site for the folding, 2 per mode and site.  `padded` additionally counts the DMMA rows that pad the mode blocks
+    (None for the GEMM forms).  Returns a dict: form, plane_wave, folded, kernel, executed, padded."""
+    form = int(q.get("contraction_form", 1))
+    pw_form, folded = form in (2, 3), form == 3
+    if not pw_form:
+        kernel = "gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel"
+        executed = 2.0 * q["real_mma_per_complex_block"] * Ne * Ne * 3 * V * q["pair_momentum_gemms"]
+        return {"form": form, "plane_wave": False, "folded": False, "kernel": kernel, "executed": executed, "padded": None}
+    modes = int(q["plane_wave_modes"])
+    per_mode, fold_adds = (2.0, 2.0) if folded else (4.0, 0.0)
+    # rows the DMMAs run over: blocks of 8 modes (form 2); per pass of 8 couples a cos block and a sin block (form 3)
+    rows = 16 * (((modes + 1) // 2 + 7) // 8) if folded else 8 * ((modes + 7) // 8)
+    base = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V
+    return {"form": form, "plane_wave": True, "folded": folded, "kernel": "gram_pwf_kernel" if folded else "gram_pw_kernel",
+            "executed": base * (24.0 + fold_adds + per_mode * modes), "padded": base * (24.0 + fold_adds + per_mode * rows)}
+
+
 def momentum_set(count):
     r = range(-3, 4)
     allp = sorted(((px * px + py * py + pz * pz, (px, py, pz)) for px in r for py in r for pz in r))
@@ -499,20 +524,8 @@ def run_native(args):
         # the 3M complex product needs 3 real MMAs instead of 4.
         # `achieved`/`frac` are the executed rate (what the FP64 pipe really does); the SURVEY-counted
         # rate is reported beside it as survey_equivalent_tflops.
-        exec_flops = 2.0 * q["real_mma_per_complex_block"] * Ne * Ne * 3 * V * q["pair_momentum_gemms"]
-        pw_form = q.get("contraction_form") in (2, 3)
-        folded = q.get("contraction_form") == 3
-        if pw_form:
-            # plane-wave factorised form (EDK_GRAM_ALGO=2): per (pair, e, f, site) 12 DFMA for the colour-summed
-            # site product and, for each of the real xy-modes, one multiply-add on its real and imaginary part
-            # (DMMA rows padded to blocks of 8 modes are not counted)
-            # folded form (3): the two sites of a centre-symmetric pair share one multiply-add per mode after one add /
-            # subtract per real and imaginary part: 2 flops per site for the folding, 2 per mode and site
-            per_mode = 2.0 if folded else 4.0
-            fold_adds = 2.0 if folded else 0.0
-            exec_flops = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V * (24.0 + fold_adds + per_mode * q["plane_wave_modes"])
-            rows = 16 * ((q["plane_wave_modes"] // 2 + 8) // 8) if folded else 8 * ((q["plane_wave_modes"] + 7) // 8)
-            pw_padded_flops = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V * (24.0 + fold_adds + per_mode * rows)
+        acct = contraction_accounting(q, Ne, V)
+        exec_flops, pw_padded_flops, pw_form, folded = acct["executed"], acct["padded"], acct["plane_wave"], acct["folded"]
         achieved_tf = exec_flops / (gram_ms * 1e-3) / 1e12
         survey_tf = flops / (gram_ms * 1e-3) / 1e12
         # stencil: bytes of ONE launch (nabla3: 1 source, 3 outputs, links once; displacement step: 6 in, 6 + mean out)
@@ -524,7 +537,7 @@ def run_native(args):
             cpu_val, cpu_smp = cpu_sample(name, W0_host.astype(np.complex64), U_sp_host)
         elif W0_host is not None:
             cpu_val, cpu_smp = cpu_sample_displacement(name, dist_, W0_host.astype(np.complex64), U_sp_host)
-        gram_name = "gram_pwf_kernel" if folded else "gram_pw_kernel" if pw_form else ("gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel")
+        gram_name = acct["kernel"]
         st_name = "nabla3_kernel" if dist_ is None else "displace_step6_kernel"
         line = {
             "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s", "n_gpus": world,

@@ -438,3 +438,32 @@ def test_parallel_copy_matches_plain_copy():
     with pytest.raises(ValueError):
         parallel_copy(np.zeros((4, 3)), np.zeros((3, 4)))
 
+
+def test_bench_contraction_accounting():
+    """The flop accounting behind bench.py's roofline object, for the three contraction forms (config-5 numbers)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("edk_bench", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    Ne, V = 200, 48 ** 3
+    gemm = bench.contraction_accounting({"contraction_form": 1, "tma_stages": 3, "real_mma_per_complex_block": 3,
+                                         "pair_momentum_gemms": 563}, Ne, V)
+    assert gemm["kernel"] == "gram_tma_kernel" and not gemm["plane_wave"] and gemm["padded"] is None
+    assert abs(gemm["executed"] / 4.48e13 - 1) < 2e-3  # DESIGN.md 3.3: 4.48e13 executed flops per timeslice at config 5
+    q = {"contraction_form": 2, "pair_gemms_per_momentum": 19, "plane_wave_modes": 13}
+    pw = bench.contraction_accounting(q, Ne, V)
+    assert pw["kernel"] == "gram_pw_kernel" and pw["plane_wave"] and not pw["folded"]
+    assert pw["executed"] == 19.0 * Ne * Ne * V * (24 + 4 * 13) and pw["padded"] == 19.0 * Ne * Ne * V * (24 + 4 * 16)
+    q["contraction_form"] = 3
+    pwf = bench.contraction_accounting(q, Ne, V)
+    assert pwf["kernel"] == "gram_pwf_kernel" and pwf["folded"]
+    assert pwf["executed"] == 19.0 * Ne * Ne * V * (24 + 2 + 2 * 13) and pwf["padded"] == 19.0 * Ne * Ne * V * (24 + 2 + 2 * 16)
+    q["plane_wave_modes"] = 19  # 10 couples: two passes of a cos and a sin block
+    assert bench.contraction_accounting(q, Ne, V)["padded"] == 19.0 * Ne * Ne * V * (24 + 2 + 2 * 32)
+    assert bench.stencil_bytes_moved("config5", planes=False) == bench.algorithmic("config5")[1]
+    assert bench.stencil_bytes_moved("config5") == bench.algorithmic("config5")[1] + 3 * Ne * V * 24.0
+    old = bench.contraction_accounting({"contraction_form": 0, "tma_stages": 0, "real_mma_per_complex_block": 4,
+                                        "pair_momentum_gemms": 10}, 8, 64)
+    assert old["kernel"] == "gram_dmma_kernel" and old["executed"] == 2.0 * 4 * 64 * 3 * 64 * 10
+
