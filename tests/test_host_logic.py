@@ -467,3 +467,54 @@ def test_bench_contraction_accounting():
                                         "pair_momentum_gemms": 10}, 8, 64)
     assert old["kernel"] == "gram_dmma_kernel" and old["executed"] == 2.0 * 4 * 64 * 3 * 64 * 10
 
+
+@pytest.mark.parametrize("form,dist_", [(1, None), (2, None), (3, None), (1, 2), (3, 2)])
+def test_bench_result_line_assembles_for_every_contraction_form(form, dist_):
+    """bench.py's native arm needs a GPU, but the block that turns its measurements into the contract's JSON line is
+    plain Python: it is cut out of run_native() here and executed on stand-in measurements for each contraction form,
+    so that a renamed variable or a missing key cannot cost the round-end benchmark its result."""
+    import ast
+    import importlib.util
+    import json
+    import types
+
+    path = os.path.join(REPO, "bench.py")
+    spec = importlib.util.spec_from_file_location("edk_bench_line", path)
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "run_native")
+    block = next(n for n in ast.walk(fn) if isinstance(n, ast.If) and ast.unparse(n.test) == "rank == 0"
+                 and any("json.dumps" in ast.unparse(b) for b in n.body))
+    code = compile(ast.Module(body=block.body, type_ignores=[]), path, "exec")
+    name = "config5"
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = bench.WORKLOADS[name]
+    q = {"hermitian_pairing": True, "internal_momenta": 33, "pair_gemms_per_momentum": 19, "ksplit": 4 if form == 1 else 1, "mfrag": 13,
+         "jobs": 19, "tma_stages": 3, "real_mma_per_complex_block": 3 if form == 1 else 4 - form, "pair_momentum_gemms": 563,
+         "half_set_momenta": 17, "contraction_form": form, "plane_wave_modes": 13 if form > 1 else 0, "plane_wave_tile": 25 if form > 1 else 0}
+    K = 3
+    prof = {"prepare": {"ms": 1.5, "launches": 2 * K}, "stencil": {"ms": 12.0, "launches": 4 * K},
+            "contraction": {"ms": {1: 4173.0, 2: 600.0, 3: 450.0}[form], "launches": K}, "combine": {"ms": 20.0, "launches": 2 * K}}
+    ns = dict(vars(bench))
+    ns.update(name=name, dist_=dist_, Lx=Lx, Ly=Ly, Lz=Lz, Ne=Ne, nabla=nabla, nmom=nmom, V=Lx * Ly * Lz, K=K, W=3, world=1, rank=0,
+              prof=prof, q=q, ms=640.0, ms_max=640.0, value=K / 0.64, e2e_value=4.4, h2d=595000000, d2h=274560000, checksum=1.0,
+              launches=27, workspace_mb=31000.0, W0_host=None, U_sp_host=None, dmma_tf=37.0, dfma_tf=36.3,
+              contraction={"requested": "auto", "form": form, "reason": "stand-in"}, torch=None, dev=None, args=types.SimpleNamespace(),
+              clocks=types.SimpleNamespace(summary=lambda: {"sm_mhz": 1965.0, "sm_max_mhz": 1965, "reasons": []}),
+              fp64_gemm_peak=lambda torch, dev: {"dgemm": 35.5, "zgemm": 36.8}, print=lambda *a, **k: None)
+    exec(code, ns)
+    line = json.loads(json.dumps(ns["line"]))
+    assert line["metric"] == "elemental_timeslices_per_sec" and line["unit"] == "timeslices/s" and line["n_gpus"] == 1
+    for key in ("value", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e",
+                "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in line, key
+    roof = line["roofline"]
+    assert roof["bound"] == "tensor" and 0 < roof["frac"] < 1.5 and roof["unit"] == "TFLOP/s" and roof["peak"] == 36.8
+    assert roof["kernel"].startswith({1: "gram_tma_kernel", 2: "gram_pw_kernel", 3: "gram_pwf_kernel"}[form])
+    assert ("executed_tflops_incl_padded_mode_rows" in roof) == (form > 1)
+    st = line["roofline_stencil"]
+    planes = 3 * Ne * Lx * Ly * Lz * 24.0
+    assert st["algorithmic_bytes_per_launch"] == st["survey_bytes_per_launch"] + (planes if form == 1 and dist_ is None else 0.0)
+    assert st["kernel"].startswith("nabla3_kernel" if dist_ is None else "displace_step6_kernel")
+    assert line["e2e"]["h2d_bytes_per_step"] == 595000000 and line["cpu_baseline"]["kind"] == "port"
+
