@@ -137,6 +137,24 @@ def test_every_contraction_path_through_the_c_abi(emu):
     assert np.array_equal(seen["algo 2"], seen["plane-wave again"])
 
 
+def test_gemm_form_tile_heights_and_split_k_through_the_launchers(emu):
+    """The template dispatch of launch_gram_tma / launch_gram_dmma (smallest and largest tile height, split-K 2) for
+    TMA 3M, TMA 4M and the cp.async loader; the full 12 x 2 x 3 sweep runs on the GPU (test_gpu_parity.py)."""
+    latt3, Ne, moms = (4, 4, 1), 9, [(0, 0, 0), (1, 0, 0)]  # 16 sites = two 8-site stages, one per K segment
+    U_file, V, ref = inputs_and_reference(latt3, Ne, D, 1, moms)
+    h = Handle(emu, latt3, Ne, D, 1, moms)
+    h.set_inputs(U_file, V)
+    for mfrag in (2, 13):
+        for algo, loader in ((1, 0), (0, 0), (0, 1)):
+            h.check(emu.edk_debug_loader(h.h, loader), "edk_debug_loader")
+            h.check(emu.edk_debug_algo(h.h, algo), "edk_debug_algo")
+            h.check(emu.edk_debug_gram_config(h.h, mfrag, 2), "edk_debug_gram_config")
+            assert h.query(4) == mfrag and h.query(3) == 2
+            assert worst_block_error(h.calc(), ref) < 1e-10, (mfrag, algo, loader)
+    assert emu.edk_debug_gram_config(h.h, 14, 0) == _capi.EDK_ERR_ARG  # not instantiated
+    h.close()
+
+
 def test_plane_wave_form_selected_by_environment_and_pairing_switches(emu, monkeypatch):
     """EDK_GRAM_ALGO=2 at edk_create (the path bench.py / tuning.apply use): configure() builds the plane-wave tables
     itself; then both pairing modes (edk_debug_symmetry re-configures: tables are rebuilt for the new job list and
