@@ -573,6 +573,10 @@ int build_pw(edk_handle* h) {
         set_error("no shared-memory plan for the plane-wave contraction");
         return EDK_ERR_ARG;
     }
+    if (const char* t = getenv("EDK_PW_STAGES")) {  // A/B hook: a shallower ring than shared memory allows (2 .. planned depth)
+        const int v = atoi(t);
+        if (v >= 2 && v < h->pw_tma.nstages) h->pw_tma.nstages = v;
+    }
     const size_t wt_bytes = (size_t)h->pw_kplane * 2 * h->pw_mbtot * 32 * sizeof(double);
     const size_t y_bytes = (size_t)h->njobs * h->g.Lz * h->pw_nmodes * h->Ne * h->Ne * sizeof(cplx);
     const size_t zp_bytes = (size_t)h->nmom_int * h->g.Lz * sizeof(cplx);

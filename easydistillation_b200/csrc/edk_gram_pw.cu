@@ -571,7 +571,7 @@ static cudaError_t launch_gram_pw_t(const PwParams& P, const PwTma& T, int bytes
 
 cudaError_t launch_gram_pwf(const PwParams& P, const PwTma& T, int el, int fl, cudaStream_t s) {
     int nst, bytes;
-    if (pwf_plan_smem(el, fl, &nst, &bytes) != 0 || nst != T.nstages || !P.slotmode || !pw_tile_available(el, fl)) return cudaErrorInvalidValue;
+    if (pwf_plan_smem(el, fl, &nst, &bytes) != 0 || T.nstages < 2 || T.nstages > nst || !P.slotmode || !pw_tile_available(el, fl)) return cudaErrorInvalidValue;
     const long long items = (long long)P.njobs * P.Lz * P.n_et * P.n_ft;
     if (items < 1 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
     auto kern = el == 1 ? gram_pwf_kernel<1, 7> : (fl == 4 ? gram_pwf_kernel<2, 4> : gram_pwf_kernel<2, 5>);
@@ -583,7 +583,7 @@ cudaError_t launch_gram_pwf(const PwParams& P, const PwTma& T, int el, int fl, c
 
 cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, int el, int fl, cudaStream_t s) {
     int nst, bytes;
-    if (pw_plan_smem(el, fl, &nst, &bytes) != 0 || nst != T.nstages || MB < 1 || MB > PW_MAX_MB) return cudaErrorInvalidValue;
+    if (pw_plan_smem(el, fl, &nst, &bytes) != 0 || T.nstages < 2 || T.nstages > nst || MB < 1 || MB > PW_MAX_MB) return cudaErrorInvalidValue;
     const long long items = (long long)P.njobs * P.Lz * P.n_et * P.n_ft;
     if (items < 1 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
     const unsigned n = (unsigned)items;

@@ -193,7 +193,7 @@ long long edk_launch_count(const edk_handle* h);
  *   7 real MMAs per complex block (3 or 4), 8 number of (pair, momentum) GEMMs contracted per timeslice
  *   (self pairs L == R only run one momentum of every +-p couple), 9 size of that half set,
  *   10 contraction form in use (0 / 1 / 2 / 3 as in edk_debug_algo), 11 real xy-modes of forms 2 / 3 (0 = not built),
- *   12 tile shape of forms 2 / 3 as 10 el + fl (24 = 16 x 32 rows, 25 = 16 x 40, 17 = 8 x 56; environment EDK_PW_TILE overrides the pick).
+ *   12 tile shape of forms 2 / 3 as 10 el + fl (24 = 16 x 32 rows, 25 = 16 x 40, 17 = 8 x 56; environment EDK_PW_TILE overrides the pick, EDK_PW_STAGES = 2.. caps the depth of the operand ring: A/B hooks).
  *   With forms 2 / 3, what = 7 answers 2 / 1 (DMMAs per site, real or imaginary part and block of 8 modes).
  */
 int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream);

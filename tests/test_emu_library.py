@@ -271,6 +271,8 @@ def test_plane_wave_form_edge_cases(emu, latt3, Ne, order, moms):
 
 @pytest.mark.parametrize("tile", ["24", "25", "17"])
 def test_folded_form_both_tile_shapes(emu, monkeypatch, tile):
+    if tile == "24":
+        monkeypatch.setenv("EDK_PW_STAGES", "2")  # A/B hook: the shallowest ring (the wrap-around parity is exercised most)
     """EDK_PW_TILE forces the 16 x 32, the 16 x 40 (re-reads its L fragments per f-block) or the 8 x 56 instance; Ne = 45
     gives several tiles in each case, with the self pair's mirror tiles."""
     latt3, Ne, moms = (4, 2, 1), 45, [(0, 0, 0), (1, 0, 0), (0, -1, 0)]
