@@ -120,6 +120,17 @@ def main():
         report["cases"].append(r)
         report["ok"] = report["ok"] and r["ok"]
         print(json.dumps(r), flush=True)
+    # every instantiated tile shape (the default pick above is by FP64-pipe time): multi-tile, mirror tiles, partial f-tiles
+    for tile in ("24", "25", "17"):
+        os.environ["EDK_PW_TILE"] = tile
+        t0 = time.time()
+        r = run_case([4, 4, 4], 70, D, 1, orc.momentum_set(7), None)
+        r["seconds"] = time.time() - t0
+        r["ok"] = bool(r["ok"] and r["tile"] == int(tile))
+        report["cases"].append(r)
+        report["ok"] = report["ok"] and r["ok"]
+        print(json.dumps(r), flush=True)
+    os.environ.pop("EDK_PW_TILE", None)
     if "--bench" in sys.argv and report["ok"]:
         report["timing"] = [time_forms([24, 24, 24], 100, 2, 33), time_forms([32, 32, 32], 200, 2, 33, reps=2)]
         print(json.dumps(report["timing"]), flush=True)
