@@ -87,6 +87,9 @@ def lib() -> C.CDLL:
                 "easydistillation_b200 has no CPU or PyTorch fallback."
             )
         L = C.CDLL(LIB_PATH)
+        if hasattr(L, "edk_host_emulator_build"):  # tests/emu: the kernels on host threads, for the CPU test suite only
+            raise ImportError(f"{LIB_PATH} is the host-emulator test build of the C ABI; the package only runs on the "
+                              "sm_100a library (no CPU path)")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the library is stale
             fn.restype = res

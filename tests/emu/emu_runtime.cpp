@@ -80,6 +80,9 @@ CUresult fake_encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t 
 
 extern "C" {
 
+// marker by which easydistillation_b200/_capi.py refuses to load this build: it is test infrastructure, not a CPU path
+int edk_host_emulator_build(void) { return 1; }
+
 cudaError_t cudaSetDevice(int dev) { return dev == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
 cudaError_t cudaGetLastError(void) {
     const cudaError_t e = edk::g_last;

@@ -235,6 +235,17 @@ def test_link_preprocessing_blending_and_host_entry_point(emu):
     assert worst_block_error(out, ref) < 1e-10
 
 
+def test_package_refuses_the_emulator_build(emu):
+    """EDK_LIBRARY may point the package at another build of the C ABI (A/B runs of kernel variants), but never at the
+    host emulator: there is no CPU path through the product."""
+    import sys
+
+    code = "from easydistillation_b200 import _capi; _capi.lib()"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=REPO,
+                       env=dict(os.environ, EDK_LIBRARY=emu._name, PYTHONPATH=REPO))
+    assert r.returncode != 0 and "host-emulator test build" in r.stderr, r.stderr[-800:]
+
+
 def test_laplacian_and_state_errors(emu):
     latt3, Ne, moms = (4, 3, 2), 3, [(0, 0, 0)]
     latt = list(latt3) + [1]
