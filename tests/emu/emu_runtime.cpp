@@ -5,7 +5,8 @@
 // (tests/emu/edk_emu.h, emu_launch) and cuTensorMapEncodeTiled = the emulator's own box descriptor.  What this
 // buys: the host glue of csrc/edk_api.cu (job lists, buffer sizes, tensor maps, launch configurations, the
 // switching between contraction forms) and every launcher run on a machine without a GPU, end to end against the
-// oracle.  It is never loaded by the package (easydistillation_b200/_capi.py only loads libedk_sm100a.so).
+// oracle.  It is never loaded by the package (easydistillation_b200/_capi.py refuses a library that exports the
+// marker edk_host_emulator_build below).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
