@@ -562,7 +562,7 @@ int build_pw(edk_handle* h) {
         h->pw_npass = (h->pw_mbtot + PW_MAX_MB - 1) / PW_MAX_MB;
         h->pw_kplane = (A + 7) / 8;
     }
-    pw_pick_tile(h->Ne, &h->pw_el, &h->pw_fl);
+    pw_pick_tile(h->Ne, fold, &h->pw_el, &h->pw_fl);
     if (const char* t = getenv("EDK_PW_TILE")) {  // A/B hook: "24" = 16 x 32 tiles, "25" = 16 x 40, "17" = 8 x 56
         const int v = atoi(t);
         if (pw_tile_available(v / 10, v % 10)) h->pw_el = v / 10, h->pw_fl = v % 10;

@@ -180,7 +180,7 @@ cudaError_t launch_combine(const CombineOp* ops_dev, int nop, const cplx* partia
                            cudaStream_t s);
 // plane-wave factorised contraction
 int pw_plan_smem(int el, int fl, int* nstages, int* smem_bytes);
-void pw_pick_tile(int Ne, int* el, int* fl);
+void pw_pick_tile(int Ne, bool folded, int* el, int* fl);
 bool pw_tile_available(int el, int fl);
 cudaError_t launch_pw_weights(double* wtiles, const int* modes3_dev, int nmodes, int mbtot, int kplane, Geom g, cudaStream_t s);
 cudaError_t launch_gram_pw(const PwParams& P, const PwTma& T, int MB, int el, int fl, cudaStream_t s);

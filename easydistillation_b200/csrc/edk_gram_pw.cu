@@ -59,14 +59,17 @@ int pw_plan_smem(int el, int fl, int* nstages, int* smem_bytes) {
 // rows.  (1, 7) = 8 x 56 halves the row granularity; it reads 1.6x the operand bytes per site product, so it has to
 // win by more than 5 %.
 static const int kPwTiles[][3] = {{2, 5, 100}, {2, 4, 100}, {1, 7, 105}};
-void pw_pick_tile(int Ne, int* el, int* fl) {
+void pw_pick_tile(int Ne, bool folded, int* el, int* fl) {
     long long best = -1;
     for (const auto& t : kPwTiles) {
         const int rl = PW_WARPS * t[0];
         const int n_et = (Ne + rl - 1) / rl;
         const int active_last = (Ne - (n_et - 1) * rl + t[0] - 1) / t[0];  // warps of the last e-tile with real rows
         const long long cost = (long long)((n_et - 1) * 2 + (active_last > 4 ? 2 : 1)) * t[0] * t[2];
-        if (best < 0 || cost < best) {
+        // the folded 16 x 40 instance pays for its register budget with program-ordered operand loads: at equal cost
+        // (16 x 32 and 16 x 40 always tie now that f-blocks past Ne are skipped) form 3 takes 16 x 32
+        const bool take = best < 0 || cost < best || (folded && cost == best && *el == 2 && *fl == 5 && t[0] == 2 && t[1] == 4);
+        if (take) {
             best = cost;
             *el = t[0];
             *fl = t[1];
