@@ -52,6 +52,19 @@ def workload_desc(name, distance=None):
             "ElementalGenerator, one timeslice per step")
 
 
+def config_dict(name, distance, K, world):
+    """The workload description both arms print (identical for `--impl native` and `--impl reference`)."""
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    V = Lx * Ly * Lz
+    fields_mb = (Ne * V * 3 * 8 + Ne * V * 48 * (SRC_OUT[nabla][1] if distance is None else 12)) / 1e6
+    return {
+        "workload": workload_desc(name, distance), "lattice": [Lx, Ly, Lz], "Ne": Ne,
+        **({"num_nabla": nabla} if distance is None else {"distance": distance}), "momenta": nmom,
+        "sharding": f"timeslices, {K} per rank, {world} rank(s)" + (", results gathered on rank 0 inside the timed region" if world > 1 else ""),
+        "l2": f"step inputs+fields ({fields_mb:.0f} MB) exceed the 126 MB L2; two input sets alternated",
+    }
+
+
 def algorithmic(name, distance=None):
     """contraction flops per timeslice and bytes of ONE stencil launch."""
     Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
@@ -81,29 +94,67 @@ def measured_traffic(kernel, name):
         return None
 
 
-def contraction_accounting(q, Ne, V):
-    """Flops the contraction kernel of this handle EXECUTES per timeslice, from `ElementalEngine.query()`.
+def _executed_elements(Ne, te, tf, self_pair):
+    """(e, f) elements a plane kernel with te x tf tiles really computes for one job: every valid element, except that a
+    self pair (L == R) skips its tiles entirely below the diagonal (the fold kernel reads the mirror element)."""
+    if not self_pair:
+        return Ne * Ne
+    n = 0
+    for e0 in range(0, Ne, te):
+        for f0 in range(0, Ne, tf):
+            if e0 > f0 + tf - 1:
+                continue
+            n += (min(e0 + te, Ne) - e0) * (min(f0 + tf, Ne) - f0)
+    return n
 
-    GEMM forms: 2 x (real MMAs per complex block) x Ne^2 x 3V per (pair, momentum) - the Hermitian pairing contracts
-    19 instead of SURVEY 8d's 34 pairs (self pairs only for one momentum of each +-p couple) and the 3M product needs
-    3 real MMAs instead of 4.  Plane-wave form (2): per (pair, e, f, site) 12 DFMA for the colour-summed site product
-    and, for each real xy-mode, one multiply-add on its real and imaginary part.  Folded form (3): the two sites of a
-    centre-symmetric pair share that multiply-add after one add / subtract per real and imaginary part - 2 flops per
-    site for the folding, 2 per mode and site.  `padded` additionally counts the DMMA rows that pad the mode blocks
-    (None for the GEMM forms).  Returns a dict: form, plane_wave, folded, kernel, executed, padded."""
+
+def contraction_accounting(q, Ne, latt3, self_pairs=0):
+    """Work the contraction kernel of this handle EXECUTES per timeslice, from `ElementalEngine.query()`.
+
+    Returns a dict: form, kernel, executed (real flops: FMA = 2, add / multiply = 1), slots (FP64-pipe lane-operations:
+    one per DFMA / DADD / DMUL lane, 8 per lane of a DMMA.8x8x4 - the unit the shared FP64 pipe of B200 retires 16 of per
+    cycle and SM sub-partition, so slots / (592 x 16 x clock x time) is the pipe utilisation ncu reports as
+    sm__pipe_fp64_cycles_active + sm__pipe_tensor_subpipe_dmma_cycles_active), padded (forms 2 / 3: flops including the
+    DMMA rows that pad the mode blocks).
+      GEMM forms: 2 x (real MMAs per complex block) x Ne^2 x 3V per (pair, momentum) - the Hermitian pairing contracts 19
+        instead of SURVEY 8d's 34 pairs (self pairs only one momentum of each +-p couple), 3M needs 3 real MMAs, not 4.
+      Plane-wave form (2): per (pair, e, f, site) 12 DFMA for the colour-summed site product and, for each real xy-mode,
+        one multiply-add on its real and imaginary part.  Folded (3): the two sites of a centre-symmetric pair share that
+        multiply-add after one add / subtract per part.
+      Separable form (4): per pair of sites (x, Lx-1-x): 2 x (10 DFMA + 2 DMUL) site products, 4 DADD (sum, difference),
+        2 DADD + 8 DFMA (5 x-modes; 4 DFMA with 3); per row and (e, f) one multiply-add (or add) per separable xy-mode on
+        the real and imaginary part.
+    Self pairs (L == R) skip the tiles below the diagonal in forms 2 - 4: only executed tiles are counted."""
+    Lx, Ly, Lz = latt3
+    V = Lx * Ly * Lz
     form = int(q.get("contraction_form", 1))
-    pw_form, folded = form in (2, 3), form == 3
-    if not pw_form:
+    segs = float(q["pair_gemms_per_momentum"])  # (left, right) segments contracted
+    if form < 2:
         kernel = "gram_tma_kernel" if q.get("tma_stages") else "gram_dmma_kernel"
         executed = 2.0 * q["real_mma_per_complex_block"] * Ne * Ne * 3 * V * q["pair_momentum_gemms"]
-        return {"form": form, "plane_wave": False, "folded": False, "kernel": kernel, "executed": executed, "padded": None}
+        return {"form": form, "kernel": kernel, "executed": executed, "slots": executed / 2.0, "padded": None}
+    tile = int(q["plane_wave_tile"])
+    # forms 2 / 3 skip whole CTA tiles of a self pair below the diagonal, form 4 (gram_sepx_kernel) warp tiles of 8 x 16 elements
+    te, tf = (8, 16) if form == 4 else (8 * (tile // 10), 8 * (tile % 10))
+    elems = (segs - self_pairs) * Ne * Ne + self_pairs * _executed_elements(Ne, te, tf, True)
+    base = elems * V
     modes = int(q["plane_wave_modes"])
+    if form == 4:
+        nx = {5: 3, 9: 3, 13: 5}[modes]                    # x modes: constant + cos / sin of 1 (and 2)
+        ymul = {5: 2, 9: 6, 13: 8}[modes]                  # separable modes with a non-constant y weight
+        per_site_flops = 22.0 + 2.0 + 1.0 + 2.0 * (nx - 1)  # site product, sum / difference, X[1], X[c_q] / X[s_q]
+        per_site_slots = 12.0 + 2.0 + 1.0 + 1.0 * (nx - 1)
+        per_row_flops = 4.0 * ymul + 2.0 * (modes - ymul)
+        per_row_slots = 2.0 * modes
+        return {"form": 4, "kernel": "gram_sepx_kernel", "executed": base * (per_site_flops + per_row_flops / Lx),
+                "slots": base * (per_site_slots + per_row_slots / Lx), "padded": None}
+    folded = form == 3
     per_mode, fold_adds = (2.0, 2.0) if folded else (4.0, 0.0)
     # rows the DMMAs run over: blocks of 8 modes (form 2); per pass of 8 couples a cos block and a sin block (form 3)
     rows = 16 * (((modes + 1) // 2 + 7) // 8) if folded else 8 * ((modes + 7) // 8)
-    base = float(q["pair_gemms_per_momentum"]) * Ne * Ne * V
-    return {"form": form, "plane_wave": True, "folded": folded, "kernel": "gram_pwf_kernel" if folded else "gram_pw_kernel",
-            "executed": base * (24.0 + fold_adds + per_mode * modes), "padded": base * (24.0 + fold_adds + per_mode * rows)}
+    return {"form": form, "kernel": "gram_pwf_kernel" if folded else "gram_pw_kernel",
+            "executed": base * (24.0 + fold_adds + per_mode * modes), "padded": base * (24.0 + fold_adds + per_mode * rows),
+            "slots": base * (12.0 + fold_adds + per_mode * rows / 2.0)}
 
 
 def momentum_set(count):
@@ -284,7 +335,7 @@ def run_reference(args):
         "impl": "reference", "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
-        "config": {"workload": workload_desc(name, dist_)},
+        "config": config_dict(name, dist_, args.steps, args.gpus),
         "cpu_baseline": {"value": value, "unit": "timeslices/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "timeslices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -337,12 +388,81 @@ def fp64_gemm_peak(torch, dev):
     return out
 
 
+def worst_block_error(got, ref):
+    """Largest Frobenius error of an (operator, momentum) block relative to the block's norm (blocks that vanish
+    analytically are measured against 1e-4 of the largest block): the measure of the parity tests."""
+    norms = np.sqrt((np.abs(ref) ** 2).sum(axis=(-1, -2)))
+    floor = 1e-4 * norms.max()
+    err = np.sqrt((np.abs(got - ref) ** 2).sum(axis=(-1, -2)))
+    return float((err / np.maximum(norms, floor)).max())
+
+
+def file_backed_leg(edb, torch, dev, name, dist_, moms, U_two, V_two, K, barrier):
+    """End to end from FILES: the timeslices are read through the typed file handles - an ILDG gauge
+    configuration, eigenvectors once as a `.npy` file and once as a QDP timeslice `.mod` file (big-endian complex64,
+    byte-swapped on the device) - by the streamed pipeline of calc_range, results to host arrays.  Replaces the reference's
+    per-eigenvector open + mmap + copy loop (filedata/ndarray.py:17-47, timeslice.py:65-99, elemental.py:297-298)."""
+    import shutil
+    import tempfile
+
+    from easydistillation_b200.fileio import write_ildg, write_qdp_timeslices
+
+    Lx, Ly, Lz, Lt, Ne, nabla, nmom = WORKLOADS[name]
+    Kf = max(2, min(K, 4))
+    need = Kf * (V_two[0].nbytes * 3 + U_two[0].nbytes) * 1.2
+    root = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need else None
+    tmp = tempfile.mkdtemp(prefix="edk_bench_", dir=root)
+    out = {"timeslices": Kf, "directory": "tmpfs" if root else "default temporary directory"}
+    try:
+        prefix = tmp + "/"
+        t0 = time.perf_counter()
+        write_ildg(prefix + "cfg.lime", np.stack([U_two[i % 2] for i in range(Kf)]))
+        Vc16 = np.lib.format.open_memmap(prefix + "cfg.eigenvector.npy", mode="w+", dtype="<c16", shape=(Kf, Ne, Lz, Ly, Lx, 3))
+        for i in range(Kf):
+            Vc16[i] = V_two[i % 2]
+        Vc16.flush()
+        del Vc16
+        write_qdp_timeslices(prefix + "cfg.mod", np.stack([V_two[i % 2] for i in range(Kf)]).reshape(Kf, Ne, Lz * Ly * Lx, 3), [Lx, Ly, Lz, Kf])
+        out["write_seconds"] = time.perf_counter() - t0
+        gauge = edb.GaugeFieldIldg(prefix, ".lime", [Kf, Lz, Ly, Lx, 4, 3, 3])
+        legs = {"npy_c16": edb.EigenvectorNpy(prefix, ".eigenvector.npy", [Kf, Ne, Lz, Ly, Lx, 3], Ne),
+                "qdp_mod_c8_big_endian": edb.EigenvectorTimeSlice(prefix, ".mod", [Kf, Ne, Lz * Ly * Lx, 3], Ne)}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for tag, evec in legs.items():
+            if dist_ is None:
+                gen = edb.ElementalGenerator([Lx, Ly, Lz, Kf], gauge, evec, nabla, moms, device=dev.index)
+            else:
+                gen = edb.DisplacementElementalGenerator([Lx, Ly, Lz, Kf], gauge, evec, dist_, moms, device=dev.index)
+            gen.load("cfg")
+            gen.calc_range(0, 2)  # warm-up: staging buffers
+            pipe = gen._pipeline
+            h2d0 = pipe.h2d_bytes
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            res = gen.calc_range(0, Kf)
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            read_bytes = (pipe.h2d_bytes - h2d0)  # every byte uploaded was read from the files first
+            out[tag] = {"value": Kf / (e0.elapsed_time(e1) * 1e-3), "unit": "timeslices/s", "file_read_GBps": read_bytes / wall / 1e9,
+                        "file_bytes_per_step": read_bytes // Kf, "checksum": float(np.abs(res[0, 0, 0]).sum())}
+            del gen, res
+            torch.cuda.empty_cache()
+    except Exception as exc:  # the file leg must never cost the main line
+        out["error"] = repr(exc)[:300]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
 
+    import easydistillation_b200 as edb
     from easydistillation_b200 import _capi
-    from easydistillation_b200.engine import ElementalEngine, microbench_fp64
+    from easydistillation_b200.engine import microbench_fp64
     from easydistillation_b200.sharding import gather_timeslices
 
     if not torch.cuda.is_available():
@@ -366,46 +486,35 @@ def run_native(args):
     dist_ = args.distance if args.generator == "displacement" else None
     mode_, order_ = (_capi.MODE_DERIVATIVE, nabla) if dist_ is None else (_capi.MODE_DISPLACEMENT, dist_)
 
-    # ---- contraction form (untimed set-up, like a user's one-off `python -m easydistillation_b200.tuning`) ----
-    # "auto": a child process validates the plane-wave form against the GEMM form at this workload's shape and
-    # through the public class API, times both, and the faster validated one becomes the default of this process.
+    # ---- contraction form: the library plans it per handle (edk_plan_form); `--contraction X` asks for one form through
+    # the A/B hook EDK_GRAM_ALGO, for measurements only ----
     contraction = {"requested": args.contraction}
-    if os.environ.get("EDK_GRAM_ALGO"):
-        contraction.update(form=int(os.environ["EDK_GRAM_ALGO"]), reason="EDK_GRAM_ALGO set by the caller")
-    elif args.contraction == "auto":
-        from easydistillation_b200 import tuning
-
-        decision = tuning.select_contraction((Lx, Ly, Lz), Ne, mode_, order_, moms, device=local, reps=2, timeout=420.0)
-        form = int(decision["form"])
-        if world > 1:  # every rank uses the same form: the slowest decision wins
-            tf = torch.tensor([form], dtype=torch.int32, device=dev)
-            dist.all_reduce(tf, op=dist.ReduceOp.MIN)
-            form = int(tf.item())
-        if form != decision["form"]:
-            decision.update(form=form, tile=None)
-        tuning.apply(decision)
-        contraction.update(decision)
-        if rank == 0:
-            print(f"bench.py: contraction form {form} ({decision['reason']})", file=sys.stderr, flush=True)
+    forced = {"gemm": 1, "planewave": 2, "planewave-folded": 3, "separable": 4}.get(args.contraction)
+    if forced is not None:
+        os.environ["EDK_GRAM_ALGO"] = str(forced)
+        contraction["reason"] = "forced by --contraction"
+    elif os.environ.get("EDK_GRAM_ALGO"):
+        contraction["reason"] = "EDK_GRAM_ALGO set by the caller"
     else:
-        form = {"planewave": 2, "planewave-folded": 3}.get(args.contraction, 1)
-        os.environ["EDK_GRAM_ALGO"] = str(form)
-        contraction.update(form=form, reason="forced by --contraction")
-    eng = ElementalEngine((Lx, Ly, Lz), Ne, mode_, order_, moms, device=local)
+        contraction["reason"] = "planned by the library (edk_plan_form)"
+        contraction["plan"] = _capi.plan_form((Lx, Ly, Lz), mode_, order_, moms)
+
+    def make_generator(gauge, evec, Lt_run):
+        if dist_ is None:
+            return edb.ElementalGenerator([Lx, Ly, Lz, Lt_run], gauge, evec, nabla, moms, device=local)
+        return edb.DisplacementElementalGenerator([Lx, Ly, Lz, Lt_run], gauge, evec, dist_, moms, device=local)
+
+    # ---- device-resident throughput through the public class: K timeslices per rank, sharded by calc_all() ----
+    # two resident input sets, alternated, each far larger than L2 at the graded workloads
+    inputs = [synth_device_inputs(torch, dev, name, 1000 * rank + i) for i in range(2)]
+    gen = make_generator(edb.GaugeFieldDevice([U.reshape(Lz, Ly, Lx, 4, 3, 3) for U, _ in inputs], cyclic=True),
+                         edb.EigenvectorDevice([v.reshape(Ne, Lz, Ly, Lx, 3) for _, v in inputs], cyclic=True), K * world)
+    gen.load("bench")
+    eng = gen._engine
 
     if os.environ.get("EDK_BENCH_GRAM"):  # tuning hook: "mfrag,ksplit" (0 = auto)
         mf, ks = (int(v) for v in os.environ["EDK_BENCH_GRAM"].split(","))
         eng.debug_gram_config(mf, ks)
-
-    # two resident input sets, alternated, each far larger than L2 at the graded workloads
-    inputs = [synth_device_inputs(torch, dev, name, 1000 * rank + i) for i in range(2)]
-    outs = torch.empty((K,) + eng.out_shape, dtype=torch.complex128, device=dev)
-
-    def step(i, out):
-        U, v = inputs[i % 2]
-        eng.set_links(U, _capi.LINKS_FILE_T)
-        eng.set_eigvecs(v)
-        eng.calc(out)
 
     def barrier():
         if world > 1:
@@ -414,21 +523,18 @@ def run_native(args):
 
     scratch = torch.empty(eng.out_shape, dtype=torch.complex128, device=dev)
     for i in range(W):
-        step(i, scratch)
-    if world > 1:  # first use of the collective sets up the NCCL channels: not part of a step
-        gather_timeslices(outs[:1], world, dst=0)
+        gen.calc_device(i, out=scratch)
+    if world > 1:  # first use of the communicator sets up the NCCL channels: not part of a step
+        gather_timeslices(scratch[None, :1, :1].contiguous().expand(1, 1, 1, Ne, Ne).contiguous(), world, dst=0)
     barrier()
 
-    # ---- device-resident throughput --------------------------------------------------------
     launches0 = eng.launch_count
     eng.set_profiling(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
         e0.record()
-        for i in range(K):
-            step(i, outs[i])
-        gathered = gather_timeslices(outs, K * world, dst=0) if world > 1 else outs
+        gathered = gen.calc_all(dst=0)  # this rank's K timeslices; finished chunks travel to rank 0 while the next are computed
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
@@ -440,10 +546,21 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * K / (ms_max * 1e-3)
+    first = gathered[0].clone() if rank == 0 else None  # timeslice 0 = rank 0's first: input set 0
     del gathered
 
-    # everything that needs the first handle, then free its 14 GB workspace for the end-to-end leg
+    # ---- observed error of the planned form at this shape: the same timeslice through the GEMM form (untimed) ----
     q = eng.query()
+    parity = None
+    if rank == 0 and q["contraction_form"] != 1 and not args.no_parity_check:
+        eng.debug_algo(1)
+        ref1 = gen.calc_device(0, out=scratch)
+        parity = {"against": "GEMM form (3M arithmetic on DMMA) on the same timeslice", "tolerance": 1e-10,
+                  "worst_block_rel_err": worst_block_error(first.cpu().numpy(), ref1.cpu().numpy())}
+        eng.debug_algo(-1 if forced is None and not os.environ.get("EDK_GRAM_ALGO") else int(os.environ["EDK_GRAM_ALGO"]))
+    del first
+
+    # everything that needs the first handle, then free its workspace for the end-to-end legs
     workspace_mb = eng.workspace_bytes / 1e6
     W0_host = eng.debug_field(0).cpu().numpy() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     U0, v0 = inputs[0]
@@ -451,15 +568,15 @@ def run_native(args):
     if W0_host is not None:
         U_sp_host = np.ascontiguousarray(np.moveaxis(U0.cpu().numpy().reshape(Lz, Ly, Lx, 4, 3, 3), 3, 0)[:3])
     dmma_tf, dfma_tf = microbench_fp64(local) if rank == 0 else (0.0, 0.0)
-    eng.close()
-    del eng, outs, scratch
+    U_two = [inputs[i][0].cpu().numpy().reshape(Lz, Ly, Lx, 4, 3, 3) for i in range(2)]
+    V_two = [inputs[i][1].cpu().numpy().reshape(Ne, Lz, Ly, Lx, 3) for i in range(2)]
+    del gen, eng, scratch, inputs, U0, v0
+    torch.cuda.empty_cache()
 
     # ---- end to end through the public class API: host arrays in, numpy out ---------------------
     # ElementalGenerator.calc_range streams the timeslices: pinned staging + H2D of t+1 and D2H of
     # t-1 overlap the kernels of t (easydistillation_b200/pipeline.py); every step uploads its links
-    # and eigenvectors and downloads its result.
-    import easydistillation_b200 as edb
-
+    # and eigenvectors and downloads its result.  With N ranks each streams its own K timeslices.
     class CyclicEigenvectors:  # duck-typed eigenvector handle: two distinct host timeslices, repeated
         def __init__(self, two):
             self.two, self.Ne = two, Ne
@@ -472,19 +589,12 @@ def run_native(args):
             blk = self.two[t % 2]
             return blk[key[1]] if isinstance(key, tuple) and len(key) > 1 else blk
 
-    U_two = [inputs[i][0].cpu().numpy().reshape(Lz, Ly, Lx, 4, 3, 3) for i in range(2)]
     U_host = np.stack([U_two[i % 2] for i in range(K)])
-    V_two = [inputs[i][1].cpu().numpy().reshape(Ne, Lz, Ly, Lx, 3) for i in range(2)]
     if K * V_two[0].nbytes <= 8 << 30:  # small enough to hold K timeslices: the ordinary in-memory handle
         evec = edb.EigenvectorHostmem(np.stack([V_two[i % 2] for i in range(K)]))
     else:
         evec = CyclicEigenvectors(V_two)
-    del inputs, U0, v0
-    torch.cuda.empty_cache()
-    if dist_ is None:
-        gen = edb.ElementalGenerator([Lx, Ly, Lz, K], edb.GaugeFieldHostmem(U_host), evec, nabla, moms, device=local)
-    else:
-        gen = edb.DisplacementElementalGenerator([Lx, Ly, Lz, K], edb.GaugeFieldHostmem(U_host), evec, dist_, moms, device=local)
+    gen = make_generator(edb.GaugeFieldHostmem(U_host), evec, K)
     gen.load("bench")
     gen.calc_range(0, min(K, 2))  # warm-up: allocates the staging buffers
     pipe = gen._pipeline
@@ -501,7 +611,11 @@ def run_native(args):
     h2d = (pipe.h2d_bytes - h2d0) // K
     d2h = (pipe.d2h_bytes - d2h0) // K
     checksum = float(np.abs(res[0, 0, 0]).sum())
-    del res
+    del res, gen, pipe, evec, U_host
+    torch.cuda.empty_cache()
+    files = None
+    if world == 1 and not args.no_file_leg:
+        files = file_backed_leg(edb, torch, dev, name, dist_, moms, U_two, V_two, K, barrier)
 
     line = None
     if rank == 0:
@@ -518,14 +632,16 @@ def run_native(args):
         hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         gemm = fp64_gemm_peak(torch, dev)
         fp64_peak = max(gemm.values())
-        # flops the kernel EXECUTES: 2 x (real MMAs per complex block) x Ne^2 x 3V per (pair, momentum).
-        # Algorithmic savings make this smaller than SURVEY 8d's count (8 Ne^2 3V x 34 pairs x Nmom): the
-        # Hermitian pairing contracts 19 pairs (self pairs only for one momentum of each +-p couple), and
-        # the 3M complex product needs 3 real MMAs instead of 4.
-        # `achieved`/`frac` are the executed rate (what the FP64 pipe really does); the SURVEY-counted
-        # rate is reported beside it as survey_equivalent_tflops.
-        acct = contraction_accounting(q, Ne, V)
-        exec_flops, pw_padded_flops, pw_form, folded = acct["executed"], acct["padded"], acct["plane_wave"], acct["folded"]
+        self_pairs = _capi.plan(mode_, order_, moms)["self_pairs"] if (dist_ is None and q["hermitian_pairing"]) else 0
+        acct = contraction_accounting(q, Ne, (Lx, Ly, Lz), self_pairs)
+        exec_flops, pw_padded_flops, form_used = acct["executed"], acct["padded"], acct["form"]
+        pw_form = form_used >= 2
+        contraction["form"] = form_used
+        if parity is not None:
+            contraction["parity_check"] = parity
+        # FP64-pipe utilisation: lane-operations retired / (592 sub-partitions x 16 lanes per cycle x SM clock x time)
+        sm_clock_hz = 1e6 * float(clocks.summary().get("sm_mhz") or 1965.0)
+        pipe_util = acct["slots"] / (gram_ms * 1e-3) / (592.0 * 16.0 * sm_clock_hz)
         achieved_tf = exec_flops / (gram_ms * 1e-3) / 1e12
         survey_tf = flops / (gram_ms * 1e-3) / 1e12
         # stencil: bytes of ONE launch (nabla3: 1 source, 3 outputs, links once; displacement step: 6 in, 6 + mean out)
@@ -543,35 +659,40 @@ def run_native(args):
             "metric": "elemental_timeslices_per_sec", "value": value, "unit": "timeslices/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128 (f64)", "data": "synthetic",
-            "config": {
-                "workload": workload_desc(name, dist_), "lattice": [Lx, Ly, Lz], "Ne": Ne,
-                **({"num_nabla": nabla} if dist_ is None else {"distance": dist_}), "momenta": nmom,
-                "sharding": f"timeslices, {K} per rank, {world} rank(s)" + (", NCCL gather to rank 0 inside the timed region" if world > 1 else ""),
-                "l2": f"step inputs+fields ({(Ne * V * 3 * 8 + Ne * V * 48 * (SRC_OUT[nabla][1] if dist_ is None else 12)) / 1e6:.0f} MB) exceed the 126 MB L2; two input sets alternated",
-                "workspace_MB": workspace_mb,
-            },
+            "config": config_dict(name, dist_, K, world),
+            "api": "ElementalGenerator.calc_all() over device-resident inputs (GaugeFieldDevice / EigenvectorDevice): timeslices sharded "
+                   "over the ranks, finished chunks gathered on rank 0 while the next are computed",
+            "workspace_MB": workspace_mb,
             "e2e": {"value": e2e_value, "unit": "timeslices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "ElementalGenerator.calc_range over host arrays (streamed: pinned staging, H2D/D2H overlapped with the kernels)",
-                    "checksum": checksum},
+                    "api": "ElementalGenerator.calc_range over host arrays (streamed: pinned staging, H2D/D2H overlapped with the kernels)"
+                           + ("; every rank streams its own timeslices" if world > 1 else ""),
+                    "checksum": checksum, **({"from_files": files} if files is not None else {})},
             "gpu_launches": int(launches),
             "contraction": contraction,
             "clocks": clocks.summary(),
             "roofline": {
-                "kernel": gram_name + (" (plane-wave factorised contraction: site products by DFMA, real xy-mode transform by "
-                                       "DMMA.8x8x4" + (", centre-symmetric site pairs folded" if folded else "") +
-                                       ", TMA producer warp + mbarrier ring; z fold timed with the combine step)" if pw_form
-                                       else " (momentum-phased contraction, DMMA.8x8x4, TMA producer warp + mbarrier ring)"),
+                "kernel": gram_name + {
+                    4: " (separable contraction: site products, x transform per site pair and y transform per row by DFMA, y-stage "
+                       "accumulators in tensor memory; swizzled TMA tiles, producer warp + mbarrier ring; z fold timed with the combine step)",
+                    3: " (plane-wave factorised contraction: site products by DFMA, real xy-mode transform by DMMA.8x8x4, "
+                       "centre-symmetric site pairs folded, TMA producer warp + mbarrier ring; z fold timed with the combine step)",
+                    2: " (plane-wave factorised contraction: site products by DFMA, real xy-mode transform by DMMA.8x8x4, "
+                       "TMA producer warp + mbarrier ring; z fold timed with the combine step)",
+                }.get(form_used, " (momentum-phased contraction, DMMA.8x8x4, TMA producer warp + mbarrier ring)"),
                 "bound": "tensor",
                 "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
                 "traffic": measured_traffic(gram_name, name if dist_ is None else name + "_displacement"),
                 "peak_source": f"cuBLAS FP64 GEMM measured in this run (dgemm {gemm['dgemm']:.1f}, zgemm {gemm['zgemm']:.1f} TFLOP/s); "
                                f"DMMA issue-rate microbench {dmma_tf:.1f}, DFMA {dfma_tf:.1f} TFLOP/s; nominal 37-40",
                 "algorithmic_flops_per_launch": exec_flops, "ms_per_launch": gram_ms,
+                "fp64_pipe_utilisation": pipe_util,
                 "pairing": q, "survey_flops_per_launch": flops, "survey_equivalent_tflops": survey_tf,
-                **({"executed_tflops_incl_padded_mode_rows": pw_padded_flops / (gram_ms * 1e-3) / 1e12} if pw_form else {}),
-                "note": ("achieved = flops the plane-wave form needs / time: the phase factorises, so the site product is formed once "
-                         "for all momenta and only the real xy-modes are transformed per plane; the FP64 pipe is the bound, "
-                         "survey_equivalent_tflops = SURVEY 8d flops (GEMM form, 34 pairs x Nmom) / time") if pw_form else
+                **({"executed_tflops_incl_padded_mode_rows": pw_padded_flops / (gram_ms * 1e-3) / 1e12} if pw_padded_flops else {}),
+                "note": ("bound = the FP64 pipe that DFMA and DMMA share on B200 (same rate: microbench above); achieved = real "
+                         "flops executed / time (FMA = 2, add / multiply = 1; tiles a self pair skips are not counted); "
+                         "fp64_pipe_utilisation = FP64 lane-operations / (592 x 16 x SM clock x time), the figure ncu reports as "
+                         "sm__pipe_fp64_cycles_active (+ the DMMA sub-pipe); the phase factorises over the axes, so these forms "
+                         "need far fewer flops than SURVEY 8d's GEMM count: survey_equivalent_tflops = that count / time") if pw_form else
                         ("achieved = real flops the DMMA kernel executes / time (useful rows only); the Hermitian pairing "
                          "G(L,R,p)^dag = G(R,L,-p) contracts 19 instead of SURVEY 8d's 34 pairs and the 3M product uses 3 "
                          "instead of 4 real MMAs per complex block; survey_equivalent_tflops = SURVEY 8d flops / time"),
@@ -584,7 +705,7 @@ def run_native(args):
                 "traffic": measured_traffic(st_name, name if dist_ is None else name + "_displacement"), "peak_source": hbm_src, "algorithmic_bytes_per_launch": st_moved,
                 "survey_bytes_per_launch": st_bytes_launch, "survey_equivalent_gbs": st_survey_gbs,
                 "note": ("algorithmic bytes = 1 field in + 3 fields out + links (SURVEY 8d); the Re+Im planes are not written "
-                         "when the plane-wave form of the contraction is in use") if (pw_form or dist_ is not None) else
+                         "when a plane-wave / separable form of the contraction is in use") if (pw_form or dist_ is not None) else
                         ("algorithmic bytes = 1 field in + 3 fields out + links (SURVEY 8d) + the 3 Re+Im planes (8 B per element) "
                          "this build's stencil writes for the 3M contraction; survey_equivalent_gbs counts SURVEY's bytes only"),
                 "ms_per_launch": st_ms, "launches_per_step": st_launch / K,
@@ -608,9 +729,11 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=os.environ.get("EDK_BENCH_WORKLOAD", "config5"), choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contraction", default=os.environ.get("EDK_BENCH_CONTRACTION", "auto"), choices=["auto", "gemm", "planewave", "planewave-folded"],
-                    help="contraction form: auto = validate and time the plane-wave form against the GEMM form in a child "
-                         "process first and use the faster validated one; gemm / planewave force one")
+    ap.add_argument("--no-file-leg", action="store_true", help="skip the file-backed end-to-end leg (ILDG / .npy / QDP .mod files)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the untimed comparison of the planned form with the GEMM form")
+    ap.add_argument("--contraction", default=os.environ.get("EDK_BENCH_CONTRACTION", "auto"), choices=["auto", "gemm", "planewave", "planewave-folded", "separable"],
+                    help="contraction form: auto = the form the library plans for the shape (edk_plan_form); the others ask "
+                         "for one form through the A/B hook EDK_GRAM_ALGO")
     ap.add_argument("--generator", default="derivative", choices=["derivative", "displacement"],
                     help="ElementalGenerator (default, the graded workload) or DisplacementElementalGenerator")
     ap.add_argument("--distance", type=int, default=2, help="displacement generator: number of link steps")

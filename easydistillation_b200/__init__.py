@@ -6,12 +6,14 @@ from .generator import DisplacementElementalGenerator, ElementalGenerator, Lapla
 from .insertion.derivative import derivative
 from .insertion.phase import MomentumPhase
 from .preset import (
+    EigenvectorDevice,
     EigenvectorHostmem,
     EigenvectorNpy,
     EigenvectorTimeSlice,
     ElementalBinary,
     ElementalNpy,
     GaugeFieldBinary,
+    GaugeFieldDevice,
     GaugeFieldHostmem,
     GaugeFieldIldg,
     GaugeFieldNpy,
@@ -20,6 +22,6 @@ from .preset import (
 __all__ = [
     "ElementalGenerator", "DisplacementElementalGenerator", "Laplacian", "MomentumPhase", "derivative",
     "GaugeFieldBinary", "GaugeFieldNpy", "GaugeFieldHostmem", "GaugeFieldIldg", "EigenvectorNpy", "EigenvectorHostmem",
-    "EigenvectorTimeSlice",
+    "EigenvectorTimeSlice", "GaugeFieldDevice", "EigenvectorDevice",
     "ElementalNpy", "ElementalBinary", "Nc", "Ns", "Nd",
 ]

@@ -40,6 +40,8 @@ SIGNATURES = {
     "edk_phase_table": (_i, [_i, _i, _i, _i, C.POINTER(_i), _vp, _i, _vp]),
     "edk_plan": (_i, [_i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i)]),
     "edk_plan_modes": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "edk_plan_form": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "edk_plan_tiles": (_i, [_i, _i, C.POINTER(_i)]),
     "edk_num_operators": (_i, [_vp]),
     "edk_output_bytes": (_sz, [_vp]),
     "edk_workspace_bytes": (_sz, [_vp]),
@@ -121,6 +123,33 @@ def plan(mode: int, order: int, momentum_list, sym_request: int = -1) -> dict:
     d = dict(zip(keys, list(out)))
     d["hermitian_pairing"] = bool(d["hermitian_pairing"])
     return d
+
+
+def plan_form(latt3, mode: int, order: int, momentum_list) -> dict:
+    """Host-only choice of the contraction form (edk_plan_form): what a handle of this shape will run."""
+    import numpy as np
+
+    mom = np.ascontiguousarray(np.asarray(momentum_list, dtype=np.int32).reshape(-1, 3))
+    out = (C.c_int * 6)()
+    check(lib().edk_plan_form(int(latt3[0]), int(latt3[1]), mode, order, mom.shape[0], mom.ctypes.data_as(C.POINTER(C.c_int)), out),
+          "edk_plan_form")
+    keys = ("form", "separable_available", "separable_qmax", "separable_r2", "pairs_per_stage", "separable_modes")
+    d = dict(zip(keys, list(out)))
+    d["separable_available"] = bool(d["separable_available"])
+    return d
+
+
+def plan_tiles(Ne: int):
+    """CTA tiles of the separable contraction for Ne eigenvectors (edk_plan_tiles): int array [ntiles, 4] of
+    (first row, first column, rows, columns)."""
+    import numpy as np
+
+    n = lib().edk_plan_tiles(int(Ne), 0, None)
+    if n < 0:
+        check(n, "edk_plan_tiles")
+    out = np.zeros((n, 4), dtype=np.int32)
+    lib().edk_plan_tiles(int(Ne), n, out.ctypes.data_as(C.POINTER(C.c_int)))
+    return out
 
 
 def plan_modes(momentum_list):

@@ -57,7 +57,8 @@ struct edk_handle {
     bool tma_ready = false;
     int loader = 0;
     int algo = 1;  // contraction: 1 = GEMM form, 3M arithmetic (three real MMAs per complex block), 0 = GEMM form, 4M,
-                   // 2 = plane-wave factorised form (edk_gram_pw.cu), 3 = the same with centre-symmetric site pairs folded
+                   // 2 = plane-wave factorised form (edk_gram_pw.cu), 3 = the same with centre-symmetric site pairs folded,
+                   // 4 = separable form (edk_gram_sep.cu): x and y transforms in registers, row by row
     // plane-wave factorised contraction (algo 2): xy-mode weights, per-plane sums Y, z phases
     PwTma pw_tma{};
     bool pw_ready = false;
@@ -72,6 +73,24 @@ struct edk_handle {
     cplx* pw_zphase = nullptr;    // [nmom_int][Lz]
     int* pw_momode = nullptr;     // [nmom_int][3]: cos mode, sin mode, sigma
     size_t pw_bytes = 0;
+    // separable contraction (algo 4): x / y weight tables, per-plane sums of the separable modes, fold tables
+    SepTma sep_tma{};
+    bool sep_ready = false;
+    int sep_qmax = 0, sep_r2 = 0, sep_pairs = 0, sep_nmodes = 0, sep_nclass = 0;
+    int sep_variant = 0;  // kernel variant (edk_gram_sep.cu: launch_gram_sep)
+    SepWeights sep_wx_host{};  // the x weights as a kernel parameter (constant cache)
+    SepTmaX sep_tmax{};        // variant 6: tensor maps and ring depth per tile shape
+    SepTile* sep_tiles = nullptr;  // grouped by shape
+    int sep_ntiles = 0;
+    int sep_shape_first[SEP_NSHAPES] = {0, 0, 0}, sep_shape_count[SEP_NSHAPES] = {0, 0, 0};
+    double* sep_wx = nullptr;      // [Lx/2][4]
+    double* sep_wy = nullptr;      // [Ly][4]
+    cplx* sep_Y = nullptr;         // [njobs][Lz][nmodes][Ne][Ne]
+    cplx* sep_zphase = nullptr;    // [nmom_int][Lz]
+    SepClass* sep_classes = nullptr;
+    int* sep_mom = nullptr;
+    size_t sep_bytes = 0;
+    int algo_request = -1;  // -1 = pick the form from the cost plan (plan_contraction_form), else the form asked for
     size_t field_cplx;  // Ne * V * 3
     // device buffers
     cplx* links = nullptr;    // [3][V][9]
@@ -149,6 +168,31 @@ struct PhaseTimer {
         h->events.push_back(ev);
     }
 };
+
+// Every entry point that launches or allocates runs on the handle's device and leaves the caller's current device as
+// it found it (two generators on different GPUs in one process).
+struct DeviceGuard {
+    int prev = -1, dev;
+    bool ok = true;
+    explicit DeviceGuard(int dev_) : dev(dev_) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) {
+            ok = false;
+            cudaGetLastError();
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define EDK_ON_DEVICE(h)                                                  \
+    DeviceGuard _guard((h)->device);                                      \
+    if (!_guard.ok) {                                                     \
+        set_error("cudaSetDevice(%d) failed", (h)->device);               \
+        return EDK_ERR_CUDA;                                              \
+    }
 
 // field index of a direction sequence in application order (see edk.h, edk_debug_field)
 int seq_index(const std::vector<int>& seq) {
@@ -718,6 +762,324 @@ int run_gram_pw(edk_handle* h, cudaStream_t s) {
     return EDK_OK;
 }
 
+// exp(2 pi i num / den), exact on the axes
+void unit_circle(long long num, long long den, double& c, double& sn) {
+    const long long r = (num % den + den) % den;
+    c = 1.0, sn = 0.0;
+    if (4 * r == den) {
+        c = 0.0, sn = 1.0;
+    } else if (2 * r == den) {
+        c = -1.0, sn = 0.0;
+    } else if (4 * r == 3 * den) {
+        c = 0.0, sn = -1.0;
+    } else if (r != 0) {
+        const double a = 2.0 * 3.14159265358979323846 * (double)r / (double)den;
+        c = cos(a);
+        sn = sin(a);
+    }
+}
+
+// ---- separable contraction (algo 4), host side ------------------------------------------------------------
+// Which lattices / momentum lists the separable kernel covers, pure host logic (edk_plan_form): an even Lx >= 8 whose
+// half row is a multiple of 8, 6 or 4 site pairs and fits the weight table, and momenta whose (|px|, |py|) lie in one
+// of the instantiated mode structures: max <= 1 with px^2 + py^2 <= 1 (5 modes) or <= 2 (9 modes), max <= 2 with
+// px^2 + py^2 <= 4 (13 modes: every list inside |p|^2 <= 4).
+struct SepPlan {
+    bool ok = false;
+    int qmax = 0, r2 = 0, pairs = 0, nmodes = 0;
+};
+SepPlan plan_sep(int Lx, const std::vector<int>& mom) {
+    SepPlan S;
+    if (Lx < 8 || (Lx & 1) || Lx / 2 > SEP_MAX_PR) return S;
+    const int PR = Lx / 2;
+    S.pairs = PR % 8 == 0 ? 8 : (PR % 6 == 0 ? 6 : (PR % 4 == 0 ? 4 : 0));
+    if (!S.pairs) return S;
+    int qm = 0, r2 = 0;
+    for (size_t i = 0; i < mom.size() / 3; ++i) {
+        const int ax = abs(mom[3 * i]), ay = abs(mom[3 * i + 1]);
+        qm = std::max(qm, std::max(ax, ay));
+        r2 = std::max(r2, ax * ax + ay * ay);
+    }
+    if (qm <= 1)
+        S.qmax = 1, S.r2 = r2 <= 1 ? 1 : 2;
+    else if (qm == 2 && r2 <= 4)
+        S.qmax = 2, S.r2 = 4;
+    else
+        return S;
+    S.nmodes = sep_num_modes(S.qmax, S.r2);
+    S.ok = S.nmodes > 0;
+    return S;
+}
+
+// CTA tiles of gram_sepx_kernel for an Ne x Ne block of elements (pure host logic, edk_plan_tiles): 32 x 32 tiles over the
+// part of the square that whole tiles fill, 8 x 128 tiles over the rows left below it (one 8-row unit each, all
+// columns), 64 x 16 tiles over the columns left beside it (one 16-column unit each, the rows of the square).  Every
+// element lies in exactly one tile; only the last tile of a strip can have idle warps.
+std::vector<SepTile> sep_build_tiles(int Ne) {
+    std::vector<SepTile> t;
+    const int a = Ne / 32, sq = 32 * a;
+    for (int i = 0; i < a; ++i)
+        for (int j = 0; j < a; ++j) t.push_back(SepTile{32 * i, 32 * j, 0, 32 * i + 32, 32 * j + 32, 0});
+    for (int e0 = sq; e0 < Ne; e0 += 8)
+        for (int f0 = 0; f0 < Ne; f0 += 128) t.push_back(SepTile{e0, f0, 1, std::min(e0 + 8, Ne), std::min(f0 + 128, Ne), 0});
+    for (int f0 = sq; f0 < Ne; f0 += 16)
+        for (int e0 = 0; e0 < sq; e0 += 64) t.push_back(SepTile{e0, f0, 2, std::min(e0 + 64, sq), std::min(f0 + 16, Ne), 0});
+    return t;
+}
+
+void free_sep(edk_handle* h) {
+    cudaFree(h->sep_tiles);
+    h->sep_tiles = nullptr;
+    h->sep_ntiles = 0;
+    cudaFree(h->sep_wx);
+    cudaFree(h->sep_wy);
+    cudaFree(h->sep_Y);
+    cudaFree(h->sep_zphase);
+    cudaFree(h->sep_classes);
+    cudaFree(h->sep_mom);
+    h->sep_wx = h->sep_wy = nullptr;
+    h->sep_Y = nullptr;
+    h->sep_zphase = nullptr;
+    h->sep_classes = nullptr;
+    h->sep_mom = nullptr;
+    h->sep_ready = false;
+    h->sep_bytes = 0;
+}
+
+// Tables, per-plane buffer and tensor maps of algo 4; needs the job list and the internal momenta.
+int build_sep(edk_handle* h) {
+    free_sep(h);
+    EncodeFn encode = tensor_map_encoder();
+    if (!encode) return EDK_ERR_CUDA;
+    const SepPlan S = plan_sep(h->g.Lx, h->mom_int);
+    if (!S.ok) {
+        set_error("the separable contraction does not cover this lattice / momentum list (Lx even, >= 8, Lx/2 a multiple of 4, 6 or 8; "
+                  "|px|, |py| <= 2 with px^2 + py^2 <= 4)");
+        return EDK_ERR_ARG;
+    }
+    int smem = 0;
+    h->sep_variant = SEP_DEFAULT_VARIANT;
+    if (const char* t = getenv("EDK_SEP_VARIANT")) {  // A/B hook: 0 = the first kernel (accumulators in registers), 6 = the product
+        const int v = atoi(t);
+        if (v == 0 || v == 6) h->sep_variant = v;
+    }
+    if (h->sep_variant == 6) {
+        for (int sh = 0; sh < SEP_NSHAPES; ++sh)
+            if (sepx_plan_smem(sh, &h->sep_tmax.nstages[sh], &smem) != 0) {
+                set_error("no shared-memory plan for the separable contraction");
+                return EDK_ERR_ARG;
+            }
+        h->sep_tma.nstages = h->sep_tmax.nstages[0];
+    } else if (sep_variant_plan(h->sep_variant, &h->sep_tma.nstages, &smem) != 0) {
+        set_error("no shared-memory plan for the separable contraction");
+        return EDK_ERR_ARG;
+    }
+    if (const char* t = getenv("EDK_SEP_STAGES")) {  // A/B hook: a shallower operand ring (2 .. planned depth)
+        const int v = atoi(t);
+        if (v >= 2 && v < h->sep_tma.nstages) h->sep_tma.nstages = v;
+        for (int sh = 0; sh < SEP_NSHAPES; ++sh)
+            if (v >= 2 && v < h->sep_tmax.nstages[sh]) h->sep_tmax.nstages[sh] = v;
+    }
+    h->sep_qmax = S.qmax, h->sep_r2 = S.r2, h->sep_pairs = S.pairs, h->sep_nmodes = S.nmodes;
+    const int Lx = h->g.Lx, Ly = h->g.Ly, Lz = h->g.Lz, PR = Lx / 2;
+    // weights about the centre of the lattice: c_q(x) + i s_q(x) = exp(i pi q (2x - L + 1)/L), q = 1, 2
+    std::vector<double> wx((size_t)PR * 4), wy((size_t)Ly * 4);
+    for (int x = 0; x < PR; ++x)
+        for (int q = 1; q <= 2; ++q) unit_circle((long long)q * (2 * x - Lx + 1), 2LL * Lx, wx[4 * x + 2 * (q - 1)], wx[4 * x + 2 * (q - 1) + 1]);
+    for (int y = 0; y < Ly; ++y)
+        for (int q = 1; q <= 2; ++q) unit_circle((long long)q * (2 * y - Ly + 1), 2LL * Ly, wy[4 * y + 2 * (q - 1)], wy[4 * y + 2 * (q - 1) + 1]);
+    std::copy(wx.begin(), wx.end(), h->sep_wx_host.w);
+    // classes of momenta with the same (|px|, |py|), and exp(2 pi i pz z/Lz) times the constant left by the centring
+    std::vector<SepClass> classes;
+    std::vector<std::pair<int, int>> keys;
+    std::vector<std::vector<int>> members;
+    for (int p = 0; p < h->nmom_int; ++p) {
+        const std::pair<int, int> key{abs(h->mom_int[3 * p]), abs(h->mom_int[3 * p + 1])};
+        size_t c = 0;
+        while (c < keys.size() && keys[c] != key) ++c;
+        if (c == keys.size()) {
+            keys.push_back(key);
+            members.emplace_back();
+        }
+        members[c].push_back(p);  // ascending p
+    }
+    std::vector<int> mom3;
+    for (size_t c = 0; c < keys.size(); ++c) {
+        SepClass K{};
+        const int ax = keys[c].first, ay = keys[c].second;
+        K.mode[0] = sep_mode_index(S.qmax, S.r2, ax, 0, ay, 0);
+        K.mode[1] = ay ? sep_mode_index(S.qmax, S.r2, ax, 0, ay, 1) : -1;
+        K.mode[2] = ax ? sep_mode_index(S.qmax, S.r2, ax, 1, ay, 0) : -1;
+        K.mode[3] = (ax && ay) ? sep_mode_index(S.qmax, S.r2, ax, 1, ay, 1) : -1;
+        if (K.mode[0] < 0 || (ay && K.mode[1] < 0) || (ax && K.mode[2] < 0) || (ax && ay && K.mode[3] < 0)) {
+            set_error("separable contraction: momentum class (%d, %d) is not in the mode structure", ax, ay);
+            return EDK_ERR_STATE;
+        }
+        K.first = (int)mom3.size() / 3;
+        K.count = (int)members[c].size();
+        for (int p : members[c]) {
+            const int px = h->mom_int[3 * p], py = h->mom_int[3 * p + 1];
+            mom3.insert(mom3.end(), {p, (px > 0) - (px < 0), (py > 0) - (py < 0)});
+        }
+        classes.push_back(K);
+    }
+    h->sep_nclass = (int)classes.size();
+    std::vector<double> zp((size_t)h->nmom_int * Lz * 2);
+    for (int p = 0; p < h->nmom_int; ++p) {
+        double cx, sx, cy, sy;
+        unit_circle((long long)h->mom_int[3 * p] * (Lx - 1), 2LL * Lx, cx, sx);
+        unit_circle((long long)h->mom_int[3 * p + 1] * (Ly - 1), 2LL * Ly, cy, sy);
+        const double kc = cx * cy - sx * sy, ks = cx * sy + sx * cy;
+        for (int z = 0; z < Lz; ++z) {
+            double c, sn;
+            unit_circle((long long)h->mom_int[3 * p + 2] * z, Lz, c, sn);
+            zp[2 * ((size_t)p * Lz + z)] = c * kc - sn * ks;
+            zp[2 * ((size_t)p * Lz + z) + 1] = c * ks + sn * kc;
+        }
+    }
+    const size_t y_bytes = (size_t)h->njobs * Lz * S.nmodes * h->Ne * h->Ne * sizeof(cplx);
+    EDK_CUDA_TRY(cudaMalloc(&h->sep_wx, wx.size() * sizeof(double)));
+    EDK_CUDA_TRY(cudaMalloc(&h->sep_wy, wy.size() * sizeof(double)));
+    EDK_CUDA_TRY(cudaMalloc(&h->sep_zphase, zp.size() * sizeof(double)));
+    EDK_CUDA_TRY(cudaMalloc(&h->sep_classes, classes.size() * sizeof(SepClass)));
+    EDK_CUDA_TRY(cudaMalloc(&h->sep_mom, mom3.size() * sizeof(int)));
+    {
+        const cudaError_t e = cudaMalloc(&h->sep_Y, y_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaMalloc of %zu bytes (per-plane mode sums) failed: %s", y_bytes, cudaGetErrorString(e));
+            free_sep(h);
+            return e == cudaErrorMemoryAllocation ? EDK_ERR_NOMEM : EDK_ERR_CUDA;
+        }
+    }
+    EDK_CUDA_TRY(cudaMemcpy(h->sep_wx, wx.data(), wx.size() * sizeof(double), cudaMemcpyHostToDevice));
+    EDK_CUDA_TRY(cudaMemcpy(h->sep_wy, wy.data(), wy.size() * sizeof(double), cudaMemcpyHostToDevice));
+    EDK_CUDA_TRY(cudaMemcpy(h->sep_zphase, zp.data(), zp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    EDK_CUDA_TRY(cudaMemcpy(h->sep_classes, classes.data(), classes.size() * sizeof(SepClass), cudaMemcpyHostToDevice));
+    EDK_CUDA_TRY(cudaMemcpy(h->sep_mom, mom3.data(), mom3.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // the field array as [nfield][Ne][6V doubles]; boxes of 16 doubles (8 complex = 128 bytes) x rows, 128-byte swizzle
+    const cuuint64_t Kd = (cuuint64_t)2 * 3 * h->g.V;
+    const cuuint64_t gdim[3] = {Kd, (cuuint64_t)h->Ne, (cuuint64_t)h->nfield};
+    const cuuint64_t gstr[2] = {Kd * 8, Kd * 8 * (cuuint64_t)h->Ne};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t boxL[3] = {16, (cuuint32_t)sep_variant_rows(h->sep_variant), 1};
+    const cuuint32_t boxR[3] = {16, (cuuint32_t)SEP_TF, 1};
+    CUresult r = encode((CUtensorMap*)h->sep_tma.mapL, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, boxL, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+        r = encode((CUtensorMap*)h->sep_tma.mapR, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, boxR, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && h->sep_variant == 6) {
+        for (int sh = 0; sh < SEP_NSHAPES && r == CUDA_SUCCESS; ++sh) {
+            int we = 0, wf = 0;
+            sepx_shape(sh, &we, &wf);
+            const cuuint32_t bL[3] = {16, (cuuint32_t)(8 * we), 1}, bR[3] = {16, (cuuint32_t)(16 * wf), 1};
+            r = encode((CUtensorMap*)h->sep_tmax.mapL[sh], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, bL, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS)
+                r = encode((CUtensorMap*)h->sep_tmax.mapR[sh], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->fields, gdim, gstr, bR, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        const std::vector<SepTile> tiles = sep_build_tiles(h->Ne);  // shape 0 first, then 1, then 2
+        h->sep_ntiles = (int)tiles.size();
+        for (int sh = 0; sh < SEP_NSHAPES; ++sh) h->sep_shape_first[sh] = h->sep_shape_count[sh] = 0;
+        for (size_t i = 0; i < tiles.size(); ++i) {
+            if (h->sep_shape_count[tiles[i].shape]++ == 0) h->sep_shape_first[tiles[i].shape] = (int)i;
+        }
+        EDK_CUDA_TRY(cudaMalloc(&h->sep_tiles, tiles.size() * sizeof(SepTile)));
+        EDK_CUDA_TRY(cudaMemcpy(h->sep_tiles, tiles.data(), tiles.size() * sizeof(SepTile), cudaMemcpyHostToDevice));
+    }
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (separable contraction) failed with CUresult %d", (int)r);
+        return EDK_ERR_CUDA;
+    }
+    h->sep_bytes = y_bytes + (wx.size() + wy.size() + zp.size()) * sizeof(double);
+    h->sep_ready = true;
+    return EDK_OK;
+}
+
+int run_gram_sep(edk_handle* h, cudaStream_t s) {
+    SepParams Q{};
+    Q.jobs = h->jobs_dev;
+    Q.njobs = h->njobs;
+    Q.Ne = h->Ne;
+    Q.Lx = h->g.Lx, Q.Ly = h->g.Ly, Q.Lz = h->g.Lz;
+    Q.SR = h->g.Lx / 2 / h->sep_pairs;
+    const int rows_l = sep_variant_rows(h->sep_variant);
+    Q.n_et = (h->Ne + rows_l - 1) / rows_l;
+    Q.n_ft = (h->Ne + SEP_TF - 1) / SEP_TF;
+    Q.nmodes = h->sep_nmodes;
+    Q.wx = h->sep_wx;
+    Q.wy = h->sep_wy;
+    Q.Y = h->sep_Y;
+    if (h->sep_variant == 6) {
+        int nlaunch = 0;
+        for (int sh = 0; sh < SEP_NSHAPES; ++sh) nlaunch += h->sep_shape_count[sh] > 0;
+        PhaseTimer t(h, s, PH_GRAM, nlaunch);
+        for (int sh = 0; sh < SEP_NSHAPES; ++sh) {  // one launch per tile shape: the 32 x 32 tiles, then the edge strips
+            if (!h->sep_shape_count[sh]) continue;
+            Q.tiles = h->sep_tiles + h->sep_shape_first[sh];
+            Q.ntiles = h->sep_shape_count[sh];
+            EDK_CUDA_TRY(launch_gram_sepx(Q, h->sep_tmax, h->sep_wx_host, h->sep_qmax, h->sep_r2, h->sep_pairs, sh, s));
+        }
+    } else {
+        PhaseTimer t(h, s, PH_GRAM, 1);
+        EDK_CUDA_TRY(launch_gram_sep(Q, h->sep_tma, h->sep_wx_host, h->sep_qmax, h->sep_r2, h->sep_pairs, h->sep_variant, s));
+    }
+    // the z fold is a reduction like the combine step and is timed with it
+    PhaseTimer t(h, s, PH_COMBINE, 1);
+    SepFold F{};
+    F.jobs = h->jobs_dev;
+    F.njobs = h->njobs;
+    F.Ne = h->Ne;
+    F.Lz = h->g.Lz;
+    F.nmodes = h->sep_nmodes;
+    F.nmom_int = h->nmom_int;
+    F.rows_l = h->sep_variant == 6 ? 8 : rows_l;  // variant 6 skips 8 x 8 blocks of a self pair below the diagonal
+    F.rows_r = h->sep_variant == 6 ? 8 : SEP_TF;
+    F.Y = h->sep_Y;
+    F.zphase = h->sep_zphase;
+    F.nclass = h->sep_nclass;
+    F.classes = h->sep_classes;
+    F.mom = h->sep_mom;
+    F.partial = h->partial;
+    EDK_CUDA_TRY(launch_sep_zfold(F, s));
+    return EDK_OK;
+}
+
+// The contraction form a handle uses unless one is asked for (edk_debug_algo, EDK_GRAM_ALGO), from the FP64-pipe work
+// per (e, f, site) of each form and the fraction of the pipe each kernel was measured to sustain on B200:
+//   GEMM form (1):       9 DMMA-slot equivalents per (pair, momentum) - three real MMAs over three colours
+//   folded plane wave (3): 12 + 2 + 16 per pair and pass of 8 {+q, -q} couples, needs planes of at least 8 sites
+//   separable (4):       12 + (4 + 2 + 4 qmax)/2 per pair, needs plan_sep
+// Pure host logic; edk_plan_form exposes it to the CPU tests.
+int plan_contraction_form(int Lx, int Ly, const std::vector<int>& mom_int, const std::vector<GramJob>& jobs) {
+    double w_gemm = 0.0, segs = 0.0;
+    for (const auto& j : jobs) {
+        w_gemm += 9.0 * j.nseg * j.nmom;
+        segs += j.nseg;
+    }
+    double best = w_gemm / 0.88;
+    int form = 1;
+    if (Lx * Ly >= 8) {
+        const ModePlan mp = plan_modes(mom_int);
+        int couples = 0;
+        for (size_t m = 0; m < mp.modes3.size() / 3; ++m) couples += mp.modes3[3 * m + 2] == 0;
+        const double w = segs * (14.0 + 16.0) * ((couples + 7) / 8) / 0.66;
+        if (w < best) best = w, form = 3;
+    }
+    const SepPlan S = plan_sep(Lx, mom_int);
+    if (S.ok) {
+        const double w = segs * (12.0 + 0.5 * (6.0 + 4.0 * S.qmax)) / 0.80;
+        if (w < best) best = w, form = 4;
+    }
+    return form;
+}
+
 // Momentum bookkeeping of the contraction, pure host logic (unit-tested on CPU through edk_plan):
 // whether the Hermitian pairing pays, the internal momentum list (the caller's distinct momenta plus
 // missing negatives, one representative of every {p, -p} couple first), the index of -p for every
@@ -800,8 +1162,10 @@ int configure(edk_handle* h) {
     else
         build_displacement_jobs(h);
     h->njobs = (int)h->jobs_host.size();
+    h->algo = h->algo_request >= 0 ? h->algo_request : plan_contraction_form(h->g.Lx, h->g.Ly, h->mom_int, h->jobs_host);
 
     free_pw(h);
+    free_sep(h);
     cudaFree(h->phase);
     cudaFree(h->phase_tiles);
     h->phase_tiles = nullptr;
@@ -852,7 +1216,17 @@ int configure(edk_handle* h) {
     }
     h->cfg_bytes = 4 * nm * h->g.Vpad * sizeof(cplx) + partial_bytes;
     if (h->algo >= 2) {
-        const int rc = build_pw(h);
+        int rc = h->algo == 4 ? build_sep(h) : build_pw(h);
+        if (rc == EDK_ERR_NOMEM && h->algo_request < 0) {
+            // the per-plane sums of the planned form do not fit: the GEMM form needs no such buffer
+            free_sep(h);
+            free_pw(h);
+            h->algo = 1;
+            pick_gram_config(h);
+            rc = build_tma(h);
+            if (rc == EDK_OK) rc = ensure_partial(h);
+            if (rc == EDK_OK) h->cfg_bytes = 4 * nm * h->g.Vpad * sizeof(cplx) + (size_t)h->ksplit * h->njobs * nm * h->Ne * h->Ne * sizeof(cplx);
+        }
         if (rc != EDK_OK) return rc;
     }
     return EDK_OK;
@@ -871,11 +1245,11 @@ int run_gram_and_combine(edk_handle* h, cplx* out, cudaStream_t s) {
     P.n_mt = row_tiles(h);
     const bool use_pw = !h->naive && h->loader == 0 && h->algo >= 2;
     if (use_pw) {
-        if (!h->pw_ready || h->pw_algo != h->algo) {
-            set_error("plane-wave contraction selected but its tables are not built");
+        if (h->algo == 4 ? !h->sep_ready : (!h->pw_ready || h->pw_algo != h->algo)) {
+            set_error("plane-wave / separable contraction selected but its tables are not built");
             return EDK_ERR_STATE;
         }
-        const int rc = run_gram_pw(h, s);
+        const int rc = h->algo == 4 ? run_gram_sep(h, s) : run_gram_pw(h, s);
         if (rc != EDK_OK) return rc;
         PhaseTimer t(h, s, PH_COMBINE, 1);
         EDK_CUDA_TRY(launch_combine(h->ops_dev, h->nop, h->partial, h->njobs, 1, h->nmom_int, h->nmom, h->pmap_dev,
@@ -946,7 +1320,11 @@ int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, co
         set_error("edk_create: spatial volume too large for 32-bit k indices");
         return EDK_ERR_ARG;
     }
-    EDK_CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);  // the caller's current device is restored on return
+    if (!guard.ok) {
+        set_error("edk_create: cudaSetDevice(%d) failed", device);
+        return EDK_ERR_CUDA;
+    }
     edk_handle* h = new edk_handle();
     h->g.Lx = Lx;
     h->g.Ly = Ly;
@@ -988,9 +1366,11 @@ int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, co
     if (mode == EDK_MODE_DISPLACEMENT && order >= 1) EDK_ALLOC(h->lines, (size_t)12 * h->field_cplx * sizeof(cplx));
     EDK_ALLOC(h->coeff, (size_t)Ne * Ne * sizeof(double));
     h->mom_user.assign(mom3, mom3 + 3 * (size_t)nmom);
-    if (const char* a = getenv("EDK_GRAM_ALGO")) {  // A/B hook: 0 = 4M GEMM, 1 = 3M GEMM (default), 2 / 3 = plane-wave forms
+    // The form of the contraction is planned per handle (plan_contraction_form).  A/B hook for measurements only:
+    // EDK_GRAM_ALGO = 0 (4M GEMM), 1 (3M GEMM), 2 / 3 (plane-wave forms), 4 (separable form) asks for one form.
+    if (const char* a = getenv("EDK_GRAM_ALGO")) {
         const int v = atoi(a);
-        if (v >= 0 && v <= 3) h->algo = v;
+        if (v >= 0 && v <= 4 && a[0] >= '0' && a[0] <= '9') h->algo_request = v;
     }
     {
         const int rc = configure(h);
@@ -1007,7 +1387,7 @@ int edk_create(int Lx, int Ly, int Lz, int Ne, int mode, int order, int nmom, co
 
 int edk_destroy(edk_handle* h) {
     if (!h) return EDK_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaFree(h->links);
     cudaFree(h->links_tmp);
     cudaFree(h->fields);
@@ -1023,6 +1403,7 @@ int edk_destroy(edk_handle* h) {
     cudaFree(h->cta_map_dev);
     cudaFree(h->phase_tiles);
     free_pw(h);
+    free_sep(h);
     cudaFree(h->stage_U);
     cudaFree(h->stage_V);
     cudaFree(h->stage_out);
@@ -1043,7 +1424,11 @@ int edk_phase_table(int Lx, int Ly, int Lz, int nmom, const int* mom3, void* out
         set_error("edk_phase_table: bad argument");
         return EDK_ERR_ARG;
     }
-    EDK_CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        set_error("edk_phase_table: cudaSetDevice(%d) failed", device);
+        return EDK_ERR_CUDA;
+    }
     Geom g{Lx, Ly, Lz, Lx * Ly * Lz, Lx * Ly * Lz};  // unpadded rows: the caller's buffer is [nmom][V]
     int* mom_dev = nullptr;
     EDK_CUDA_TRY(cudaMalloc(&mom_dev, (size_t)nmom * 3 * sizeof(int)));
@@ -1096,11 +1481,62 @@ int edk_plan_modes(int nmom, const int* mom3, int* nmodes, int* modes3, int* mom
     return EDK_OK;
 }
 
+int edk_plan_form(int Lx, int Ly, int mode, int order, int nmom, const int* mom3, int out[6]) {
+    if (Lx < 1 || Ly < 1 || nmom < 1 || !mom3 || !out || order < 0 || (mode != EDK_MODE_DERIVATIVE && mode != EDK_MODE_DISPLACEMENT) ||
+        (mode == EDK_MODE_DERIVATIVE && order > 3)) {
+        set_error("edk_plan_form: bad argument");
+        return EDK_ERR_ARG;
+    }
+    // the job list of a handle, built on the host only (field pointers are never dereferenced here)
+    edk_handle tmp;
+    tmp.mode = mode;
+    tmp.order = order;
+    tmp.nmom = nmom;
+    tmp.Ne = 1;
+    tmp.field_cplx = 0;
+    tmp.nop = mode == EDK_MODE_DERIVATIVE ? pow3sum(order) : order + 1;
+    tmp.mom_user.assign(mom3, mom3 + 3 * (size_t)nmom);
+    const MomentumPlan plan = plan_momenta(mode, order, -1, tmp.mom_user);
+    tmp.symmetric = plan.symmetric;
+    tmp.mom_int = plan.mom_int;
+    tmp.n_half = plan.n_half;
+    tmp.nmom_int = (int)plan.mom_int.size() / 3;
+    if (mode == EDK_MODE_DERIVATIVE)
+        build_derivative_jobs(&tmp);
+    else
+        build_displacement_jobs(&tmp);
+    const SepPlan S = plan_sep(Lx, tmp.mom_int);
+    out[0] = plan_contraction_form(Lx, Ly, tmp.mom_int, tmp.jobs_host);
+    out[1] = S.ok ? 1 : 0;
+    out[2] = S.qmax;
+    out[3] = S.r2;
+    out[4] = S.pairs;
+    out[5] = S.nmodes;
+    return EDK_OK;
+}
+
+int edk_plan_tiles(int Ne, int max_tiles, int* tiles4) {
+    if (Ne < 1 || max_tiles < 0 || (max_tiles > 0 && !tiles4)) {
+        set_error("edk_plan_tiles: bad argument");
+        return EDK_ERR_ARG;
+    }
+    const std::vector<SepTile> t = sep_build_tiles(Ne);
+    for (size_t i = 0; i < t.size() && (int)i < max_tiles; ++i) {
+        int we = 0, wf = 0;
+        sepx_shape(t[i].shape, &we, &wf);
+        tiles4[4 * i] = t[i].e0;
+        tiles4[4 * i + 1] = t[i].f0;
+        tiles4[4 * i + 2] = t[i].e1 - t[i].e0;
+        tiles4[4 * i + 3] = t[i].f1 - t[i].f0;
+    }
+    return (int)t.size();
+}
+
 int edk_num_operators(const edk_handle* h) { return h ? h->nop : EDK_ERR_ARG; }
 size_t edk_output_bytes(const edk_handle* h) {
     return h ? (size_t)h->nop * h->nmom * h->Ne * h->Ne * sizeof(cplx) : 0;
 }
-size_t edk_workspace_bytes(const edk_handle* h) { return h ? h->ws_bytes + h->cfg_bytes + h->pw_bytes : 0; }
+size_t edk_workspace_bytes(const edk_handle* h) { return h ? h->ws_bytes + h->cfg_bytes + h->pw_bytes + h->sep_bytes : 0; }
 
 int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream) {
     const int big_endian = (layout & EDK_LINKS_BIG_ENDIAN) ? 1 : 0;
@@ -1110,6 +1546,7 @@ int edk_set_links(edk_handle* h, const void* U_dev, int layout, void* stream) {
         return EDK_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    EDK_ON_DEVICE(h);
     {
         PhaseTimer t(h, s, PH_PREP, 1);
         EDK_CUDA_TRY(launch_reorder_links((const cplx*)U_dev, layout, big_endian, h->links, h->g, s));
@@ -1151,6 +1588,7 @@ int edk_set_link_ops(edk_handle* h, int nops, const int* kinds, const int* nstep
 
 int edk_debug_links(edk_handle* h, void* dst_dev, void* stream) {
     if (!h || !dst_dev) return EDK_ERR_ARG;
+    EDK_ON_DEVICE(h);
     EDK_CUDA_TRY(cudaMemcpyAsync(dst_dev, h->links, (size_t)3 * h->g.V * 9 * sizeof(cplx), cudaMemcpyDeviceToDevice,
                                  (cudaStream_t)stream));
     return EDK_OK;
@@ -1162,6 +1600,7 @@ int edk_set_eigvecs(edk_handle* h, const void* V_dev, int is_c8, void* stream) {
         return EDK_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    EDK_ON_DEVICE(h);
     PhaseTimer t(h, s, PH_PREP, 1);
     EDK_CUDA_TRY(launch_round_eigvecs(V_dev, is_c8, h->field(0), h->field_sum(0), h->field_cplx, (size_t)3 * h->g.V,
                                       h->sum_row, s));
@@ -1178,6 +1617,7 @@ int edk_set_blending(edk_handle* h, const double* coeff_dev, void* stream) {
         h->have_coeff = false;
         return EDK_OK;
     }
+    EDK_ON_DEVICE(h);
     EDK_CUDA_TRY(cudaMemcpyAsync(h->coeff, coeff_dev, (size_t)h->Ne * h->Ne * sizeof(double), cudaMemcpyDeviceToDevice,
                                  (cudaStream_t)stream));
     h->have_coeff = true;
@@ -1194,7 +1634,7 @@ int edk_calc(edk_handle* h, void* out_dev, void* stream) {
         return EDK_ERR_STATE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    EDK_CUDA_TRY(cudaSetDevice(h->device));
+    EDK_ON_DEVICE(h);
     if (h->mode == EDK_MODE_DERIVATIVE) {
         // only the GEMM form's 3M arithmetic reads the Re + Im planes of the derived fields; the fields are rebuilt by
         // every call, so the choice follows the contraction form in use right now (W0's plane is always written)
@@ -1230,7 +1670,7 @@ int edk_laplacian(edk_handle* h, const void* F_dev, void* out_dev, int nvec, voi
         return EDK_ERR_STATE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    EDK_CUDA_TRY(cudaSetDevice(h->device));
+    EDK_ON_DEVICE(h);
     PhaseTimer t(h, s, PH_STENCIL, 1);
     EDK_CUDA_TRY(launch_laplacian((const cplx*)F_dev, (cplx*)out_dev, h->links, h->g, nvec, s));
     return EDK_OK;
@@ -1243,7 +1683,7 @@ int edk_calc_host(edk_handle* h, const void* U_host, int layout, const void* V_h
         return EDK_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    EDK_CUDA_TRY(cudaSetDevice(h->device));
+    EDK_ON_DEVICE(h);
     const size_t ub = (size_t)((layout & ~EDK_LINKS_BIG_ENDIAN) == EDK_LINKS_FILE_T ? 4 : 3) * h->g.V * 9 * sizeof(cplx);
     const size_t vb = h->field_cplx * ((is_c8 & EDK_EIGVECS_C8) ? 8 : 16);
     if (h->stage_U_bytes < ub) {
@@ -1334,6 +1774,7 @@ int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream) {
         set_error("edk_debug_field: bad argument");
         return EDK_ERR_ARG;
     }
+    EDK_ON_DEVICE(h);
     EDK_CUDA_TRY(cudaMemcpyAsync(dst_dev, h->field(idx), h->field_cplx * sizeof(cplx), cudaMemcpyDeviceToDevice,
                                  (cudaStream_t)stream));
     return EDK_OK;
@@ -1344,6 +1785,7 @@ int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream) {
         set_error("edk_debug_phase: bad argument");
         return EDK_ERR_ARG;
     }
+    EDK_ON_DEVICE(h);
     EDK_CUDA_TRY(cudaMemcpyAsync(dst_dev, h->phase + (size_t)ip * h->g.Vpad, (size_t)h->g.V * sizeof(cplx),
                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return EDK_OK;
@@ -1362,6 +1804,7 @@ int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit) {
         set_error("edk_debug_gram_config: mfrag %d not instantiated (2..13)", mfrag);
         return EDK_ERR_ARG;
     }
+    EDK_ON_DEVICE(h);
     h->force_mfrag = mfrag;
     h->force_ksplit = ksplit;
     pick_gram_config(h);
@@ -1374,28 +1817,40 @@ int edk_debug_gram_config(edk_handle* h, int mfrag, int ksplit) {
 
 int edk_debug_loader(edk_handle* h, int mode) {
     if (!h || mode < 0 || mode > 1) return EDK_ERR_ARG;
+    EDK_ON_DEVICE(h);
     h->loader = mode;
     pick_gram_config(h);
     return ensure_partial(h);
 }
 
 int edk_debug_algo(edk_handle* h, int algo) {
-    if (!h || algo < 0 || algo > 3) return EDK_ERR_ARG;
-    EDK_CUDA_TRY(cudaSetDevice(h->device));
-    h->algo = algo;
+    if (!h || algo < -1 || algo > 4) return EDK_ERR_ARG;
+    EDK_ON_DEVICE(h);
+    if (algo == 4 && !plan_sep(h->g.Lx, h->mom_int).ok) {
+        set_error("edk_debug_algo: the separable form does not cover this lattice / momentum list");
+        return EDK_ERR_ARG;
+    }
+    EDK_CUDA_TRY(cudaDeviceSynchronize());
+    h->algo_request = algo;
+    h->algo = algo >= 0 ? algo : plan_contraction_form(h->g.Lx, h->g.Ly, h->mom_int, h->jobs_host);
     pick_gram_config(h);
     int rc = build_tma(h);
     if (rc != EDK_OK) return rc;
-    if (algo >= 2 && (!h->pw_ready || h->pw_algo != algo)) {  // the two plane-wave forms have different tables
-        rc = build_pw(h);
-        if (rc != EDK_OK) return rc;
+    // only the buffers of the form in use are kept (the per-plane sums are the largest part of the workspace)
+    if (h->algo == 4) {
+        free_pw(h);
+        if (!h->sep_ready) rc = build_sep(h);
+    } else if (h->algo >= 2) {
+        free_sep(h);
+        if (!h->pw_ready || h->pw_algo != h->algo) rc = build_pw(h);  // the two plane-wave forms have different tables
     }
+    if (rc != EDK_OK) return rc;
     return ensure_partial(h);
 }
 
 int edk_debug_symmetry(edk_handle* h, int mode) {
     if (!h || mode < -1 || mode > 1) return EDK_ERR_ARG;
-    EDK_CUDA_TRY(cudaSetDevice(h->device));
+    EDK_ON_DEVICE(h);
     EDK_CUDA_TRY(cudaDeviceSynchronize());
     h->sym_request = mode;
     return configure(h);
@@ -1415,7 +1870,7 @@ int edk_query(const edk_handle* h, int what) {
         case 4: return h->mfrag;
         case 5: return h->njobs;
         case 6: return (h->loader == 0 && h->tma_ready) ? h->tma.nstages : 0;
-        case 7: return effective_algo(h) >= 2 ? 4 - effective_algo(h) : (effective_algo(h) ? 3 : 4);
+        case 7: return effective_algo(h) == 4 ? 0 : (effective_algo(h) >= 2 ? 4 - effective_algo(h) : (effective_algo(h) ? 3 : 4));
         case 8: {  // (pair, momentum) GEMMs actually contracted
             int n = 0;
             for (const auto& j : h->jobs_host) n += j.nseg * j.nmom;
@@ -1423,15 +1878,22 @@ int edk_query(const edk_handle* h, int what) {
         }
         case 9: return h->n_half;
         case 10: return effective_algo(h);
-        case 11: return h->pw_ready ? h->pw_nmodes : 0;
-        case 12: return h->pw_ready ? 10 * h->pw_el + h->pw_fl : 0;
+        case 11: return effective_algo(h) == 4 ? (h->sep_ready ? h->sep_nmodes : 0) : (h->pw_ready ? h->pw_nmodes : 0);
+        case 12: return effective_algo(h) == 4 ? (h->sep_ready ? (h->sep_variant == 6 ? 3232 : 100 * sep_variant_rows(h->sep_variant) + SEP_TF) : 0) : (h->pw_ready ? 10 * h->pw_el + h->pw_fl : 0);
+        case 13: return h->algo_request;
+        case 14: return effective_algo(h) == 4 && h->sep_ready ? h->sep_pairs : 0;
+        case 15: return effective_algo(h) == 4 && h->sep_ready ? h->sep_variant : -1;
         default: return EDK_ERR_ARG;
     }
 }
 
 int edk_microbench_fp64(int device, double* dmma_tflops, double* dfma_tflops) {
     if (!dmma_tflops || !dfma_tflops) return EDK_ERR_ARG;
-    EDK_CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        set_error("edk_microbench_fp64: cudaSetDevice(%d) failed", device);
+        return EDK_ERR_CUDA;
+    }
     EDK_CUDA_TRY(microbench_fp64(dmma_tflops, dfma_tflops));
     return EDK_OK;
 }

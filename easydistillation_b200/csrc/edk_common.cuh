@@ -146,6 +146,79 @@ struct PwFold {
     cplx* partial;        // [njobs][nmom_int][Ne][Ne] (split 0 of the partial-sum buffer)
 };
 
+// ---- separable contraction (algo 4, edk_gram_sep.cu) ------------------------------------------
+// The phase also factorises between x and y.  With the modes taken about the centre of the lattice,
+//   exp(2 pi i (px x/Lx + py y/Ly)) = k_p (c_|px|(x) + i sgn(px) s_|px|(x)) (c_|py|(y) + i sgn(py) s_|py|(y)),
+//   c_q(x) = cos(pi q (2x - Lx + 1)/Lx),  s_q(x) = sin(pi q (2x - Lx + 1)/Lx),  k_p a constant of modulus 1,
+// the transform of the site product C over a plane is done row by row in registers, with plain DFMAs:
+//   x stage, per pair of sites (x, Lx-1-x) of a row:  S = C(x) + C(xbar), D = C(x) - C(xbar),
+//       X[1] += S,  X[c_q] += c_q(x) S,  X[s_q] += s_q(x) D                      (2 QMAX + 1 complex accumulators)
+//   y stage, once per row:  Y[(m, c_q')] += c_q'(y) X[m],  Y[(m, s_q')] += s_q'(y) X[m],  X = 0
+// i.e. 12 (site product) + 7 FP64 operations per (pair, e, f, site) for the 33 momenta with |p|^2 <= 4 against
+// 12 + 2 + 16 of the folded plane-wave form (DMMA and DFMA share one FP64 pipe at the same rate on B200, so the
+// operation count is the cost).  Every lane owns its (e, f) elements privately - no MMA fragments - and all lanes of
+// a warp walk the same sites, so operands are broadcast reads of 128-byte-swizzled TMA tiles.
+// Y[job][z][m][e][f] holds the NM separable modes (m = (x mode, y mode), SepModes below); sep_zfold_kernel folds z
+// and recombines them into the momenta.
+constexpr int SEP_WARPS = 8;              // compute warps: 4 along e x 2 along f, warp tile 4 x 16
+constexpr int SEP_TE = 16, SEP_TF = 32;   // CTA tile: rows of L x rows of R
+constexpr int SEP_MAX_PR = 64;            // site pairs per row (Lx/2) the shared-memory weight table holds
+constexpr int SEP_DEFAULT_VARIANT = 6;    // kernel variant of a new handle (launch_gram_sep); EDK_SEP_VARIANT overrides (A/B hook)
+
+// CTA tiles of gram_sepx_kernel: 8 compute warps arranged we x wf over (8 we) rows of L and (16 wf) rows of R.  The host
+// covers the Ne x Ne elements with 32 x 32 tiles where they fit and with 8 x 128 / 64 x 16 tiles along the ragged edges,
+// so that a CTA with idle warps is the exception at any Ne (sep_build_tiles).
+struct SepTile {
+    int e0, f0;
+    int shape;   // 0: 4 x 2 warps = 32 x 32, 1: 1 x 8 = 8 x 128, 2: 8 x 1 = 64 x 16
+    int e1, f1;  // the tile's elements are e0 <= e < e1, f0 <= f < f1 (clipped to its region and to Ne)
+    int pad;
+};
+struct SepParams {
+    const GramJob* jobs;
+    int njobs;
+    int Ne;
+    int Lx, Ly, Lz;
+    int SR;          // stages per row = (Lx/2) / pairs per stage
+    int n_et, n_ft;  // tiles of SEP_TE x SEP_TF
+    int nmodes;      // separable xy-modes kept in Y (5 / 9 / 13)
+    const double* wx;  // [Lx/2][4]: c_1, s_1, c_2, s_2 at the front site x of pair (x, Lx-1-x)
+    const double* wy;  // [Ly][4]: c_1, s_1, c_2, s_2 at y
+    cplx* Y;           // [njobs][Lz][nmodes][Ne][Ne]
+    const SepTile* tiles;  // gram_sepx_kernel: the CTA tiles (of the launch's shape) of one (job, plane); grid = njobs * Lz * ntiles
+    int ntiles;
+};
+constexpr int SEP_NSHAPES = 3;
+struct SepTmaX {
+    alignas(64) unsigned char mapL[SEP_NSHAPES][128];  // boxes 16 doubles x {32, 8, 64} rows, 128-byte swizzle
+    alignas(64) unsigned char mapR[SEP_NSHAPES][128];  // boxes 16 doubles x {32, 128, 16} rows
+    int nstages[SEP_NSHAPES];
+};
+struct SepWeights {  // the x weights again, as a kernel parameter: read through the constant cache
+    double w[SEP_MAX_PR * 4];
+};
+struct SepTma {
+    alignas(64) unsigned char mapL[128];  // CUtensorMap over [nfield][Ne][6V doubles], box 16 x SEP_TE x 1, 128-byte swizzle
+    alignas(64) unsigned char mapR[128];  // box 16 x SEP_TF x 1
+    int nstages;
+};
+// z fold: one block folds one class of momenta (same |px|, |py|: they read the same <= 4 separable modes)
+struct SepClass {
+    int mode[4];  // cc, cs, sc, ss mode index in Y, -1 = absent
+    int first, count;  // its momenta: entries [first, first + count) of `mom`
+};
+struct SepFold {
+    const GramJob* jobs;
+    int njobs, Ne, Lz, nmodes, nmom_int;
+    int rows_l, rows_r;      // tile shape of the plane kernel (self pairs: tiles below the diagonal are mirror reads)
+    const cplx* Y;
+    const cplx* zphase;      // [nmom_int][Lz]: exp(2 pi i pz z/Lz) k_p
+    int nclass;
+    const SepClass* classes;
+    const int* mom;          // per entry: internal momentum index, sgn(px), sgn(py); ascending momentum index inside a class
+    cplx* partial;           // [njobs][nmom_int][Ne][Ne]
+};
+
 // ---- launchers (defined in the .cu files) -------------------------------------------------
 // prepare
 cudaError_t launch_round_eigvecs(const void* V_in, int flags, cplx* W0, double* W0_sum, size_t n_cplx, size_t row,
@@ -190,6 +263,20 @@ cudaError_t launch_gram_pwf(const PwParams& P, const PwTma& T, int el, int fl, c
 cudaError_t launch_pwf_weights(double* wtiles, const int* modes3_dev, const int* slotmode_dev, int mbtot, int kplane, Geom g,
                                cudaStream_t s);
 cudaError_t launch_pw_zfold(const PwFold& F, cudaStream_t s);
+// separable contraction: qmax / r2 select the mode structure (max |px|,|py| and max px^2 + py^2 covered),
+// pairs = site pairs per stage (8, 6 or 4, a divisor of Lx/2)
+int sep_num_modes(int qmax, int r2);                    // 0 = structure not instantiated
+int sep_mode_index(int qmax, int r2, int qx, int xk, int qy, int yk);  // xk, yk: 0 cos, 1 sin; -1 = not in the structure
+int sep_plan_smem(int* nstages, int* smem_bytes);
+// variant 0 = accumulators in registers, 1 x 2 elements per lane (gram_sep_kernel); variant 6 = y-stage accumulators in tensor
+// memory, 2 x 2 elements per lane, tile table (gram_sepx_kernel, launch_gram_sepx)
+int sep_variant_rows(int variant);  // rows of L per CTA tile of variant 0 (16); variant 6: 8, the unit of its tile table
+int sepx_shape(int shape, int* we, int* wf);                       // warp arrangement of a tile shape; -1 if unknown
+int sepx_plan_smem(int shape, int* nstages, int* smem_bytes);      // ring depth of a shape, dynamic shared memory of the kernel
+cudaError_t launch_gram_sepx(const SepParams& P, const SepTmaX& T, const SepWeights& W, int qmax, int r2, int pairs, int shape, cudaStream_t s);
+int sep_variant_plan(int variant, int* nstages, int* smem_bytes);
+cudaError_t launch_gram_sep(const SepParams& P, const SepTma& T, const SepWeights& W, int qmax, int r2, int pairs, int variant, cudaStream_t s);
+cudaError_t launch_sep_zfold(const SepFold& F, cudaStream_t s);
 // microbench
 cudaError_t microbench_fp64(double* dmma_tflops, double* dfma_tflops);
 

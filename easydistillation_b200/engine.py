@@ -39,6 +39,7 @@ class ElementalEngine:
         self.mode, self.order = int(mode), int(order)
         mom = np.ascontiguousarray(np.asarray(momentum_list, dtype=np.int32).reshape(-1, 3))
         self.nmom = mom.shape[0]
+        self.momenta = [tuple(int(c) for c in m) for m in mom]
         h = C.c_void_p()
         rc = self.lib.edk_create(Lx, Ly, Lz, self.Ne, self.mode, self.order, self.nmom,
                                  mom.ctypes.data_as(C.POINTER(C.c_int)), self.device.index, C.byref(h))
@@ -199,8 +200,9 @@ class ElementalEngine:
         _capi.check(self.lib.edk_debug_loader(self.h, int(mode)), "edk_debug_loader")
 
     def debug_algo(self, algo: int):
-        """Contraction form: 1 = GEMM form, 3M arithmetic (default), 0 = GEMM form, 4M, 2 = plane-wave factorised form,
-        3 = plane-wave form with centre-symmetric site pairs folded (include/edk.h, edk_debug_algo)."""
+        """Ask for one contraction form instead of the planned one (tests / A-B measurements): 1 = GEMM form, 3M
+        arithmetic, 0 = GEMM form, 4M, 2 = plane-wave factorised form, 3 = plane-wave form with centre-symmetric site
+        pairs folded, 4 = separable form, -1 = back to the form the library plans (include/edk.h, edk_debug_algo)."""
         _capi.check(self.lib.edk_debug_algo(self.h, int(algo)), "edk_debug_algo")
 
     def query(self):
@@ -208,7 +210,8 @@ class ElementalEngine:
         return {"hermitian_pairing": bool(q(0)), "internal_momenta": q(1), "pair_gemms_per_momentum": q(2),
                 "ksplit": q(3), "mfrag": q(4), "jobs": q(5), "tma_stages": q(6),
                 "real_mma_per_complex_block": q(7), "pair_momentum_gemms": q(8), "half_set_momenta": q(9),
-                "contraction_form": q(10), "plane_wave_modes": q(11), "plane_wave_tile": q(12)}
+                "contraction_form": q(10), "plane_wave_modes": q(11), "plane_wave_tile": q(12),
+                "form_requested": q(13), "pairs_per_stage": q(14)}
 
 
 def microbench_fp64(device: int = 0):

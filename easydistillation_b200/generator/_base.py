@@ -52,13 +52,16 @@ class _TimesliceGenerator:
         data = self.gauge_field.load(key)
         U = data[:]
         torch = self._engine.torch
-        if isinstance(U, torch.Tensor):
-            self._U = U
+        if isinstance(U, torch.Tensor) or getattr(U, "device_resident", False):
+            self._U = U  # already in HBM: a tensor [Lt, ...] or per-timeslice tensors (preset.DeviceTimeslices)
         else:
             U = np.asarray(U)
             Lx, Ly, Lz, Lt = (int(v) for v in self.latt_size)
             if U.ndim == 5 and U.shape == (Lt, Lz * Ly * Lx, Nd, Nc, Nc):  # the flattened default shape of preset.py:142,152
                 U = U.reshape(Lt, Lz, Ly, Lx, Nd, Nc, Nc)
+            if U.dtype.kind != "c":
+                raise ValueError(f"gauge field must be complex, got dtype {U.dtype} (GaugeFieldBinary defaults to '<f8' as in "
+                                 "the reference, lattice/preset.py:162-170: pass dtype='<c16')")
             if U.ndim != 7 or U.shape[4:] != (Nd, Nc, Nc):
                 raise ValueError(f"gauge field must be [Lt, Lz, Ly, Lx, {Nd}, {Nc}, {Nc}], got {U.shape}")
             if U.shape[:4] != (Lt, Lz, Ly, Lx):
@@ -91,6 +94,8 @@ class _TimesliceGenerator:
         torch = self._engine.torch
         if isinstance(ev, torch.Tensor):
             return ev[t, : self.Ne].reshape(shape).contiguous()
+        if getattr(ev, "device_resident", False):
+            return ev[t][: self.Ne].reshape(shape).contiguous()
         block = None
         try:
             block = np.asarray(ev[t])
@@ -118,7 +123,7 @@ class _TimesliceGenerator:
         eng = self._engine
         torch = eng.torch
         V_t = self._eigvecs_of(t)
-        if isinstance(self._U, torch.Tensor) or isinstance(V_t, torch.Tensor):
+        if not self._host_inputs() or isinstance(V_t, torch.Tensor):
             out = self.calc_device(t)
             self._VPV[...] = out.cpu().numpy()
             return self._VPV
@@ -145,7 +150,11 @@ class _TimesliceGenerator:
     # ---- batch / sharded form (each rank owns a contiguous t-range) -------------------
     def _host_inputs(self) -> bool:
         torch = self._engine.torch
-        return not isinstance(self._U, torch.Tensor) and not isinstance(self._eigenvector_data, torch.Tensor)
+
+        def on_device(x):
+            return isinstance(x, torch.Tensor) or getattr(x, "device_resident", False)
+
+        return not on_device(self._U) and not on_device(self._eigenvector_data)
 
     def calc_range(self, t0: int, t1: int) -> np.ndarray:
         """(t1-t0, Nop, Nmom, Ne, Ne) for t in [t0, t1).  Host-resident inputs go through the
@@ -164,19 +173,44 @@ class _TimesliceGenerator:
             out[i] = self.calc(t)
         return out
 
-    def calc_to_file(self, elemental, key: str, t_range: Optional[Tuple[int, int]] = None, dtype: str = "<c16"):
+    def calc_to_file(self, elemental, key: str, t_range: Optional[Tuple[int, int]] = None, dtype: str = "<c16", group=None,
+                     shard: bool = False):
         """Write the elemental file of configuration `key` in the reference's layout
         [Nop, Nmom, Lt, Ne, Ne] (tests/test_elemental.py:47, read back by ElementalNpy / lattice/data.py:26).
 
-        `elemental` is an ElementalNpy-like handle with `create(key, shape, dtype)`; the file is
-        pre-sized once and every batch of timeslices drops its slab in place on a writer thread
-        while the next batch is being computed.  `t_range=(t0, t1)` writes
-        only that slab (one rank of a sharded run; ranks share the file), `dtype="<c8"` down-casts
-        to the complex64 the reference declares for stored elementals (preset.py:176)."""
+        `elemental` is an ElementalNpy-like handle; the file is pre-sized once and every batch of timeslices drops
+        its slab in place on a writer thread while the next batch is being computed.  `dtype="<c8"` down-casts to the
+        complex64 the reference declares for stored elementals (preset.py:176).
+
+        Sharded runs: `shard=True` writes this rank's timeslice range of the torch.distributed `group`,
+        `t_range=(t0, t1)` an explicit slab; ranks share the file.  Creation is separate from slab writing: under
+        torch.distributed rank 0 makes sure the file exists (replacing one of another shape) and every rank waits at
+        a barrier before it opens it; independent processes (no process group) create a missing file atomically and
+        never truncate an existing one of the right shape, so slabs may be written in any order."""
+        from ..sharding import timeslice_range, world
+
         Lt = int(self.latt_size[3])
+        rank, size = world(group)
+        if shard:
+            if t_range is not None:
+                raise ValueError("shard=True derives the timeslice range from the rank; do not pass t_range too")
+            t_range = timeslice_range(Lt, rank, size)
         t0, t1 = (0, Lt) if t_range is None else t_range
+        if not 0 <= t0 <= t1 <= Lt:
+            raise IndexError(f"timeslice range {t_range} outside [0, {Lt}]")
         shape = (self._engine.out_shape[0], self._engine.out_shape[1], Lt, self.Ne, self.Ne)
-        mm = elemental.create(key, shape, dtype) if (t_range is None or t0 == 0) else elemental.open_rw(key, shape, dtype)
+        if not hasattr(elemental, "ensure"):  # a foreign handle with create / open_rw only: whole-file runs
+            mm = elemental.create(key, shape, dtype) if t_range is None else elemental.open_rw(key, shape, dtype)
+        elif size > 1:
+            import torch.distributed as dist
+
+            if rank == 0:
+                elemental.ensure(key, shape, dtype, replace=True)
+            dist.barrier(group)
+            mm = elemental.open_rw(key, shape, dtype)
+        else:
+            elemental.ensure(key, shape, dtype, replace=t_range is None)
+            mm = elemental.open_rw(key, shape, dtype)
         chunk = 4  # timeslices per streamed batch: bounds the host buffers (two batches alive at a time)
 
         def drop(a, b, block):  # transposing (and down-casting) copy into the file mapping; numpy releases the GIL
@@ -196,27 +230,40 @@ class _TimesliceGenerator:
         mm.flush()
         return mm
 
-    def calc_all(self, group=None, dst: Optional[int] = 0):
-        """All Lt timeslices, sharded over the ranks of `group` (default: the world group if
-        torch.distributed is initialised, else this process alone) and gathered with one
-        collective.  Returns [Lt, Nop, Nmom, Ne, Ne] on rank `dst` (every rank if dst is None)."""
-        from ..sharding import gather_timeslices, timeslice_range, world
+    def calc_all(self, group=None, dst: Optional[int] = 0, chunk: int = 4):
+        """All Lt timeslices, sharded over the ranks of `group` (default: the world group if torch.distributed is
+        initialised, else this process alone): rank r computes its contiguous range and its finished timeslices
+        travel, `chunk` at a time, straight into the one [Lt, Nop, Nmom, Ne, Ne] buffer on rank `dst` while the next
+        ones are computed (sharding.TimesliceGatherer) - the only exchange of the path.  Returns that device tensor on
+        rank `dst` (on every rank if dst is None), None elsewhere."""
+        from ..sharding import TimesliceGatherer
 
-        rank, size = world(group)
-        Lt = int(self.latt_size[3])
-        t0, t1 = timeslice_range(Lt, rank, size)
         torch = self._engine.torch
-        local = torch.empty((t1 - t0,) + self._engine.out_shape, dtype=torch.complex128, device=self._engine.device)
+        Lt = int(self.latt_size[3])
+        g = TimesliceGatherer(Lt, self._engine.out_shape, torch.complex128, self._engine.device, group=group, dst=dst, chunk=chunk)
+        local, n = g.local, g.n_local
+        if n:
+            self._check_loaded(g.t0)
+            self._check_loaded(g.t1 - 1)
+        sent = 0
+
+        def done(i):  # local timeslice i is queued on the current stream: hand over full chunks
+            nonlocal sent
+            if (i + 1) % g.chunk == 0 or i + 1 == n:
+                g.push(sent, i + 1)
+                sent = i + 1
+
         if self._host_inputs():
             from ..pipeline import TimeslicePipeline
 
             if self._pipeline is None:
                 self._pipeline = TimeslicePipeline(self)
-            self._pipeline.run_device(range(t0, t1), local)
+            self._pipeline.run_device(range(g.t0, g.t1), local, on_done=done)
         else:
-            for i, t in enumerate(range(t0, t1)):
+            for i, t in enumerate(range(g.t0, g.t1)):
                 self.calc_device(t, out=local[i])
-        return gather_timeslices(local, Lt, group=group, dst=dst)
+                done(i)
+        return g.finish()
 
     # ---- gauge preprocessing of the reference classes (SURVEY 8f N2) -----------------------------
     # The reference rewrites the whole loaded configuration at once (elemental.py:107-117,264-277).

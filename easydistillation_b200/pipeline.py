@@ -139,8 +139,9 @@ class TimeslicePipeline:
         self.ev_consumed[b] = ev
         return self.eng.calc(out)
 
-    def run_device(self, timeslices: Iterable[int], out):
-        """out[i] (device tensor [n, Nop, Nmom, Ne, Ne]) <- elementals of timeslices[i]."""
+    def run_device(self, timeslices: Iterable[int], out, on_done=None):
+        """out[i] (device tensor [n, Nop, Nmom, Ne, Ne]) <- elementals of timeslices[i]; `on_done(i)` is called once the
+        kernels of timeslice i are queued (the sharded run hands finished chunks to the gather from it)."""
         ts = list(timeslices)
         if not ts:
             return out
@@ -149,6 +150,8 @@ class TimeslicePipeline:
             if i + 1 < len(ts):
                 self._stage((i + 1) & 1, ts[i + 1])  # overlaps with the kernels of timeslice t-1 / t
             self._compute(i & 1, out[i])
+            if on_done is not None:
+                on_done(i)
         return out
 
     def run_host(self, timeslices: Iterable[int], out: np.ndarray):

@@ -92,6 +92,28 @@ int edk_plan(int mode, int order, int nmom, const int* mom3, int sym_request, in
  */
 int edk_plan_modes(int nmom, const int* mom3, int* nmodes, int* modes3, int* momode);
 
+/*
+ * Form of the contraction a handle of this lattice / operator set / momentum list uses, pure host logic (no device
+ * needed).  The reference has one form (one einsum per (split, momentum), lattice/generator/elemental.py:322-329); here
+ * edk_create picks, from the FP64-pipe work per (e, f, site) of each form, between
+ *   1 the GEMM form (3M arithmetic on DMMA; cheapest for one or two momenta),
+ *   3 the plane-wave form with folded site pairs (site product once per site, real xy-modes by DMMA; any momentum list,
+ *     planes of at least 8 sites),
+ *   4 the separable form (x and y transforms of the site product in registers, row by row; Lx even and >= 8 with Lx/2 a
+ *     multiple of 4, 6 or 8, |px|, |py| <= 2 and px^2 + py^2 <= 4).
+ * out[0] form, out[1] separable form available (0/1), out[2] its max |px|,|py| (1 or 2), out[3] its max px^2 + py^2,
+ * out[4] site pairs per stage (8, 6, 4), out[5] separable xy-modes (5, 9, 13).
+ */
+int edk_plan_form(int Lx, int Ly, int mode, int order, int nmom, const int* mom3, int out[6]);
+
+/*
+ * CTA tiles the separable contraction covers the Ne x Ne elements of one (pair, plane) with, pure host logic:
+ * tiles4[i] = (first row, first column, rows, columns) of tile i (32 x 32 where whole tiles fit, up to 8 x 128 and
+ * 64 x 16 along the ragged edges); every element lies in exactly one tile.  Returns the number of tiles (writes at
+ * most max_tiles of them).
+ */
+int edk_plan_tiles(int Ne, int max_tiles, int* tiles4);
+
 /* number of operators in the output: (3^(num_nabla+1)-1)/2 or distance+1 (elemental.py:48, displacement_elemental.py:45) */
 int edk_num_operators(const edk_handle* h);
 /* bytes of one timeslice result [Nop][Nmom][Ne][Ne] complex128 */
@@ -186,15 +208,20 @@ long long edk_launch_count(const edk_handle* h);
  *   2 = plane-wave factorised form: site products conj(L).R formed once per site, real xy-mode transform by
  *   DMMA per z-plane, z folded by a second kernel (csrc/edk_gram_pw.cu), 3 = form 2 with centre-symmetric site pairs
  *   folded (modes about the centre of the plane are even / odd under s -> A-1-s: the sum of the two site products
- *   feeds the cos modes, their difference the sin modes - half the DMMAs per site).  The environment variable
- *   EDK_GRAM_ALGO=0|1|2|3 sets the initial value of every new handle (A/B runs of bench.py).
+ *   feeds the cos modes, their difference the sin modes - half the DMMAs per site), 4 = separable form
+ *   (csrc/edk_gram_sep.cu: x transform per pair of sites (x, Lx-1-x) and y transform per row in registers, plain DFMAs;
+ *   EDK_ERR_ARG where edk_plan_form says it is not available), -1 = back to the planned form.  A handle starts with the
+ *   form edk_plan_form plans; the environment variable EDK_GRAM_ALGO=0..4 asks for one form in every new handle
+ *   instead (A/B measurements only; nothing in the package sets it).
  * edk_query: what = 0 pairing in use (0/1), 1 internal momentum count, 2 pair-GEMMs per momentum,
  *   3 split-K factor, 4 m-fragments per tile, 5 contraction jobs, 6 TMA ring depth (0 = cp.async loader),
  *   7 real MMAs per complex block (3 or 4), 8 number of (pair, momentum) GEMMs contracted per timeslice
  *   (self pairs L == R only run one momentum of every +-p couple), 9 size of that half set,
  *   10 contraction form in use (0 / 1 / 2 / 3 as in edk_debug_algo), 11 real xy-modes of forms 2 / 3 (0 = not built),
  *   12 tile shape of forms 2 / 3 as 10 el + fl (24 = 16 x 32 rows, 25 = 16 x 40, 17 = 8 x 56; environment EDK_PW_TILE overrides the pick, EDK_PW_STAGES = 2.. caps the depth of the operand ring: A/B hooks).
- *   With forms 2 / 3, what = 7 answers 2 / 1 (DMMAs per site, real or imaginary part and block of 8 modes).
+ *   With forms 2 / 3, what = 7 answers 2 / 1 (DMMAs per site, real or imaginary part and block of 8 modes), with
+ *   form 4 it answers 0 (no MMA), 11 the separable xy-modes and 12 the tile as 100 rows_L + rows_R (1632).
+ *   13 the form asked for (-1 = planned), 14 site pairs per stage of form 4.
  */
 int edk_debug_field(edk_handle* h, int idx, void* dst_dev, void* stream);
 int edk_debug_phase(edk_handle* h, int ip, void* dst_dev, void* stream);

@@ -90,9 +90,20 @@ def main():
         # the two ends of num_nabla: no derivative on odd y, z extents (the reference needs an even Lx: phase.py:25), and all 40 third-order operators
         "deriv_n0_random_6x3x5x1": ([6, 3, 5, 1], 4, "random", dict(num_nabla=0, momentum_list=[(0, 0, 0), (1, -2, 0), (0, 0, 3)])),
         "deriv_n3_random_4x4x6x1": ([4, 4, 6, 1], 4, "random", dict(num_nabla=3, momentum_list=[(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, -2)])),
+        # config 1 at its own shape: the inputs of the reference's tests/test_elemental.py:15-24 and
+        # tests/test_displacement_elemental.py:15-23 (4^3 x 8, Ne = 20, their momentum lists) on a synthetic weak field
+        # (the stored weak_field.* files are git-LFS pointers); all 8 timeslices of input, results of three / two of them
+        "config1_deriv_weak_4x4x4x8": ([4, 4, 4, 8], 20, "weak", dict(num_nabla=2, momentum_list=[(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 2), (0, 1, 2), (1, 1, 2)]), (0, 3, 7)),
+        "config1_disp_weak_4x4x4x8": ([4, 4, 4, 8], 20, "weak", dict(distance=8, momentum_list=[(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 1, 2), (1, 1, 2)]), (0, 5)),
+        # lattices the separable contraction covers (Lx even, >= 8): 4 / 6 / 8 site pairs per stage, 13 / 9 / 9 xy-modes
+        "deriv_sep_8x4x6x1": ([8, 4, 6, 1], 6, "random", dict(num_nabla=2, momentum_list=orc.momentum_set(33))),
+        "deriv_sep_12x4x2x1": ([12, 4, 2, 1], 5, "random", dict(num_nabla=1, momentum_list=orc.momentum_set(9))),
+        "disp_sep_16x2x4x1": ([16, 2, 4, 1], 5, "random", dict(distance=2, momentum_list=orc.momentum_set(19))),
     }
     only = set(sys.argv[1:])
-    for name, (latt, Ne, kind, kw) in cases.items():
+    for name, case in cases.items():
+        latt, Ne, kind, kw = case[:4]
+        keep = case[4] if len(case) > 4 else None  # timeslices whose results are stored (all by default)
         if only and name not in only:
             continue
         Lx, Ly, Lz, Lt = latt
@@ -100,6 +111,9 @@ def main():
         V_file = np.stack([orc.synthetic_eigvecs(latt, Ne, t) for t in range(Lt)])
         ref = run_reference(lattice, latt, Ne, U_file, V_file, **kw)
         meta = dict(latt_size=np.array(latt), Ne=Ne, momentum_list=np.array(kw["momentum_list"]))
+        if keep is not None:
+            ref = ref[list(keep)]
+            meta["timeslices"] = np.array(keep)
         if "num_nabla" in kw:
             meta["num_nabla"] = kw["num_nabla"]
         if "distance" in kw:

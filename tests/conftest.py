@@ -26,3 +26,39 @@ def load_golden(name):
     import numpy as np
 
     return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_timeslices(g):
+    """(index into g["E"], timeslice) pairs: fixtures at config 1's own shape keep all inputs but only some results."""
+    if "timeslices" in g.files:
+        return [(i, int(t)) for i, t in enumerate(g["timeslices"])]
+    return [(t, t) for t in range(int(g["latt_size"][3]))]
+
+
+# SURVEY section 4: the reference's stored fixtures are git-LFS pointers in this checkout; if they are ever
+# materialised (sha256 below) the tests additionally run the reference's exact inputs against its stored results.
+WEAK_FIELD_SHA256 = {
+    "weak_field.lime": "de4de48d80869ed537432e237e7cdd99aae36b31f05e2e6f6b4d0b0bc3b28576",
+    "weak_field.eigenvector.input.npy": "a6a84f704a86c563066149704851e7579c6ed809cac6b69eeff7f912f64e39c5",
+    "weak_field.elemental.npy": "5a244d9c04a94a809adc45f7eec4019dc36fb98218a8259ce6c64c0ac4225193",
+    "weak_field.displacement_elemental.npy": "6b706962020f21f4f6f7d4bda3bfbd6163bdb22c0cadb0751c283af9ee375bf4",
+}
+
+
+def reference_weak_field_files():
+    """Paths of the reference's tests/weak_field.* when they are the real files, else None (with the reason)."""
+    import hashlib
+
+    root = os.path.join(os.environ.get("EDK_REFERENCE_ROOT", "/root/reference"), "tests")
+    paths = {}
+    for name, sha in WEAK_FIELD_SHA256.items():
+        path = os.path.join(root, name)
+        if not os.path.exists(path):
+            return None, f"{path} does not exist"
+        if os.path.getsize(path) < 1024:
+            return None, f"{path} is a git-LFS pointer ({os.path.getsize(path)} bytes)"
+        with open(path, "rb") as f:
+            if hashlib.sha256(f.read()).hexdigest() != sha:
+                return None, f"{path} does not have the sha256 of the reference's LFS pointer"
+        paths[name] = path
+    return paths, ""

@@ -92,6 +92,8 @@ struct EmuCta {
     std::mutex mb_mutex;
     std::condition_variable mb_cv;
     EmuMbar mbar[EMU_SMEM_BYTES / 8];
+    uint32_t tmem[128][512];
+    int tmem_cols = 0;  // columns allocated by tcgen05.alloc (0 = none); a CTA that exits with columns allocated is a bug
     bool failed = false;
 };
 extern EmuCta g_cta;
@@ -101,6 +103,7 @@ struct EmuTensorMap {  // what the driver stores in the 128 bytes of a CUtensorM
     long long dim[3];
     long long stride_bytes[2];  // of dimensions 1 and 2
     int box[3];
+    int swizzle128;  // CU_TENSOR_MAP_SWIZZLE_128B: 16-byte slot s of box row r lands at slot s ^ (r % 8) of its 128-byte row
 };
 
 inline uint32_t __cvta_generic_to_shared(const void* p) {
@@ -137,6 +140,10 @@ inline void dmma884(double& c0, double& c1, const double a, const double b) {
 }
 
 inline double flip_sign(double x) { return -x; }
+inline double2 lds128(uint32_t addr) {
+    if (addr % 16 != 0 || addr + 16 > (uint32_t)EMU_SMEM_BYTES) throw std::runtime_error("bad 16-byte shared-memory load");
+    return *reinterpret_cast<const double2*>(smem + addr);
+}
 inline double2 lds128_again(const void* p) { return *reinterpret_cast<const double2*>(p); }
 
 using std::max;
@@ -234,6 +241,12 @@ inline void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, in
     const long long bytes = 8LL * T.box[0] * T.box[1] * T.box[2];
     if ((long long)dst + bytes > EMU_SMEM_BYTES) throw std::runtime_error("TMA box past the end of shared memory");
     double* out = reinterpret_cast<double*>(smem + dst);
+    if (T.swizzle128) {
+        // the hardware XORs address bits [4:6] with bits [7:9] of the shared-memory address; with 128-byte box rows
+        // that is slot ^ (row % 8) provided the tile starts on a 1024-byte boundary
+        if (T.box[0] != 16) throw std::runtime_error("128-byte swizzle needs an inner box of 128 bytes");
+        if (dst % 1024 != 0) throw std::runtime_error("swizzled TMA destination not 1024-byte aligned");
+    }
     for (int k = 0; k < T.box[2]; ++k)
         for (int j = 0; j < T.box[1]; ++j)
             for (int i = 0; i < T.box[0]; ++i) {
@@ -242,7 +255,12 @@ inline void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, in
                 if (x0 >= 0 && x0 < T.dim[0] && x1 >= 0 && x1 < T.dim[1] && x2 >= 0 && x2 < T.dim[2])
                     v = *reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(T.base) + x0 * 8 +
                                                          x1 * T.stride_bytes[0] + x2 * T.stride_bytes[1]);
-                *out++ = v;
+                if (T.swizzle128) {
+                    const long long r = (long long)k * T.box[1] + j;
+                    out[r * 16 + (((i >> 1) ^ (int)(r & 7)) << 1) + (i & 1)] = v;
+                } else {
+                    *out++ = v;
+                }
             }
     emu_complete_tx(bar, bytes);
 }
@@ -253,6 +271,51 @@ inline void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t ba
     std::memcpy(smem + dst, src, bytes);
     emu_complete_tx(bar, bytes);
 }
+
+// ---- tensor memory: 128 lanes x 512 columns of 32-bit words per CTA; warp w reaches lanes 32 (w % 4) .. + 31 ----------
+inline void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    if (ncols < 32 || ncols > 512 || (ncols & (ncols - 1))) throw std::runtime_error("tcgen05.alloc: columns must be a power of two in [32, 512]");
+    if (smem_dst % 4 != 0 || smem_dst + 4 > (uint32_t)EMU_SMEM_BYTES) throw std::runtime_error("tcgen05.alloc: bad shared-memory address");
+    if ((emu_tid() & 31) == 0) {
+        std::lock_guard<std::mutex> lk(g_cta.mb_mutex);
+        if (g_cta.tmem_cols) throw std::runtime_error("tcgen05.alloc: tensor memory already allocated by this CTA");
+        g_cta.tmem_cols = (int)ncols;
+        const uint32_t base = 0;
+        std::memcpy(smem + smem_dst, &base, 4);
+    }
+    g_cta.warp_barrier[emu_tid() >> 5].wait(emu_warp_size(emu_tid() >> 5));  // .sync.aligned
+}
+inline void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if ((emu_tid() & 31) == 0) {
+        std::lock_guard<std::mutex> lk(g_cta.mb_mutex);
+        if (taddr != 0 || (int)ncols != g_cta.tmem_cols) throw std::runtime_error("tcgen05.dealloc does not match the allocation");
+        g_cta.tmem_cols = 0;
+    }
+    g_cta.warp_barrier[emu_tid() >> 5].wait(emu_warp_size(emu_tid() >> 5));
+}
+inline void tmem_fence_before_sync() {}
+inline void tmem_fence_after_sync() {}
+inline void tmem_wait_ld() {}
+inline void tmem_wait_st() {}
+inline uint32_t* emu_tmem_row(uint32_t taddr, int ncols) {
+    const int warp = emu_tid() >> 5, lane = emu_tid() & 31;
+    const int lane0 = (int)(taddr >> 16), col = (int)(taddr & 0xffff);
+    if (lane0 != 32 * (warp & 3)) throw std::runtime_error("TMEM access outside the warp's lane quadrant");
+    if (col < 0 || col + ncols > g_cta.tmem_cols) throw std::runtime_error("TMEM access outside the allocated columns");
+    return &g_cta.tmem[lane0 + lane][col];
+}
+inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) { std::memcpy(r, emu_tmem_row(taddr, 32), sizeof(r)); }
+inline void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) { std::memcpy(emu_tmem_row(taddr, 32), r, sizeof(r)); }
+inline void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) { std::memcpy(r, emu_tmem_row(taddr, 16), sizeof(r)); }
+inline void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) { std::memcpy(emu_tmem_row(taddr, 16), r, sizeof(r)); }
+template <int N>
+inline double tmem_get_f64(const uint32_t (&r)[N], int k) {
+    double v;
+    std::memcpy(&v, &r[2 * k], 8);
+    return v;
+}
+template <int N>
+inline void tmem_put_f64(uint32_t (&r)[N], int k, double v) { std::memcpy(&r[2 * k], &v, 8); }
 
 inline void sincospi(double x, double* s, double* c) {
     // exact on multiples of 1/2, like the device function
@@ -313,6 +376,13 @@ cudaError_t emu_launch(dim3 grid, dim3 block, size_t smem_bytes, Body body) {
         for (long long c = 0; c < nctas; ++c) {
             if (t == 0) {
                 for (auto& b : g_cta.mbar) b.live = false;
+                if (g_cta.tmem_cols != 0 && !g_cta.failed) {
+                    std::lock_guard<std::mutex> lk(err_m);
+                    if (err.empty()) err = "a CTA exited without tcgen05.dealloc";
+                    g_cta.failed = true;
+                }
+                g_cta.tmem_cols = 0;
+                std::memset(g_cta.tmem, 0xff, sizeof(g_cta.tmem));
                 g_cta.cta_barrier.reset();
                 for (auto& w : g_cta.warp_barrier) w.reset();
                 std::memset(smem, 0xff, smem_bytes ? smem_bytes : 0);

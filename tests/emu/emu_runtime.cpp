@@ -55,8 +55,9 @@ CUresult fake_encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t 
                            CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill fill) {
     // the constraints of the real encoder that the library could violate
     if (!map || !base || rank != 3 || dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT64 || il != CU_TENSOR_MAP_INTERLEAVE_NONE ||
-        sw != CU_TENSOR_MAP_SWIZZLE_NONE || fill != CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+        (sw != CU_TENSOR_MAP_SWIZZLE_NONE && sw != CU_TENSOR_MAP_SWIZZLE_128B) || fill != CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
         return CUDA_ERROR_INVALID_VALUE;
+    if (sw == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * 8 > 128) return CUDA_ERROR_INVALID_VALUE;  // inner extent <= swizzle span
     if (reinterpret_cast<uintptr_t>(map) % 64 || reinterpret_cast<uintptr_t>(base) % 16) return CUDA_ERROR_INVALID_VALUE;
     for (int i = 0; i < 3; ++i)
         if (gdim[i] < 1 || gdim[i] > (1ULL << 32) || box[i] < 1 || box[i] > 256 || estride[i] != 1) return CUDA_ERROR_INVALID_VALUE;
@@ -71,6 +72,7 @@ CUresult fake_encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t 
     }
     M.stride_bytes[0] = (long long)gstride[0];
     M.stride_bytes[1] = (long long)gstride[1];
+    M.swizzle128 = sw == CU_TENSOR_MAP_SWIZZLE_128B;
     static_assert(sizeof(edk::EmuTensorMap) <= sizeof(CUtensorMap), "descriptor fits");
     std::memset(map, 0, sizeof(CUtensorMap));
     std::memcpy(map, &M, sizeof(M));
@@ -85,6 +87,10 @@ extern "C" {
 int edk_host_emulator_build(void) { return 1; }
 
 cudaError_t cudaSetDevice(int dev) { return dev == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaGetDevice(int* dev) {
+    *dev = 0;
+    return cudaSuccess;
+}
 cudaError_t cudaGetLastError(void) {
     const cudaError_t e = edk::g_last;
     edk::g_last = cudaSuccess;

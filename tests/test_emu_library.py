@@ -19,7 +19,7 @@ from conftest import REPO
 from easydistillation_b200 import _capi
 from oracle import elemental_oracle as orc
 
-SOURCES = ["edk_stencil.cu", "edk_gauge.cu", "edk_gram.cu", "edk_gram_pw.cu", "edk_api.cu"]
+SOURCES = ["edk_stencil.cu", "edk_gauge.cu", "edk_gram.cu", "edk_gram_pw.cu", "edk_gram_sep.cu", "edk_api.cu"]
 D, X = _capi.MODE_DERIVATIVE, _capi.MODE_DISPLACEMENT
 
 
@@ -115,8 +115,10 @@ def test_every_contraction_path_through_the_c_abi(emu):
     U_file, V, ref = inputs_and_reference(latt3, Ne, D, 1, moms)
     h = Handle(emu, latt3, Ne, D, 1, moms)
     h.set_inputs(U_file, V)
-    assert h.query(10) == 1 and h.query(7) == 3  # the library default: GEMM form, 3M
-    seen = {}
+    # the library plans the form per handle (edk_plan_form): 7 momenta on planes of 16 sites -> folded plane-wave form
+    # (Lx = 4 is below what the separable form covers)
+    assert h.query(13) == -1 and h.query(10) == 3 == _capi.plan_form(latt3, D, 1, moms)["form"]
+    seen = {"planned form": h.calc()}
     for algo, form, mmas in ((1, 1, 3), (0, 0, 4), (2, 2, 2)):
         h.check(emu.edk_debug_algo(h.h, algo), "edk_debug_algo")
         assert h.query(10) == form and h.query(7) == mmas
@@ -254,7 +256,9 @@ def test_laplacian_and_state_errors(emu):
     out = np.empty((1, 1, Ne, Ne), np.complex128)
     assert emu.edk_calc(h.h, out.ctypes.data, None) == _capi.EDK_ERR_STATE  # nothing set yet
     assert b"must be set first" in emu.edk_last_error()
-    assert emu.edk_debug_algo(h.h, 4) == _capi.EDK_ERR_ARG
+    assert h.query(10) == 1  # one momentum: the GEMM form is the cheapest
+    assert emu.edk_debug_algo(h.h, 4) == _capi.EDK_ERR_ARG  # Lx = 4: not covered by the separable form
+    assert emu.edk_debug_algo(h.h, 5) == _capi.EDK_ERR_ARG
     h.set_inputs(U_file, V)
     F = np.ascontiguousarray(orc.round_through_c8(V).astype(np.complex128))
     LF = np.empty_like(F)
@@ -333,7 +337,81 @@ def test_folded_plane_wave_form(emu, latt3, Ne, mode, order, moms, sym, switch):
     h.close()
 
 
+@pytest.mark.parametrize("latt3,Ne,mode,order,moms,sym", [
+    ((8, 4, 2), 5, D, 1, orc.momentum_set(7), None),        # 4 site pairs per stage, 5 separable modes
+    ((16, 3, 2), 20, D, 1, orc.momentum_set(9), None),      # 8 pairs per stage, 9 modes, 2 x 1 tiles with a mirror tile
+    ((12, 2, 2), 35, D, 1, orc.momentum_set(33), 1),        # 6 pairs per stage, 13 modes, 3 x 2 tiles, idle edge warps
+    ((8, 4, 1), 4, D, 2, orc.momentum_set(33), 0),          # direct pairs: multi-segment jobs with signs
+    ((8, 6, 2), 12, X, 2, orc.momentum_set(19), None),      # displacement lines
+    ((8, 4, 2), 7, D, 2, [(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 2), (0, 1, 2), (1, 1, 2)], None),  # the reference's test list
+    ((24, 2, 1), 3, D, 1, [(2, 0, 0), (-1, 1, 3), (0, -2, -1)], None),  # two stages per row, non-closed list, pz > Lz
+    ((8, 2, 1), 75, D, 1, orc.momentum_set(7), None),     # Ne = 75: 2 x 2 tiles of 32 x 32, two 8 x 128 and one 64 x 16 strip tiles
+])
+def test_separable_form(emu, latt3, Ne, mode, order, moms, sym):
+    """Form 4 (gram_sep_kernel + sep_zfold_kernel: swizzled TMA tiles, x transform per site pair, y transform per row)
+    through the C ABI against the oracle; it is what edk_create plans for these shapes.  Switching to the folded
+    plane-wave form and back on the same handle rebuilds the other form's tables and reproduces the result bit for bit."""
+    U_file, V, ref = inputs_and_reference(latt3, Ne, mode, order, moms)
+    h = Handle(emu, latt3, Ne, mode, order, moms)
+    plan = _capi.plan_form(latt3, mode, order, moms)
+    assert plan["separable_available"] and h.query(10) == plan["form"] == 4 and h.query(11) == plan["separable_modes"]
+    assert h.query(14) == plan["pairs_per_stage"] and h.query(12) == 3232 and h.query(15) == 6 and h.query(3) == 1 and h.query(7) == 0
+    if sym is not None:
+        h.check(emu.edk_debug_symmetry(h.h, sym), "edk_debug_symmetry")
+        assert h.query(10) == 4 and h.query(0) == sym
+    h.set_inputs(U_file, V)
+    sep = h.calc()
+    assert worst_block_error(sep, ref) < 1e-10
+    h.check(emu.edk_debug_algo(h.h, 3), "edk_debug_algo")
+    assert h.query(10) == 3 and h.query(13) == 3
+    assert worst_block_error(h.calc(), ref) < 1e-10
+    h.check(emu.edk_debug_algo(h.h, -1), "edk_debug_algo")  # back to the planned form
+    assert h.query(10) == 4 and h.query(13) == -1
+    assert np.array_equal(sep, h.calc())
+    h.close()
+
+
+def test_separable_form_shallow_ring_and_environment(emu, monkeypatch):
+    """EDK_SEP_STAGES=2 (A/B hook): the shallowest operand ring, where the wrap-around parity of the full / empty
+    barriers is exercised most; EDK_GRAM_ALGO=4 asks for the form at edk_create, and is refused for a momentum list
+    outside the instantiated mode structures."""
+    latt3, Ne, moms = (16, 2, 2), 9, orc.momentum_set(9)
+    U_file, V, ref = inputs_and_reference(latt3, Ne, D, 1, moms)
+    monkeypatch.setenv("EDK_SEP_STAGES", "2")
+    monkeypatch.setenv("EDK_GRAM_ALGO", "4")
+    h = Handle(emu, latt3, Ne, D, 1, moms)
+    assert h.query(10) == 4 and h.query(13) == 4
+    h.set_inputs(U_file, V)
+    assert worst_block_error(h.calc(), ref) < 1e-10
+    h.close()
+    # EDK_SEP_VARIANT=0 (A/B hook): the first kernel of the form, 1 x 2 elements per lane, accumulators in registers
+    monkeypatch.setenv("EDK_SEP_VARIANT", "0")
+    h = Handle(emu, latt3, Ne, D, 1, moms)
+    assert h.query(10) == 4 and h.query(15) == 0 and h.query(12) == 1632
+    h.set_inputs(U_file, V)
+    assert worst_block_error(h.calc(), ref) < 1e-10
+    h.close()
+    monkeypatch.delenv("EDK_SEP_VARIANT")
+    mom = np.ascontiguousarray(np.asarray([(3, 0, 0), (0, 0, 1)], np.int32))
+    hh = C.c_void_p()
+    rc = emu.edk_create(16, 2, 2, 3, D, 1, 2, mom.ctypes.data_as(C.POINTER(C.c_int)), 0, C.byref(hh))
+    assert rc == _capi.EDK_ERR_ARG and b"separable" in emu.edk_last_error()
+    monkeypatch.delenv("EDK_GRAM_ALGO")
+    many = [(3, 0, 0), (0, 0, 1), (1, 0, 0), (0, 1, 0), (0, 0, 2), (1, 1, 0)]
+    hp = Handle(emu, (16, 2, 2), 3, D, 1, many)  # planned: |px| = 3 is outside the structures -> folded plane-wave form
+    assert hp.query(10) == 3
+    hp.close()
+    hp = Handle(emu, (16, 2, 2), 3, D, 1, many[:2])  # two momenta: the GEMM form is the cheapest
+    assert hp.query(10) == 1
+    hp.close()
+
+
 @pytest.mark.parametrize("name,forms,timeslices", [
+    ("deriv_sep_8x4x6x1", (4, 3), (0,)),        # lattices the separable form covers: 13 / 9 / 9 modes, 4 / 6 / 8 pairs per stage
+    ("deriv_sep_12x4x2x1", (4,), (0,)),
+    ("disp_sep_16x2x4x1", (4, 2), (0,)),
+    ("config1_deriv_weak_4x4x4x8", (3,), (7,)),  # config 1 at its own shape (4^3 x 8, Ne = 20, 7 momenta; distance 8, 6 momenta)
+    ("config1_disp_weak_4x4x4x8", (3,), (5,)),
     ("deriv_n1_random_6x4x2x1", (1, 2, 3), (0,)),
     ("deriv_n0_random_6x3x5x1", (2, 3), (0,)),
     ("deriv_blend_4x4x4x1", (2, 3), (0,)),
@@ -357,11 +435,14 @@ def test_reference_goldens_through_every_contraction_form(emu, name, forms, time
     if "dilution_tot" in g.files:
         coeff = np.ascontiguousarray(orc.blending_matrix(Ne, (list(g["dilution_tot"]), list(g["dilution_used"]))), np.float64)
         h.check(emu.edk_set_blending(h.h, coeff.ctypes.data, None), "edk_set_blending")
+    from conftest import golden_timeslices
+
+    stored = {t: i for i, t in golden_timeslices(g)}
     for t in timeslices:
         h.set_inputs(g["U"][t], g["V"][t])
         for form in forms:
             h.check(emu.edk_debug_algo(h.h, form), "edk_debug_algo")
-            assert worst_block_error(h.calc(), g["E"][t]) < 1e-10, (name, t, form)
+            assert worst_block_error(h.calc(), g["E"][stored[t]]) < 1e-10, (name, t, form)
     h.close()
 
 
@@ -407,7 +488,9 @@ def memcheck_cases(lib):
              ((4, 2, 2), 3, D, 1, orc.momentum_set(7), (3,)),                   # folded form, planes of exactly one stage
              ((3, 5, 1), 3, D, 2, [(1, -1, 0), (0, 2, 1)], (3, 1)),            # ragged / odd planes, second-order fields
              ((3, 5, 2), 7, X, 2, orc.momentum_set(9), (1, 2)),                 # displacement lines
-             ((4, 2, 1), 35, D, 1, orc.momentum_set(7), (2, 3))]                # multi-tile plane-wave runs with mirror tiles
+             ((4, 2, 1), 35, D, 1, orc.momentum_set(7), (2, 3)),                # multi-tile plane-wave runs with mirror tiles
+             ((8, 2, 2), 35, D, 1, orc.momentum_set(9), (4,)),                  # separable form: multi-tile, mirror tile, idle edge warps
+             ((12, 2, 1), 5, X, 2, orc.momentum_set(33), (4,))]                 # separable form: 6 pairs per stage, 13 modes
     worst = 0.0
     for latt3, Ne, mode, order, moms, algos in cases:
         U_file, V, ref = inputs_and_reference(latt3, Ne, mode, order, moms)

@@ -6,7 +6,7 @@ Tolerance: 1e-10 relative (Frobenius) per (operator, momentum) block, as north_s
 import numpy as np
 import pytest
 
-from conftest import load_golden, rel_err
+from conftest import golden_timeslices, load_golden, reference_weak_field_files, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -53,11 +53,40 @@ def _golden_case(name):
     return g, latt, moms
 
 
+def _forms_of(eng):
+    """Every contraction form this handle can run, the planned one first: 1 = GEMM form (3M on DMMA), 2 / 3 = plane-wave
+    forms, 4 = separable form where the lattice / momentum list allow it (easydistillation_b200._capi.plan_form)."""
+    from easydistillation_b200 import _capi
+
+    Lx, Ly, Lz = eng.latt3
+    plan = _capi.plan_form((Lx, Ly, Lz), eng.mode, eng.order, [tuple(m) for m in eng.momenta])
+    planned = eng.query()["contraction_form"]
+    assert planned == plan["form"], (planned, plan)
+    forms = [1, 2, 3] + ([4] if plan["separable_available"] else [])
+    return [planned] + [f for f in forms if f != planned]
+
+
+def _all_forms(gen, t, ref, what):
+    """calc(t) with the planned form and then with every other form, each against `ref`; leaves the planned form on."""
+    eng = gen._engine
+    forms = _forms_of(eng)
+    worst = {}
+    for form in forms:
+        eng.debug_algo(form)
+        assert eng.query()["contraction_form"] == form
+        worst[form] = _blocks_close(np.array(gen.calc(t)), ref, what=f"{what} form {form}")
+    eng.debug_algo(-1)
+    assert eng.query()["contraction_form"] == forms[0]
+    return worst
+
+
 # ---------------------------------------------------------------------------------------------
 # (1) reference golden vectors
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["deriv_weak_4x4x4x2", "deriv_random_4x6x8x1", "deriv_n1_random_6x4x2x1",
-                                  "deriv_n0_random_6x3x5x1", "deriv_n3_random_4x4x6x1"])
+                                  "deriv_n0_random_6x3x5x1", "deriv_n3_random_4x4x6x1",
+                                  "config1_deriv_weak_4x4x4x8",  # config 1 at its own shape: tests/test_elemental.py:15-24
+                                  "deriv_sep_8x4x6x1", "deriv_sep_12x4x2x1"])
 def test_derivative_elementals_match_reference_golden(edb, name):
     g, latt, moms = _golden_case(name)
     gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]),
@@ -67,24 +96,59 @@ def test_derivative_elementals_match_reference_golden(edb, name):
     data = np.zeros((latt[3],) + g["E"].shape[1:], "<c16")
     for t in range(latt[3]):
         data[t] = gen.calc(t)  # same idiom as the reference's test script
-    for t in range(latt[3]):
-        _blocks_close(data[t], g["E"][t], what=f"{name} t={t}")
+    stored = golden_timeslices(g)
+    for i, t in stored:
+        _blocks_close(data[t], g["E"][i], what=f"{name} t={t}")
+    # every contraction form of the library against the reference's output, not only the planned one
+    i, t = stored[-1]
+    _all_forms(gen, t, g["E"][i], name)
     # complex128 input goes through the device-side complex64 rounding and must agree too
     gen2 = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]),
                                   edb.EigenvectorHostmem(g["V"].astype(np.complex128)), int(g["num_nabla"]), moms)
     gen2.load("cfg")
-    _blocks_close(gen2.calc(0), g["E"][0], what=name + " c16 input")
+    _blocks_close(gen2.calc(stored[0][1]), g["E"][stored[0][0]], what=name + " c16 input")
 
 
-@pytest.mark.parametrize("name", ["disp_weak_4x4x4x2", "disp_random_4x6x8x1"])
+@pytest.mark.parametrize("name", ["disp_weak_4x4x4x2", "disp_random_4x6x8x1",
+                                  "config1_disp_weak_4x4x4x8",  # tests/test_displacement_elemental.py:15-23: distance 8, 6 momenta
+                                  "disp_sep_16x2x4x1"])
 def test_displacement_elementals_match_reference_golden(edb, name):
     g, latt, moms = _golden_case(name)
     gen = edb.DisplacementElementalGenerator(latt, edb.GaugeFieldHostmem(g["U"]), edb.EigenvectorHostmem(g["V"]),
                                              int(g["distance"]), moms)
     assert gen.distance == int(g["distance"])
     gen.load("cfg")
-    for t in range(latt[3]):
-        _blocks_close(np.array(gen.calc(t)), g["E"][t], what=f"{name} t={t}")
+    for i, t in golden_timeslices(g):
+        _blocks_close(np.array(gen.calc(t)), g["E"][i], what=f"{name} t={t}")
+    i, t = golden_timeslices(g)[-1]
+    _all_forms(gen, t, g["E"][i], name)
+
+
+def test_reference_stored_goldens_when_materialised(edb):
+    """the reference's tests/weak_field.* are git-LFS pointers in its checkout.  Where they are the real
+    files (sha256 of SURVEY section 4) the reference's own test scripts are replayed here: same loaders' inputs
+    (ILDG gauge field, .npy eigenvectors), same constructor arguments, against its stored elemental files."""
+    paths, why = reference_weak_field_files()
+    if paths is None:
+        pytest.skip("stored goldens of the reference unavailable: " + why)
+    import os
+
+    prefix = os.path.dirname(paths["weak_field.lime"]) + "/"
+    latt, Ne = [4, 4, 4, 8], 20
+    gauge = edb.GaugeFieldIldg(prefix, ".lime", [8, 4, 4, 4, 4, 3, 3])
+    evec = edb.EigenvectorNpy(prefix, ".eigenvector.input.npy", [8, Ne, 4, 4, 4, 3], Ne)
+    moms = [(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 2), (0, 1, 2), (1, 1, 2)]
+    gen = edb.ElementalGenerator(latt, gauge, evec, 2, moms)
+    gen.load("weak_field")
+    ref = np.load(paths["weak_field.elemental.npy"], mmap_mode="r")
+    for t in range(8):
+        _blocks_close(np.array(gen.calc(t)), np.asarray(ref[:, :, t]), what=f"weak_field elemental t={t}")
+    dmoms = [(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 1, 2), (1, 1, 2)]
+    dgen = edb.DisplacementElementalGenerator(latt, gauge, evec, 8, dmoms)
+    dgen.load("weak_field")
+    dref = np.load(paths["weak_field.displacement_elemental.npy"], mmap_mode="r")
+    for t in range(8):
+        _blocks_close(np.array(dgen.calc(t)), np.asarray(dref[:, :, t]), what=f"weak_field displacement t={t}")
 
 
 def test_blending_matches_reference_golden(edb):
@@ -261,6 +325,7 @@ def test_derivative_elementals_match_oracle_edge_shapes(edb, latt, Ne, nabla, nm
     else:
         ref = orc.elemental_timeslice(V[0], U, latt, nabla, moms)
     _blocks_close(got, ref, what=f"{latt} Ne={Ne} nabla={nabla}")
+    _all_forms(gen, 0, ref, f"{latt} Ne={Ne} nabla={nabla}")
 
 
 def test_dmma_tile_variants_and_split_k_agree_with_scalar_kernel(edb):
@@ -479,6 +544,15 @@ def test_laplacian_matches_reference_golden(edb):
     Xd = torch.from_numpy(g["F"]).cuda()
     assert rel_err(lap.matmat(Xd).cpu().numpy(), g["LF"]) < 1e-14
     assert rel_err(lap.matvec(g["F"][2]), g["LF"][2]) < 1e-14
+    # the reference's own convention (lattice/generator/eigenvector.py:11-26): flat vectors, vector index fastest
+    N = lap.shape[0]
+    F_flat = np.ascontiguousarray(np.moveaxis(g["F"], 0, -1)).reshape(N, -1)
+    LF_flat = np.ascontiguousarray(np.moveaxis(g["LF"], 0, -1)).reshape(N, -1)
+    assert rel_err(lap.matmat(F_flat), LF_flat) < 1e-14
+    assert rel_err(lap.matvec(F_flat[:, 1]), LF_flat[:, 1]) < 1e-14
+    assert rel_err(lap.matmat(torch.from_numpy(F_flat).cuda()).cpu().numpy(), LF_flat) < 1e-14
+    op = lap.as_linear_operator()
+    assert op.shape == (N, N) and rel_err(op @ F_flat[:, :2], LF_flat[:, :2]) < 1e-14
     # odd volume, many vectors (several vector chunks), smeared links
     latt2 = [3, 5, 7, 1]
     U_file = orc.synthetic_links(latt2, 1, "weak")
@@ -519,7 +593,7 @@ def test_streamed_pipeline_matches_per_timeslice_calls(edb):
 # (3) BASELINE.json sizes: direct oracle where it takes seconds, properties beyond
 # ---------------------------------------------------------------------------------------------
 def test_config2_shape_against_oracle(edb):
-    """16^3, Ne=100, num_nabla=1, 9 momenta: one timeslice against the closed-form oracle."""
+    """16^3, Ne=100, num_nabla=1, 9 momenta: one timeslice against the closed-form oracle, every contraction form."""
     orc = _orc()
     latt, Ne = [16, 16, 16, 1], 100
     moms = orc.momentum_set(9)
@@ -527,70 +601,106 @@ def test_config2_shape_against_oracle(edb):
     V = orc.synthetic_eigvecs(latt, Ne, 0)[None].astype(np.complex64)
     gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), 1, moms)
     gen.load("x")
+    assert gen._engine.query()["contraction_form"] == 4  # what a user gets: the separable form
     got = np.array(gen.calc(0))
     ref = orc.elemental_timeslice_closed_form(V[0], orc.links_file_to_spatial(U_file[0]), latt, 1, moms)
     _blocks_close(got, ref, what="config 2")
+    _all_forms(gen, 0, ref, "config 2")
 
 
-def test_config3_shape_properties(edb):
-    """24^3, Ne=100, num_nabla=2, 33 momenta: too slow for the full oracle, so check
-    (a) Hermiticity  E[0,p]^dag = E[0,-p],  E[a,p]^dag = -E[a,-p],  E[(a,b),p]^dag = E[(b,a),-p];
-    (b) p = 0, n = 0 block is the Gram matrix of unit-norm vectors (diagonal 1 to c8 accuracy);
-    (c) a random sub-block of every operator against the oracle run on 6 of the 100 vectors."""
+def _hermiticity(E, moms, tol=TOL):
+    """E[0,p]^dag = E[0,-p],  E[a,p]^dag = -E[a,-p],  E[(a,b),p]^dag = E[(b,a),-p] (num_nabla = 2)."""
+    neg = [moms.index(tuple(-c for c in p)) for p in moms]
+    for ip in range(len(moms)):
+        assert rel_err(E[0, ip].conj().T, E[0, neg[ip]]) < tol
+        for a in range(3):
+            assert rel_err(-E[1 + a, ip].conj().T, E[1 + a, neg[ip]]) < tol
+            for b in range(3):
+                assert rel_err(E[4 + 3 * a + b, ip].conj().T, E[4 + 3 * b + a, neg[ip]]) < tol
+
+
+def _large_shape_check(edb, latt, Ne, sel, what, cross_check_forms):
+    """A BASELINE.json shape too slow for the full oracle (num_nabla = 2, 33 momenta), with the library default:
+    (a) the form the library plans is the separable one (what ElementalGenerator.calc gives a user);
+    (b) Hermiticity of every block and the unit Gram diagonal at p = 0 (complex64 accuracy of the inputs);
+    (c) the sub-block of every (operator, momentum) on the eigenvectors `sel` against the closed-form oracle run on
+        those vectors alone - for the planned form and for each form of `cross_check_forms`;
+    (d) the whole result of each cross-check form against the planned form's, to 1e-10."""
+    import torch
+
     orc = _orc()
-    latt, Ne = [24, 24, 24, 1], 100
     moms = orc.momentum_set(33)
     U_file = orc.synthetic_links(latt, 0)[None]
     V = orc.synthetic_eigvecs(latt, Ne, 0)[None].astype(np.complex64)
     gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), 2, moms)
     gen.load("x")
+    q = gen._engine.query()
+    assert q["contraction_form"] == 4 and q["form_requested"] == -1 and q["plane_wave_modes"] == 13, q
+    assert q["hermitian_pairing"] and q["pair_gemms_per_momentum"] == 19
     E = np.array(gen.calc(0))
-    neg = [moms.index(tuple(-c for c in p)) for p in moms]
-    for ip in range(len(moms)):
-        assert rel_err(E[0, ip].conj().T, E[0, neg[ip]]) < TOL
-        for a in range(3):
-            assert rel_err(-E[1 + a, ip].conj().T, E[1 + a, neg[ip]]) < TOL
-            for b in range(3):
-                assert rel_err(E[4 + 3 * a + b, ip].conj().T, E[4 + 3 * b + a, neg[ip]]) < TOL
+    _hermiticity(E, moms)
     assert np.max(np.abs(np.diag(E[0, 0]) - 1.0)) < 1e-6
-    sel = [3, 17, 42, 64, 65, 99]
     ref = orc.elemental_timeslice_closed_form(V[0][sel], orc.links_file_to_spatial(U_file[0]), latt, 2, moms)
-    _blocks_close(E[:, :, sel][:, :, :, sel], ref, what="config 3 sub-block")
-    # (d) the two evaluation orders (Hermitian pairing on: 19 pair-GEMMs, off: 34) agree at full size
-    assert gen._engine.query()["hermitian_pairing"]
+    worst = {4: _blocks_close(E[:, :, sel][:, :, :, sel], ref, what=f"{what} sub-block, planned form")}
+    for form in cross_check_forms:
+        gen._engine.debug_algo(form)
+        assert gen._engine.query()["contraction_form"] == form
+        F = np.array(gen.calc(0))
+        worst[form] = _blocks_close(F[:, :, sel][:, :, :, sel], ref, what=f"{what} sub-block, form {form}")
+        _blocks_close(F, E, what=f"{what}: form {form} vs planned form, full result")
+    print(f"{what}: worst sub-block error vs oracle by form: {worst}")
+    gen._engine.debug_algo(-1)
+    del gen
+    torch.cuda.empty_cache()
+    return E
+
+
+def test_config3_shape_properties(edb):
+    """24^3, Ne=100, num_nabla=2, 33 momenta (BASELINE config 3; 6 site pairs per stage): every form, plus the two
+    evaluation orders (Hermitian pairing on: 19 pair contractions, off: 34 with multi-segment jobs) at full size."""
+    orc = _orc()
+    latt, Ne = [24, 24, 24, 1], 100
+    E = _large_shape_check(edb, latt, Ne, [3, 17, 42, 64, 65, 99], "config 3", (3, 2, 1))
+    moms = orc.momentum_set(33)
+    U_file = orc.synthetic_links(latt, 0)[None]
+    V = orc.synthetic_eigvecs(latt, Ne, 0)[None].astype(np.complex64)
+    gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), 2, moms)
+    gen.load("x")
     gen._engine.debug_symmetry(0)
+    q = gen._engine.query()
+    assert not q["hermitian_pairing"] and q["contraction_form"] == 4 and q["pair_gemms_per_momentum"] == 34
     _blocks_close(np.array(gen.calc(0)), E, tol=1e-11, what="config 3 direct pairs vs Hermitian pairing")
 
 
 def test_config4_shape_properties(edb):
-    """32^3, Ne=200, num_nabla=2, 33 momenta (BASELINE config 4, the production tile shapes: two row
-    tiles of 13 + 12 fragments, 24-wave grids).  The full oracle would take ~50 min here, so:
-    (a) the product path (TMA, 3M, Hermitian pairing + half-set self pairs) against the same
-        timeslice evaluated with every pair contracted directly in 4M arithmetic (34 x 33 GEMMs),
-    (b) a 5-vector sub-block of every operator against the oracle,
-    (c) unit Gram diagonal at p = 0."""
+    """32^3, Ne=200, num_nabla=2, 33 momenta (BASELINE config 4: 13 x 7 tiles of 16 x 32 with idle edge warps and the
+    self pairs' mirror tiles).  The full oracle would take ~50 min here: sub-block, properties, and the GEMM form with
+    every pair contracted directly in 4M arithmetic (34 x 33 GEMMs) as an independent evaluation at full size."""
     import torch
 
     orc = _orc()
     latt, Ne = [32, 32, 32, 1], 200
+    E = _large_shape_check(edb, latt, Ne, [0, 57, 103, 104, 199], "config 4", (3, 1))
     moms = orc.momentum_set(33)
     U_file = orc.synthetic_links(latt, 0)[None]
     V = orc.synthetic_eigvecs(latt, Ne, 0)[None].astype(np.complex64)
     gen = edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U_file), edb.EigenvectorHostmem(V), 2, moms)
     gen.load("x")
-    E = np.array(gen.calc(0))
-    q = gen._engine.query()
-    assert q["hermitian_pairing"] and q["real_mma_per_complex_block"] == 3 and q["pair_momentum_gemms"] == 15 * 33 + 4 * 17
-    gen._engine.debug_symmetry(0)
     gen._engine.debug_algo(0)
-    assert gen._engine.query()["pair_momentum_gemms"] == 34 * 33
-    _blocks_close(np.array(gen.calc(0)), E, tol=1e-11, what="config 4: direct pairs / 4M vs pairing / 3M")
-    sel = [0, 57, 103, 104, 199]
-    ref = orc.elemental_timeslice_closed_form(V[0][sel], orc.links_file_to_spatial(U_file[0]), latt, 2, moms)
-    _blocks_close(E[:, :, sel][:, :, :, sel], ref, what="config 4 sub-block")
-    assert np.max(np.abs(np.diag(E[0, 0]) - 1.0)) < 1e-6
+    gen._engine.debug_symmetry(0)
+    q = gen._engine.query()
+    assert q["pair_momentum_gemms"] == 34 * 33 and q["real_mma_per_complex_block"] == 4 and q["contraction_form"] == 0
+    _blocks_close(np.array(gen.calc(0)), E, what="config 4: direct pairs / 4M GEMM form vs planned form")
     del gen
     torch.cuda.empty_cache()
+
+
+def test_config5_shape_properties(edb):
+    """48^3, Ne=200, num_nabla=2, 33 momenta: the graded configuration (BASELINE config 5, 8 site pairs per stage, three
+    stages per row).  The reference would need hours per timeslice here (elemental.py:309-329 at K = 331 776): the
+    library default against the closed-form oracle on 6 of the 200 eigenvectors, Hermiticity of all 429 blocks, and
+    the folded plane-wave form as an independent evaluation of the whole result."""
+    _large_shape_check(edb, [48, 48, 48, 1], 200, [0, 1, 77, 128, 198, 199], "config 5", (3,))
 
 
 def test_linearity_and_scaling_property(edb):
@@ -615,30 +725,121 @@ def test_linearity_and_scaling_property(edb):
 
 
 # ---------------------------------------------------------------------------------------------
-# (6) experimental: plane-wave factorised contraction (edk_debug_algo 2), checked in its own process
+# (6) every contraction form, strictly: oracle and GEMM-form parity on ragged / multi-tile / multi-segment shapes
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("form", [2, 3])
-def test_zz_plane_wave_form_in_subprocess(edb, form):
-    """csrc/edk_gram_pw.cu (form 2, and its folded variant, form 3) was written after the round's GPU budget was spent:
-    the kernel sources and the host glue are validated on the host emulator (tests/test_pw_model.py,
-    tests/test_emu_library.py), but they have not run on hardware yet and are NOT the default contraction.  The check
-    (tools/check_plane_wave.py: oracle + GEMM-form parity on ragged / multi-tile / multi-segment shapes) runs in a
-    subprocess so that a fault cannot poison this process's CUDA context; a failure is reported as xfail with the
-    tail of its output, a pass is a real pass."""
-    import os
-    import subprocess
-    import sys
+_SPECIAL = [(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 2), (0, 1, 2), (1, 1, 2)]  # the reference's test list
+_D, _X = 0, 1
+FORM_CASES = {
+    "plane-wave": [
+        ([4, 4, 4], 8, _D, 0, 7, None),
+        ([3, 5, 2], 5, _D, 1, 7, None),        # plane of 15 sites: ragged 4-site groups and stages
+        ([4, 6, 8], 30, _D, 2, 9, None),       # 2 x 1 tiles, pairing by cost
+        ([4, 6, 8], 35, _D, 2, 33, 1),         # 3 x 2 tiles, 13 modes, Hermitian pairing + half set
+        ([4, 6, 8], 19, _D, 2, 33, 0),         # direct pairs: multi-segment jobs with signs
+        ([6, 4, 2], 21, _D, 2, [(0, 0, 1), (1, 2, 0), (3, -1, 2), (0, -2, 1)], None),  # non-closed, larger momenta
+        ([2, 2, 2], 1, _D, 2, 7, None),        # planes of 4 sites (form 3 runs them unfolded)
+        ([3, 3, 2], 9, _D, 2, 33, None),       # odd planes of 9 sites (form 3: self-paired middle site)
+        ([4, 4, 6], 13, _D, 3, 7, None),
+        ([4, 6, 8], 12, _X, 3, 9, None),
+        ([5, 3, 7], 110, _D, 1, 9, None),      # 7 x 4 tiles
+    ],
+    "separable": [
+        ([8, 4, 4], 8, _D, 0, 7, None),        # 4 pairs per stage, 5 modes
+        ([8, 5, 2], 5, _D, 1, 9, None),        # 9 modes
+        ([16, 3, 2], 20, _D, 1, 9, None),      # 8 pairs per stage
+        ([12, 6, 4], 30, _D, 2, 9, None),      # 6 pairs per stage, pairing by cost
+        ([12, 6, 4], 35, _D, 2, 33, 1),        # 3 x 2 tiles, 13 modes, Hermitian pairing + half set
+        ([8, 6, 4], 19, _D, 2, 33, 0),         # direct pairs: multi-segment jobs with signs
+        ([8, 4, 2], 21, _D, 2, _SPECIAL, None),
+        ([24, 2, 2], 9, _D, 2, 33, None),      # two stages per row
+        ([8, 4, 6], 13, _D, 3, 7, None),
+        ([8, 6, 8], 12, _X, 3, 19, None),
+        ([8, 3, 7], 110, _D, 1, 9, None),      # 7 x 4 tiles, idle edge warps
+        ([16, 4, 4], 70, _D, 1, 33, None),     # mirror tiles of the self pair
+    ],
+}
 
-    from conftest import REPO
 
-    try:
-        r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "check_plane_wave.py"), *(["--form3"] if form == 3 else [])],
-                           capture_output=True, text=True, timeout=600)
-    except subprocess.TimeoutExpired:
-        pytest.xfail("plane-wave form (experimental, not the default path): check timed out")
-    except Exception as exc:  # the experimental check must never turn the default path's suite red
-        pytest.xfail(f"plane-wave form (experimental, not the default path): check could not run: {exc!r}")
-    tail = (r.stdout + r.stderr)[-1500:]
-    print(tail)
-    if r.returncode != 0:
-        pytest.xfail("plane-wave form (experimental, not the default path) failed its first hardware run:\n" + tail)
+@pytest.mark.parametrize("form,case", [(f, c) for f in (2, 3) for c in range(len(FORM_CASES["plane-wave"]))] +
+                         [(4, c) for c in range(len(FORM_CASES["separable"]))])
+def test_contraction_forms_against_oracle_and_gemm_form(edb, form, case):
+    """Forms 2 / 3 (csrc/edk_gram_pw.cu) and 4 (csrc/edk_gram_sep.cu) in process, no tolerance for failure: block-wise
+    1e-10 against the numpy oracle and against the GEMM form, and bit-identical when repeated."""
+    import torch
+
+    from easydistillation_b200 import _capi
+    from easydistillation_b200.engine import ElementalEngine
+
+    orc = _orc()
+    latt, Ne, mode, order, moms, sym = FORM_CASES["separable" if form == 4 else "plane-wave"][case]
+    moms = orc.momentum_set(moms) if isinstance(moms, int) else moms
+    U_file = orc.synthetic_links(latt + [1], 3)
+    V = orc.synthetic_eigvecs(latt + [1], Ne, 3)
+    U = orc.links_file_to_spatial(U_file)
+    if mode == _capi.MODE_DERIVATIVE:
+        ref = (orc.elemental_timeslice_closed_form if order <= 2 else orc.elemental_timeslice)(V, U, latt + [1], order, moms)
+    else:
+        ref = orc.displacement_timeslice(V, U, latt + [1], order, moms)
+    eng = ElementalEngine(latt, Ne, mode, order, moms)
+    if sym is not None:
+        eng.debug_symmetry(sym)
+    eng.set_links(torch.from_numpy(U_file).cuda(), _capi.LINKS_FILE_T)
+    eng.set_eigvecs(torch.from_numpy(V).cuda())
+    eng.debug_algo(1)
+    gemm = eng.calc().cpu().numpy()
+    eng.debug_algo(form)
+    q = eng.query()
+    assert q["contraction_form"] == form and q["plane_wave_modes"] >= 1 and q["ksplit"] == 1, q
+    got = eng.calc().cpu().numpy()
+    _blocks_close(got, ref, what=f"form {form} {latt} Ne={Ne} vs oracle")
+    _blocks_close(got, gemm, what=f"form {form} {latt} Ne={Ne} vs GEMM form")
+    assert np.array_equal(got, eng.calc().cpu().numpy())
+    eng.close()
+
+
+@pytest.mark.parametrize("tile", ["24", "25", "17"])
+def test_plane_wave_tile_shapes(edb, monkeypatch, tile):
+    """Every instantiated tile shape of forms 2 / 3 (EDK_PW_TILE, an A/B hook): multi-tile, mirror tiles, partial f-tiles."""
+    import torch
+
+    from easydistillation_b200 import _capi
+    from easydistillation_b200.engine import ElementalEngine
+
+    orc = _orc()
+    latt, Ne, moms = [4, 4, 4], 70, orc.momentum_set(7)
+    U_file = orc.synthetic_links(latt + [1], 3)
+    V = orc.synthetic_eigvecs(latt + [1], Ne, 3)
+    ref = orc.elemental_timeslice_closed_form(V, orc.links_file_to_spatial(U_file), latt + [1], 1, moms)
+    monkeypatch.setenv("EDK_PW_TILE", tile)
+    for form in (2, 3):
+        monkeypatch.setenv("EDK_GRAM_ALGO", str(form))
+        eng = ElementalEngine(latt, Ne, _capi.MODE_DERIVATIVE, 1, moms)
+        assert eng.query()["contraction_form"] == form and eng.query()["plane_wave_tile"] == int(tile)
+        eng.set_links(torch.from_numpy(U_file).cuda(), _capi.LINKS_FILE_T)
+        eng.set_eigvecs(torch.from_numpy(V).cuda())
+        _blocks_close(eng.calc().cpu().numpy(), ref, what=f"form {form} tile {tile}")
+        eng.close()
+
+
+def test_two_generators_on_one_device_and_the_callers_current_device(edb):
+    """Every entry point runs on its handle's device and restores the caller's current device (two GPUs: one
+    generator each in one process; one GPU: two handles interleaved)."""
+    import torch
+
+    orc = _orc()
+    latt, Ne = [8, 4, 4, 2], 6
+    moms = orc.momentum_set(7)
+    U = np.stack([orc.synthetic_links(latt, t) for t in range(2)])
+    V = np.stack([orc.synthetic_eigvecs(latt, Ne, t) for t in range(2)])
+    ndev = torch.cuda.device_count()
+    devs = [0, 1] if ndev > 1 else [0, 0]
+    before = torch.cuda.current_device()
+    gens = [edb.ElementalGenerator(latt, edb.GaugeFieldHostmem(U), edb.EigenvectorHostmem(V), 1, moms, device=d) for d in devs]
+    assert torch.cuda.current_device() == before
+    for g in gens:
+        g.load("x")
+    outs = [np.array(g.calc_device(1).cpu().numpy()) for g in gens]  # set_links / set_eigvecs first, on each device
+    assert torch.cuda.current_device() == before
+    ref = orc.elemental_timeslice_closed_form(V[1], orc.links_file_to_spatial(U[1]), latt, 1, moms)
+    for o in outs:
+        _blocks_close(o, ref, what="two generators")

@@ -115,6 +115,42 @@ def test_presets_roundtrip(tmp_path):
         edb.EigenvectorHostmem(np.zeros((2, 3, 2, 2, 2, 3)), totNe=5)
 
 
+def test_preset_signatures_follow_the_reference():
+    """Constructor signatures of lattice/preset.py: EigenvectorHostmem(host_ndarray, shape, totNe) (:77-89, ValueError on
+    a shape mismatch), GaugeFieldBinary(prefix, suffix, shape=[128, 16^3, 4, 3, 3], dtype="<f8") (:162-170)."""
+    import inspect
+
+    V = np.zeros((2, 5, 2, 2, 2, 3), np.complex64)
+    ev = edb.EigenvectorHostmem(V, [2, 5, 2, 2, 2, 3], 4)       # the reference's positional form (a list is accepted)
+    assert ev.Ne == 4 and ev.load("any")[1, 2].shape == (2, 2, 2, 3)
+    assert edb.EigenvectorHostmem(V, (2, 5, 2, 2, 2, 3)).Ne == 5  # totNe defaults to what is stored
+    assert edb.EigenvectorHostmem(V, totNe=3).Ne == 3 and edb.EigenvectorHostmem(V, 3).Ne == 3  # this package's earlier form
+    with pytest.raises(ValueError, match="does not match expected shape"):
+        edb.EigenvectorHostmem(V, [2, 5, 8, 3], 5)
+    flat = np.zeros((2, 5, 8, 3), np.complex64)                  # the flattened [Lt, Ne, Lz*Ly*Lx, Nc] layout
+    assert edb.EigenvectorHostmem(flat, [2, 5, 8, 3], 5).load()[0].shape == (5, 8, 3)
+    sig = inspect.signature(edb.GaugeFieldBinary.__init__).parameters
+    assert sig["shape"].default == [128, 16**3, 4, 3, 3] and sig["dtype"].default == "<f8"
+    assert list(inspect.signature(edb.EigenvectorHostmem.__init__).parameters)[1:] == ["host_ndarray", "shape", "totNe"]
+
+
+def test_device_resident_handles_index_like_the_file_handles():
+    """GaugeFieldDevice / EigenvectorDevice wrap per-timeslice tensors (any object with the tensor interface the
+    generators use); `[:]` returns the indexable, `[t]` a timeslice, `[t, e]` one eigenvector; cyclic repeats."""
+    import torch
+
+    U = [torch.zeros((2, 2, 2, 4, 3, 3), dtype=torch.complex128) + t for t in range(2)]
+    V = [torch.zeros((3, 2, 2, 2, 3), dtype=torch.complex64) + t for t in range(2)]
+    g = edb.GaugeFieldDevice(U, cyclic=True).load("k")
+    assert g[:] is g and g.device_resident and g[5] is U[1] and g.file == "<device>"
+    ev = edb.EigenvectorDevice(V, cyclic=True)
+    assert ev.Ne == 3 and ev.load("k")[4] is V[0] and ev.load("k")[3, 1].shape == (2, 2, 2, 3)
+    with pytest.raises(IndexError):
+        edb.EigenvectorDevice(V).load("k")[2]
+    with pytest.raises(ValueError):
+        edb.EigenvectorDevice(V, totNe=4)
+
+
 GLOO_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["EDB_REPO"])
@@ -133,6 +169,25 @@ else:
     assert got is None
 got = gather_timeslices(local, Lt, dst=None)
 assert torch.equal(got, full), "all-gather"
+# the streamed form calc_all() uses: chunks of finished timeslices travel while the next ones are "computed"; the
+# destination (here rank 1, which owns fewer timeslices than rank 0) writes its own in place
+from easydistillation_b200.sharding import TimesliceGatherer
+Lt = 7
+full = (torch.arange(Lt * 4, dtype=torch.float64).reshape(Lt, 2, 2) * (2 - 1j)).to(torch.complex128)
+g = TimesliceGatherer(Lt, (2, 2), torch.complex128, "cpu", dst=1, chunk=2)
+assert (g.t0, g.t1) == timeslice_range(Lt, rank, size) and g.n_local == (4 if rank == 0 else 3)
+sent = 0
+for i in range(g.n_local):
+    g.local[i] = full[g.t0 + i]
+    if (i + 1) % g.chunk == 0 or i + 1 == g.n_local:
+        g.push(sent, i + 1)
+        sent = i + 1
+out = g.finish()
+if rank == 1:
+    assert torch.equal(out, full), "streamed gather"
+    assert out.data_ptr() == g.out.data_ptr() and g.local.data_ptr() == out[g.t0:].data_ptr()  # one buffer, own slab in place
+else:
+    assert out is None
 dist.destroy_process_group()
 print("OK", rank)
 """
@@ -334,6 +389,25 @@ def test_calc_to_file_layout_slabs_and_downcast(tmp_path):
     assert stored.dtype == np.dtype("<c8") and np.array_equal(stored, full.transpose(1, 2, 0, 3, 4).astype("<c8"))
     with pytest.raises(ValueError):
         gen.calc_to_file(handle, "two", t_range=(5, 10), dtype="<c16")  # existing file has another dtype
+    # slabs in any order: creation is separate from slab writing, and an existing file of the right shape is never
+    # truncated (a later slab - or the slab that holds t = 0 - must not wipe what another rank has written)
+    gen.calc_to_file(handle, "ooo", t_range=(5, 10))
+    gen.calc_to_file(handle, "ooo", t_range=(0, 5))
+    assert np.array_equal(np.load(tmp_path / "ooo.elemental.npy"), full.transpose(1, 2, 0, 3, 4))
+    gen.calc_to_file(handle, "ooo", t_range=(0, 2))  # rewriting a slab leaves the others alone
+    assert np.array_equal(np.load(tmp_path / "ooo.elemental.npy"), full.transpose(1, 2, 0, 3, 4))
+    assert handle.ensure("ooo", [Nop, Nmom, Lt, Ne, Ne]) is False and handle.ensure("fresh", [Nop, Nmom, Lt, Ne, Ne]) is True
+    assert not [f for f in os.listdir(tmp_path) if ".tmp." in f]
+    with pytest.raises(IndexError):
+        gen.calc_to_file(handle, "ooo", t_range=(8, 12))
+    with pytest.raises(ValueError):
+        gen.calc_to_file(handle, "ooo", t_range=(0, 5), shard=True)
+    # a whole-file run (the one coordinating process) replaces a stale file of another shape
+    np.save(tmp_path / "stale.elemental.npy", np.zeros((2, 2), np.complex128))
+    with pytest.raises(ValueError):
+        gen.calc_to_file(handle, "stale", t_range=(0, 5))
+    gen.calc_to_file(handle, "stale")
+    assert np.array_equal(np.load(tmp_path / "stale.elemental.npy"), full.transpose(1, 2, 0, 3, 4))
 
     # the reference's other elemental preset: headerless raw binary, shape and dtype declared by the handle
     # (lattice/preset.py:129-137); written here, read back by the REFERENCE's byte layout (numpy.fromfile)
@@ -358,64 +432,53 @@ def test_calc_to_file_layout_slabs_and_downcast(tmp_path):
         bad.calc_to_file(handle, "broken")
 
 
-def test_contraction_tuning_falls_back_to_the_gemm_form_without_a_gpu():
-    """tuning.select_contraction runs its trial in a child process; anything but a clean, faster, validated
-    plane-wave run - here: no CUDA device - must leave the validated GEMM form (1) in place."""
-    import torch
+def test_contraction_form_plan_host_logic():
+    """edk_plan_form: the form a handle runs is planned from the FP64-pipe work per (e, f, site) of each form - no
+    environment variable, no run-time trial.  BASELINE.json's configurations all take the separable form; one or two
+    momenta take the GEMM form; lattices / momentum lists the separable kernel does not cover take the folded
+    plane-wave form, toy planes of fewer than 8 sites the GEMM form."""
+    D, X = _capi.MODE_DERIVATIVE, _capi.MODE_DISPLACEMENT
+    from oracle.elemental_oracle import momentum_set
 
-    if torch.cuda.is_available():
-        pytest.skip("GPU present")
-    from easydistillation_b200 import tuning
+    for latt3, order, nmom, pairs in (((16, 16, 16), 1, 9, 8), ((24, 24, 24), 2, 33, 6), ((32, 32, 32), 2, 33, 8), ((48, 48, 48), 2, 33, 8)):
+        p = _capi.plan_form(latt3, D, order, momentum_set(nmom))
+        assert p["form"] == 4 and p["separable_available"] and p["pairs_per_stage"] == pairs
+        assert p["separable_modes"] == (13 if nmom == 33 else 9) and p["separable_qmax"] == (2 if nmom == 33 else 1)
+    assert _capi.plan_form((24, 24, 24), X, 2, momentum_set(33))["form"] == 4
+    assert _capi.plan_form((48, 48, 48), D, 2, [(0, 0, 0)])["form"] == 1                     # one momentum: 9 slots per pair
+    assert _capi.plan_form((48, 48, 48), D, 0, momentum_set(7))["separable_modes"] == 5      # |p|^2 <= 1: the 5-mode structure
+    config1 = [(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 2), (0, 1, 2), (1, 1, 2)]  # the reference's test list
+    assert _capi.plan_form((4, 4, 4), D, 2, config1)["form"] == 3 and not _capi.plan_form((4, 4, 4), D, 2, config1)["separable_available"]
+    assert _capi.plan_form((8, 8, 8), D, 2, config1) == {"form": 4, "separable_available": True, "separable_qmax": 1, "separable_r2": 2,
+                                                         "pairs_per_stage": 4, "separable_modes": 9}
+    assert _capi.plan_form((20, 20, 20), D, 2, momentum_set(33))["form"] == 3                 # Lx/2 = 10: no stage width divides it
+    assert _capi.plan_form((16, 16, 16), D, 2, [(1, 2, 0), (0, 0, 1), (2, 2, 1), (3, 0, 0), (0, 1, 0)])["form"] == 3  # outside |p_xy|^2 <= 4
+    assert _capi.plan_form((2, 2, 8), D, 2, momentum_set(33))["form"] == 1                    # planes of 4 sites
+    with pytest.raises(ValueError):
+        _capi.plan_form((0, 4, 4), D, 1, [(0, 0, 0)])
 
-    d = tuning.select_contraction((4, 4, 4), 8, _capi.MODE_DERIVATIVE, 2, tuning.momentum_set(7), device=0, timeout=300)
-    assert d["form"] == 1 and not d["validated"] and "child failed" in d["reason"]
-    saved = os.environ.pop("EDK_GRAM_ALGO", None)
-    try:
-        assert tuning.apply(d) == 1 and os.environ["EDK_GRAM_ALGO"] == "1"
-    finally:
-        os.environ.pop("EDK_GRAM_ALGO", None)
-        if saved is not None:
-            os.environ["EDK_GRAM_ALGO"] = saved
 
+def test_separable_tile_table_covers_every_element_once():
+    """edk_plan_tiles: 32 x 32 tiles where whole tiles fit, 8 x 128 / 64 x 16 tiles along the ragged edges; every
+    element in exactly one tile, and (the point of the table) few tiles with idle warps: the CTA time it stands for
+    stays within a few per cent of the useful work at the production Ne."""
+    for Ne in (1, 7, 8, 20, 33, 64, 70, 96, 97, 100, 129, 200, 256, 300):
+        t = _capi.plan_tiles(Ne)
+        cover = np.zeros((Ne, Ne), int)
+        for e0, f0, rows, cols in t:
+            assert rows >= 1 and cols >= 1 and e0 + rows <= Ne and f0 + cols <= Ne
+            assert (rows, cols) <= (32, 32) or rows <= 8 or cols <= 16
+            cover[e0:e0 + rows, f0:f0 + cols] += 1
+        assert (cover == 1).all(), Ne
+    assert len(_capi.plan_tiles(256)) == 64 and len(_capi.plan_tiles(200)) == 36 + 2 + 3
 
-def test_contraction_selection_picks_the_fastest_validated_candidate(monkeypatch):
-    """Decision logic of tuning.select_contraction with the child processes replaced by canned reports: a candidate
-    that failed validation or crashed is never chosen, the fastest validated one wins only if it beats the GEMM form,
-    and the chosen tile shape travels with the decision (tuning.apply exports EDK_GRAM_ALGO / EDK_PW_TILE)."""
-    from easydistillation_b200 import tuning
+    def cta_time(Ne):  # a tile costs the time of its busiest warp: a lane owns 2 x 2 elements, 4 rows and 8 columns apart
+        total = 0.0
+        for e0, f0, rows, cols in _capi.plan_tiles(Ne):
+            total += (0.5 if rows <= 4 else 1.0) * (0.5 if cols <= 8 else 1.0)
+        return total
 
-    ok = lambda ms: {"ok": True, "cases": [{"case": "x", "err": 3e-14}], "form1_ms": 100.0, "form2_ms": ms}  # noqa: E731
-    canned = {(2, None): ok(40.0), (3, "25"): {"ok": False, "reason": "tuning child failed (exit -6): trap"}, (3, "24"): ok(25.0)}
-    calls = []
-
-    def fake(form, tile, *a):
-        calls.append((form, tile))
-        return dict(canned[(form, tile)])
-
-    monkeypatch.setattr(tuning, "_run_candidate", fake)
-    three = ((2, None), (3, "25"), (3, "24"))
-    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900, candidates=three)
-    assert calls == [(2, None), (3, "25"), (3, "24")]
-    assert d["form"] == 3 and d["tile"] == "24" and d["validated"] and d["form2_ms"] == 25.0 and "4.00x faster" in d["reason"]
-    assert [c["ok"] for c in d["candidates"]] == [True, False, True]
-    for k in ("EDK_GRAM_ALGO", "EDK_PW_TILE"):
-        monkeypatch.delenv(k, raising=False)
-    assert tuning.apply(d) == 3 and os.environ["EDK_GRAM_ALGO"] == "3" and os.environ["EDK_PW_TILE"] == "24"
-    # validated but slower than the GEMM form: stay on form 1, no tile
-    canned[(2, None)], canned[(3, "24")] = ok(140.0), ok(120.0)
-    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900, candidates=three)
-    assert d["form"] == 1 and d["tile"] is None and d["validated"] and "not faster" in d["reason"]
-    assert tuning.apply(d) == 1 and os.environ["EDK_GRAM_ALGO"] == "1" and "EDK_PW_TILE" not in os.environ
-    # a differing result is never chosen, however fast
-    canned[(2, None)] = {"ok": False, "cases": [{"case": "x", "err": 2e-3}], "form1_ms": 100.0, "form2_ms": 1.0, "reason": "differs"}
-    canned[(3, "24")] = {"ok": False, "reason": "tuning child timed out after 10 s"}
-    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=900, candidates=three)
-    assert d["form"] == 1 and not d["validated"] and "no plane-wave candidate validated" in d["reason"]
-    # no time left: candidates are skipped, not started
-    calls.clear()
-    d = tuning.select_contraction((8, 8, 8), 16, 0, 2, [(0, 0, 0)], timeout=5)
-    assert calls == [] and d["form"] == 1
-    os.environ.pop("EDK_GRAM_ALGO", None)
+    assert cta_time(200) / (200 * 200 / 1024) < 1.02 and cta_time(100) / (100 * 100 / 1024) < 1.10
 
 
 def test_parallel_copy_matches_plain_copy():
@@ -440,35 +503,54 @@ def test_parallel_copy_matches_plain_copy():
 
 
 def test_bench_contraction_accounting():
-    """The flop accounting behind bench.py's roofline object, for the three contraction forms (config-5 numbers)."""
+    """The work accounting behind bench.py's roofline object, for every contraction form (config-5 numbers)."""
     import importlib.util
 
     spec = importlib.util.spec_from_file_location("edk_bench", os.path.join(REPO, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    Ne, V = 200, 48 ** 3
+    Ne, latt3 = 200, (48, 48, 48)
+    V = 48 ** 3
     gemm = bench.contraction_accounting({"contraction_form": 1, "tma_stages": 3, "real_mma_per_complex_block": 3,
-                                         "pair_momentum_gemms": 563}, Ne, V)
-    assert gemm["kernel"] == "gram_tma_kernel" and not gemm["plane_wave"] and gemm["padded"] is None
+                                         "pair_momentum_gemms": 563, "pair_gemms_per_momentum": 19}, Ne, latt3)
+    assert gemm["kernel"] == "gram_tma_kernel" and gemm["padded"] is None and gemm["slots"] == gemm["executed"] / 2
     assert abs(gemm["executed"] / 4.48e13 - 1) < 2e-3  # DESIGN.md 3.3: 4.48e13 executed flops per timeslice at config 5
-    q = {"contraction_form": 2, "pair_gemms_per_momentum": 19, "plane_wave_modes": 13}
-    pw = bench.contraction_accounting(q, Ne, V)
-    assert pw["kernel"] == "gram_pw_kernel" and pw["plane_wave"] and not pw["folded"]
+    q = {"contraction_form": 2, "pair_gemms_per_momentum": 19, "plane_wave_modes": 13, "plane_wave_tile": 24}
+    pw = bench.contraction_accounting(q, Ne, latt3)
+    assert pw["kernel"] == "gram_pw_kernel"
     assert pw["executed"] == 19.0 * Ne * Ne * V * (24 + 4 * 13) and pw["padded"] == 19.0 * Ne * Ne * V * (24 + 4 * 16)
     q["contraction_form"] = 3
-    pwf = bench.contraction_accounting(q, Ne, V)
-    assert pwf["kernel"] == "gram_pwf_kernel" and pwf["folded"]
+    pwf = bench.contraction_accounting(q, Ne, latt3)
+    assert pwf["kernel"] == "gram_pwf_kernel"
     assert pwf["executed"] == 19.0 * Ne * Ne * V * (24 + 2 + 2 * 13) and pwf["padded"] == 19.0 * Ne * Ne * V * (24 + 2 + 2 * 16)
+    assert pwf["slots"] == 19.0 * Ne * Ne * V * (12 + 2 + 16)  # 12 DFMA + 2 DADD + 2 x 8 DMMA lane-slots per site
+    # the 4 self pairs skip their tiles below the diagonal (16 x 32 tiles: 16 896 of 40 000 elements each)
+    skipped = bench.contraction_accounting(q, Ne, latt3, self_pairs=4)
+    elems = bench._executed_elements(Ne, 16, 32, True)
+    assert elems == 40000 - 16896 and skipped["executed"] == (15 * 40000 + 4 * elems) * V * (24 + 2 + 2 * 13.0)
     q["plane_wave_modes"] = 19  # 10 couples: two passes of a cos and a sin block
-    assert bench.contraction_accounting(q, Ne, V)["padded"] == 19.0 * Ne * Ne * V * (24 + 2 + 2 * 32)
+    assert bench.contraction_accounting(q, Ne, latt3)["padded"] == 19.0 * Ne * Ne * V * (24 + 2 + 2 * 32)
+    # separable form: 19 operations per site (12 site product, 2 sum / difference, 1 + 4 x-stage), 26 per row and element
+    sep = bench.contraction_accounting({"contraction_form": 4, "pair_gemms_per_momentum": 19, "plane_wave_modes": 13,
+                                        "plane_wave_tile": 3232}, Ne, latt3)
+    assert sep["kernel"] == "gram_sepx_kernel" and sep["padded"] is None
+    assert sep["slots"] == 19.0 * Ne * Ne * V * (19 + 26 / 48) and sep["executed"] == 19.0 * Ne * Ne * V * (33 + 42 / 48)
+    sep_self = bench.contraction_accounting({"contraction_form": 4, "pair_gemms_per_momentum": 19, "plane_wave_modes": 13,
+                                             "plane_wave_tile": 3232}, Ne, latt3, self_pairs=4)
+    assert sep_self["slots"] == (15 * 40000 + 4 * bench._executed_elements(Ne, 8, 16, True)) * V * (19 + 26 / 48)
+    assert bench._executed_elements(Ne, 8, 8, True) == 25 * 26 // 2 * 64  # 8 x 8 blocks on and above the diagonal ...
+    assert bench._executed_elements(Ne, 8, 16, True) == 20800 + 12 * 64   # ... plus the lower block of the 12 warp tiles across it
     assert bench.stencil_bytes_moved("config5", planes=False) == bench.algorithmic("config5")[1]
     assert bench.stencil_bytes_moved("config5") == bench.algorithmic("config5")[1] + 3 * Ne * V * 24.0
     old = bench.contraction_accounting({"contraction_form": 0, "tma_stages": 0, "real_mma_per_complex_block": 4,
-                                        "pair_momentum_gemms": 10}, 8, 64)
+                                        "pair_momentum_gemms": 10, "pair_gemms_per_momentum": 1}, 8, (4, 4, 4))
     assert old["kernel"] == "gram_dmma_kernel" and old["executed"] == 2.0 * 4 * 64 * 3 * 64 * 10
+    # both arms print the same workload description
+    assert bench.config_dict("config5", None, 20, 8) == bench.config_dict("config5", None, 20, 8)
+    assert set(bench.config_dict("config3", 2, 3, 1)) == {"workload", "lattice", "Ne", "distance", "momenta", "sharding", "l2"}
 
 
-@pytest.mark.parametrize("form,dist_", [(1, None), (2, None), (3, None), (1, 2), (3, 2)])
+@pytest.mark.parametrize("form,dist_", [(1, None), (2, None), (3, None), (4, None), (1, 2), (4, 2)])
 def test_bench_result_line_assembles_for_every_contraction_form(form, dist_):
     """bench.py's native arm needs a GPU, but the block that turns its measurements into the contract's JSON line is
     plain Python: it is cut out of run_native() here and executed on stand-in measurements for each contraction form,
@@ -489,32 +571,40 @@ def test_bench_result_line_assembles_for_every_contraction_form(form, dist_):
     code = compile(ast.Module(body=block.body, type_ignores=[]), path, "exec")
     name = "config5"
     Lx, Ly, Lz, Lt, Ne, nabla, nmom = bench.WORKLOADS[name]
-    q = {"hermitian_pairing": True, "internal_momenta": 33, "pair_gemms_per_momentum": 19, "ksplit": 4 if form == 1 else 1, "mfrag": 13,
-         "jobs": 19, "tma_stages": 3, "real_mma_per_complex_block": 3 if form == 1 else 4 - form, "pair_momentum_gemms": 563,
-         "half_set_momenta": 17, "contraction_form": form, "plane_wave_modes": 13 if form > 1 else 0, "plane_wave_tile": 25 if form > 1 else 0}
+    q = {"hermitian_pairing": dist_ is None, "internal_momenta": 33, "pair_gemms_per_momentum": 19 if dist_ is None else 3,
+         "ksplit": 4 if form == 1 else 1, "mfrag": 13, "jobs": 19, "tma_stages": 3,
+         "real_mma_per_complex_block": 3 if form == 1 else max(0, 4 - form), "pair_momentum_gemms": 563,
+         "half_set_momenta": 17, "contraction_form": form, "plane_wave_modes": 13 if form > 1 else 0,
+         "plane_wave_tile": {1: 0, 2: 25, 3: 24, 4: 3232}[form], "form_requested": -1, "pairs_per_stage": 8 if form == 4 else 0}
     K = 3
     prof = {"prepare": {"ms": 1.5, "launches": 2 * K}, "stencil": {"ms": 12.0, "launches": 4 * K},
-            "contraction": {"ms": {1: 4173.0, 2: 600.0, 3: 450.0}[form], "launches": K}, "combine": {"ms": 20.0, "launches": 2 * K}}
+            "contraction": {"ms": {1: 4173.0, 2: 600.0, 3: 450.0, 4: 360.0}[form], "launches": K}, "combine": {"ms": 20.0, "launches": 2 * K}}
+    mode_, order_ = (_capi.MODE_DERIVATIVE, nabla) if dist_ is None else (_capi.MODE_DISPLACEMENT, dist_)
     ns = dict(vars(bench))
     ns.update(name=name, dist_=dist_, Lx=Lx, Ly=Ly, Lz=Lz, Ne=Ne, nabla=nabla, nmom=nmom, V=Lx * Ly * Lz, K=K, W=3, world=1, rank=0,
               prof=prof, q=q, ms=640.0, ms_max=640.0, value=K / 0.64, e2e_value=4.4, h2d=595000000, d2h=274560000, checksum=1.0,
-              launches=27, workspace_mb=31000.0, W0_host=None, U_sp_host=None, dmma_tf=37.0, dfma_tf=36.3,
-              contraction={"requested": "auto", "form": form, "reason": "stand-in"}, torch=None, dev=None, args=types.SimpleNamespace(),
+              launches=27, workspace_mb=31000.0, W0_host=None, U_sp_host=None, dmma_tf=37.0, dfma_tf=36.3, _capi=_capi,
+              mode_=mode_, order_=order_, moms=bench.momentum_set(nmom), files={"timeslices": 2}, forced=None,
+              parity={"against": "GEMM form", "tolerance": 1e-10, "worst_block_rel_err": 3e-14},
+              contraction={"requested": "auto", "reason": "stand-in"}, torch=None, dev=None, args=types.SimpleNamespace(),
               clocks=types.SimpleNamespace(summary=lambda: {"sm_mhz": 1965.0, "sm_max_mhz": 1965, "reasons": []}),
               fp64_gemm_peak=lambda torch, dev: {"dgemm": 35.5, "zgemm": 36.8}, print=lambda *a, **k: None)
     exec(code, ns)
     line = json.loads(json.dumps(ns["line"]))
     assert line["metric"] == "elemental_timeslices_per_sec" and line["unit"] == "timeslices/s" and line["n_gpus"] == 1
     for key in ("value", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e",
-                "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+                "gpu_launches", "clocks", "roofline", "cpu_baseline", "workspace_MB", "api"):
         assert key in line, key
+    assert line["config"] == bench.config_dict(name, dist_, K, 1)  # what `--impl reference` prints too
     roof = line["roofline"]
     assert roof["bound"] == "tensor" and 0 < roof["frac"] < 1.5 and roof["unit"] == "TFLOP/s" and roof["peak"] == 36.8
-    assert roof["kernel"].startswith({1: "gram_tma_kernel", 2: "gram_pw_kernel", 3: "gram_pwf_kernel"}[form])
-    assert ("executed_tflops_incl_padded_mode_rows" in roof) == (form > 1)
+    assert 0 < roof["fp64_pipe_utilisation"] < 1.2
+    assert roof["kernel"].startswith({1: "gram_tma_kernel", 2: "gram_pw_kernel", 3: "gram_pwf_kernel", 4: "gram_sepx_kernel"}[form])
+    assert ("executed_tflops_incl_padded_mode_rows" in roof) == (form in (2, 3))
+    assert line["contraction"]["form"] == form and line["contraction"]["parity_check"]["worst_block_rel_err"] == 3e-14
     st = line["roofline_stencil"]
     planes = 3 * Ne * Lx * Ly * Lz * 24.0
     assert st["algorithmic_bytes_per_launch"] == st["survey_bytes_per_launch"] + (planes if form == 1 and dist_ is None else 0.0)
     assert st["kernel"].startswith("nabla3_kernel" if dist_ is None else "displace_step6_kernel")
     assert line["e2e"]["h2d_bytes_per_step"] == 595000000 and line["cpu_baseline"]["kind"] == "port"
-
+    assert line["e2e"]["from_files"] == {"timeslices": 2}
