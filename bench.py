@@ -620,7 +620,10 @@ def run_native(args):
     line = None
     if rank == 0:
         flops, st_bytes_launch = algorithmic(name, dist_)
-        gram_ms = prof["contraction"]["ms"] / max(1, prof["contraction"]["launches"])
+        # the contraction of one timeslice: one launch, or one per tile shape (separable form: 32 x 32 tiles, then the two
+        # edge strips) - timed together by the CUDA events around the phase, accounted per timeslice
+        gram_launches = max(1, prof["contraction"]["launches"]) / K
+        gram_ms = prof["contraction"]["ms"] / K
         st_launch = max(1, prof["stencil"]["launches"])
         st_ms = prof["stencil"]["ms"] / st_launch
         peaks = {}
@@ -684,7 +687,8 @@ def run_native(args):
                 "traffic": measured_traffic(gram_name, name if dist_ is None else name + "_displacement"),
                 "peak_source": f"cuBLAS FP64 GEMM measured in this run (dgemm {gemm['dgemm']:.1f}, zgemm {gemm['zgemm']:.1f} TFLOP/s); "
                                f"DMMA issue-rate microbench {dmma_tf:.1f}, DFMA {dfma_tf:.1f} TFLOP/s; nominal 37-40",
-                "algorithmic_flops_per_launch": exec_flops, "ms_per_launch": gram_ms,
+                "algorithmic_flops_per_launch": exec_flops, "ms_per_launch": gram_ms, "launches_per_step": gram_launches,
+                "per_launch_means": "the contraction of one timeslice" + (f" ({gram_launches:.0f} launches of the kernel, one per tile shape, timed together)" if gram_launches > 1 else ""),
                 "fp64_pipe_utilisation": pipe_util,
                 "pairing": q, "survey_flops_per_launch": flops, "survey_equivalent_tflops": survey_tf,
                 **({"executed_tflops_incl_padded_mode_rows": pw_padded_flops / (gram_ms * 1e-3) / 1e12} if pw_padded_flops else {}),

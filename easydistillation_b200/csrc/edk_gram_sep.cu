@@ -858,11 +858,63 @@ cudaError_t launch_gram_sep(const SepParams& P, const SepTma& T, const SepWeight
 
 // G[job][p][e][f] = sum_z zphase[p][z] (Y[cc] + i sy Y[cs] + i sx Y[sc] - sx sy Y[ss])[job][z][e][f].
 // One block folds one class of momenta - those with the same (|px|, |py|), which read the same <= 4 separable modes -
-// of one (job, 256 matrix elements), up to SEP_FOLD_MAXM momenta at a time (12 = the largest class of the |p|^2 <= 4
-// set), so every plane of Y is read once.
-constexpr int SEP_FOLD_THREADS = 256;
+// of one (job, 128 matrix elements), up to SEP_FOLD_MAXM momenta at a time (12 = the largest class of the |p|^2 <= 4
+// set), so every plane of Y is read once: the kernel is a stream over Y (7.6 GB at config 5).  Per plane the four sign
+// combinations are formed once,
+//   P = cc - ss, Q = cc + ss, R = cs + sc, S = sc - cs:   u = P + i sigma R (sx sy >= 0, sigma = sy or sx),  u = Q + i sx S (sx sy < 0),
+// so a momentum costs two multiply-adds for u and four for zphase * u; the z phases of the block's momenta sit in
+// shared memory.  CNT (momenta of this pass) is a template parameter: no predicated-off work, and the accumulators of
+// a small class do not cost the registers of a large one.
+constexpr int SEP_FOLD_THREADS = 128;
 constexpr int SEP_FOLD_MAXM = 12;
-__global__ void __launch_bounds__(SEP_FOLD_THREADS) sep_zfold_kernel(const SepFold F) {
+
+template <int CNT>
+__device__ __forceinline__ void sep_fold_pass(const SepFold& F, const cplx* Yj, double cj, const SepClass& K, const int* m3,
+                                              const cplx* sph, size_t mat, size_t out_base) {
+    // m3: (internal momentum, sgn px, sgn py) of the CNT momenta of this pass; sph[k][z] their z phases
+    double ar[CNT], ai[CNT], sig[CNT];
+    bool useq[CNT];
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) {
+        ar[k] = ai[k] = 0.0;
+        const int sx = m3[3 * k + 1], sy = m3[3 * k + 2];
+        useq[k] = sx * sy < 0;
+        sig[k] = useq[k] ? (double)sx : (double)(sy != 0 ? sy : sx);
+    }
+    const size_t zstride = (size_t)F.nmodes * mat;
+    const bool has1 = K.mode[1] >= 0, has2 = K.mode[2] >= 0, has3 = K.mode[3] >= 0;
+    const cplx* p0 = Yj + (size_t)K.mode[0] * mat;
+    const cplx* p1 = Yj + (size_t)(has1 ? K.mode[1] : K.mode[0]) * mat;
+    const cplx* p2 = Yj + (size_t)(has2 ? K.mode[2] : K.mode[0]) * mat;
+    const cplx* p3 = Yj + (size_t)(has3 ? K.mode[3] : K.mode[0]) * mat;
+    const cplx zero = make_double2(0.0, 0.0);
+#pragma unroll(CNT > 6 ? 2 : 4)
+    for (int z = 0; z < F.Lz; ++z) {
+        const cplx cc = p0[(size_t)z * zstride];
+        const cplx cs = has1 ? p1[(size_t)z * zstride] : zero;
+        const cplx sc = has2 ? p2[(size_t)z * zstride] : zero;
+        const cplx ss = has3 ? p3[(size_t)z * zstride] : zero;
+        // (the conjugation of a mirror read, cj = -1, acts on the imaginary parts)
+        const double Pr = cc.x - ss.x, Pi = cj * (cc.y - ss.y), Qr = cc.x + ss.x, Qi = cj * (cc.y + ss.y);
+        const double Rr = cs.x + sc.x, Ri = cj * (cs.y + sc.y), Sr = sc.x - cs.x, Si = cj * (sc.y - cs.y);
+#pragma unroll
+        for (int k = 0; k < CNT; ++k) {
+            const double br = useq[k] ? Qr : Pr, bi = useq[k] ? Qi : Pi, rr = useq[k] ? Sr : Rr, ri = useq[k] ? Si : Ri;
+            const double ur = fma(-sig[k], ri, br), ui = fma(sig[k], rr, bi);  // base + i sigma rot
+            const cplx ph = sph[k * F.Lz + z];
+            ar[k] = fma(ph.x, ur, ar[k]);
+            ar[k] = fma(-ph.y, ui, ar[k]);
+            ai[k] = fma(ph.x, ui, ai[k]);
+            ai[k] = fma(ph.y, ur, ai[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) F.partial[out_base + (size_t)m3[3 * k] * mat] = make_double2(ar[k], ai[k]);
+}
+
+__global__ void __launch_bounds__(SEP_FOLD_THREADS, 2) sep_zfold_kernel(const SepFold F) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    cplx* sph = reinterpret_cast<cplx*>(smem);  // [SEP_FOLD_MAXM][Lz]
     const size_t mat = (size_t)F.Ne * F.Ne;
     const int nblk = (int)((mat + SEP_FOLD_THREADS - 1) / SEP_FOLD_THREADS);
     int b = blockIdx.x;
@@ -871,64 +923,36 @@ __global__ void __launch_bounds__(SEP_FOLD_THREADS) sep_zfold_kernel(const SepFo
     const int blk = b % nblk;
     const int job = b / nblk;
     const GramJob& J = F.jobs[job];
-    const size_t ef = (size_t)blk * SEP_FOLD_THREADS + threadIdx.x;
-    if (ef >= mat) return;
-    // tiles of a self pair below the diagonal were not computed: read the mirror element, conjugated
-    const int e = (int)(ef / F.Ne), f = (int)(ef - (size_t)e * F.Ne);
-    const bool mirror = J.nseg == 1 && J.Lf[0] == J.Rf[0] && (e / F.rows_l) * F.rows_l > (f / F.rows_r) * F.rows_r + F.rows_r - 1;
-    const double cj = mirror ? -1.0 : 1.0;
-    const cplx* Yj = F.Y + (size_t)job * F.Lz * F.nmodes * mat + (mirror ? (size_t)f * F.Ne + e : ef);
     const SepClass K = F.classes[cls];
     // the job's momenta are the first J.nmom of the internal list (self pairs contract the half set only); the class
     // lists its momenta in ascending order, so the ones this job needs are a prefix
     int nvalid = 0;
     for (int i = 0; i < K.count; ++i) nvalid += F.mom[3 * (K.first + i)] < J.nmom;
+    const size_t ef_raw = (size_t)blk * SEP_FOLD_THREADS + threadIdx.x;
+    const bool live = ef_raw < mat;
+    const size_t ef = live ? ef_raw : 0;
+    // blocks of a self pair below the diagonal were not computed: read the mirror element, conjugated
+    const int e = (int)(ef / F.Ne), f = (int)(ef - (size_t)e * F.Ne);
+    const bool mirror = J.nseg == 1 && J.Lf[0] == J.Rf[0] && (e / F.rows_l) * F.rows_l > (f / F.rows_r) * F.rows_r + F.rows_r - 1;
+    const double cj = mirror ? -1.0 : 1.0;
+    const cplx* Yj = F.Y + (size_t)job * F.Lz * F.nmodes * mat + (mirror ? (size_t)f * F.Ne + e : ef);
+    const size_t out_base = (size_t)job * F.nmom_int * mat + ef;
     for (int c0 = 0; c0 < nvalid; c0 += SEP_FOLD_MAXM) {
         const int cnt = min(SEP_FOLD_MAXM, nvalid - c0);
-        int pl[SEP_FOLD_MAXM];
-        double sx[SEP_FOLD_MAXM], sy[SEP_FOLD_MAXM], ar[SEP_FOLD_MAXM], ai[SEP_FOLD_MAXM];
-#pragma unroll
-        for (int k = 0; k < SEP_FOLD_MAXM; ++k) {
-            ar[k] = ai[k] = 0.0;
-            pl[k] = 0;
-            sx[k] = sy[k] = 0.0;
-            if (k < cnt) {
-                const int* m3 = F.mom + 3 * (K.first + c0 + k);
-                pl[k] = m3[0];
-                sx[k] = (double)m3[1];
-                sy[k] = (double)m3[2];
+        const int* m3 = F.mom + 3 * (K.first + c0);
+        __syncthreads();  // the previous pass is through with the table
+        for (int i = threadIdx.x; i < cnt * F.Lz; i += SEP_FOLD_THREADS) sph[i] = F.zphase[(size_t)m3[3 * (i / F.Lz)] * F.Lz + i % F.Lz];
+        __syncthreads();
+        if (live) {
+            switch (cnt) {
+#define EDK_FOLD_CASE(N) \
+    case N: sep_fold_pass<N>(F, Yj, cj, K, m3, sph, mat, out_base); break;
+                EDK_FOLD_CASE(1) EDK_FOLD_CASE(2) EDK_FOLD_CASE(3) EDK_FOLD_CASE(4) EDK_FOLD_CASE(5) EDK_FOLD_CASE(6)
+                EDK_FOLD_CASE(7) EDK_FOLD_CASE(8) EDK_FOLD_CASE(9) EDK_FOLD_CASE(10) EDK_FOLD_CASE(11) EDK_FOLD_CASE(12)
+#undef EDK_FOLD_CASE
+                default: break;
             }
         }
-#pragma unroll 2
-        for (int z = 0; z < F.Lz; ++z) {
-            const cplx* Yz = Yj + (size_t)z * F.nmodes * mat;
-            cplx v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = K.mode[i] >= 0 ? Yz[(size_t)K.mode[i] * mat] : make_double2(0.0, 0.0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i].y *= cj;
-#pragma unroll
-            for (int k = 0; k < SEP_FOLD_MAXM; ++k) {
-                if (k < cnt) {
-                    // u = cc + i sy cs + i sx sc - sx sy ss
-                    const double sxy = sx[k] * sy[k];
-                    double ur = fma(-sy[k], v[1].y, v[0].x);
-                    double ui = fma(sy[k], v[1].x, v[0].y);
-                    ur = fma(-sx[k], v[2].y, ur);
-                    ui = fma(sx[k], v[2].x, ui);
-                    ur = fma(-sxy, v[3].x, ur);
-                    ui = fma(-sxy, v[3].y, ui);
-                    const cplx ph = F.zphase[(size_t)pl[k] * F.Lz + z];
-                    ar[k] = fma(ph.x, ur, ar[k]);
-                    ar[k] = fma(-ph.y, ui, ar[k]);
-                    ai[k] = fma(ph.x, ui, ai[k]);
-                    ai[k] = fma(ph.y, ur, ai[k]);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < SEP_FOLD_MAXM; ++k)
-            if (k < cnt) F.partial[((size_t)job * F.nmom_int + pl[k]) * mat + ef] = make_double2(ar[k], ai[k]);
     }
 }
 
@@ -937,8 +961,13 @@ cudaError_t launch_sep_zfold(const SepFold& F, cudaStream_t s) {
     const size_t mat = (size_t)F.Ne * F.Ne;
     const long long nblk = (long long)((mat + SEP_FOLD_THREADS - 1) / SEP_FOLD_THREADS);
     const long long blocks = nblk * F.njobs * F.nclass;
-    if (blocks < 1 || blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    EDK_LAUNCH(sep_zfold_kernel, (unsigned)blocks, SEP_FOLD_THREADS, 0, s, F);
+    const size_t smem = (size_t)SEP_FOLD_MAXM * F.Lz * sizeof(cplx);
+    if (blocks < 1 || blocks > 0x7fffffffLL || smem > 160 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)sep_zfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    EDK_LAUNCH(sep_zfold_kernel, (unsigned)blocks, SEP_FOLD_THREADS, smem, s, F);
     return cudaGetLastError();
 }
 #endif  // EDK_EMU_NO_LAUNCHERS

@@ -14,7 +14,7 @@ from . import _capi
 
 
 _COPY_POOL = None
-_COPY_THREADS = 4
+_COPY_THREADS = 8
 
 
 def parallel_copy(dst: np.ndarray, src: np.ndarray, min_bytes: int = 8 << 20) -> None:
@@ -116,7 +116,7 @@ class TimeslicePipeline:
         else:
             if self.V_pin[b] is None or self.V_pin[b].dtype != tdt:
                 self.V_pin[b] = torch.empty(V_t.shape, dtype=tdt, pin_memory=True)
-            np.copyto(self.V_pin[b].numpy(), V_t)
+            parallel_copy(self.V_pin[b].numpy(), V_t)  # file / memory-map reads of ~0.5 - 1 GB: a few threads, not one
             V_src = self.V_pin[b]
         with torch.cuda.stream(self.copy_stream):
             if self.ev_consumed[b] is not None:
