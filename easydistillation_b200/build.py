@@ -14,8 +14,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libedk_sm100a.so")
-SOURCES = ["edk_stencil.cu", "edk_gauge.cu", "edk_gram.cu", "edk_gram_pw.cu", "edk_gram_sep.cu", "edk_api.cu"]
-HEADERS = [os.path.join(CSRC, "edk_common.cuh"), os.path.join(CSRC, "edk_pipe.cuh"), os.path.join(REPO, "include", "edk.h")]
+SOURCES = ["edk_stencil.cu", "edk_gauge.cu", "edk_gram.cu", "edk_gram_pw.cu", "edk_gram_sep.cu", "edk_gram_sep_s11.cu", "edk_gram_sep_s12.cu", "edk_gram_sep_s24.cu", "edk_api.cu"]
+HEADERS = [os.path.join(CSRC, "edk_common.cuh"), os.path.join(CSRC, "edk_pipe.cuh"), os.path.join(CSRC, "edk_gram_sep.cuh"),
+           os.path.join(REPO, "include", "edk.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

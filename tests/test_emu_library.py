@@ -19,7 +19,7 @@ from conftest import REPO
 from easydistillation_b200 import _capi
 from oracle import elemental_oracle as orc
 
-SOURCES = ["edk_stencil.cu", "edk_gauge.cu", "edk_gram.cu", "edk_gram_pw.cu", "edk_gram_sep.cu", "edk_api.cu"]
+SOURCES = ["edk_stencil.cu", "edk_gauge.cu", "edk_gram.cu", "edk_gram_pw.cu", "edk_gram_sep.cu", "edk_gram_sep_s11.cu", "edk_gram_sep_s12.cu", "edk_gram_sep_s24.cu", "edk_api.cu"]
 D, X = _capi.MODE_DERIVATIVE, _capi.MODE_DISPLACEMENT
 
 
@@ -340,12 +340,12 @@ def test_folded_plane_wave_form(emu, latt3, Ne, mode, order, moms, sym, switch):
 @pytest.mark.parametrize("latt3,Ne,mode,order,moms,sym", [
     ((8, 4, 2), 5, D, 1, orc.momentum_set(7), None),        # 4 site pairs per stage, 5 separable modes
     ((16, 3, 2), 20, D, 1, orc.momentum_set(9), None),      # 8 pairs per stage, 9 modes, 2 x 1 tiles with a mirror tile
-    ((12, 2, 2), 35, D, 1, orc.momentum_set(33), 1),        # 6 pairs per stage, 13 modes, 3 x 2 tiles, idle edge warps
+    ((12, 2, 1), 35, D, 1, orc.momentum_set(33), 1),        # 6 pairs per stage, 13 modes, one 32 x 32 tile and both edge strips
     ((8, 4, 1), 4, D, 2, orc.momentum_set(33), 0),          # direct pairs: multi-segment jobs with signs
     ((8, 6, 2), 12, X, 2, orc.momentum_set(19), None),      # displacement lines
     ((8, 4, 2), 7, D, 2, [(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 2), (0, 1, 2), (1, 1, 2)], None),  # the reference's test list
     ((24, 2, 1), 3, D, 1, [(2, 0, 0), (-1, 1, 3), (0, -2, -1)], None),  # two stages per row, non-closed list, pz > Lz
-    ((8, 2, 1), 75, D, 1, orc.momentum_set(7), None),     # Ne = 75: 2 x 2 tiles of 32 x 32, two 8 x 128 and one 64 x 16 strip tiles
+    ((8, 2, 1), 43, D, 1, orc.momentum_set(7), None),     # Ne = 43: one 32 x 32 tile, two 8 x 128 strip tiles, one 64 x 16
 ])
 def test_separable_form(emu, latt3, Ne, mode, order, moms, sym):
     """Form 4 (gram_sep_kernel + sep_zfold_kernel: swizzled TMA tiles, x transform per site pair, y transform per row)
