@@ -628,34 +628,43 @@ __global__ void __launch_bounds__(SepxGeom::THREADS, 1) gram_sepx_kernel(const S
             tmem_wait_st();  // the stores of the previous row
             constexpr int NQ = (NM + 3) / 4;  // transfers of 16 words (4 complex modes) per element
             constexpr int NTR = 4 * NQ;       // transfer n = (element n / NQ = 2 i + j, modes 4 (n % NQ) ..)
-            uint32_t yb[2][16];
             auto wanted = [&](int n) { return (n / NQ) / 2 < ni && (n / NQ) % 2 < nj; };
             auto taddr = [&](int n) { return ty + (uint32_t)(64 * (n / NQ) + 16 * (n % NQ)); };
+            // multiply-adds of transfer n on the words in `in`, results to tensor memory from a buffer of their own (in
+            // place, ptxas copies all 16 registers into the store's operand tuple)
+            auto update = [&](auto N_, const uint32_t(&in)[16]) {
+                constexpr int n = decltype(N_)::value;
+                constexpr int i = (n / NQ) / 2, j = (n / NQ) % 2, m0 = 4 * (n % NQ), m1 = (NM < m0 + 4 ? NM : m0 + 4);
+                uint32_t ys[16];
+                sep_static_for<(m1 - m0)>([&](auto K) {
+                    constexpr int m = m0 + decltype(K)::value;
+                    constexpr int mx = M::xm(m), my = M::yw(m);
+                    double re = tmem_get_f64(in, 2 * (m - m0)), im = tmem_get_f64(in, 2 * (m - m0) + 1);
+                    if constexpr (my == 0) {
+                        re += xr[i][j][mx];
+                        im += xi[i][j][mx];
+                    } else {
+                        re = fma(wyv[my], xr[i][j][mx], re);
+                        im = fma(wyv[my], xi[i][j][mx], im);
+                    }
+                    tmem_put_f64(ys, 2 * (m - m0), re);
+                    tmem_put_f64(ys, 2 * (m - m0) + 1, im);
+                });
+                if constexpr (m1 - m0 < 4) {
+#pragma unroll
+                    for (int w = 4 * (m1 - m0); w < 16; ++w) ys[w] = 0u;  // columns of no mode
+                }
+                tmem_st16(taddr(n), ys);
+            };
+            uint32_t yb[2][16];
             tmem_ld16(taddr(0), yb[0]);
             sep_static_for<NTR>([&](auto N_) {
                 constexpr int n = decltype(N_)::value;
-                constexpr int i = (n / NQ) / 2, j = (n / NQ) % 2, m0 = 4 * (n % NQ), m1 = (NM < m0 + 4 ? NM : m0 + 4);
                 tmem_wait_ld();
                 if constexpr (n + 1 < NTR) {
                     if (wanted(n + 1)) tmem_ld16(taddr(n + 1), yb[(n + 1) & 1]);
                 }
-                if (wanted(n)) {
-                    sep_static_for<(m1 - m0)>([&](auto K) {
-                        constexpr int m = m0 + decltype(K)::value;
-                        constexpr int mx = M::xm(m), my = M::yw(m);
-                        double re = tmem_get_f64(yb[n & 1], 2 * (m - m0)), im = tmem_get_f64(yb[n & 1], 2 * (m - m0) + 1);
-                        if constexpr (my == 0) {
-                            re += xr[i][j][mx];
-                            im += xi[i][j][mx];
-                        } else {
-                            re = fma(wyv[my], xr[i][j][mx], re);
-                            im = fma(wyv[my], xi[i][j][mx], im);
-                        }
-                        tmem_put_f64(yb[n & 1], 2 * (m - m0), re);
-                        tmem_put_f64(yb[n & 1], 2 * (m - m0) + 1, im);
-                    });
-                    tmem_st16(taddr(n), yb[n & 1]);
-                }
+                if (wanted(n)) update(N_, yb[n & 1]);
             });
 #pragma unroll
             for (int i = 0; i < 2; ++i)

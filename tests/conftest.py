@@ -14,6 +14,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.hookimpl(tryfirst=True)
+def pytest_cmdline_main(config):
+    """The CPU suite spends most of its time in the host emulator (one host thread per emulated CUDA thread: latency-,
+    not throughput-bound), so on a machine without a GPU the tests are spread over worker processes when pytest-xdist is
+    installed and no -n was given (EDK_TEST_WORKERS=0 keeps one process).  Never on a GPU box: the parity tests share
+    one device and its memory."""
+    opt = config.option
+    if getattr(opt, "numprocesses", "no xdist") is not None or os.environ.get("PYTEST_XDIST_WORKER"):
+        return None
+    if getattr(opt, "collectonly", False) or getattr(opt, "usepdb", False):
+        return None
+    want = os.environ.get("EDK_TEST_WORKERS", "")
+    try:
+        import torch
+
+        on_gpu_box = torch.cuda.is_available()
+    except Exception:
+        on_gpu_box = False
+    n = int(want) if want.isdigit() else (0 if on_gpu_box else min(8, os.cpu_count() or 1))
+    if n > 1 and not on_gpu_box:
+        opt.numprocesses = n
+    return None
+
+
 def rel_err(a, b):
     """Block-wise Frobenius relative error, the measure SURVEY 8c(iii) fixes."""
     import numpy as np

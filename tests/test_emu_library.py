@@ -343,7 +343,7 @@ def test_folded_plane_wave_form(emu, latt3, Ne, mode, order, moms, sym, switch):
     ((12, 2, 1), 35, D, 1, orc.momentum_set(33), 1),        # 6 pairs per stage, 13 modes, one 32 x 32 tile and both edge strips
     ((8, 4, 1), 4, D, 2, orc.momentum_set(33), 0),          # direct pairs: multi-segment jobs with signs
     ((8, 6, 2), 12, X, 2, orc.momentum_set(19), None),      # displacement lines
-    ((8, 4, 2), 7, D, 2, [(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 2), (0, 1, 2), (1, 1, 2)], None),  # the reference's test list
+    ((8, 4, 1), 7, D, 2, [(0, 0, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (0, 0, 2), (0, 1, 2), (1, 1, 2)], None),  # the reference's test list
     ((24, 2, 1), 3, D, 1, [(2, 0, 0), (-1, 1, 3), (0, -2, -1)], None),  # two stages per row, non-closed list, pz > Lz
     ((8, 2, 1), 43, D, 1, orc.momentum_set(7), None),     # Ne = 43: one 32 x 32 tile, two 8 x 128 strip tiles, one 64 x 16
 ])
@@ -362,12 +362,13 @@ def test_separable_form(emu, latt3, Ne, mode, order, moms, sym):
     h.set_inputs(U_file, V)
     sep = h.calc()
     assert worst_block_error(sep, ref) < 1e-10
-    h.check(emu.edk_debug_algo(h.h, 3), "edk_debug_algo")
-    assert h.query(10) == 3 and h.query(13) == 3
-    assert worst_block_error(h.calc(), ref) < 1e-10
-    h.check(emu.edk_debug_algo(h.h, -1), "edk_debug_algo")  # back to the planned form
-    assert h.query(10) == 4 and h.query(13) == -1
-    assert np.array_equal(sep, h.calc())
+    if Ne <= 12:  # switching forms on a live handle (the larger cases only run the planned form: CPU time)
+        h.check(emu.edk_debug_algo(h.h, 3), "edk_debug_algo")
+        assert h.query(10) == 3 and h.query(13) == 3
+        assert worst_block_error(h.calc(), ref) < 1e-10
+        h.check(emu.edk_debug_algo(h.h, -1), "edk_debug_algo")  # back to the planned form
+        assert h.query(10) == 4 and h.query(13) == -1
+        assert np.array_equal(sep, h.calc())
     h.close()
 
 
@@ -407,7 +408,7 @@ def test_separable_form_shallow_ring_and_environment(emu, monkeypatch):
 
 
 @pytest.mark.parametrize("name,forms,timeslices", [
-    ("deriv_sep_8x4x6x1", (4, 3), (0,)),        # lattices the separable form covers: 13 / 9 / 9 modes, 4 / 6 / 8 pairs per stage
+    ("deriv_sep_8x4x6x1", (4,), (0,)),          # lattices the separable form covers: 13 / 9 / 9 modes, 4 / 6 / 8 pairs per stage
     ("deriv_sep_12x4x2x1", (4,), (0,)),
     ("disp_sep_16x2x4x1", (4, 2), (0,)),
     ("config1_deriv_weak_4x4x4x8", (3,), (7,)),  # config 1 at its own shape (4^3 x 8, Ne = 20, 7 momenta; distance 8, 6 momenta)
@@ -484,12 +485,12 @@ def test_reference_class_bound_to_the_c_abi_matches_its_own_numpy_path(emu):
 
 def memcheck_cases(lib):
     """Small runs that touch every kernel family; executed by the AddressSanitizer test below in a child process."""
-    cases = [((4, 4, 2), 5, D, 1, orc.momentum_set(7), (1, 0, 2, 3)),         # stencil + GEMM forms + plane-wave forms
+    cases = [((4, 4, 2), 5, D, 1, orc.momentum_set(7), (1, 0, 2)),            # stencil + GEMM forms + plane-wave form
              ((4, 2, 2), 3, D, 1, orc.momentum_set(7), (3,)),                   # folded form, planes of exactly one stage
              ((3, 5, 1), 3, D, 2, [(1, -1, 0), (0, 2, 1)], (3, 1)),            # ragged / odd planes, second-order fields
-             ((3, 5, 2), 7, X, 2, orc.momentum_set(9), (1, 2)),                 # displacement lines
-             ((4, 2, 1), 35, D, 1, orc.momentum_set(7), (2, 3)),                # multi-tile plane-wave runs with mirror tiles
-             ((8, 2, 2), 35, D, 1, orc.momentum_set(9), (4,)),                  # separable form: multi-tile, mirror tile, idle edge warps
+             ((3, 5, 2), 7, X, 2, orc.momentum_set(9), (2,)),                   # displacement lines
+             ((4, 2, 1), 35, D, 1, orc.momentum_set(7), (3,)),                  # multi-tile plane-wave runs with mirror tiles
+             ((8, 2, 1), 35, D, 1, orc.momentum_set(9), (4,)),                  # separable form: multi-tile, mirror tile, idle edge warps
              ((12, 2, 1), 5, X, 2, orc.momentum_set(33), (4,))]                 # separable form: 6 pairs per stage, 13 modes
     worst = 0.0
     for latt3, Ne, mode, order, moms, algos in cases:
@@ -513,7 +514,7 @@ def test_emulated_library_is_clean_under_address_sanitizer(tmp_path):
     libasan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(libasan) or not os.path.exists(libasan):
         pytest.skip("no AddressSanitizer runtime for this g++")
-    so = build_emulator_library(tmp_path, ("-g", "-fsanitize=address", "-fno-omit-frame-pointer"))
+    so = build_emulator_library(tmp_path, ("-g1", "-fsanitize=address", "-fno-omit-frame-pointer"))
     code = ("import sys; sys.path[:0] = [%r, %r]; import test_emu_library as T; "
             "w = T.memcheck_cases(T.load_emulator_library(%r)); print('EDK_ASAN_OK', w); assert w < 1e-10"
             % (REPO, os.path.join(REPO, "tests"), so))

@@ -843,3 +843,34 @@ def test_two_generators_on_one_device_and_the_callers_current_device(edb):
     ref = orc.elemental_timeslice_closed_form(V[1], orc.links_file_to_spatial(U[1]), latt, 1, moms)
     for o in outs:
         _blocks_close(o, ref, what="two generators")
+
+
+def test_integration_md_ctypes_stub_on_the_real_library(edb):
+    """INTEGRATION.md section B's ctypes stub (the file a reference maintainer would add as lattice/generator/_edk.py),
+    executed as written against the real libedk_sm100a.so on the GPU: EdkHandle.calc(U_t, V_t, out) with the reference's
+    host buffers (file-order links of one timeslice, complex64 staging buffer) against the oracle, at the shape of the
+    reference's own tests (4^3, Ne = 20, num_nabla = 2, 7 momenta) and at a shape the separable form takes."""
+    import os
+    import re
+
+    from easydistillation_b200 import _capi
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    block = re.search(r"```python\n(# lattice/generator/_edk\.py.*?)```", open(os.path.join(repo, "INTEGRATION.md")).read(), re.S).group(1)
+    assert 'C.CDLL("libedk_sm100a.so")' in block
+    ns = {}
+    exec(compile(block.replace('C.CDLL("libedk_sm100a.so")', f"C.CDLL({_capi.LIB_PATH!r})"), "INTEGRATION.md", "exec"), ns)
+    orc = _orc()
+    for latt, Ne, nabla, nmom in [([4, 4, 4, 1], 20, 2, 7), ([8, 6, 4, 1], 12, 1, 9)]:
+        moms = orc.momentum_set(nmom)
+        U_t = np.ascontiguousarray(orc.synthetic_links(latt, 0))
+        V_t = orc.synthetic_eigvecs(latt, Ne, 0)
+        V8 = np.ascontiguousarray(V_t.astype(np.complex64))  # the reference's staging buffer (elemental.py:55)
+        ref = orc.elemental_timeslice_closed_form(V8.astype(np.complex128), orc.links_file_to_spatial(U_t), latt, nabla, moms)
+        out = np.zeros(ref.shape, np.complex128)
+        handle = ns["EdkHandle"](latt, Ne, ns["EDK_MODE_DERIVATIVE"], nabla, moms)
+        handle.calc(U_t, V8, out)
+        _blocks_close(out, ref, what=f"INTEGRATION.md stub {latt}")
+        del handle
+    with pytest.raises(ValueError):  # EDK_ERR_ARG maps to the reference's ValueError
+        ns["EdkHandle"]([4, 4, 4, 1], 0, ns["EDK_MODE_DERIVATIVE"], 1, orc.momentum_set(1))

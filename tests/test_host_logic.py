@@ -583,7 +583,7 @@ def test_bench_result_line_assembles_for_every_contraction_form(form, dist_):
     ns = dict(vars(bench))
     ns.update(name=name, dist_=dist_, Lx=Lx, Ly=Ly, Lz=Lz, Ne=Ne, nabla=nabla, nmom=nmom, V=Lx * Ly * Lz, K=K, W=3, world=1, rank=0,
               prof=prof, q=q, ms=640.0, ms_max=640.0, value=K / 0.64, e2e_value=4.4, h2d=595000000, d2h=274560000, checksum=1.0,
-              launches=27, workspace_mb=31000.0, W0_host=None, U_sp_host=None, dmma_tf=37.0, dfma_tf=36.3, _capi=_capi,
+              launches=27, workspace_mb=31000.0, host_queue_ms=1.2, W0_host=None, U_sp_host=None, dmma_tf=37.0, dfma_tf=36.3, _capi=_capi,
               mode_=mode_, order_=order_, moms=bench.momentum_set(nmom), files={"timeslices": 2}, forced=None,
               parity={"against": "GEMM form", "tolerance": 1e-10, "worst_block_rel_err": 3e-14},
               contraction={"requested": "auto", "reason": "stand-in"}, torch=None, dev=None, args=types.SimpleNamespace(),
@@ -593,7 +593,7 @@ def test_bench_result_line_assembles_for_every_contraction_form(form, dist_):
     line = json.loads(json.dumps(ns["line"]))
     assert line["metric"] == "elemental_timeslices_per_sec" and line["unit"] == "timeslices/s" and line["n_gpus"] == 1
     for key in ("value", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e",
-                "gpu_launches", "clocks", "roofline", "cpu_baseline", "workspace_MB", "api"):
+                "gpu_launches", "clocks", "roofline", "cpu_baseline", "workspace_MB", "host_queue_ms", "api"):
         assert key in line, key
     assert line["config"] == bench.config_dict(name, dist_, K, 1)  # what `--impl reference` prints too
     roof = line["roofline"]

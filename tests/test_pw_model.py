@@ -252,7 +252,7 @@ def _run_emulator(exe, tmp_path, fields, jobs, latt3, moms, max_mb, nstages, el=
     ((5, 8, 2), 35, 33, 2, 0, 4),   # 3 x 2 tiles, 13 modes in one pass, 15 stages through the 8-deep ring, mirror tiles
     ((3, 5, 2), 5, 33, 1, 3, 4),    # ragged plane (15 sites), two passes of one m-block, 3-deep ring
     ((5, 8, 1), 43, 33, 2, 0, 5),   # 16 x 40 tiles: 3 x 2 tiles, mirror tile (e0 = 32 > f0 + 39 is never true: none skipped)
-    ((3, 3, 2), 90, 7, 2, 2, 5),    # 16 x 40 tiles with skipped mirror tiles (e0 >= 48), 2-deep ring
+    ((3, 3, 1), 90, 7, 2, 2, 5),    # 16 x 40 tiles with skipped mirror tiles (e0 >= 48), 2-deep ring
     ((2, 2, 2), 1, 1, 2, 0, 4),     # one eigenvector, p = 0 only (a single constant mode), planes of 4 sites
     ((4, 3, 2), 7, [(0, 0, 1), (1, 2, 0), (3, -1, 2), (0, -2, 1), (-5, 0, 7)], 2, 0, 5),  # non-closed list, |p| > L
 ])
