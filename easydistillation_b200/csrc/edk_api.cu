@@ -78,6 +78,7 @@ struct edk_handle {
     bool sep_ready = false;
     int sep_qmax = 0, sep_r2 = 0, sep_pairs = 0, sep_nmodes = 0, sep_nclass = 0;
     int sep_variant = 0;  // kernel variant (edk_gram_sep.cu: launch_gram_sep)
+    bool sep_per_shape = false;  // gram_sepx: one launch per tile shape instead of one over the whole tile table (A/B)
     SepWeights sep_wx_host{};  // the x weights as a kernel parameter (constant cache)
     SepTmaX sep_tmax{};        // variant 6: tensor maps and ring depth per tile shape
     SepTile* sep_tiles = nullptr;  // grouped by shape
@@ -990,6 +991,11 @@ int build_sep(edk_handle* h) {
         for (size_t i = 0; i < tiles.size(); ++i) {
             if (h->sep_shape_count[tiles[i].shape]++ == 0) h->sep_shape_first[tiles[i].shape] = (int)i;
         }
+        // One launch over the whole tile table saves two launches and two tails (config 2: 0.36 -> 0.33 ms); with tens of
+        // thousands of CTAs a launch per shape is faster (config 5: 116.0 against 117.7 ms), the strips then run after the
+        // 32 x 32 tiles instead of among them.  EDK_SEP_LAUNCHES = 1 | 3 overrides (A/B hook).
+        h->sep_per_shape = (long long)h->njobs * Lz * (long long)tiles.size() >= 148LL * 64;
+        if (const char* t = getenv("EDK_SEP_LAUNCHES")) h->sep_per_shape = atoi(t) == 3 ? true : (atoi(t) == 1 ? false : h->sep_per_shape);
         EDK_CUDA_TRY(cudaMalloc(&h->sep_tiles, tiles.size() * sizeof(SepTile)));
         EDK_CUDA_TRY(cudaMemcpy(h->sep_tiles, tiles.data(), tiles.size() * sizeof(SepTile), cudaMemcpyHostToDevice));
     }
@@ -1016,11 +1022,16 @@ int run_gram_sep(edk_handle* h, cudaStream_t s) {
     Q.wx = h->sep_wx;
     Q.wy = h->sep_wy;
     Q.Y = h->sep_Y;
-    if (h->sep_variant == 6) {
+    if (h->sep_variant == 6 && !h->sep_per_shape) {
+        PhaseTimer t(h, s, PH_GRAM, 1);  // one launch over the whole tile table
+        Q.tiles = h->sep_tiles;
+        Q.ntiles = h->sep_ntiles;
+        EDK_CUDA_TRY(launch_gram_sepx(Q, h->sep_tmax, h->sep_wx_host, h->sep_qmax, h->sep_r2, h->sep_pairs, SEP_NSHAPES, s));
+    } else if (h->sep_variant == 6) {
         int nlaunch = 0;
         for (int sh = 0; sh < SEP_NSHAPES; ++sh) nlaunch += h->sep_shape_count[sh] > 0;
         PhaseTimer t(h, s, PH_GRAM, nlaunch);
-        for (int sh = 0; sh < SEP_NSHAPES; ++sh) {  // one launch per tile shape: the 32 x 32 tiles, then the edge strips
+        for (int sh = 0; sh < SEP_NSHAPES; ++sh) {  // A/B reference: one launch per tile shape
             if (!h->sep_shape_count[sh]) continue;
             Q.tiles = h->sep_tiles + h->sep_shape_first[sh];
             Q.ntiles = h->sep_shape_count[sh];

@@ -81,10 +81,15 @@ int sep_variant_plan(int variant, int* nstages, int* smem_bytes) {
     return -1;
 }
 
-// One launch per tile shape: P.tiles / P.ntiles are the tiles of `shape` (sep_build_tiles keeps them grouped).
+// shape 0 .. 2: P.tiles / P.ntiles are the tiles of that shape only (sep_build_tiles keeps them grouped; A/B reference);
+// shape 3 = SEP_NSHAPES: the whole tile table in one launch (the product).
 cudaError_t launch_gram_sepx(const SepParams& P, const SepTmaX& T, const SepWeights& W, int qmax, int r2, int pairs, int shape, cudaStream_t s) {
     int nst, bytes = 0;
-    if (sepx_plan_smem(shape, &nst, &bytes) != 0 || T.nstages[shape] < 2 || T.nstages[shape] > nst) return cudaErrorInvalidValue;
+    if (shape < 0 || shape > SEP_NSHAPES) return cudaErrorInvalidValue;
+    for (int sh = 0; sh < SEP_NSHAPES; ++sh) {
+        if (shape != SEP_NSHAPES && shape != sh) continue;
+        if (sepx_plan_smem(sh, &nst, &bytes) != 0 || T.nstages[sh] < 2 || T.nstages[sh] > nst) return cudaErrorInvalidValue;
+    }
     if ((pairs != 8 && pairs != 6 && pairs != 4) || (P.Lx & 1) || P.Lx < 8 || (P.Lx / 2) % pairs != 0 || P.Lx / 2 > SEP_MAX_PR ||
         P.SR != P.Lx / 2 / pairs || !P.tiles || P.ntiles < 1)
         return cudaErrorInvalidValue;

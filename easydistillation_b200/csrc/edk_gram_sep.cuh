@@ -360,8 +360,7 @@ struct SepxGeom {
 };
 
 template <int QMAX, int R2, int PAIRS, int WE>
-__global__ void __launch_bounds__(SepxGeom::THREADS, 1) gram_sepx_kernel(const SepParams P, const __grid_constant__ SepTmaX Tm,
-                                                                         const __grid_constant__ SepWeights Wx) {
+__device__ __forceinline__ void sepx_cta(const SepParams& P, const SepTmaX& Tm, const SepWeights& Wx) {
     using M = SepModes<QMAX, R2>;
     using G = SepxGeom;
     constexpr int NX = M::NX, NM = M::N;
@@ -711,6 +710,28 @@ __global__ void __launch_bounds__(SepxGeom::THREADS, 1) gram_sepx_kernel(const S
     if (lane == 0) mbar_arrive(bar_done);
 }
 
+// One launch over the whole tile table: the CTA takes the warp grid of its tile (a block-uniform branch into one of three
+// bodies whose strides are compile-time constants).  Used for small problems, where two launches and two tails less
+// count (config 2: 0.36 -> 0.33 ms); at config 4 / 5 the strips running among the 32 x 32 tiles cost more than their
+// L2 hits bring (117.7 against 116.0 ms) and the host launches one shape at a time (build_sep).
+template <int QMAX, int R2, int PAIRS>
+__global__ void __launch_bounds__(SepxGeom::THREADS, 1) gram_sepx_kernel(const SepParams P, const __grid_constant__ SepTmaX Tm,
+                                                                         const __grid_constant__ SepWeights Wx) {
+    const int shape = P.tiles[blockIdx.x % P.ntiles].shape;
+    if (shape == 0)
+        sepx_cta<QMAX, R2, PAIRS, 4>(P, Tm, Wx);
+    else if (shape == 1)
+        sepx_cta<QMAX, R2, PAIRS, 1>(P, Tm, Wx);
+    else
+        sepx_cta<QMAX, R2, PAIRS, 8>(P, Tm, Wx);
+}
+// One launch per shape: P.tiles holds tiles of one shape only.
+template <int QMAX, int R2, int PAIRS, int WE>
+__global__ void __launch_bounds__(SepxGeom::THREADS, 1) gram_sepx1_kernel(const SepParams P, const __grid_constant__ SepTmaX Tm,
+                                                                          const __grid_constant__ SepWeights Wx) {
+    sepx_cta<QMAX, R2, PAIRS, WE>(P, Tm, Wx);
+}
+
 #ifndef EDK_EMU_NO_LAUNCHERS
 // ---- launch helpers of one mode structure (instantiated in edk_gram_sep_s*.cu) --------------------------------
 template <int QMAX, int R2, int PAIRS>
@@ -731,7 +752,9 @@ cudaError_t launch_gram_sep_q(const SepParams& P, const SepTma& T, int pairs, in
 template <int QMAX, int R2, int PAIRS>
 cudaError_t launch_gram_sepx_p(const SepParams& P, const SepTmaX& T, const SepWeights& W, int shape, int bytes, unsigned items,
                                cudaStream_t s) {
-    auto kern = shape == 0 ? gram_sepx_kernel<QMAX, R2, PAIRS, 4> : (shape == 1 ? gram_sepx_kernel<QMAX, R2, PAIRS, 1> : gram_sepx_kernel<QMAX, R2, PAIRS, 8>);
+    auto kern = shape == 0 ? gram_sepx1_kernel<QMAX, R2, PAIRS, 4>
+                           : (shape == 1 ? gram_sepx1_kernel<QMAX, R2, PAIRS, 1>
+                                         : (shape == 2 ? gram_sepx1_kernel<QMAX, R2, PAIRS, 8> : gram_sepx_kernel<QMAX, R2, PAIRS>));
     cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     EDK_LAUNCH(kern, items, SepxGeom::THREADS, bytes, s, P, T, W);

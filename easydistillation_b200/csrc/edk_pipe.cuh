@@ -33,15 +33,6 @@ __device__ __forceinline__ double2 lds128_again(const void* p) {
     return v;
 }
 
-// 16-byte load from a shared-memory address (not a generic pointer: no window arithmetic per stage).  volatile only pins
-// the program order NVVM sees - the stage buffers are rewritten by the TMA unit between mbarrier waits, so the loads must
-// not be merged across iterations that reuse an address; ptxas schedules the plain ld.shared freely.
-__device__ __forceinline__ double2 lds128(uint32_t addr) {
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
-}
-
 // sign flip on the integer pipe: the FP64 pipe is the one the DMMAs need
 __device__ __forceinline__ double flip_sign(double x) {
     return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));

@@ -396,11 +396,14 @@ cudaError_t launch_displace_step6(Ptr6 p, cplx* mean_out, const cplx* links, Geo
 // (vector, site).
 // ---------------------------------------------------------------------------------------
 constexpr int LAP_SITES = 64;
-constexpr int LAP_EB = 16;
+constexpr int LAP_EB = 50;  // vectors per CTA at most: the 288 B of links a thread holds are amortised as in nabla3
 
+// Thread (site, direction) keeps U_d(x) and U_d(x - d) in registers across the CTA's vectors.  The neighbour colour
+// vectors and the centre value of vector e + 1 are fetched into registers before the partial sums of vector e are
+// reduced over the three directions through shared memory (two buffers, so one barrier per vector).
 __global__ void __launch_bounds__(LAP_SITES * 3)
-laplacian_kernel(const cplx* __restrict__ F, cplx* __restrict__ out, const cplx* __restrict__ links, Geom g, int nvec) {
-    EDK_SHARED cplx red[3][LAP_SITES][3];
+laplacian_kernel(const cplx* __restrict__ F, cplx* __restrict__ out, const cplx* __restrict__ links, Geom g, int nvec, int eb) {
+    EDK_SHARED cplx red[2][3][LAP_SITES][3];
     const int site = blockIdx.x * LAP_SITES + threadIdx.x;
     const int d = threadIdx.y;
     const bool active = site < g.V;
@@ -419,22 +422,36 @@ laplacian_kernel(const cplx* __restrict__ F, cplx* __restrict__ out, const cplx*
             Ub[m] = ldg(pl + m);
         }
     }
-    const int e0 = blockIdx.y * LAP_EB;
-    const int e1 = min(e0 + LAP_EB, nvec);
+    const int e0 = blockIdx.y * eb;
+    const int e1 = min(e0 + eb, nvec);
     const size_t fs = (size_t)g.V * 3;
     const int tid = threadIdx.y * LAP_SITES + threadIdx.x;
+    // the element this thread finishes: component a of site sl of the CTA (consecutive threads, consecutive 16 bytes)
+    const int sl = tid / 3, a_out = tid % 3;
+    const int so = blockIdx.x * LAP_SITES + sl;
+    const bool writer = so < g.V;
+    const size_t out_off = (size_t)so * 3 + a_out;
+    cplx wf[3], wb[3], fc = make_double2(0.0, 0.0);
+    auto fetch = [&](int e, cplx(&f)[3], cplx(&b)[3], cplx& c) {
+        const cplx* Fe = F + (size_t)e * fs;
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                f[k] = ldg(Fe + (size_t)sf * 3 + k);
+                b[k] = ldg(Fe + (size_t)sb * 3 + k);
+            }
+        }
+        if (writer) c = ldg(Fe + out_off);
+    };
+    if (e0 < e1) fetch(e0, wf, wb, fc);
+    int buf = 0;
     for (int e = e0; e < e1; ++e) {
+        cplx nf[3], nb[3], nc = make_double2(0.0, 0.0);
+        if (e + 1 < e1) fetch(e + 1, nf, nb, nc);
         cplx r[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) r[a] = make_double2(0.0, 0.0);
         if (active) {
-            const cplx* Fe = F + (size_t)e * fs;
-            cplx wf[3], wb[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                wf[c] = ldg(Fe + (size_t)sf * 3 + c);
-                wb[c] = ldg(Fe + (size_t)sb * 3 + c);
-            }
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -444,27 +461,35 @@ laplacian_kernel(const cplx* __restrict__ F, cplx* __restrict__ out, const cplx*
                 }
         }
 #pragma unroll
-        for (int a = 0; a < 3; ++a) red[d][threadIdx.x][a] = r[a];
+        for (int a = 0; a < 3; ++a) red[buf][d][threadIdx.x][a] = r[a];
         __syncthreads();
-        if (tid < LAP_SITES * 3) {
-            const int sl = tid / 3, a = tid % 3;
-            const int so = blockIdx.x * LAP_SITES + sl;
-            if (so < g.V) {
-                const size_t idx = (size_t)e * fs + (size_t)so * 3 + a;
-                const cplx f = ldg(F + idx);
-                const double hx = red[0][sl][a].x + red[1][sl][a].x + red[2][sl][a].x;
-                const double hy = red[0][sl][a].y + red[1][sl][a].y + red[2][sl][a].y;
-                out[idx] = make_double2(6.0 * f.x - hx, 6.0 * f.y - hy);
-            }
+        if (writer) {
+            const double hx = red[buf][0][sl][a_out].x + red[buf][1][sl][a_out].x + red[buf][2][sl][a_out].x;
+            const double hy = red[buf][0][sl][a_out].y + red[buf][1][sl][a_out].y + red[buf][2][sl][a_out].y;
+            out[(size_t)e * fs + out_off] = make_double2(6.0 * fc.x - hx, 6.0 * fc.y - hy);
         }
-        __syncthreads();
+        // no second barrier: buffer `buf` is written again two vectors on, after every thread has passed the next barrier
+        buf ^= 1;
+        if (e + 1 < e1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) wf[k] = nf[k], wb[k] = nb[k];
+            fc = nc;
+        }
     }
 }
 
 cudaError_t launch_laplacian(const cplx* F, cplx* out, const cplx* links, Geom g, int nvec, cudaStream_t s) {
+    if (nvec < 1) return cudaSuccess;
+    // balanced chunks of <= LAP_EB vectors, more of them on small lattices so that the 148 SMs (2 CTAs each) see ~3 waves
+    const int nsb = (g.V + LAP_SITES - 1) / LAP_SITES;
+    int nchunk = (nvec + LAP_EB - 1) / LAP_EB;
+    const int want = (148 * 2 * 3 + nsb - 1) / nsb;
+    if (nchunk < want) nchunk = want < nvec ? want : nvec;
+    const int eb = (nvec + nchunk - 1) / nchunk;
+    nchunk = (nvec + eb - 1) / eb;
     dim3 block(LAP_SITES, 3);
-    dim3 grid((g.V + LAP_SITES - 1) / LAP_SITES, (nvec + LAP_EB - 1) / LAP_EB);
-    EDK_LAUNCH(laplacian_kernel, grid, block, 0, s, F, out, links, g, nvec);
+    dim3 grid(nsb, nchunk);
+    EDK_LAUNCH(laplacian_kernel, grid, block, 0, s, F, out, links, g, nvec, eb);
     return cudaGetLastError();
 }
 

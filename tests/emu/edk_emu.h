@@ -140,10 +140,6 @@ inline void dmma884(double& c0, double& c1, const double a, const double b) {
 }
 
 inline double flip_sign(double x) { return -x; }
-inline double2 lds128(uint32_t addr) {
-    if (addr % 16 != 0 || addr + 16 > (uint32_t)EMU_SMEM_BYTES) throw std::runtime_error("bad 16-byte shared-memory load");
-    return *reinterpret_cast<const double2*>(smem + addr);
-}
 inline double2 lds128_again(const void* p) { return *reinterpret_cast<const double2*>(p); }
 
 using std::max;

@@ -393,6 +393,24 @@ def test_separable_form_shallow_ring_and_environment(emu, monkeypatch):
     assert worst_block_error(h.calc(), ref) < 1e-10
     h.close()
     monkeypatch.delenv("EDK_SEP_VARIANT")
+    # EDK_SEP_LAUNCHES=3 (A/B hook): one launch per tile shape instead of one over the whole tile table
+    monkeypatch.setenv("EDK_SEP_LAUNCHES", "3")
+    lt, Nt = (8, 2, 1), 43  # Ne = 43: all three tile shapes
+    Ut, Vt, reft = inputs_and_reference(lt, Nt, D, 1, orc.momentum_set(7))
+    h = Handle(emu, lt, Nt, D, 1, orc.momentum_set(7))
+    h.set_inputs(Ut, Vt)
+    n0 = emu.edk_launch_count(h.h)
+    per_shape = h.calc()
+    n_per_shape = emu.edk_launch_count(h.h) - n0
+    assert worst_block_error(per_shape, reft) < 1e-10
+    h.close()
+    monkeypatch.delenv("EDK_SEP_LAUNCHES")
+    h = Handle(emu, lt, Nt, D, 1, orc.momentum_set(7))
+    h.set_inputs(Ut, Vt)
+    n0 = emu.edk_launch_count(h.h)
+    assert np.array_equal(h.calc(), per_shape)  # same tiles, same arithmetic: bit-identical
+    assert n_per_shape - (emu.edk_launch_count(h.h) - n0) == 2
+    h.close()
     mom = np.ascontiguousarray(np.asarray([(3, 0, 0), (0, 0, 1)], np.int32))
     hh = C.c_void_p()
     rc = emu.edk_create(16, 2, 2, 3, D, 1, 2, mom.ctypes.data_as(C.POINTER(C.c_int)), 0, C.byref(hh))
