@@ -4,13 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config5] [--impl reference]
 
 A "step" is one timeslice of the workload: all Nop x Nmom matrices E[d,p](t) of size Ne x Ne.
-Native arm: `value` is measured with the step's inputs already resident in HBM, `e2e` through
-the host-buffer C-ABI call (edk_calc_host) with H2D/D2H inside the timed region.  For N > 1 each
-rank owns its own timeslices (weak scaling), and the timed region ends with the NCCL gather of
-all results onto rank 0 - the only exchange step this path has.
-Contraction form: by default (`--contraction auto`) an untimed set-up step validates the newer plane-wave
-factorised form against the GEMM form at the workload's shape in a child process and uses it only if it agrees to
-1e-10 and is faster (easydistillation_b200/tuning.py); the line reports the decision under "contraction".
+Native arm: `value` is measured through the public sharded call gen.calc_all() with the step's inputs already
+resident in HBM (device handles), `e2e` through gen.calc_range() on host arrays (streamed pipeline over the
+C ABI) with H2D/D2H inside the timed region, and `e2e.from_files` through the file presets (ILDG, .npy, QDP).
+For N > 1 each rank owns its own timeslices (weak scaling); finished chunks travel to rank 0 over NCCL inside
+the timed region while the next are computed - the only exchange step this path has.
+Contraction form: the one the library plans for the handle (`edk_plan_form`; `--contraction X` forces another
+through the A/B hook for measurements).  Every run also checks the planned form against the GEMM form on one
+timeslice and reports the observed error under "contraction".
 Reference arm (`--impl reference`): the numpy restatement of the reference algorithm
 (oracle/elemental_oracle.py, kind "port": the reference itself is a Python package that does
 not exist on the GPU box) timed on the host cores on a bounded sample of the same workload.

@@ -158,7 +158,7 @@ def test_gemm_form_tile_heights_and_split_k_through_the_launchers(emu):
 
 
 def test_plane_wave_form_selected_by_environment_and_pairing_switches(emu, monkeypatch):
-    """EDK_GRAM_ALGO=2 at edk_create (the path bench.py / tuning.apply use): configure() builds the plane-wave tables
+    """EDK_GRAM_ALGO=2 at edk_create (the A/B hook `bench.py --contraction` uses): configure() builds the plane-wave tables
     itself; then both pairing modes (edk_debug_symmetry re-configures: tables are rebuilt for the new job list and
     internal momentum list) and a switch back to the GEMM form.  num_nabla = 2, non-closed momentum list, ragged
     planes of 15 sites."""
