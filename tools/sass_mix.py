@@ -50,15 +50,27 @@ def main():
         demangled = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip().split("(")[0]
         print(f"{demangled}: {n} instructions, {mix}")
     print()
+    print("# separable contraction (form 4): whole-kernel instruction counts of the 13-mode, 8-pairs-per-stage instances.")
+    print("# The kernel holds four copies of the stage body (1 or 2 blocks of L x 1 or 2 blocks of R per lane), each fully")
+    print("# unrolled over the 8 site pairs of a stage; LDTM / STTM are tcgen05.ld / tcgen05.st (y accumulators in tensor")
+    print("# memory), UTMALDG the TMA boxes, UTCATOMSWS / UTCBAR the tensor-memory allocation, no DMMA anywhere.")
+    sep_keep = ("DFMA", "DADD", "DMUL", "LDS", "LDC", "LDTM", "STTM", "UTMALDG", "SYNCS", "LDL", "STL", "IMAD", "MOV", "LDG", "STG", "UTCATOMSWS", "UTCBAR")
+    for name in sorted(funcs):
+        if not re.search(r"gram_sepx1?_kernelILi2ELi4ELi8E", name):
+            continue
+        ops = collections.Counter(re.sub(r"@!?U?P\d+\s+", "", x[1]).split()[0].split(".")[0] for x in funcs[name])
+        demangled = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip().split("(")[0]
+        print(f"{demangled}: {len(funcs[name])} instructions, {({k: ops[k] for k in sep_keep if ops.get(k)})}")
+    print()
     print("# ptxas -v (registers at launch; the MMA warps raise their budget to 232 with setmaxnreg)")
-    for log in ("edk_gram.o.log", "edk_gram_pw.o.log"):
+    for log in ("edk_gram.o.log", "edk_gram_pw.o.log", "edk_gram_sep_s24.o.log"):
         path = os.path.join(REPO, "easydistillation_b200", "build", log)
         if not os.path.exists(path):
             continue
         lines = open(path).read().splitlines()
         for i, ln in enumerate(lines):
             m = re.search(r"Compiling entry function '(\S+)'", ln)
-            if m and re.search(r"gram_(pw|pwf|tma)_kernel", m.group(1)):
+            if m and re.search(r"gram_(pw|pwf|tma|sepx|sepx1)_kernel", m.group(1)):
                 d = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
                 print(d + ":", " | ".join(x.replace("ptxas info    : ", "").strip() for x in lines[i + 2:i + 4]))
 
