@@ -1,13 +1,14 @@
 """Randomised sweep of the plane-wave contraction forms on the host emulator (TEST INFRASTRUCTURE ONLY, not part of the
 pytest suite: run it by hand after touching csrc/edk_gram_pw.cu or the plane-wave part of csrc/edk_api.cu).
 
-    python tests/emu/sweep.py [--seconds 600] [--seed 1] [--tiles]
+    python tests/emu/sweep.py [--seconds 600] [--seed 1] [--tiles | --separable]
 
 Builds libedk_emu.so like tests/test_emu_library.py, then draws lattice extents, Ne, generator mode, order, momentum
 lists (random triples incl. negative and larger-than-lattice components, or prefixes of the |p|^2-ordered set),
 pairing mode and form (2 or 3), runs the C ABI and compares with the oracle (1e-10, block-wise).  `--tiles` instead
 sweeps Ne = 17..120 on tiny lattices over the three tile shapes (EDK_PW_TILE = 24 / 25 / 17): multi-tile runs, mirror
-tiles of self pairs, partial f-tiles, padding-only warps.
+tiles of self pairs, partial f-tiles, padding-only warps.  `--separable` sweeps the separable form (4, the planned
+default on the production lattices) over Lx, Ne (all three warp grids), mode structures and both launch modes.
 """
 import argparse
 import os
@@ -30,6 +31,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=600.0)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--tiles", action="store_true")
+    ap.add_argument("--separable", action="store_true", help="sweep the separable form (4): Lx in {8, 12, 16, 24, 32}, all tile shapes")
     args = ap.parse_args()
     rnd = random.Random(args.seed)
     with tempfile.TemporaryDirectory() as tmp:
@@ -37,7 +39,30 @@ def main():
         t_end, n, worst = time.time() + args.seconds, 0, 0.0
         while time.time() < t_end:
             sym = None
-            if args.tiles:
+            form = rnd.choice([2, 3, 3])
+            if args.separable:
+                # the planned default wherever plan_sep accepts the lattice and the list: 4 / 6 / 8 pairs per stage, one to
+                # four stages per row, 5 / 9 / 13 modes, Ne across the three warp grids, both launch modes
+                latt3 = (rnd.choice([8, 8, 12, 16, 24, 32]), rnd.randint(1, 5), rnd.randint(1, 3))
+                Ne = rnd.choice([1, 3, 8, 9, 16, 31, 32, 33, 40, 47, 64, 70])
+                mode = rnd.choice([T.D, T.D, T.X])
+                order = rnd.randint(0, 2)
+                kind = rnd.random()
+                if kind < 0.5:
+                    moms = orc.momentum_set(rnd.choice([1, 7, 9, 19, 27, 33]))
+                else:  # any list inside the instantiated structures: |px|, |py| <= 2, px^2 + py^2 <= 4, pz free
+                    moms = []
+                    while len(moms) < rnd.randint(3, 8):
+                        px, py = rnd.randint(-2, 2), rnd.randint(-2, 2)
+                        if px * px + py * py <= 4:
+                            moms.append((px, py, rnd.randint(-3, 3)))
+                sym = rnd.choice([None, None, 0, 1]) if mode == T.D and order else None
+                os.environ["EDK_SEP_LAUNCHES"] = rnd.choice(["1", "3"])
+                form = 4
+                nfield = {0: 1, 1: 4, 2: 13}[order] if mode == T.D else 2
+                if latt3[0] * latt3[1] * latt3[2] * max(Ne, 32) ** 2 * nfield * nfield > 6e7:
+                    continue  # keep a case within a few seconds of emulation
+            elif args.tiles:
                 latt3 = rnd.choice([(2, 2, 1), (4, 2, 1), (3, 3, 1), (4, 4, 1), (3, 5, 1)])
                 Ne, mode, order = rnd.randint(17, 120), T.D, rnd.choice([0, 1])
                 moms = rnd.choice([[(0, 0, 0)], [(0, 0, 0), (1, 0, 0), (-1, 0, 0)], [(1, 1, 0), (0, -1, 0)]])
@@ -53,12 +78,14 @@ def main():
                 sym = rnd.choice([None, None, 0, 1]) if mode == T.D else None
                 if latt3[0] * latt3[1] * latt3[2] * Ne * Ne * len(moms) * (1 + order) ** 2 > 4e6:
                     continue  # keep a case within a few seconds of emulation
-            form = rnd.choice([2, 3, 3])
             U_file, V, ref = T.inputs_and_reference(latt3, Ne, mode, order, moms, seed=n)
             h = T.Handle(lib, latt3, Ne, mode, order, moms)
             if sym is not None:
                 h.check(lib.edk_debug_symmetry(h.h, sym), "edk_debug_symmetry")
             h.check(lib.edk_debug_algo(h.h, form), "edk_debug_algo")
+            if form == 4 and h.query(10) != 4:
+                print(f"FAIL latt={latt3} moms={moms}: the separable form was not accepted")
+                return 1
             h.set_inputs(U_file, V)
             err = T.worst_block_error(h.calc(), ref)
             tile = h.query(12)
