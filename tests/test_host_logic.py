@@ -500,6 +500,14 @@ def test_parallel_copy_matches_plain_copy():
     assert wide[:, ::2].sum() == 12 and wide[:, 1::2].sum() == 0
     with pytest.raises(ValueError):
         parallel_copy(np.zeros((4, 3)), np.zeros((3, 4)))
+    # what calc_to_file's writer does: a batch [t, Nop, Nmom, Ne, Ne] dropped, transposed, into the time slab of the
+    # [Nop, Nmom, Lt, Ne, Ne] file mapping; also down-cast to the complex64 the reference stores
+    batch = (rng.standard_normal((3, 5, 4, 12, 12)) + 1j * rng.standard_normal((3, 5, 4, 12, 12))).astype(np.complex128)
+    for dt in (np.complex128, np.complex64):
+        filed = np.zeros((5, 4, 7, 12, 12), dt)
+        parallel_copy(filed[:, :, 2:5], batch.transpose(1, 2, 0, 3, 4), min_bytes=1)
+        assert np.array_equal(filed[:, :, 2:5], batch.transpose(1, 2, 0, 3, 4).astype(dt))
+        assert not filed[:, :, :2].any() and not filed[:, :, 5:].any()
 
 
 def test_bench_contraction_accounting():
