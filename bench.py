@@ -350,6 +350,16 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # native arm
 # --------------------------------------------------------------------------------------------
+def synth_links(torch, dev, V, g):
+    """Random SU(3) links [V,4,3,3] c128 (file order of one timeslice) from the generator g, on the device."""
+    a = torch.randn((V, 4, 3, 3), dtype=torch.complex128, device=dev, generator=g)
+    q, r = torch.linalg.qr(a)
+    d = torch.diagonal(r, dim1=-2, dim2=-1)
+    q = q * (d / d.abs()).unsqueeze(-2)
+    det = torch.linalg.det(q)
+    return (q / det.pow(1.0 / 3.0)[..., None, None]).contiguous()
+
+
 def synth_device_inputs(torch, dev, name, seed):
     """Random SU(3) links [V,4,3,3] c128 (file order of one timeslice) and unit-norm complex64
     eigenvectors [Ne,V,3], generated on the device (bench only; tests use the oracle's numpy ones)."""
@@ -357,12 +367,7 @@ def synth_device_inputs(torch, dev, name, seed):
     V = Lx * Ly * Lz
     g = torch.Generator(device=dev)
     g.manual_seed(20261017 + seed)
-    a = torch.randn((V, 4, 3, 3), dtype=torch.complex128, device=dev, generator=g)
-    q, r = torch.linalg.qr(a)
-    d = torch.diagonal(r, dim1=-2, dim2=-1)
-    q = q * (d / d.abs()).unsqueeze(-2)
-    det = torch.linalg.det(q)
-    U = (q / det.pow(1.0 / 3.0)[..., None, None]).contiguous()
+    U = synth_links(torch, dev, V, g)
     v = torch.randn((Ne, V, 3), dtype=torch.complex64, device=dev, generator=g)
     v = v / torch.linalg.vector_norm(v.reshape(Ne, -1), dim=1)[:, None, None]
     return U, v.contiguous()

@@ -1,6 +1,6 @@
 """Multi-GPU check of the public sharded call, run under torch.distributed.run on N GPUs of one box:
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29531 tools/check_calc_all_nccl.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29531 tests/check_calc_all_nccl.py
 
 Every rank builds the same generator (seeded synthetic inputs, host handles and device-resident handles), calls
 gen.calc_all(dst=0) / calc_all(dst=None) over NCCL and calc_to_file(shard=True) into one shared .npy; rank 0 compares

@@ -1,6 +1,6 @@
 """GPU check of one contraction form against the numpy oracle and the GEMM form, in its own process.
 
-    python tools/check_forms.py --form 4 [--bench] [--bench-shapes config3,config4,config5]
+    python tests/check_forms.py --form 4 [--bench] [--bench-shapes config3,config4,config5]
 
 Runs the form through the engine on ragged and multi-tile shapes, both pairing modes, derivative and displacement
 jobs, every stage width of the separable kernel (8 / 6 / 4 site pairs) and every mode structure (5 / 9 / 13 modes),

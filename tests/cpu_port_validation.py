@@ -6,7 +6,7 @@ per timeslice): they time its two primitives at full size - one `_nD` hop (latti
 oracle's FAITHFUL restatement of the reference (78 hops, 43 x Nmom einsums, the reference's own loop structure) in full on
 one timeslice of config 3 (24^3, Ne = 100, 33 momenta) on this machine's cores and prints both figures side by side.
 
-    python tools/cpu_port_validation.py [--workload config3] > profiles/r02/cpu_port_config3_full.json
+    python tests/cpu_port_validation.py [--workload config3] > profiles/r02/cpu_port_config3_full.json
 """
 import argparse
 import importlib.util

@@ -15,7 +15,7 @@ print('AB $wl launches=$n', 'value %.3f ms/step %.3f pipe %.3f frac %.3f'%(d['va
   done
 done
 timeout 300 python tools/laplacian_bandwidth.py > gpurun_out/laplacian_bandwidth.json 2> gpurun_out/laplacian.err; cat gpurun_out/laplacian_bandwidth.json | tr -d '\n ' | cut -c1-700; echo
-python tools/check_forms.py --form 4 > gpurun_out/check_form4_merged.log 2>&1; tail -1 gpurun_out/check_form4_merged.log
+python tests/check_forms.py --form 4 > gpurun_out/check_form4_merged.log 2>&1; tail -1 gpurun_out/check_form4_merged.log
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_config5.csv \

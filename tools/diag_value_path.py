@@ -21,9 +21,7 @@ def main():
     K = 10
     Lx, Ly, Lz, Lt, Ne, nabla, nmom = bench.WORKLOADS[name]
     dev = torch.device("cuda", 0)
-    from oracle import elemental_oracle as orc
-
-    moms = orc.momentum_set(nmom)
+    moms = bench.momentum_set(nmom)
     inputs = [bench.synth_device_inputs(torch, dev, name, i) for i in range(2)]
     gen = edb.ElementalGenerator([Lx, Ly, Lz, K], edb.GaugeFieldDevice([U.reshape(Lz, Ly, Lx, 4, 3, 3) for U, _ in inputs], cyclic=True),
                                  edb.EigenvectorDevice([v.reshape(Ne, Lz, Ly, Lx, 3) for _, v in inputs], cyclic=True), nabla, moms, device=0)

@@ -15,7 +15,7 @@ import torch  # noqa: E402
 
 from easydistillation_b200 import _capi  # noqa: E402
 from easydistillation_b200.engine import ElementalEngine  # noqa: E402
-from oracle import elemental_oracle as orc  # noqa: E402
+import bench  # noqa: E402
 
 
 def block_errors(got, ref):
@@ -25,7 +25,7 @@ def block_errors(got, ref):
 
 
 def main():
-    moms = orc.momentum_set(33)
+    moms = bench.momentum_set(33)
     p2 = np.array([sum(c * c for c in m) for m in moms])
     out = []
     for L, Ne in ((8, 32), (16, 32), (24, 32), (32, 32), (48, 32), (48, 200)):
@@ -35,7 +35,7 @@ def main():
         V = Ne * L ** 3 * 3
         v = torch.view_as_complex(torch.randn((V, 2), generator=g, device="cuda", dtype=torch.float32)).reshape(Ne, L, L, L, 3)
         v = (v / torch.linalg.vector_norm(v.reshape(Ne, -1), dim=1)[:, None, None, None, None]).contiguous()
-        U = torch.from_numpy(orc.synthetic_links(latt + [1], 1)).cuda()
+        U = bench.synth_links(torch, torch.device("cuda"), L ** 3, g)
         eng.set_links(U, _capi.LINKS_FILE_T)
         eng.set_eigvecs(v)
         res = {}

@@ -5,7 +5,7 @@ set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 \
-  tools/check_calc_all_nccl.py > gpurun_out/calc_all_nccl_${N}gpu.json 2> gpurun_out/calc_all_nccl_${N}gpu.err
+  tests/check_calc_all_nccl.py > gpurun_out/calc_all_nccl_${N}gpu.json 2> gpurun_out/calc_all_nccl_${N}gpu.err
 tail -3 gpurun_out/calc_all_nccl_${N}gpu.err | cut -c1-300; cat gpurun_out/calc_all_nccl_${N}gpu.json | cut -c1-1200
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 \
   bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_config5_${N}gpu.json 2> gpurun_out/bench_config5_${N}gpu.err

@@ -9,8 +9,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
 import easydistillation_b200 as edb  # noqa: E402
-from oracle import elemental_oracle as orc  # noqa: E402
 
 
 def main():
@@ -23,7 +23,9 @@ def main():
     dev = torch.device("cuda", 0)
     for L, nvec in ((24, 100), (32, 200), (48, 200)):
         latt = [L, L, L, 1]
-        U = orc.synthetic_links(latt, 0)[None]
+        g0 = torch.Generator(device=dev)
+        g0.manual_seed(1000 + L)
+        U = bench.synth_links(torch, dev, L**3, g0).cpu().numpy().reshape(1, L, L, L, 4, 3, 3)
         lap = edb.Laplacian(latt, edb.GaugeFieldHostmem(U), device=0)
         lap.load("x")
         lap.set_timeslice(0)
