@@ -346,12 +346,13 @@ __global__ void __launch_bounds__(SEP_THREADS, 1) gram_sep_kernel(const SepParam
 //    flight meanwhile.  Layout: lane quadrant 32 (warp % 4), columns 256 (warp / 4) + 128 i + 64 j + 4 m + {0, 1: Re,
 //    2, 3: Im} for mode m of element (i, j).  The producer warp allocates the 512 columns and frees them after the
 //    last compute warp has arrived on bar_done.
-//  * tiles: 8 compute warps arranged 4 x 2 (32 x 32 elements), 1 x 8 (8 x 128) or 8 x 1 (64 x 16), one launch per shape
-//    over the host's tile table (SepTile, sep_build_tiles).  One fixed 32 x 32 tile leaves, at Ne = 200, a ragged row
-//    and column of tiles whose CTAs run two to four of their eight warps; the flat shapes cover those edges.
+//  * tiles: 8 compute warps arranged 4 x 2 (32 x 32 elements), 1 x 8 (8 x 128) or 8 x 1 (64 x 16) over the host's tile
+//    table (SepTile, sep_build_tiles), one launch per shape or one in all (see the kernels below).  One fixed 32 x 32
+//    tile leaves, at Ne = 200, a ragged row and column of tiles whose CTAs run two to four of their eight warps; the
+//    flat shapes cover those edges.
 // Lane (le, lf) of warp (a, b) owns rows e0 + 8 a + le + {0, 4} of L and rows f0 + 16 b + lf + {0, 8} of R.
-// Measured at config 5 (48^3, Ne = 200, 33 momenta): 121 ms per timeslice against 172 ms of gram_sep_kernel and 179 ms
-// of gram_pwf_kernel; FP64 pipe 68 % busy over the launch of 32 x 32 tiles, 84 % inside the stage loop.
+// Measured at config 5 (48^3, Ne = 200, 33 momenta): 116 ms per timeslice against 172 ms of gram_sep_kernel and 179 ms
+// of gram_pwf_kernel; FP64 pipe 71 % busy over the launch of 32 x 32 tiles, about 84 % inside the stage loop.
 // ---------------------------------------------------------------------------------------------------------
 struct SepxGeom {
     static constexpr int WARPS = 8, THREADS = (WARPS + 4) * 32;
