@@ -1080,12 +1080,12 @@ int plan_contraction_form(int Lx, int Ly, const std::vector<int>& mom_int, const
         const ModePlan mp = plan_modes(mom_int);
         int couples = 0;
         for (size_t m = 0; m < mp.modes3.size() / 3; ++m) couples += mp.modes3[3 * m + 2] == 0;
-        const double w = segs * (14.0 + 16.0) * ((couples + 7) / 8) / 0.66;
+        const double w = segs * (14.0 + 16.0) * ((couples + 7) / 8) / 0.61;  // measured: FP64 pipe 61 % busy at config 5
         if (w < best) best = w, form = 3;
     }
     const SepPlan S = plan_sep(Lx, mom_int);
     if (S.ok) {
-        const double w = segs * (12.0 + 0.5 * (6.0 + 4.0 * S.qmax)) / 0.80;
+        const double w = segs * (12.0 + 0.5 * (6.0 + 4.0 * S.qmax)) / 0.70;  // measured: 69 - 71 % at configs 4 / 5
         if (w < best) best = w, form = 4;
     }
     return form;
